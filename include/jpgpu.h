@@ -1,0 +1,189 @@
+/*
+ * jpgpu.h — C ABI of the B200-native JPEG decode path (libjpgpu.so).
+ *
+ * Drop-in boundary: the reference (martinhath/jpeg-rust) has no FFI of its own;
+ * the seam is the builder + call at src/jpeg/mod.rs:388-416:
+ *
+ *     JPEGDecoder::new(data)              decoder.rs:55
+ *         .frame_header(..)               decoder.rs:83    per component id, H, V, Tq
+ *         .scan_header(..)                decoder.rs:113   per component Td, Ta; scan order
+ *         .dimensions((W, H))             decoder.rs:66
+ *     .huffman_ac_tables / .huffman_dc_tables / .quantization_table   decoder.rs:71-81
+ *     .decode() -> (Vec<(u8,u8,u8)>, usize)                           decoder.rs:162
+ *
+ * Everything those builder calls carry is one POD `jpgpu_image_desc`; `.decode()`
+ * is `jpgpu_decode()` (one image, reference semantics) or the `jpgpu_batch_*`
+ * family (many independent images, the path the benchmark measures).  Marker and
+ * header parsing stays on the host (Rust in the reference, `jpgpu_parse()` here).
+ * All pointers are plain host or device pointers; no torch/C++ types cross this
+ * boundary.  There is no CPU fallback: every entry point that computes fails with
+ * JPGPU_ERR_NO_DEVICE / JPGPU_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef JPGPU_H
+#define JPGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JPGPU_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ statuses
+ * 0 = success.  1..15 mirror the panics of the reference so that a host shim
+ * can re-raise them (src/jpeg/mod.rs / decoder.rs / huffman.rs line numbers in
+ * the comments).  >= 32 are errors of this library. */
+enum {
+    JPGPU_OK = 0,
+    JPGPU_PANIC_UNHANDLED_MARKER = 1, /* mod.rs:457 */
+    JPGPU_PANIC_DRI = 2,              /* mod.rs:427 "got to restart interval def" */
+    JPGPU_PANIC_APP12_14 = 3,         /* mod.rs:446,449 */
+    JPGPU_PANIC_DQT_PRECISION = 4,    /* mod.rs:258 */
+    JPGPU_PANIC_SAMPLING_ASSERT = 5,  /* mod.rs:275-277 */
+    JPGPU_PANIC_INDEX_OOB = 6,        /* slice index out of bounds anywhere in parse */
+    JPGPU_PANIC_NO_FRAME_HEADER = 7,  /* mod.rs:388 */
+    JPGPU_PANIC_MISSING_TABLE = 8,    /* decoder.rs:155,159,224 */
+    JPGPU_PANIC_DC_LOOKUP = 9,        /* huffman.rs:156 */
+    JPGPU_PANIC_AC_LOOKUP = 10,       /* huffman.rs:162 */
+    JPGPU_PANIC_COMPONENT_COUNT = 11, /* decoder.rs:330 */
+    JPGPU_PANIC_READ_BITS_ASSERT = 12,/* huffman.rs:202 */
+    JPGPU_PANIC_SCAN_COMPONENT = 13,  /* decoder.rs:148 */
+    JPGPU_NO_SCAN = 14,               /* parse() reached the end without SOS (image_data None) */
+    JPGPU_PANIC_ARITH = 15,           /* debug-build arithmetic overflow, e.g. mod.rs:218 */
+
+    JPGPU_ERR_INVALID_ARG = 32,
+    JPGPU_ERR_NO_DEVICE = 33,         /* no CUDA device / not sm_100: there is no CPU fallback */
+    JPGPU_ERR_CUDA = 34,              /* a CUDA runtime call failed; see jpgpu_last_error() */
+    JPGPU_ERR_UNSUPPORTED = 35,       /* outside the decodable subset (e.g. H or V not in {1,2}) */
+    JPGPU_ERR_BAD_HUFFMAN_TABLE = 36, /* BITS/HUFFVAL do not describe a prefix code */
+    JPGPU_ERR_TRUNCATED = 37,         /* entropy data ended before all MCUs were decoded */
+    JPGPU_ERR_BAD_CODE = 38,          /* bit pattern that is no code of the selected table
+                                         (reference: huffman.rs:156/162 panic) */
+    JPGPU_ERR_RESTART = 39,           /* RSTn markers missing / out of sequence */
+    JPGPU_ERR_OOM = 40
+};
+
+/* Output geometry (SURVEY.md §8 "parity policy").
+ * REF  = bug-compatible with the reference's placement (decoder.rs:259-312,
+ *        347-379) and its MCU count (decoder.rs:191-192).
+ * SPEC = what that code intends: T.81 A.2.3 MCU order, true MCU count, box
+ *        replication of sub-sampled components, crop at right/bottom edge.
+ * For gray, 4:4:4 with W%8==0 and 4:2:2 (H2V1) with W%16==0 both are identical. */
+enum { JPGPU_LAYOUT_REF = 0, JPGPU_LAYOUT_SPEC = 1 };
+
+/* Parser extensions beyond the reference's accepted subset (bit flags). */
+enum {
+    JPGPU_EXT_NONE = 0,
+    JPGPU_EXT_SKIP_APPN = 1, /* skip APPn/JPGn segments (incl. APP12/APP14) by their length */
+    JPGPU_EXT_DRI = 2        /* accept DRI; the scan is decoded per restart interval */
+};
+
+/* One component, in SCAN order (decoder.rs:39-52, after scan_header() reordering). */
+typedef struct jpgpu_component {
+    uint8_t id; /* Ci */
+    uint8_t h;  /* horizontal sampling factor, 1 or 2 (mod.rs:275) */
+    uint8_t v;  /* vertical sampling factor, 1 or 2 (mod.rs:277) */
+    uint8_t tq; /* quantisation table selector */
+    uint8_t td; /* DC Huffman table selector */
+    uint8_t ta; /* AC Huffman table selector */
+} jpgpu_component;
+
+/* Everything mod.rs:388-413 hands to the JPEGDecoder builder. */
+typedef struct jpgpu_image_desc {
+    uint32_t width, height;        /* SOF0 X, Y (mod.rs:295) */
+    uint32_t ncomp;                /* components in the scan */
+    jpgpu_component comp[4];
+    uint16_t qt[4][64];            /* DQT entries in zigzag order, as in the file (mod.rs:238-256) */
+    uint8_t qt_present[4];
+    uint8_t dc_bits[4][16];        /* DHT BITS (mod.rs:313) */
+    uint8_t dc_vals[4][256];       /* DHT HUFFVAL (mod.rs:321) */
+    uint16_t dc_nvals[4];
+    uint8_t dc_present[4];
+    uint8_t ac_bits[4][16];
+    uint8_t ac_vals[4][256];
+    uint16_t ac_nvals[4];
+    uint8_t ac_present[4];
+    uint32_t restart_interval;     /* MCUs per interval; 0 = none (always 0 inside the reference's subset) */
+    uint32_t layout;               /* JPGPU_LAYOUT_* */
+    /* RAW (still byte-stuffed) entropy-coded bytes from the first byte after the
+     * SOS header to the end of the file — the range mod.rs:371-385 walks.  The
+     * GPU removes the stuffing and finds RSTn markers itself. */
+    const uint8_t *scan;
+    size_t scan_len;
+} jpgpu_image_desc;
+
+typedef struct jpgpu_ctx jpgpu_ctx;     /* one per process and device */
+typedef struct jpgpu_batch jpgpu_batch; /* a planned set of images with its device buffers */
+
+/* ------------------------------------------------------------ host-only part */
+
+/* Replaces JPEGImage::parse() up to the decode() call (mod.rs:202-414): walks
+ * the markers, fills `out`, points out->scan into `file`.  Returns JPGPU_OK or
+ * the status naming the panic the reference would raise.  `layout` is copied
+ * into the descriptor.  Needs no GPU. */
+int jpgpu_parse(const uint8_t *file, size_t len, uint32_t ext_flags, uint32_t layout, jpgpu_image_desc *out);
+
+/* Number of MCUs decode() reads and blocks per MCU for a descriptor (decoder.rs:164-192
+ * for REF; true MCU count for SPEC).  Returns a status. */
+int jpgpu_geometry(const jpgpu_image_desc *desc, uint32_t *mcus, uint32_t *blocks_per_mcu, uint32_t nblocks_per_comp[4]);
+
+const char *jpgpu_status_string(int status);
+int jpgpu_abi_version(void);
+
+/* ------------------------------------------------------------- device part */
+
+/* Creates the context on CUDA device `device` (cudaSetDevice ordinal). */
+int jpgpu_create(int device, jpgpu_ctx **out);
+void jpgpu_destroy(jpgpu_ctx *ctx);
+const char *jpgpu_last_error(const jpgpu_ctx *ctx);
+/* All work of the context is enqueued on this cudaStream_t (default: a stream the
+ * context owns).  Pass torch.cuda.current_stream().cuda_stream to time with torch events. */
+int jpgpu_set_stream(jpgpu_ctx *ctx, void *cuda_stream);
+int jpgpu_sync(jpgpu_ctx *ctx);
+
+/* JPEGDecoder::decode() for one image (decoder.rs:162): writes W*H*3 interleaved
+ * RGB bytes to the HOST buffer `rgb_out` and the reference's `bytes_read`. */
+int jpgpu_decode(jpgpu_ctx *ctx, const jpgpu_image_desc *desc, uint8_t *rgb_out, size_t *bytes_read);
+
+/* Convenience: parse + decode of a whole file (JPEGImage::parse, mod.rs:202). */
+int jpgpu_decode_file(jpgpu_ctx *ctx, const uint8_t *file, size_t len, uint32_t ext_flags, uint32_t layout,
+                      uint8_t *rgb_out, size_t rgb_cap, uint32_t *width, uint32_t *height, size_t *bytes_read);
+
+/* Batch path (no counterpart in the reference; images are independent, so a batch
+ * is simply many decode() calls sharing kernel launches).  Usage:
+ *   create -> upload -> decode (= entropy + idct) -> download / device_rgb -> results.
+ * A batch may be uploaded/decoded repeatedly (buffers are reused). */
+int jpgpu_batch_create(jpgpu_ctx *ctx, const jpgpu_image_desc *descs, size_t n, jpgpu_batch **out);
+void jpgpu_batch_destroy(jpgpu_batch *b);
+/* Host->device copy of every image's scan bytes (async on the context stream).
+ * desc.scan memory must stay valid until the stream has passed this point. */
+int jpgpu_batch_upload(jpgpu_batch *b);
+/* Alternative to upload: the raw scan bytes of all images are already in device
+ * memory, image i at dev_base + offsets[i] (length = descs[i].scan_len). */
+int jpgpu_batch_set_device_scans(jpgpu_batch *b, const void *dev_base, const uint64_t *offsets);
+int jpgpu_batch_entropy(jpgpu_batch *b); /* stage 1: unstuff/RST pre-pass, self-synchronising Huffman decode */
+int jpgpu_batch_idct(jpgpu_batch *b);    /* stage 2+3: dequant, IDCT, upsample, YCbCr->RGB, interleaved store */
+int jpgpu_batch_decode(jpgpu_batch *b);  /* entropy + idct */
+/* Device->host copy of image i's RGB into outs[i] (host pointers, W*H*3 bytes each); async. */
+int jpgpu_batch_download(jpgpu_batch *b, uint8_t *const *outs);
+/* Device pointer / size of image i's interleaved RGB output. */
+void *jpgpu_batch_device_rgb(jpgpu_batch *b, size_t i, size_t *nbytes);
+/* Synchronises the stream; per image: status (JPGPU_*) and the reference's bytes_read. Either may be NULL. */
+int jpgpu_batch_results(jpgpu_batch *b, int32_t *statuses, uint64_t *bytes_read);
+/* Debug export for the bit-exact gate: the decoded coefficients of image i in the
+ * reference's own arrangement — blocks[component] after decoder.rs:208-212:
+ * components in scan order, blocks in decode order, 64 x int16 in ZIGZAG order,
+ * absolute DC.  `out` holds `cap` int16; nblocks[c] receives the block counts. Synchronises. */
+int jpgpu_batch_coefficients(jpgpu_batch *b, size_t i, int16_t *out, size_t cap, uint32_t nblocks[4]);
+/* Algorithmic byte counts of the last plan (for roofline arithmetic):
+ * [0] raw scan bytes, [1] coefficient bytes (blocks*128), [2] RGB bytes, [3] pixels, [4] blocks. */
+int jpgpu_batch_stats(jpgpu_batch *b, uint64_t stats[8]);
+/* Number of kernel launches enqueued by this batch object so far. */
+uint64_t jpgpu_batch_launch_count(const jpgpu_batch *b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPGPU_H */

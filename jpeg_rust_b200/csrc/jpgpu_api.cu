@@ -1,0 +1,341 @@
+// jpgpu_api.cu — device part of the C ABI (include/jpgpu.h): context, batch
+// planning on the device, stage launches, transfers.  There is no CPU fallback:
+// without a usable sm_100 device every entry point returns JPGPU_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "jpgpu_host.h"
+#include "jpgpu_kernels.cuh"
+
+using namespace jpgpu;
+
+struct jpgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+};
+
+struct jpgpu_batch {
+    jpgpu_ctx* ctx = nullptr;
+    size_t n = 0;
+    HostPlan plan;
+    std::vector<const uint8_t*> host_scan;
+    std::vector<size_t> host_scan_len;
+    BatchDev dev;
+    std::vector<void*> allocs;
+    uint64_t launches = 0;
+    size_t coef_bytes = 0;
+    bool decoded = false;
+};
+
+namespace {
+
+int fail(jpgpu_ctx* c, cudaError_t e, const char* what) {
+    if (c) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        c->err = buf;
+    }
+    return e == cudaErrorMemoryAllocation ? JPGPU_ERR_OOM : JPGPU_ERR_CUDA;
+}
+
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return fail(ctx, e_, #call);   \
+    } while (0)
+
+template <typename T>
+int dev_alloc(jpgpu_batch* b, T** out, size_t count) {
+    jpgpu_ctx* ctx = b->ctx;
+    void* p = nullptr;
+    CK(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 256)));
+    b->allocs.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return JPGPU_OK;
+}
+
+template <typename T>
+int dev_upload(jpgpu_batch* b, const T** out, const std::vector<T>& v) {
+    jpgpu_ctx* ctx = b->ctx;
+    T* p = nullptr;
+    int st = dev_alloc(b, &p, v.size());
+    if (st != JPGPU_OK) return st;
+    if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = p;
+    return JPGPU_OK;
+}
+
+}  // namespace
+
+extern "C" int jpgpu_create(int device, jpgpu_ctx** out) {
+    if (!out) return JPGPU_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return JPGPU_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return JPGPU_ERR_NO_DEVICE;
+    if (prop.major != 10) return JPGPU_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return JPGPU_ERR_NO_DEVICE;
+    jpgpu_ctx* c = new jpgpu_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return JPGPU_ERR_CUDA; }
+    c->own_stream = true;
+    if (init_constants() != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return JPGPU_ERR_CUDA; }
+    *out = c;
+    return JPGPU_OK;
+}
+
+extern "C" void jpgpu_destroy(jpgpu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char* jpgpu_last_error(const jpgpu_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+extern "C" int jpgpu_set_stream(jpgpu_ctx* c, void* s) {
+    if (!c) return JPGPU_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = reinterpret_cast<cudaStream_t>(s);
+    c->own_stream = false;
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_sync(jpgpu_ctx* ctx) {
+    if (!ctx) return JPGPU_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JPGPU_OK;
+}
+
+extern "C" void jpgpu_batch_destroy(jpgpu_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    for (void* p : b->allocs) cudaFree(p);
+    delete b;
+}
+
+extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs, size_t n, jpgpu_batch** out) {
+    if (!ctx || !out || (!descs && n)) return JPGPU_ERR_INVALID_ARG;
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    jpgpu_batch* b = new jpgpu_batch();
+    b->ctx = ctx;
+    b->n = n;
+    int st = build_plan(descs, n, b->plan);
+    if (st != JPGPU_OK) { delete b; return st; }
+    b->host_scan.resize(n);
+    b->host_scan_len.resize(n);
+    for (size_t i = 0; i < n; i++) { b->host_scan[i] = descs[i].scan; b->host_scan_len[i] = descs[i].scan_len; }
+    HostPlan& p = b->plan;
+    memset(&b->dev, 0, sizeof b->dev);
+    BatchDev& d = b->dev;
+    d.n_images = (uint32_t)n;
+    d.n_seqs = (uint32_t)p.seqs.size();
+#define TRY(x) do { st = (x); if (st != JPGPU_OK) { jpgpu_batch_destroy(b); return st; } } while (0)
+    TRY(dev_upload(b, &d.imgs, p.imgs));
+    TRY(dev_upload(b, &d.seqs, p.seqs));
+    TRY(dev_upload(b, &d.luts, p.luts));
+    TRY(dev_upload(b, &d.qt, p.qt));
+    for (int k = 0; k < kNumKinds; k++) {
+        d.kind_count[k] = (uint32_t)p.kind_imgs[k].size();
+        d.kind_max_tiles[k] = p.kind_max_tiles[k];
+        TRY(dev_upload(b, &d.kind_imgs[k], p.kind_imgs[k]));
+    }
+    uint8_t* raw = nullptr;
+    TRY(dev_alloc(b, &raw, p.raw_bytes + 64));
+    d.raw = raw;
+    TRY(dev_alloc(b, &d.dyn, n + 1));
+    TRY(dev_alloc(b, &d.stream, p.stream_words + 64));
+    TRY(dev_alloc(b, &d.segtab, p.seg_entries + 8));
+    TRY(dev_alloc(b, &d.subs, p.sub_entries + 1));
+    TRY(dev_alloc(b, &d.seq_flags, 2 * p.seqs.size() + 2));
+    TRY(dev_alloc(b, &d.coefs, p.coef_elems + 64));
+    TRY(dev_alloc(b, &d.rgb, p.rgb_bytes + 256));
+#undef TRY
+    b->coef_bytes = p.coef_elems * sizeof(int16_t);
+    // defined contents for everything a speculative decoder may read
+    if (cudaMemsetAsync(raw, 0, p.raw_bytes + 64, ctx->stream) != cudaSuccess ||
+        cudaMemsetAsync(d.stream, 0, (p.stream_words + 64) * 4, ctx->stream) != cudaSuccess ||
+        cudaMemsetAsync(d.dyn, 0, (n + 1) * sizeof(ImgDyn), ctx->stream) != cudaSuccess ||
+        cudaMemsetAsync(d.segtab, 0, (p.seg_entries + 8) * 4, ctx->stream) != cudaSuccess) {
+        int r = fail(ctx, cudaGetLastError(), "cudaMemsetAsync");
+        jpgpu_batch_destroy(b);
+        return r;
+    }
+    *out = b;
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_batch_upload(jpgpu_batch* b) {
+    if (!b) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* raw = const_cast<uint8_t*>(b->dev.raw);
+    for (size_t i = 0; i < b->n; i++) {
+        if (b->plan.status[i] != JPGPU_OK) continue;
+        CK(cudaMemcpyAsync(raw + b->plan.imgs[i].raw_off, b->host_scan[i], b->plan.imgs[i].raw_len,
+                           cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_batch_set_device_scans(jpgpu_batch* b, const void* dev_base, const uint64_t* offsets) {
+    if (!b || !dev_base || !offsets) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* raw = const_cast<uint8_t*>(b->dev.raw);
+    for (size_t i = 0; i < b->n; i++) {
+        if (b->plan.status[i] != JPGPU_OK) continue;
+        CK(cudaMemcpyAsync(raw + b->plan.imgs[i].raw_off, (const uint8_t*)dev_base + offsets[i], b->plan.imgs[i].raw_len,
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_batch_entropy(jpgpu_batch* b) {
+    if (!b) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (b->coef_bytes) CK(cudaMemsetAsync(b->dev.coefs, 0, b->coef_bytes, s));  // decode_write stores non-zeros only
+    launch_prepass(b->dev, s);
+    launch_sync_intra(b->dev, s);
+    launch_sync_inter_scan(b->dev, s);
+    launch_decode_write(b->dev, s);
+    b->launches += 5;  // memset + 4 kernels
+    CK(cudaGetLastError());
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_batch_idct(jpgpu_batch* b) {
+    if (!b) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    b->launches += (uint64_t)launch_idct_colour(b->dev, ctx->stream);
+    CK(cudaGetLastError());
+    b->decoded = true;
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_batch_decode(jpgpu_batch* b) {
+    int st = jpgpu_batch_entropy(b);
+    if (st != JPGPU_OK) return st;
+    return jpgpu_batch_idct(b);
+}
+
+extern "C" int jpgpu_batch_download(jpgpu_batch* b, uint8_t* const* outs) {
+    if (!b || !outs) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < b->n; i++) {
+        if (b->plan.status[i] != JPGPU_OK || !outs[i]) continue;
+        const ImgDev& im = b->plan.imgs[i];
+        CK(cudaMemcpyAsync(outs[i], b->dev.rgb + im.rgb_off, (size_t)im.width * im.height * 3, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    }
+    return JPGPU_OK;
+}
+
+extern "C" void* jpgpu_batch_device_rgb(jpgpu_batch* b, size_t i, size_t* nbytes) {
+    if (!b || i >= b->n || b->plan.status[i] != JPGPU_OK) return nullptr;
+    const ImgDev& im = b->plan.imgs[i];
+    if (nbytes) *nbytes = (size_t)im.width * im.height * 3;
+    return b->dev.rgb + im.rgb_off;
+}
+
+extern "C" int jpgpu_batch_results(jpgpu_batch* b, int32_t* statuses, uint64_t* bytes_read) {
+    if (!b) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<ImgDyn> dyn(b->n);
+    if (b->n) CK(cudaMemcpyAsync(dyn.data(), b->dev.dyn, b->n * sizeof(ImgDyn), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < b->n; i++) {
+        int32_t st = b->plan.status[i];
+        uint64_t br = 0;
+        if (st == JPGPU_OK) {
+            const uint32_t f = dyn[i].status;
+            if (f & kStDcSize) st = JPGPU_PANIC_READ_BITS_ASSERT;
+            else if (f & kStBadCode) st = JPGPU_ERR_BAD_CODE;
+            else if (!(f & kStDone)) st = (f & kStRestart) ? JPGPU_ERR_RESTART : JPGPU_ERR_TRUNCATED;
+            br = ((uint64_t)dyn[i].bits_consumed + 7) / 8;  // decoder.rs:336-340
+        }
+        if (statuses) statuses[i] = st;
+        if (bytes_read) bytes_read[i] = br;
+    }
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_batch_coefficients(jpgpu_batch* b, size_t i, int16_t* out, size_t cap, uint32_t nblocks[4]) {
+    if (!b || i >= b->n || !out || !nblocks) return JPGPU_ERR_INVALID_ARG;
+    if (b->plan.status[i] != JPGPU_OK) return b->plan.status[i];
+    jpgpu_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    const ImgDev& im = b->plan.imgs[i];
+    if (cap < im.total_coefs) return JPGPU_ERR_INVALID_ARG;
+    std::vector<int16_t> arena(im.total_coefs);
+    CK(cudaMemcpyAsync(arena.data(), b->dev.coefs + im.coef_off, (size_t)im.total_coefs * 2, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    export_reference_order(im, arena.data(), out, nblocks);
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_batch_stats(jpgpu_batch* b, uint64_t stats[8]) {
+    if (!b || !stats) return JPGPU_ERR_INVALID_ARG;
+    const HostPlan& p = b->plan;
+    stats[0] = p.tot_scan_bytes;
+    stats[1] = p.tot_blocks * 128;
+    stats[2] = p.tot_rgb_bytes;
+    stats[3] = p.tot_pixels;
+    stats[4] = p.tot_blocks;
+    stats[5] = p.seqs.size();
+    stats[6] = p.sub_entries;
+    stats[7] = p.raw_bytes + p.stream_words * 4 + p.coef_elems * 2 + p.rgb_bytes + p.sub_entries * sizeof(SubInfo);
+    return JPGPU_OK;
+}
+
+extern "C" uint64_t jpgpu_batch_launch_count(const jpgpu_batch* b) { return b ? b->launches : 0; }
+
+extern "C" int jpgpu_decode(jpgpu_ctx* ctx, const jpgpu_image_desc* desc, uint8_t* rgb_out, size_t* bytes_read) {
+    if (!ctx || !desc || !rgb_out) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_batch* b = nullptr;
+    int st = jpgpu_batch_create(ctx, desc, 1, &b);
+    if (st != JPGPU_OK) return st;
+    int32_t ist = JPGPU_OK;
+    uint64_t br = 0;
+    uint8_t* outs[1] = {rgb_out};
+    st = jpgpu_batch_upload(b);
+    if (st == JPGPU_OK) st = jpgpu_batch_decode(b);
+    if (st == JPGPU_OK) st = jpgpu_batch_download(b, outs);
+    if (st == JPGPU_OK) st = jpgpu_batch_results(b, &ist, &br);
+    jpgpu_batch_destroy(b);
+    if (st != JPGPU_OK) return st;
+    if (bytes_read) *bytes_read = (size_t)br;
+    return ist;
+}
+
+extern "C" int jpgpu_decode_file(jpgpu_ctx* ctx, const uint8_t* file, size_t len, uint32_t ext_flags, uint32_t layout,
+                                 uint8_t* rgb_out, size_t rgb_cap, uint32_t* width, uint32_t* height, size_t* bytes_read) {
+    if (!ctx || !file || !rgb_out) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_image_desc d;
+    int st = jpgpu_parse(file, len, ext_flags, layout, &d);
+    if (st != JPGPU_OK) return st;
+    if (width) *width = d.width;
+    if (height) *height = d.height;
+    if ((size_t)d.width * d.height * 3 > rgb_cap) return JPGPU_ERR_INVALID_ARG;
+    return jpgpu_decode(ctx, &d, rgb_out, bytes_read);
+}

@@ -1,0 +1,475 @@
+// jpgpu_host.cpp — host side of the drop-in boundary: the marker/header parser that
+// stands in for JPEGImage::parse (reference src/jpeg/mod.rs:202-414), geometry
+// (decoder.rs:164-192), Huffman/quantisation table preparation and batch planning.
+// Pure host code; the image data itself is only ever touched by the CUDA kernels.
+#include "jpgpu_host.h"
+
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+
+namespace jpgpu {
+
+namespace {
+
+struct ParseError {
+    int code;
+};
+
+struct Cursor {  // Rust-style bounds-checked view of the file (index OOB -> reference panic)
+    const uint8_t* p;
+    size_t len;
+    uint8_t at(size_t i) const {
+        if (i >= len) throw ParseError{JPGPU_PANIC_INDEX_OOB};
+        return p[i];
+    }
+    void range(size_t a, size_t b) const {
+        if (b > len || a > b) throw ParseError{JPGPU_PANIC_INDEX_OOB};
+    }
+    uint16_t be16(size_t i) const { return (uint16_t)((at(i) << 8) + at(i + 1)); }  // mod.rs:9-13
+};
+
+}  // namespace
+
+int compute_geometry(const jpgpu_image_desc& d, Geometry& g) {
+    g = Geometry();
+    if (d.ncomp != 1 && d.ncomp != 3) return JPGPU_PANIC_COMPONENT_COUNT;  // decoder.rs:330
+    if (d.width == 0 || d.height == 0) return JPGPU_ERR_UNSUPPORTED;
+    for (uint32_t c = 0; c < d.ncomp; c++) {
+        const jpgpu_component& k = d.comp[c];
+        if (k.h < 1 || k.h > 2 || k.v < 1 || k.v > 2) return JPGPU_ERR_UNSUPPORTED;  // mod.rs:275-277
+        if (k.tq >= 4 || k.td >= 4 || k.ta >= 4) return JPGPU_PANIC_INDEX_OOB;      // decoder.rs:155,159,222
+        if (!d.qt_present[k.tq] || !d.dc_present[k.td] || !d.ac_present[k.ta]) return JPGPU_PANIC_MISSING_TABLE;
+        g.h[c] = k.h;
+        g.v[c] = k.v;
+    }
+    if (d.layout == JPGPU_LAYOUT_SPEC && d.ncomp == 1) { g.h[0] = 1; g.v[0] = 1; }  // T.81 A.2.2
+    g.hmax = g.vmax = 1;
+    g.blocks_per_mcu = 0;
+    for (uint32_t c = 0; c < d.ncomp; c++) {
+        g.hmax = std::max(g.hmax, g.h[c]);
+        g.vmax = std::max(g.vmax, g.v[c]);
+        g.blocks_per_mcu += g.h[c] * g.v[c];
+    }
+    g.mcux = (d.width + 8 * g.hmax - 1) / (8 * g.hmax);
+    g.mcuy = (d.height + 8 * g.vmax - 1) / (8 * g.vmax);
+    const uint32_t nbx = (d.width + 7) / 8, nby = (d.height + 7) / 8;
+    if (d.layout == JPGPU_LAYOUT_REF) {
+        const uint32_t skip = (uint32_t)g.hmax * g.vmax;
+        g.units = (nbx * nby + skip - 1) / skip;  // decoder.rs:191-192
+    } else {
+        g.units = g.mcux * g.mcuy;
+    }
+    for (uint32_t c = 0; c < d.ncomp; c++) g.nblocks[c] = g.units * g.h[c] * g.v[c];
+
+    // which fused colour kernel, if any
+    g.kind = kKindGeneric;
+    if (d.ncomp == 1 && g.h[0] == 1 && g.v[0] == 1) g.kind = kKindGray;
+    if (d.ncomp == 3 && g.h[1] == 1 && g.v[1] == 1 && g.h[2] == 1 && g.v[2] == 1) {
+        if (g.h[0] == 1 && g.v[0] == 1) g.kind = kKind444;
+        else if (g.h[0] == 2 && g.v[0] == 1) g.kind = kKind422;
+        else if (g.h[0] == 2 && g.v[0] == 2) g.kind = kKind420;
+        else if (g.h[0] == 1 && g.v[0] == 2) g.kind = kKind440;
+    }
+    if (d.layout == JPGPU_LAYOUT_SPEC) {
+        g.fused_ok = g.kind != kKindGeneric;
+    } else {
+        // REF == SPEC exactly for these shape classes (SURVEY.md §8 parity policy)
+        g.fused_ok = (g.kind == kKindGray && d.width % 8 == 0) || (g.kind == kKind444 && d.width % 8 == 0) ||
+                     (g.kind == kKind422 && d.width % 16 == 0);
+        if (g.fused_ok && g.units != g.mcux * g.mcuy) g.fused_ok = false;
+    }
+    return JPGPU_OK;
+}
+
+int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, HuffLut& out) {
+    memset(&out, 0, sizeof out);
+    int total = 0;
+    for (int i = 0; i < 16; i++) total += bits[i];
+    if (total > 256 || total > nvals) return JPGPU_ERR_BAD_HUFFMAN_TABLE;
+    memcpy(out.vals, vals, (size_t)total);
+    uint32_t code = 0;
+    int k = 0;
+    for (int l = 1; l <= 16; l++) {
+        const int n = bits[l - 1];
+        out.maxcode[l] = -1;
+        out.valoff[l] = k - (int32_t)code;
+        for (int i = 0; i < n; i++, k++, code++) {
+            if (code >= (1u << l)) return JPGPU_ERR_BAD_HUFFMAN_TABLE;  // not a prefix code
+            if (l <= kLutBits) {
+                const uint32_t first = code << (kLutBits - l), cnt = 1u << (kLutBits - l);
+                for (uint32_t e = 0; e < cnt; e++) out.fast[first + e] = (uint16_t)((l << 8) | vals[k]);
+            }
+        }
+        if (n) out.maxcode[l] = (int32_t)code - 1;
+        code <<= 1;
+    }
+    out.maxcode[0] = -1;
+    out.maxcode[17] = 0x7fffffff;
+    return JPGPU_OK;
+}
+
+void build_qt_multipliers(const uint16_t qt_zigzag[64], float out[64]) {
+    for (int k = 0; k < 64; k++) {
+        const int nat = kZigzagNaturalHost[k], u = nat & 7, v = nat >> 3;
+        out[u * 8 + v] = (float)((double)qt_zigzag[k] * kAanScale[u] * kAanScale[v] / 8.0);
+    }
+}
+
+int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan) {
+    plan = HostPlan();
+    plan.imgs.resize(n);
+    plan.status.assign(n, JPGPU_OK);
+    std::map<std::string, uint32_t> lut_ids;
+    std::map<std::string, uint32_t> qt_ids;
+    auto align_up = [](uint64_t x, uint64_t a) { return (x + a - 1) / a * a; };
+
+    for (size_t i = 0; i < n; i++) {
+        const jpgpu_image_desc& d = descs[i];
+        ImgDev& im = plan.imgs[i];
+        memset(&im, 0, sizeof im);
+        Geometry g;
+        int st = compute_geometry(d, g);
+        if (st == JPGPU_OK && !g.fused_ok) st = JPGPU_ERR_UNSUPPORTED;
+        if (st == JPGPU_OK && (d.scan == nullptr || d.scan_len < 4)) st = JPGPU_PANIC_INDEX_OOB;  // huffman.rs:127-128
+        if (st == JPGPU_OK && d.scan_len > 0x1ff00000ull) st = JPGPU_ERR_UNSUPPORTED;             // bit positions are 32-bit
+        if (st == JPGPU_OK && (uint64_t)g.units * g.blocks_per_mcu * 64 > 0x7fffffffull) st = JPGPU_ERR_UNSUPPORTED;
+
+        // Huffman tables -> slots
+        uint32_t slot_lut[kMaxLutSlots];
+        int nslots = 0;
+        uint8_t dc_slot[4] = {0, 0, 0, 0}, ac_slot[4] = {0, 0, 0, 0};
+        for (uint32_t c = 0; st == JPGPU_OK && c < d.ncomp; c++) {
+            for (int cls = 0; cls < 2; cls++) {
+                const int tid = cls == 0 ? d.comp[c].td : d.comp[c].ta;
+                const uint8_t* bits = cls == 0 ? d.dc_bits[tid] : d.ac_bits[tid];
+                const uint8_t* vals = cls == 0 ? d.dc_vals[tid] : d.ac_vals[tid];
+                const int nvals = cls == 0 ? d.dc_nvals[tid] : d.ac_nvals[tid];
+                std::string key((const char*)bits, 16);
+                key.append((const char*)vals, (size_t)std::min(nvals, 256));
+                auto it = lut_ids.find(key);
+                uint32_t id;
+                if (it == lut_ids.end()) {
+                    HuffLut lut;
+                    st = build_huff_lut(bits, vals, nvals, lut);
+                    if (st != JPGPU_OK) break;
+                    id = (uint32_t)plan.luts.size();
+                    plan.luts.push_back(lut);
+                    lut_ids.emplace(key, id);
+                } else {
+                    id = it->second;
+                }
+                int s = 0;
+                while (s < nslots && slot_lut[s] != id) s++;
+                if (s == nslots) slot_lut[nslots++] = id;
+                (cls == 0 ? dc_slot : ac_slot)[c] = (uint8_t)s;
+            }
+        }
+        plan.status[i] = st;
+        if (st != JPGPU_OK) {
+            // Skipped image: zero work, but its own (tiny) arena slices so that the per-image
+            // kernels, which still visit it, never touch another image's memory.
+            im.stream_off = plan.stream_words;
+            im.stream_cap_words = 32;
+            plan.stream_words += 32;
+            im.raw_off = plan.raw_bytes;
+            plan.raw_bytes += 16;
+            im.nseg_cap = 1;
+            im.seg_off = (uint32_t)plan.seg_entries;
+            plan.seg_entries += 3;
+            im.sub_off = (uint32_t)plan.sub_entries;
+            im.seq_first = (uint32_t)plan.seqs.size();
+            im.coef_off = plan.coef_elems;
+            im.rgb_off = plan.rgb_bytes;
+            im.blocks_per_mcu = 1;
+            continue;
+        }
+
+        im.width = d.width; im.height = d.height;
+        im.raw_len = (uint32_t)d.scan_len;
+        im.ncomp = (uint8_t)d.ncomp;
+        im.blocks_per_mcu = (uint8_t)g.blocks_per_mcu;
+        im.hmax = g.hmax; im.vmax = g.vmax;
+        im.mcux = g.mcux; im.mcuy = g.mcuy; im.units = g.units;
+        im.kind = g.kind; im.layout = (uint8_t)d.layout;
+        im.restart_interval = d.restart_interval;
+        im.seg_units = d.restart_interval * g.blocks_per_mcu * 64u;
+        im.total_coefs = g.units * g.blocks_per_mcu * 64u;
+        im.nslots = (uint8_t)nslots;
+        for (int s = 0; s < nslots; s++) im.slot_lut[s] = slot_lut[s];
+        int blk = 0;
+        for (uint32_t c = 0; c < d.ncomp; c++) {
+            im.h[c] = g.h[c]; im.v[c] = g.v[c];
+            for (int k = 0; k < g.h[c] * g.v[c]; k++, blk++) {
+                im.blk_comp[blk] = (uint8_t)c;
+                im.blk_dc_slot[blk] = dc_slot[c];
+                im.blk_ac_slot[blk] = ac_slot[c];
+            }
+            // quantisation multipliers (deduplicated)
+            const uint16_t* q = d.qt[d.comp[c].tq];
+            std::string key((const char*)q, 128);
+            auto it = qt_ids.find(key);
+            if (it == qt_ids.end()) {
+                const uint32_t off = (uint32_t)plan.qt.size();
+                plan.qt.resize(off + 64);
+                build_qt_multipliers(q, plan.qt.data() + off);
+                it = qt_ids.emplace(key, off).first;
+            }
+            im.qt_off[c] = it->second;
+        }
+        // arenas
+        im.raw_off = plan.raw_bytes;
+        plan.raw_bytes += align_up((uint64_t)im.raw_len + 16, 16);
+        im.stream_off = plan.stream_words;
+        im.stream_cap_words = (uint32_t)align_up((uint64_t)(im.raw_len + 3) / 4 + 1 + kStreamPadWords, 32);
+        plan.stream_words += im.stream_cap_words;
+        im.nseg_cap = d.restart_interval ? (g.units + d.restart_interval - 1) / d.restart_interval : 1u;
+        if (im.nseg_cap == 0) im.nseg_cap = 1;
+        im.seg_off = (uint32_t)plan.seg_entries;
+        plan.seg_entries += im.nseg_cap + 2;
+        im.nsub_cap = std::max<uint32_t>(1u, (uint32_t)(((uint64_t)im.raw_len * 8 + kSubseqBits - 1) / kSubseqBits));
+        im.sub_off = (uint32_t)plan.sub_entries;
+        plan.sub_entries += im.nsub_cap;
+        im.nseq = (im.nsub_cap + kSeqThreads - 1) / kSeqThreads;
+        im.seq_first = (uint32_t)plan.seqs.size();
+        for (uint32_t q = 0; q < im.nseq; q++) plan.seqs.push_back(SeqDesc{(uint32_t)i, q * kSeqThreads});
+        im.coef_off = plan.coef_elems;
+        plan.coef_elems += im.total_coefs;
+        im.rgb_off = plan.rgb_bytes;
+        plan.rgb_bytes += align_up((uint64_t)im.width * im.height * 3, 256);
+        const uint32_t mcus_per_tile = 128u / (8u * g.hmax);
+        im.tiles_x = (g.mcux + mcus_per_tile - 1) / mcus_per_tile;
+        im.tiles_y = g.mcuy;
+        plan.kind_imgs[g.kind].push_back((uint32_t)i);
+        plan.kind_max_tiles[g.kind] = std::max(plan.kind_max_tiles[g.kind], im.tiles_x * im.tiles_y);
+
+        plan.tot_scan_bytes += im.raw_len;
+        plan.tot_blocks += (uint64_t)g.units * g.blocks_per_mcu;
+        plan.tot_pixels += (uint64_t)im.width * im.height;
+        plan.tot_rgb_bytes += (uint64_t)im.width * im.height * 3;
+    }
+    if (plan.sub_entries > 0xffffffffull || plan.seg_entries > 0xffffffffull) return JPGPU_ERR_UNSUPPORTED;
+    return JPGPU_OK;
+}
+
+void export_reference_order(const ImgDev& im, const int16_t* arena, int16_t* out, uint32_t nblocks[4]) {
+    uint8_t pos[64];
+    for (int k = 0; k < 64; k++) pos[k] = (uint8_t)zigzag_to_colmajor(k, kZigzagNaturalHost);
+    size_t comp_off[4] = {0, 0, 0, 0};
+    size_t acc = 0;
+    for (int c = 0; c < 4; c++) {
+        nblocks[c] = c < im.ncomp ? im.units * im.h[c] * im.v[c] : 0;
+        comp_off[c] = acc;
+        acc += (size_t)nblocks[c] * 64;
+    }
+    size_t written[4] = {0, 0, 0, 0};
+    for (uint32_t m = 0; m < im.units; m++)
+        for (uint32_t b = 0; b < im.blocks_per_mcu; b++) {
+            const int c = im.blk_comp[b];
+            const int16_t* src = arena + ((size_t)m * im.blocks_per_mcu + b) * 64;
+            int16_t* dst = out + comp_off[c] + written[c] * 64;
+            for (int k = 0; k < 64; k++) dst[k] = src[pos[k]];
+            written[c]++;
+        }
+}
+
+}  // namespace jpgpu
+
+// =============================================================== C ABI, host-only part
+using namespace jpgpu;
+
+extern "C" int jpgpu_abi_version(void) { return JPGPU_ABI_VERSION; }
+
+extern "C" const char* jpgpu_status_string(int s) {
+    switch (s) {
+        case JPGPU_OK: return "ok";
+        case JPGPU_PANIC_UNHANDLED_MARKER: return "Unhandled byte marker (mod.rs:457)";
+        case JPGPU_PANIC_DRI: return "got to restart interval def (mod.rs:427)";
+        case JPGPU_PANIC_APP12_14: return "got ApplicationSegment12/14 (mod.rs:446,449)";
+        case JPGPU_PANIC_DQT_PRECISION: return "Unknown precision of quantization table (mod.rs:258)";
+        case JPGPU_PANIC_SAMPLING_ASSERT: return "sampling factor assertion failed (mod.rs:275-277)";
+        case JPGPU_PANIC_INDEX_OOB: return "index out of bounds";
+        case JPGPU_PANIC_NO_FRAME_HEADER: return "SOS before SOF0 (mod.rs:388 unwrap on None)";
+        case JPGPU_PANIC_MISSING_TABLE: return "missing Huffman or quantization table (decoder.rs:155,159,224)";
+        case JPGPU_PANIC_DC_LOOKUP: return "DC lookup fail (huffman.rs:156)";
+        case JPGPU_PANIC_AC_LOOKUP: return "ILLEGAL STATE! (huffman.rs:162)";
+        case JPGPU_PANIC_COMPONENT_COUNT: return "component count is neither 1 nor 3 (decoder.rs:330)";
+        case JPGPU_PANIC_READ_BITS_ASSERT: return "Should not read more than 16 bits at a time! (huffman.rs:202)";
+        case JPGPU_PANIC_SCAN_COMPONENT: return "scan component not found (decoder.rs:148)";
+        case JPGPU_NO_SCAN: return "no SOS segment: image_data is None";
+        case JPGPU_PANIC_ARITH: return "arithmetic overflow (debug build panic)";
+        case JPGPU_ERR_INVALID_ARG: return "invalid argument";
+        case JPGPU_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+        case JPGPU_ERR_CUDA: return "CUDA runtime error";
+        case JPGPU_ERR_UNSUPPORTED: return "outside the supported subset";
+        case JPGPU_ERR_BAD_HUFFMAN_TABLE: return "BITS/HUFFVAL do not describe a prefix code";
+        case JPGPU_ERR_TRUNCATED: return "entropy-coded data ended early";
+        case JPGPU_ERR_BAD_CODE: return "bit pattern is no code of the selected Huffman table";
+        case JPGPU_ERR_RESTART: return "restart markers missing or out of sequence";
+        case JPGPU_ERR_OOM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+// JPEGImage::parse, mod.rs:202-414 — marker walk up to (not including) decode().
+extern "C" int jpgpu_parse(const uint8_t* file, size_t len, uint32_t ext, uint32_t layout, jpgpu_image_desc* out) {
+    if (!file || !out) return JPGPU_ERR_INVALID_ARG;
+    memset(out, 0, sizeof *out);
+    out->layout = layout;
+    const Cursor f{file, len};
+    struct FrameComp { uint8_t id, h, v, tq; };
+    std::vector<FrameComp> frame;
+    bool have_frame = false;
+    try {
+        size_t i = 0;
+        while (i < len) {
+            // bytes_to_marker, mod.rs:157-181 (including its "n == 0 -> look one byte further" quirk)
+            if (f.at(i) != 0xff) { (void)f.at(i + 1); return JPGPU_PANIC_UNHANDLED_MARKER; }
+            uint8_t m = f.at(i + 1);
+            if (m == 0) m = f.at(i + 2);
+            const bool known = m == 0xc0 || m == 0xc4 || m == 0xd8 || m == 0xd9 || m == 0xda || m == 0xdb ||
+                               m == 0xdd || m == 0xe0 || m == 0xec || m == 0xee || m == 0xfe;
+            const bool skippable = (ext & JPGPU_EXT_SKIP_APPN) && ((m >= 0xe1 && m <= 0xef) || (m >= 0xf0 && m <= 0xfd));
+            if (!known && !skippable) return JPGPU_PANIC_UNHANDLED_MARKER;  // mod.rs:456-462
+            if (m == 0xd8 || m == 0xd9) { i += 2; continue; }                // mod.rs:208-214
+            const uint16_t seglen = f.be16(i + 2);
+            if (seglen < 2) return JPGPU_PANIC_ARITH;                        // mod.rs:218
+            const size_t dl = (size_t)seglen - 2;
+            i += 4;
+            switch (m) {
+                case 0xfe: f.range(i, i + dl); break;                        // COM, mod.rs:222-227
+                case 0xdb: {                                                 // DQT, mod.rs:228-261
+                    size_t idx = i;
+                    while (idx < i + dl) {
+                        const uint8_t pqtq = f.at(idx);
+                        const unsigned pq = pqtq >> 4, tq = pqtq & 15;
+                        if (pq == 0) {
+                            f.range(idx + 1, idx + 65);
+                            if (tq >= 4) return JPGPU_PANIC_INDEX_OOB;
+                            for (int k = 0; k < 64; k++) out->qt[tq][k] = file[idx + 1 + k];
+                            out->qt_present[tq] = 1;
+                            idx += 65;
+                        } else if (pq == 1) {
+                            f.range(idx + 1, idx + 129);
+                            if (tq >= 4) return JPGPU_PANIC_INDEX_OOB;
+                            for (int k = 0; k < 64; k++)
+                                out->qt[tq][k] = (uint16_t)((file[idx + 1 + 2 * k] << 8) | file[idx + 2 + 2 * k]);
+                            out->qt_present[tq] = 1;
+                            idx += 129;
+                        } else {
+                            return JPGPU_PANIC_DQT_PRECISION;
+                        }
+                    }
+                    break;
+                }
+                case 0xc0: {                                                 // SOF0, mod.rs:262-298
+                    (void)f.at(i);
+                    const uint16_t lines = f.be16(i + 1), spl = f.be16(i + 3);
+                    const uint8_t nc = f.at(i + 5);
+                    frame.clear();
+                    size_t idx = i + 6;
+                    for (unsigned c = 0; c < nc; c++, idx += 3) {
+                        FrameComp fc;
+                        fc.id = f.at(idx);
+                        const uint8_t hv = f.at(idx + 1);
+                        fc.h = hv >> 4; fc.v = hv & 15;
+                        if (!(fc.h > 0 && fc.h < 3) || !(fc.v > 0 && fc.v < 3)) return JPGPU_PANIC_SAMPLING_ASSERT;
+                        fc.tq = f.at(idx + 2);
+                        frame.push_back(fc);
+                    }
+                    out->width = spl; out->height = lines;
+                    have_frame = true;
+                    break;
+                }
+                case 0xc4: {                                                 // DHT, mod.rs:299-336
+                    size_t idx = i;
+                    const size_t end = i + dl;
+                    while (idx < end) {
+                        const uint8_t tcth = f.at(idx);
+                        const unsigned tc = tcth >> 4, th = tcth & 15;
+                        idx += 1;
+                        f.range(idx, idx + 16);
+                        const uint8_t* bits = file + idx;
+                        idx += 16;
+                        size_t ncodes = 0;
+                        for (int k = 0; k < 16; k++) ncodes += bits[k];
+                        f.range(idx, idx + ncodes);
+                        if (ncodes == 0) return JPGPU_PANIC_INDEX_OOB;       // huffman.rs:85 sizes[0]
+                        if (th >= 4) return JPGPU_PANIC_INDEX_OOB;
+                        if (ncodes > 256) return JPGPU_ERR_BAD_HUFFMAN_TABLE;
+                        uint8_t* dbits = tc == 0 ? out->dc_bits[th] : out->ac_bits[th];
+                        uint8_t* dvals = tc == 0 ? out->dc_vals[th] : out->ac_vals[th];
+                        memcpy(dbits, bits, 16);
+                        memset(dvals, 0, 256);
+                        memcpy(dvals, file + idx, ncodes);
+                        (tc == 0 ? out->dc_nvals : out->ac_nvals)[th] = (uint16_t)ncodes;
+                        (tc == 0 ? out->dc_present : out->ac_present)[th] = 1;
+                        idx += ncodes;
+                    }
+                    break;
+                }
+                case 0xda: {                                                 // SOS, mod.rs:337-414
+                    const uint8_t ns = f.at(i);
+                    struct ScanComp { uint8_t id, td, ta; };
+                    std::vector<ScanComp> scan;
+                    for (unsigned c = 0; c < ns; c++) {
+                        ScanComp sc;
+                        sc.id = f.at(i + 1);
+                        const uint8_t t = f.at(i + 2);
+                        sc.td = t >> 4; sc.ta = t & 15;
+                        scan.push_back(sc);
+                        i += 2;
+                    }
+                    (void)f.at(i + 1); (void)f.at(i + 2); (void)f.at(i + 3);
+                    i += 4;
+                    if (i < len && file[len - 1] == 0xff)
+                        return JPGPU_PANIC_INDEX_OOB;                        // mod.rs:378: vec[i + 1] past the end
+                    if (!have_frame) return JPGPU_PANIC_NO_FRAME_HEADER;     // mod.rs:388
+                    // builder semantics of decoder.rs:83-152: first matching id wins, scan order kept
+                    if (scan.size() > 4) return JPGPU_PANIC_COMPONENT_COUNT;
+                    out->ncomp = (uint32_t)scan.size();
+                    for (size_t c = 0; c < scan.size(); c++) {
+                        const FrameComp* fc = nullptr;  // decoder.rs:86-95: a later frame entry with the same id overwrites
+                        for (const FrameComp& k : frame) if (k.id == scan[c].id) fc = &k;
+                        if (!fc) return JPGPU_PANIC_ARITH;  // decoder.rs:130-134: 0xff*0xff sampling product overflows
+                        // decoder.rs:116-123 updates the selectors in scan order: the last entry with this id wins
+                        uint8_t td = scan[c].td, ta = scan[c].ta;
+                        for (size_t k = 0; k < scan.size(); k++) if (scan[k].id == scan[c].id) { td = scan[k].td; ta = scan[k].ta; }
+                        out->comp[c] = jpgpu_component{fc->id, fc->h, fc->v, fc->tq, td, ta};
+                    }
+                    out->scan = i <= len ? file + i : file + len;
+                    out->scan_len = i <= len ? len - i : 0;
+                    return JPGPU_OK;                                         // mod.rs:415: decode() happens on the GPU
+                }
+                case 0xdd:                                                   // DRI, mod.rs:424-428
+                    if (!(ext & JPGPU_EXT_DRI)) return JPGPU_PANIC_DRI;
+                    out->restart_interval = f.be16(i);
+                    break;
+                case 0xe0:                                                   // APP0, mod.rs:429-444 (absolute offsets)
+                    f.range(i, i + 6);
+                    (void)f.at(7); (void)f.at(8); (void)f.at(13); f.range(10, 12); f.range(12, 14); (void)f.at(14); (void)f.at(15);
+                    break;
+                case 0xec: case 0xee:                                        // APP12 / APP14, mod.rs:445-450
+                    if (!(ext & JPGPU_EXT_SKIP_APPN)) return JPGPU_PANIC_APP12_14;
+                    break;
+                default: break;                                              // skipped extension segment
+            }
+            i += dl;                                                         // mod.rs:455
+        }
+    } catch (const ParseError& e) {
+        return e.code;
+    }
+    return JPGPU_NO_SCAN;                                                    // mod.rs:464
+}
+
+extern "C" int jpgpu_geometry(const jpgpu_image_desc* desc, uint32_t* mcus, uint32_t* blocks_per_mcu, uint32_t nblocks[4]) {
+    if (!desc) return JPGPU_ERR_INVALID_ARG;
+    Geometry g;
+    const int st = compute_geometry(*desc, g);
+    if (st != JPGPU_OK) return st;
+    if (mcus) *mcus = g.units;
+    if (blocks_per_mcu) *blocks_per_mcu = g.blocks_per_mcu;
+    if (nblocks) for (int c = 0; c < 4; c++) nblocks[c] = g.nblocks[c];
+    return JPGPU_OK;
+}

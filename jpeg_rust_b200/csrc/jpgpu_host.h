@@ -1,0 +1,58 @@
+// jpgpu_host.h — host-side planning shared by the C ABI (jpgpu_api.cu) and the
+// CPU simulation harness used by tests.  No CUDA calls in here.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/jpgpu.h"
+#include "jpgpu_kernels.cuh"
+
+namespace jpgpu {
+
+struct Geometry {
+    uint32_t units = 0;           // MCUs decode() reads
+    uint32_t blocks_per_mcu = 0;
+    uint32_t mcux = 0, mcuy = 0;  // SPEC MCU grid
+    uint8_t h[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
+    uint8_t hmax = 1, vmax = 1;
+    uint8_t kind = kKindGeneric;
+    bool fused_ok = false;        // the fused SPEC-geometry kernel reproduces the requested layout
+    uint32_t nblocks[4] = {0, 0, 0, 0};
+};
+
+// decoder.rs:164-192 (REF) / T.81 A.2 (SPEC). Returns JPGPU_* status.
+int compute_geometry(const jpgpu_image_desc& d, Geometry& g);
+
+// Builds the device Huffman table from DHT BITS/HUFFVAL (huffman.rs:37-58, 80-98).
+int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, HuffLut& out);
+
+// 64 multipliers (column-major) = q * aan[u] * aan[v] / 8 from a zigzag-order DQT table.
+void build_qt_multipliers(const uint16_t qt_zigzag[64], float out[64]);
+
+struct HostPlan {
+    std::vector<ImgDev> imgs;
+    std::vector<int32_t> status;  // per image: JPGPU_OK or why it is skipped
+    std::vector<SeqDesc> seqs;
+    std::vector<HuffLut> luts;
+    std::vector<float> qt;
+    std::vector<uint32_t> kind_imgs[kNumKinds];
+    uint32_t kind_max_tiles[kNumKinds] = {0, 0, 0, 0, 0, 0};
+    uint64_t raw_bytes = 0;      // arena sizes
+    uint64_t stream_words = 0;
+    uint64_t seg_entries = 0;
+    uint64_t sub_entries = 0;
+    uint64_t coef_elems = 0;
+    uint64_t rgb_bytes = 0;
+    // algorithmic totals over the valid images
+    uint64_t tot_scan_bytes = 0, tot_blocks = 0, tot_pixels = 0, tot_rgb_bytes = 0;
+};
+
+int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan);
+
+// Reorders one image's coefficient arena ([mcu][block][column-major]) into the
+// reference arrangement: per component, decode order, zigzag (decoder.rs:208-212).
+void export_reference_order(const ImgDev& im, const int16_t* arena, int16_t* out, uint32_t nblocks[4]);
+
+}  // namespace jpgpu

@@ -1,0 +1,551 @@
+// jpgpu_kernels.cu — hand-written sm_100a kernels of the JPEG decode hot path.
+//
+//   prepass_kernel          mod.rs:371-385 (byte unstuffing) as a parallel stream
+//                           compaction, plus RSTn detection (no reference counterpart:
+//                           mod.rs:424-428 panics on DRI)
+//   sync_intra_kernel       |
+//   sync_inter_scan_kernel  |  huffman.rs:146-227 + decoder.rs:195-215 (serial MCU loop)
+//   decode_write_kernel     |  as self-synchronising subsequence decoding
+//   idct_colour_kernel      decoder.rs:227-235 (dequant, de-zigzag), transform.rs:55-87
+//                           (IDCT), decoder.rs:290-331 + 347-402 (placement, replication,
+//                           YCbCr->RGB, +128, clamp, truncation)
+// See DESIGN.md for the algorithm, the HBM layout and the roofline of each kernel.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "jpgpu_kernels.cuh"
+
+namespace jpgpu {
+
+__constant__ uint8_t c_store_pos[64];  // zigzag index -> column-major position (see jpgpu_core.h)
+
+cudaError_t init_constants() {
+    uint8_t h[64];
+    for (int k = 0; k < 64; k++) h[k] = (uint8_t)zigzag_to_colmajor(k, kZigzagNaturalHost);
+    return cudaMemcpyToSymbol(c_store_pos, h, 64);
+}
+
+// =============================================================== stage 1a: pre-pass
+constexpr int kPreThreads = 256;
+constexpr int kPreChunk = kPreThreads * 16;  // raw bytes per CTA iteration
+
+__global__ void __launch_bounds__(kPreThreads) prepass_kernel(BatchDev b) {
+    __shared__ uint32_t s_stage[kPreChunk / 4 + 8];
+    __shared__ uint32_t s_wsum[2][kPreThreads / 32];
+    __shared__ uint32_t s_status;
+
+    const ImgDev& im = b.imgs[blockIdx.x];
+    const uint8_t* __restrict__ in = b.raw + im.raw_off;
+    const uint32_t n = im.raw_len;
+    uint32_t* __restrict__ out = b.stream + im.stream_off;
+    uint32_t* __restrict__ seg = b.segtab + im.seg_off;
+    const bool dri = im.restart_interval != 0;
+    const uint32_t nseg_cap = im.nseg_cap;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* stage_bytes = reinterpret_cast<uint8_t*>(s_stage);
+    uint32_t emitted = 0, rst_total = 0;
+    if (tid == 0) s_status = 0;
+    __syncthreads();
+
+    for (uint32_t base = 0; base < n; base += kPreChunk) {
+        const uint32_t o = base + tid * 16;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        uint32_t prev = 0, next = 0;
+        if (o < n) {
+            const uint4 v = *reinterpret_cast<const uint4*>(in + o);  // raw arena is 16-byte padded
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            if (o > 0) prev = in[o - 1];
+            if (o + 16 < n) next = in[o + 16];
+        }
+        uint32_t keep = 0, rstm = 0;
+        uint32_t p = prev;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t cur = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+            const uint32_t nxt = k < 15 ? ((w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu) : next;
+            const bool valid = o + k < n;
+            const bool has_next = o + k + 1 < n;
+            bool drop = (cur == 0u && p == 0xffu);  // stuffed zero (mod.rs:378-382)
+            bool r1 = false;
+            if (dri) {  // restart-interval extension: RSTn markers and fill bytes leave the stream
+                r1 = cur == 0xffu && has_next && (nxt & 0xf8u) == 0xd0u;
+                const bool r2 = p == 0xffu && (cur & 0xf8u) == 0xd0u;
+                const bool fill = cur == 0xffu && has_next && nxt == 0xffu;
+                drop = drop || r1 || r2 || fill;
+            }
+            if (valid && !drop) keep |= 1u << k;
+            if (valid && r1) rstm |= 1u << k;
+            p = cur;
+        }
+        const uint32_t cnt = __popc(keep), nr = __popc(rstm);
+        uint32_t ic = cnt, ir = nr;  // warp-inclusive scans
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t tc = __shfl_up_sync(0xffffffffu, ic, d);
+            const uint32_t tr = __shfl_up_sync(0xffffffffu, ir, d);
+            if (lane >= (uint32_t)d) { ic += tc; ir += tr; }
+        }
+        if (lane == 31) { s_wsum[0][warp] = ic; s_wsum[1][warp] = ir; }
+        __syncthreads();
+        uint32_t wc = 0, wr = 0, totc = 0, totr = 0;
+#pragma unroll
+        for (int i = 0; i < kPreThreads / 32; i++) {
+            const uint32_t a = s_wsum[0][i], r = s_wsum[1][i];
+            if ((uint32_t)i < warp) { wc += a; wr += r; }
+            totc += a; totr += r;
+        }
+        const uint32_t exc = wc + ic - cnt, exr = wr + ir - nr;
+        const uint32_t carry = emitted & 3u;
+        uint32_t pos = carry + exc;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (keep & (1u << k)) {
+                stage_bytes[pos ^ 3u] = (uint8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);  // first byte = MSB of the word
+                pos++;
+            }
+        }
+        if (rstm) {
+            uint32_t r = rst_total + exr;
+#pragma unroll 1
+            for (int k = 0; k < 16; k++) {
+                if (!(rstm & (1u << k))) continue;
+                const uint32_t idx = emitted + exc + __popc(keep & ((1u << k) - 1u));
+                if (r + 1 < nseg_cap) seg[r + 1] = idx * 8u;
+                const uint32_t mk = k < 15 ? ((w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu) : next;
+                if ((mk & 7u) != (r & 7u)) atomicOr(&s_status, kStRestart);
+                r++;
+            }
+        }
+        __syncthreads();
+        const uint32_t staged = carry + totc, nw = staged >> 2, wbase = (emitted - carry) >> 2;
+        for (uint32_t i = tid; i < nw; i += kPreThreads) out[wbase + i] = s_stage[i];
+        __syncthreads();
+        if (tid == 0 && (staged & 3u) && nw) s_stage[0] = s_stage[nw];
+        __syncthreads();
+        emitted += totc;
+        rst_total += totr;
+    }
+    if (tid == 0) {
+        const uint32_t carry = emitted & 3u;
+        uint32_t wbase = (emitted - carry) >> 2;
+        if (carry) { out[wbase] = s_stage[0] & (0xffffffffu << (32 - 8 * carry)); wbase++; }
+        for (int i = 0; i < kStreamPadWords; i++) out[wbase + i] = 0u;
+        uint32_t nseg = rst_total + 1;
+        uint32_t st = s_status;
+        if (nseg != nseg_cap && dri) st |= kStRestart;
+        if (nseg > nseg_cap) nseg = nseg_cap;
+        seg[0] = 0u;
+        seg[nseg] = emitted * 8u;
+        ImgDyn d;
+        d.stream_bits = emitted * 8u; d.nseg = nseg; d.status = st; d.bits_consumed = 0u;
+        b.dyn[blockIdx.x] = d;
+    }
+}
+
+// ========================================================= stage 1b-1d: entropy decode
+struct EntropySmem {
+    HuffLut lut[kMaxLutSlots];
+    ImgDev img;
+    uint8_t store_pos[64];
+};
+
+// Cooperative load of the per-image decode context into shared memory.
+__device__ __forceinline__ void load_entropy_ctx(const BatchDev& b, uint32_t img, EntropySmem& sm, int nthreads) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&b.imgs[img]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.img);
+    for (int i = threadIdx.x; i < (int)(sizeof(ImgDev) / 4); i += nthreads) dst[i] = src[i];
+    if (threadIdx.x < 64) sm.store_pos[threadIdx.x] = c_store_pos[threadIdx.x];
+    __syncthreads();
+    const int nslots = sm.img.nslots;
+    constexpr int kLutWords = sizeof(HuffLut) / 4;
+    for (int s = 0; s < nslots; s++) {
+        const uint32_t* ls = reinterpret_cast<const uint32_t*>(&b.luts[sm.img.slot_lut[s]]);
+        uint32_t* ld = reinterpret_cast<uint32_t*>(&sm.lut[s]);
+        for (int i = threadIdx.x; i < kLutWords; i += nthreads) ld[i] = ls[i];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ DecCtx make_ctx(const BatchDev& b, const EntropySmem& sm, const ImgDyn& d) {
+    DecCtx cx;
+    cx.words = b.stream + sm.img.stream_off;
+    cx.seg = b.segtab + sm.img.seg_off;
+    cx.nseg = d.nseg;
+    cx.stream_bits = d.stream_bits;
+    cx.seg_units = sm.img.seg_units;
+    cx.nblk = sm.img.blocks_per_mcu;
+    cx.luts = sm.lut;
+    cx.blk_comp = sm.img.blk_comp;
+    cx.blk_dc_slot = sm.img.blk_dc_slot;
+    cx.blk_ac_slot = sm.img.blk_ac_slot;
+    return cx;
+}
+
+// One CTA per sequence (kSeqThreads consecutive subsequences of one image). Thread i
+// decodes subsequence i from a cold state, then keeps decoding the following
+// subsequences until the state it arrives with equals the state recorded there
+// (self-synchronisation), overwriting the records on its way.  In round r only thread
+// i touches record i+r and lower-numbered (more authoritative) threads arrive later,
+// so after the last round every record holds what the lowest thread that reached it
+// computed.
+__global__ void __launch_bounds__(kSeqThreads, 3) sync_intra_kernel(BatchDev b) {
+    __shared__ EntropySmem sm;
+    __shared__ SubInfo s_info[kSeqThreads];
+
+    const SeqDesc sd = b.seqs[blockIdx.x];
+    load_entropy_ctx(b, sd.img, sm, kSeqThreads);
+    const ImgDyn dyn = b.dyn[sd.img];
+    const uint32_t nsub = (dyn.stream_bits + kSubseqBits - 1) / kSubseqBits;
+    if (sd.first_sub >= nsub) return;
+    const DecCtx cx = make_ctx(b, sm, dyn);
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t j = sd.first_sub + tid;
+    bool active = j < nsub;
+    DecState st;
+    int32_t g_base = 0;
+    if (active) {
+        init_state(cx, st, j * kSubseqBits, 0, 0, 0, 0, 0);
+        g_base = st.g;
+        decode_span<false>(cx, st, (j + 1) * kSubseqBits, 0, nullptr, nullptr);
+        SubInfo mine;
+        summarise(st, g_base, mine);
+        mine.pad[0] = mine.pad[1] = 0;
+        s_info[tid] = mine;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t r = 1; r < kSeqThreads; r++) {
+        const uint32_t tgt = tid + r;
+        if (active && (tgt >= kSeqThreads || j + r >= nsub)) active = false;
+        if (active) {
+            begin_subsequence(st, g_base);
+            decode_span<false>(cx, st, (j + r + 1) * kSubseqBits, 0, nullptr, nullptr);
+            SubInfo mine;
+            summarise(st, g_base, mine);
+            mine.pad[0] = mine.pad[1] = 0;
+            const SubInfo old = s_info[tgt];
+            const bool same = old.p == mine.p && ((old.czf ^ mine.czf) & kCzMask) == 0u;
+            s_info[tgt] = mine;  // n / dc must be those of the last (lowest) arriver
+            if (same) active = false;
+        }
+        if (!__syncthreads_or(active ? 1 : 0)) break;
+    }
+    if (j < nsub) b.subs[sm.img.sub_off + j] = s_info[tid];
+}
+
+constexpr int kInterThreads = 64;
+
+// One CTA per image. (1) Inter-sequence synchronisation: for every sequence boundary
+// a thread continues from the final record of the previous sequence until it meets
+// an equal record; repeated while a walk ran off the end of its sequence. (2) Prefix
+// scan turning per-subsequence advances into absolute end states.
+__global__ void __launch_bounds__(kInterThreads) sync_inter_scan_kernel(BatchDev b) {
+    __shared__ EntropySmem sm;
+    __shared__ int32_t s_agg[kInterThreads][5];
+
+    const uint32_t img = blockIdx.x;
+    load_entropy_ctx(b, img, sm, kInterThreads);
+    const ImgDyn dyn = b.dyn[img];
+    const uint32_t nsub = (dyn.stream_bits + kSubseqBits - 1) / kSubseqBits;
+    const uint32_t nseq = (nsub + kSeqThreads - 1) / kSeqThreads;
+    const DecCtx cx = make_ctx(b, sm, dyn);
+    SubInfo* subs = b.subs + sm.img.sub_off;
+    uint32_t* need_a = b.seq_flags + sm.img.seq_first;
+    uint32_t* need_b = b.seq_flags + b.n_seqs + sm.img.seq_first;
+    const uint32_t tid = threadIdx.x;
+
+    for (uint32_t q = tid; q < nseq; q += kInterThreads) { need_a[q] = q > 0 ? 1u : 0u; need_b[q] = 0u; }
+    __syncthreads();
+
+#pragma unroll 1
+    for (uint32_t iter = 0; iter < nseq; iter++) {
+        int any = 0;
+#pragma unroll 1
+        for (uint32_t q0 = 1; q0 < nseq; q0 += kInterThreads) {  // passes keep snapshot-before-write order
+            const uint32_t q = q0 + tid;
+            const bool work = q < nseq && need_a[q] != 0u;
+            SubInfo start;
+            if (work) start = subs[q * kSeqThreads - 1];
+            __syncthreads();
+            if (work) {
+                need_a[q] = 0u;
+                DecState st;
+                init_state(cx, st, start.p, (int32_t)(start.czf & 63u), (int32_t)((start.czf >> 6) & 15u), 0, 0, 0);
+                int32_t g_base = st.g;
+                bool first = true;
+#pragma unroll 1
+                for (uint32_t t = 0; t < (uint32_t)kSeqThreads; t++) {
+                    const uint32_t jj = q * kSeqThreads + t;
+                    if (jj >= nsub) break;
+                    if (!first) begin_subsequence(st, g_base);
+                    else { g_base = st.g; st.dc0 = st.dc1 = st.dc2 = 0; }
+                    first = false;
+                    decode_span<false>(cx, st, (jj + 1) * kSubseqBits, 0, nullptr, nullptr);
+                    SubInfo mine;
+                    summarise(st, g_base, mine);
+                    mine.pad[0] = mine.pad[1] = 0;
+                    const SubInfo old = subs[jj];
+                    const bool same = old.p == mine.p && ((old.czf ^ mine.czf) & kCzMask) == 0u;
+                    subs[jj] = mine;
+                    if (same) break;
+                    if (t == (uint32_t)kSeqThreads - 1 && q + 1 < nseq) { need_b[q + 1] = 1u; any = 1; }
+                }
+            }
+            __syncthreads();
+        }
+        if (!__syncthreads_or(any)) break;
+        for (uint32_t q = tid; q < nseq; q += kInterThreads) { need_a[q] = need_b[q]; need_b[q] = 0u; }
+        __syncthreads();
+    }
+
+    // ---- scan: n/dc become absolute end states (segmented by `crossed`)
+    const uint32_t chunk = (nsub + kInterThreads - 1) / kInterThreads;
+    const uint32_t lo = tid * chunk, hi = min(nsub, lo + chunk);
+    int32_t acc[4] = {0, 0, 0, 0};
+    int32_t crossed = 0;
+    for (uint32_t jj = lo; jj < hi; jj++) {
+        const SubInfo s = subs[jj];
+        if (s.czf & kCrossed) { acc[0] = s.n; acc[1] = s.dc[0]; acc[2] = s.dc[1]; acc[3] = s.dc[2]; crossed = 1; }
+        else { acc[0] += s.n; acc[1] += s.dc[0]; acc[2] += s.dc[1]; acc[3] += s.dc[2]; }
+    }
+    s_agg[tid][0] = acc[0]; s_agg[tid][1] = acc[1]; s_agg[tid][2] = acc[2]; s_agg[tid][3] = acc[3]; s_agg[tid][4] = crossed;
+    __syncthreads();
+    int32_t run[4] = {0, 0, 0, 0};
+    for (uint32_t k = 0; k < tid; k++) {  // exclusive prefix over the preceding chunks
+        if (s_agg[k][4]) { run[0] = s_agg[k][0]; run[1] = s_agg[k][1]; run[2] = s_agg[k][2]; run[3] = s_agg[k][3]; }
+        else { run[0] += s_agg[k][0]; run[1] += s_agg[k][1]; run[2] += s_agg[k][2]; run[3] += s_agg[k][3]; }
+    }
+    for (uint32_t jj = lo; jj < hi; jj++) {
+        SubInfo s = subs[jj];
+        if (s.czf & kCrossed) { run[0] = s.n; run[1] = s.dc[0]; run[2] = s.dc[1]; run[3] = s.dc[2]; }
+        else { run[0] += s.n; run[1] += s.dc[0]; run[2] += s.dc[1]; run[3] += s.dc[2]; }
+        s.n = run[0]; s.dc[0] = run[1]; s.dc[1] = run[2]; s.dc[2] = run[3];
+        subs[jj] = s;
+    }
+}
+
+// One CTA per sequence: every thread re-decodes its subsequence from its now exact
+// start state and scatters the non-zero coefficients into the (pre-zeroed) arena.
+__global__ void __launch_bounds__(kSeqThreads, 3) decode_write_kernel(BatchDev b) {
+    __shared__ EntropySmem sm;
+
+    const SeqDesc sd = b.seqs[blockIdx.x];
+    load_entropy_ctx(b, sd.img, sm, kSeqThreads);
+    const ImgDyn dyn = b.dyn[sd.img];
+    const uint32_t nsub = (dyn.stream_bits + kSubseqBits - 1) / kSubseqBits;
+    if (sd.first_sub >= nsub) return;
+    const DecCtx cx = make_ctx(b, sm, dyn);
+    const uint32_t j = sd.first_sub + threadIdx.x;
+    if (j >= nsub) return;
+
+    DecState st;
+    if (j == 0) {
+        init_state(cx, st, 0u, 0, 0, 0, 0, 0);
+    } else {
+        const SubInfo prev = b.subs[sm.img.sub_off + j - 1];
+        init_state(cx, st, prev.p, prev.n, (int32_t)((prev.czf >> 6) & 15u), prev.dc[0], prev.dc[1], prev.dc[2]);
+    }
+    const int32_t total = (int32_t)sm.img.total_coefs;
+    const int32_t g_start = st.g;
+    st.flags &= ~kCrossed;
+    decode_span<true>(cx, st, (j + 1) * kSubseqBits, total, b.coefs + sm.img.coef_off, sm.store_pos);
+    uint32_t bits = st.flags & (kStBadCode | kStDcSize);
+    if (g_start < total && st.g >= total) {  // this thread decoded the last block of the scan
+        b.dyn[sd.img].bits_consumed = st.br.pos();
+        bits |= kStDone;
+    }
+    if (bits) atomicOr(&b.dyn[sd.img].status, bits);
+}
+
+// ============================================ stage 2+3: dequant + IDCT + upsample + colour
+constexpr int kIdctThreads = 128;
+constexpr int kScrRowPitch = 12;     // floats; 4*odd -> conflict-free 128-bit row reads
+constexpr int kScrBlkPitch = 104;    // floats; 8 mod 32 -> conflict-free column writes across the 4 blocks of a warp
+constexpr int kOutPitch = 400;       // bytes per staged output row (128 px * 3 = 384, padded)
+
+__device__ __forceinline__ uint32_t f32_to_u8_sat(float x) {  // decoder.rs:382-390: clamp to [0,255], truncate
+    uint32_t r;
+    asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// 8 lanes own one 8x8 block; lane t loads column t (16 bytes), runs the vertical pass,
+// the block is transposed through shared memory, and lane t finishes row t.
+__device__ __forceinline__ void block_idct(const int16_t* __restrict__ src, bool valid, const float* __restrict__ qt,
+                                           int t, float* __restrict__ scr, float dc_bias, float out[8]) {
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) raw = __ldg(reinterpret_cast<const uint4*>(src) + t);
+    const float4 q0 = *reinterpret_cast<const float4*>(qt + t * 8);
+    const float4 q1 = *reinterpret_cast<const float4*>(qt + t * 8 + 4);
+    float f0 = (float)(int16_t)(raw.x & 0xffffu) * q0.x;
+    float f1 = (float)(int16_t)(raw.x >> 16) * q0.y;
+    float f2 = (float)(int16_t)(raw.y & 0xffffu) * q0.z;
+    float f3 = (float)(int16_t)(raw.y >> 16) * q0.w;
+    float f4 = (float)(int16_t)(raw.z & 0xffffu) * q1.x;
+    float f5 = (float)(int16_t)(raw.z >> 16) * q1.y;
+    float f6 = (float)(int16_t)(raw.w & 0xffffu) * q1.z;
+    float f7 = (float)(int16_t)(raw.w >> 16) * q1.w;
+    if (t == 0) f0 += dc_bias;  // level shift folded into the DC term
+    idct8(f0, f1, f2, f3, f4, f5, f6, f7);  // vertical: f[y] = sample (y, column t) before the horizontal pass
+    __syncwarp();                           // previous pass finished reading scr
+    scr[0 * kScrRowPitch + t] = f0; scr[1 * kScrRowPitch + t] = f1; scr[2 * kScrRowPitch + t] = f2;
+    scr[3 * kScrRowPitch + t] = f3; scr[4 * kScrRowPitch + t] = f4; scr[5 * kScrRowPitch + t] = f5;
+    scr[6 * kScrRowPitch + t] = f6; scr[7 * kScrRowPitch + t] = f7;
+    __syncwarp();
+    const float4 a = *reinterpret_cast<const float4*>(scr + t * kScrRowPitch);
+    const float4 c = *reinterpret_cast<const float4*>(scr + t * kScrRowPitch + 4);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = c.x; out[5] = c.y; out[6] = c.z; out[7] = c.w;
+    idct8(out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]);  // horizontal: row t
+}
+
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return a | (b << 8) | (c << 16) | (d << 24);
+}
+
+// Tile = 128 pixels x (8*VY) rows = 16/HY MCUs.  Phase A: chroma blocks -> shared f32
+// planes.  Phase B: luma blocks; each lane ends with 8 horizontally adjacent Y samples,
+// fetches the replicated chroma, converts and stages 24 output bytes.  Phase C: the
+// staged tile is stored with 16-byte vectors.
+template <int HY, int VY, bool GRAY>
+__global__ void __launch_bounds__(kIdctThreads) idct_colour_kernel(BatchDev b, const uint32_t* __restrict__ img_list) {
+    constexpr int MW = 8 * HY, MH = 8 * VY;
+    constexpr int NM = 128 / MW;               // MCUs per tile
+    constexpr int NY = HY * VY;                // luma blocks per MCU
+    constexpr int NB = GRAY ? 1 : NY + 2;      // blocks per MCU
+    constexpr int CW = NM * 8;                 // chroma samples per tile row
+    __shared__ __align__(16) float s_scr[16 * kScrBlkPitch];
+    __shared__ __align__(16) float s_chroma[GRAY ? 4 : 2 * 8 * CW];
+    __shared__ __align__(16) uint8_t s_out[MH * kOutPitch];
+    __shared__ __align__(16) float s_qt[3 * 64];
+
+    const ImgDev& im = b.imgs[img_list[blockIdx.y]];
+    const uint32_t tile = blockIdx.x;
+    if (tile >= im.tiles_x * im.tiles_y) return;
+    const uint32_t tx = tile % im.tiles_x, ty = tile / im.tiles_x;
+    const int tid = threadIdx.x, t = tid & 7, bp = tid >> 3;
+
+    for (int i = tid; i < (GRAY ? 64 : 192); i += kIdctThreads) s_qt[i] = b.qt[im.qt_off[i >> 6] + (i & 63)];
+    __syncthreads();
+
+    const int16_t* __restrict__ coefs = b.coefs + im.coef_off;
+    const uint32_t mcu0 = ty * im.mcux + tx * NM;
+    const uint32_t mcus_here = min((uint32_t)NM, im.mcux - tx * NM);
+    const uint32_t units = im.units;
+    float* scr = s_scr + bp * kScrBlkPitch;
+
+    if (!GRAY) {
+        constexpr int CH_PASSES = (2 * NM) / 16;
+#pragma unroll
+        for (int a = 0; a < CH_PASSES; a++) {
+            const int cb = a * 16 + bp, m = cb >> 1, comp = 1 + (cb & 1);
+            const bool valid = (uint32_t)m < mcus_here && mcu0 + m < units;
+            const int16_t* src = coefs + ((size_t)(mcu0 + m) * NB + NY + (comp - 1)) * 64;
+            float o[8];
+            block_idct(src, valid, s_qt + comp * 64, t, scr, 0.0f, o);
+            float* dst = s_chroma + ((comp - 1) * 8 + t) * CW + m * 8;
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        __syncthreads();
+    }
+
+    constexpr int Y_PASSES = (NM * NY) / 16;
+#pragma unroll
+    for (int p = 0; p < Y_PASSES; p++) {
+        const int yb = p * 16 + bp, m = yb / NY, sub = yb % NY, by = sub / HY, bx = sub % HY;
+        const bool valid = (uint32_t)m < mcus_here && mcu0 + m < units;
+        const int16_t* src = coefs + ((size_t)(mcu0 + m) * NB + sub) * 64;
+        float y[8];
+        block_idct(src, valid, s_qt, t, scr, 128.0f, y);
+        const int px0 = (m * HY + bx) * 8, row = by * 8 + t;
+        uint32_t r8[8], g8[8], b8[8];
+        if (GRAY) {
+#pragma unroll
+            for (int x = 0; x < 8; x++) { r8[x] = f32_to_u8_sat(y[x]); g8[x] = r8[x]; b8[x] = r8[x]; }  // decoder.rs:317-324
+        } else {
+            const int crow = row / VY, cc0 = px0 / HY;
+            float cbv[8], crv[8];
+            const float* pcb = s_chroma + (0 * 8 + crow) * CW + cc0;
+            const float* pcr = s_chroma + (1 * 8 + crow) * CW + cc0;
+            if (HY == 2) {
+                const float4 u = *reinterpret_cast<const float4*>(pcb);
+                const float4 v = *reinterpret_cast<const float4*>(pcr);
+                cbv[0] = cbv[1] = u.x; cbv[2] = cbv[3] = u.y; cbv[4] = cbv[5] = u.z; cbv[6] = cbv[7] = u.w;
+                crv[0] = crv[1] = v.x; crv[2] = crv[3] = v.y; crv[4] = crv[5] = v.z; crv[6] = crv[7] = v.w;
+            } else {
+                const float4 u0 = *reinterpret_cast<const float4*>(pcb), u1 = *reinterpret_cast<const float4*>(pcb + 4);
+                const float4 v0 = *reinterpret_cast<const float4*>(pcr), v1 = *reinterpret_cast<const float4*>(pcr + 4);
+                cbv[0] = u0.x; cbv[1] = u0.y; cbv[2] = u0.z; cbv[3] = u0.w; cbv[4] = u1.x; cbv[5] = u1.y; cbv[6] = u1.z; cbv[7] = u1.w;
+                crv[0] = v0.x; crv[1] = v0.y; crv[2] = v0.z; crv[3] = v0.w; crv[4] = v1.x; crv[5] = v1.y; crv[6] = v1.z; crv[7] = v1.w;
+            }
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                // decoder.rs:392-401 with the +128 already inside y: r = cr*(2-2*0.299) + y, b = cb*(2-2*0.114) + y,
+                // g = (y - 0.114*b - 0.299*r)/0.587 = y - 0.344136*cb - 0.714136*cr
+                const float rr = fmaf(crv[x], 1.402f, y[x]);
+                const float bb = fmaf(cbv[x], 1.772f, y[x]);
+                const float gg = fmaf(cbv[x], -0.34413629f, fmaf(crv[x], -0.71413629f, y[x]));
+                r8[x] = f32_to_u8_sat(rr); g8[x] = f32_to_u8_sat(gg); b8[x] = f32_to_u8_sat(bb);
+            }
+        }
+        uint2* dst = reinterpret_cast<uint2*>(s_out + row * kOutPitch + px0 * 3);
+        dst[0] = make_uint2(pack4(r8[0], g8[0], b8[0], r8[1]), pack4(g8[1], b8[1], r8[2], g8[2]));
+        dst[1] = make_uint2(pack4(b8[2], r8[3], g8[3], b8[3]), pack4(r8[4], g8[4], b8[4], r8[5]));
+        dst[2] = make_uint2(pack4(g8[5], b8[5], r8[6], g8[6]), pack4(b8[6], r8[7], g8[7], b8[7]));
+    }
+    __syncthreads();
+
+    uint8_t* __restrict__ rgb = b.rgb + im.rgb_off;
+    const uint32_t W = im.width, H = im.height;
+    const uint32_t x0 = tx * 128u, y0 = ty * MH;
+    const uint32_t wpx = min(128u, W - x0), rows = min((uint32_t)MH, H - y0);
+    const uint32_t rowbytes = wpx * 3u;
+    if (((W * 3u) & 15u) == 0u && (rowbytes & 15u) == 0u) {
+        const uint32_t vpr = rowbytes >> 4;
+        for (uint32_t i = tid; i < rows * vpr; i += kIdctThreads) {
+            const uint32_t r = i / vpr, k = i - r * vpr;
+            const uint4 v = *reinterpret_cast<const uint4*>(s_out + r * kOutPitch + k * 16);
+            *reinterpret_cast<uint4*>(rgb + ((size_t)(y0 + r) * W + x0) * 3u + k * 16u) = v;
+        }
+    } else {
+        for (uint32_t i = tid; i < rows * rowbytes; i += kIdctThreads) {
+            const uint32_t r = i / rowbytes, k = i - r * rowbytes;
+            rgb[((size_t)(y0 + r) * W + x0) * 3u + k] = s_out[r * kOutPitch + k];
+        }
+    }
+}
+
+// ===================================================================== launchers
+void launch_prepass(const BatchDev& b, cudaStream_t s) {
+    if (b.n_images) prepass_kernel<<<b.n_images, kPreThreads, 0, s>>>(b);
+}
+void launch_sync_intra(const BatchDev& b, cudaStream_t s) {
+    if (b.n_seqs) sync_intra_kernel<<<b.n_seqs, kSeqThreads, 0, s>>>(b);
+}
+void launch_sync_inter_scan(const BatchDev& b, cudaStream_t s) {
+    if (b.n_images) sync_inter_scan_kernel<<<b.n_images, kInterThreads, 0, s>>>(b);
+}
+void launch_decode_write(const BatchDev& b, cudaStream_t s) {
+    if (b.n_seqs) decode_write_kernel<<<b.n_seqs, kSeqThreads, 0, s>>>(b);
+}
+
+int launch_idct_colour(const BatchDev& b, cudaStream_t s) {
+    int launches = 0;
+    for (int k = 0; k < kNumKinds; k++) {
+        if (!b.kind_count[k] || !b.kind_max_tiles[k]) continue;
+        dim3 grid(b.kind_max_tiles[k], b.kind_count[k]);
+        switch (k) {
+            case kKindGray: idct_colour_kernel<1, 1, true><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;
+            case kKind444: idct_colour_kernel<1, 1, false><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;
+            case kKind422: idct_colour_kernel<2, 1, false><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;
+            case kKind420: idct_colour_kernel<2, 2, false><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;
+            case kKind440: idct_colour_kernel<1, 2, false><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;
+            default: continue;
+        }
+        launches++;
+    }
+    return launches;
+}
+
+}  // namespace jpgpu

@@ -1,0 +1,51 @@
+// jpgpu_kernels.cuh — launch wrappers of the sm_100a kernels (jpgpu_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "jpgpu_core.h"
+
+namespace jpgpu {
+
+struct SeqDesc {
+    uint32_t img;        // image index
+    uint32_t first_sub;  // first subsequence of this sequence within the image
+};
+
+constexpr int kNumKinds = 6;
+
+struct BatchDev {        // device pointers of one planned batch
+    const ImgDev* imgs;
+    ImgDyn* dyn;
+    const SeqDesc* seqs;
+    const HuffLut* luts;
+    const float* qt;     // pre-scaled dequantisation multipliers, 64 per table, column-major
+    const uint8_t* raw;
+    uint32_t* stream;
+    uint32_t* segtab;
+    SubInfo* subs;
+    uint32_t* seq_flags; // 2 x n_seqs scratch for the inter-sequence pass
+    int16_t* coefs;
+    uint8_t* rgb;
+    uint32_t n_images;
+    uint32_t n_seqs;
+    // images grouped by colour-kernel variant (ImgKind)
+    const uint32_t* kind_imgs[kNumKinds];
+    uint32_t kind_count[kNumKinds];
+    uint32_t kind_max_tiles[kNumKinds];
+};
+
+cudaError_t init_constants();
+
+// Stage 1a: byte-unstuffing + RSTn detection, one CTA per image.
+void launch_prepass(const BatchDev& b, cudaStream_t s);
+// Stage 1b: intra-sequence self-synchronisation, one CTA per sequence.
+void launch_sync_intra(const BatchDev& b, cudaStream_t s);
+// Stage 1c: inter-sequence synchronisation + prefix scan, one CTA per image.
+void launch_sync_inter_scan(const BatchDev& b, cudaStream_t s);
+// Stage 1d: final decode, coefficients written to HBM.
+void launch_decode_write(const BatchDev& b, cudaStream_t s);
+// Stage 2+3: dequantise, IDCT, upsample, YCbCr->RGB, interleaved store (SPEC geometry).
+// Returns the number of kernels launched.
+int launch_idct_colour(const BatchDev& b, cudaStream_t s);
+
+}  // namespace jpgpu

@@ -1,0 +1,82 @@
+"""ctypes binding of tests/sim/libjpsim.so — the CPU simulation of the kernels' algorithm
+(test infrastructure; see tests/sim/jpsim.cpp)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from jpeg_rust_b200 import _ffi  # noqa: E402
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "sim", "libjpsim.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-s", "-C", ROOT, "tests/sim/libjpsim.so"])
+        L = C.CDLL(path)
+        L.jpgpu_parse.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(_ffi.ImageDesc)]
+        L.jpsim_decode_batch.argtypes = [C.POINTER(_ffi.ImageDesc), C.c_size_t, C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32),
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.jpsim_idct_8x8.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class SimResult:
+    pass
+
+
+def decode_batch(files, layout=_ffi.LAYOUT_SPEC, ext=_ffi.EXT_NONE):
+    """files: list of bytes. Returns (list of SimResult, diag)."""
+    L = lib()
+    n = len(files)
+    descs = (_ffi.ImageDesc * n)()
+    bufs = [np.frombuffer(f, np.uint8).copy() for f in files]
+    parse_status = []
+    for i, b in enumerate(bufs):
+        parse_status.append(L.jpgpu_parse(b.ctypes.data, len(b), ext, layout, C.byref(descs[i])))
+    rgb = [np.zeros((max(1, descs[i].height), max(1, descs[i].width), 3), np.uint8) for i in range(n)]
+    cap = [(((descs[i].width + 15) // 16 + 1) * ((descs[i].height + 15) // 16 + 1) * 12 * 64) for i in range(n)]
+    coefs = [np.zeros(cap[i], np.int16) for i in range(n)]
+    rgb_p = (C.c_void_p * n)(*[a.ctypes.data for a in rgb])
+    coef_p = (C.c_void_p * n)(*[a.ctypes.data for a in coefs])
+    caps = (C.c_size_t * n)(*cap)
+    nblocks = (C.c_uint32 * (4 * n))()
+    statuses = (C.c_int32 * n)()
+    bytes_read = (C.c_uint64 * n)()
+    diag = (C.c_uint64 * 4)()
+    st = L.jpsim_decode_batch(descs, n, rgb_p, coef_p, caps, nblocks, statuses, bytes_read, diag)
+    assert st == 0, st
+    out = []
+    for i in range(n):
+        r = SimResult()
+        r.parse_status = parse_status[i]
+        r.status = statuses[i] if parse_status[i] == 0 else parse_status[i]
+        r.width, r.height, r.ncomp = descs[i].width, descs[i].height, descs[i].ncomp
+        r.rgb = rgb[i]
+        r.bytes_read = bytes_read[i]
+        nb = [nblocks[4 * i + c] for c in range(4)]
+        r.coefs = []
+        off = 0
+        for c in range(r.ncomp):
+            r.coefs.append(coefs[i][off:off + nb[c] * 64].reshape(-1, 64))
+            off += nb[c] * 64
+        out.append(r)
+    return out, {"max_intra_rounds": diag[0], "max_inter_iters": diag[1], "inter_walk": diag[2], "intra_decodes": diag[3]}
+
+
+def idct_8x8(block_natural):
+    a = np.ascontiguousarray(block_natural, np.float32).reshape(64)
+    out = np.empty(64, np.float32)
+    lib().jpsim_idct_8x8(a.ctypes.data, out.ctypes.data)
+    return out.reshape(8, 8)
