@@ -1,0 +1,402 @@
+"""Host-side mirror of the reference's public interface for the decode path.
+
+Reference (martinhath/jpeg-rust)            here
+-------------------------------------------  -----------------------------------------
+jpeg::JPEGImage::parse(Vec<u8>)  mod.rs:202   JPEGImage.parse(bytes)
+  .width() .height() .image_data() 467-477    same names
+jpeg::decoder::JPEGDecoder       decoder.rs:19 JPEGDecoder (same builder calls, same order)
+  ::new / .frame_header / .scan_header /
+  .dimensions / .huffman_ac_tables /
+  .huffman_dc_tables / .quantization_table /
+  .decode() -> (Vec<(u8,u8,u8)>, usize)
+jpeg::huffman::HuffmanTable
+  ::from_size_data_tables        huffman.rs:37 HuffmanTable.from_size_data_tables
+
+Every reference panic becomes a `JPEGPanic` carrying the status code of include/jpgpu.h.
+The image data never passes through Python arithmetic: parsing fills a C descriptor
+(jpgpu_parse) and decode() calls the CUDA library through the C ABI.  Without the
+library or without a B200 these calls raise — there is no CPU path.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import EXT_DRI, EXT_NONE, EXT_SKIP_APPN, LAYOUT_REF, LAYOUT_SPEC  # noqa: F401
+
+
+class JPEGPanic(_ffi.JpgpuError):
+    """The reference would have panicked (or this library rejected the input)."""
+
+
+def _check(status, what=""):
+    if status != _ffi.OK:
+        raise JPEGPanic(status, what)
+
+
+# ----------------------------------------------------------------------------- device context
+_contexts = {}
+
+
+class Context:
+    """One jpgpu_ctx per (process, device)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(_ffi.lib().jpgpu_create(device, C.byref(self._h)), f"jpgpu_create(device={device})")
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_stream(self, cuda_stream):
+        _check(_ffi.lib().jpgpu_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def sync(self):
+        self._ck(_ffi.lib().jpgpu_sync(self._h))
+
+    def _ck(self, status, what=""):
+        if status in (_ffi.ERR_CUDA, _ffi.ERR_OOM):
+            what = (what + " " if what else "") + _ffi.lib().jpgpu_last_error(self._h).decode()
+        _check(status, what)
+
+    def close(self):
+        if self._h:
+            _ffi.lib().jpgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def context(device=0):
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]
+
+
+# ----------------------------------------------------------------------------- header types (mod.rs:89-139)
+@dataclass
+class FrameComponentHeader:
+    component_id: int
+    horizontal_sampling_factor: int
+    vertical_sampling_factor: int
+    quantization_selector: int
+
+
+@dataclass
+class FrameHeader:
+    sample_precision: int = 8
+    num_lines: int = 0
+    samples_per_line: int = 0
+    image_components: int = 0
+    frame_components: List[FrameComponentHeader] = field(default_factory=list)
+
+
+@dataclass
+class ScanComponentHeader:
+    component_id: int
+    dc_table_selector: int
+    ac_table_selector: int
+
+
+@dataclass
+class ScanHeader:
+    num_components: int = 0
+    scan_components: List[ScanComponentHeader] = field(default_factory=list)
+    start_spectral_selection: int = 0
+    end_spectral_selection: int = 63
+    successive_approximation_bit_pos_high: int = 0
+    successive_approximation_bit_pos_low: int = 0
+
+
+class HuffmanTable:
+    """huffman.rs:24-58: built from DHT BITS (`size_data`) and HUFFVAL (`data_table`)."""
+
+    def __init__(self, size_data, data_table):
+        self.size_data = bytes(size_data)
+        self.data_table = bytes(data_table)
+        if len(self.size_data) != 16:
+            raise ValueError("size_data must have 16 entries")
+
+    @staticmethod
+    def from_size_data_tables(size_data, data_table):
+        return HuffmanTable(size_data, data_table)
+
+
+# ----------------------------------------------------------------------------- JPEGDecoder (decoder.rs:19-343)
+class JPEGDecoder:
+    """Builder with the reference's call sequence (mod.rs:388-415).
+
+    `data` is the RAW entropy-coded segment (still byte-stuffed, from the first byte
+    after the SOS header to the end of the file); the unstuffing loop of mod.rs:371-385
+    runs on the GPU together with the decode.
+    """
+
+    def __init__(self, data, layout=LAYOUT_REF, restart_interval=0, device=0):
+        self._data = np.frombuffer(bytes(data), np.uint8).copy() if not isinstance(data, np.ndarray) else data
+        self._frame: Optional[FrameHeader] = None
+        self._scan: Optional[ScanHeader] = None
+        self._dims: Tuple[int, int] = (0, 0)
+        self._ac = {}
+        self._dc = {}
+        self._qt = {}
+        self.layout = layout
+        self.restart_interval = restart_interval
+        self.device = device
+
+    @staticmethod
+    def new(data, **kw):
+        return JPEGDecoder(data, **kw)
+
+    def frame_header(self, frame_header: FrameHeader):      # decoder.rs:83
+        self._frame = frame_header
+        return self
+
+    def scan_header(self, scan_header: ScanHeader):         # decoder.rs:113
+        self._scan = scan_header
+        return self
+
+    def dimensions(self, dimensions):                       # decoder.rs:66
+        self._dims = (int(dimensions[0]), int(dimensions[1]))
+        return self
+
+    def huffman_ac_tables(self, id, table: HuffmanTable):   # decoder.rs:71
+        self._ac[int(id)] = table
+
+    def huffman_dc_tables(self, id, table: HuffmanTable):   # decoder.rs:75
+        self._dc[int(id)] = table
+
+    def quantization_table(self, id, table):                # decoder.rs:79 (64 entries, zigzag order)
+        self._qt[int(id)] = [int(x) for x in table]
+
+    def descriptor(self) -> _ffi.ImageDesc:
+        """The POD the C ABI takes; component order = scan order (decoder.rs:141-150)."""
+        if self._frame is None:
+            raise JPEGPanic(_ffi.PANIC_NO_FRAME_HEADER)
+        if self._scan is None:
+            raise JPEGPanic(_ffi.NO_SCAN)
+        d = _ffi.ImageDesc()
+        d.width, d.height = self._dims
+        d.layout = self.layout
+        d.restart_interval = self.restart_interval
+        comps = self._scan.scan_components
+        if len(comps) > 4:
+            raise JPEGPanic(_ffi.PANIC_COMPONENT_COUNT)
+        d.ncomp = len(comps)
+        for i, sc in enumerate(comps):
+            fc = None
+            for k in self._frame.frame_components:  # decoder.rs:86-95: later entries with the same id overwrite
+                if k.component_id == sc.component_id:
+                    fc = k
+            if fc is None:
+                raise JPEGPanic(_ffi.PANIC_ARITH)
+            d.comp[i] = _ffi.Component(fc.component_id, fc.horizontal_sampling_factor, fc.vertical_sampling_factor,
+                                       fc.quantization_selector, sc.dc_table_selector, sc.ac_table_selector)
+        for tid, q in self._qt.items():
+            if not 0 <= tid < 4 or len(q) != 64:
+                raise JPEGPanic(_ffi.PANIC_INDEX_OOB)
+            for k in range(64):
+                d.qt[tid][k] = q[k]
+            d.qt_present[tid] = 1
+        for tabs, bits, vals, nvals, present in ((self._dc, d.dc_bits, d.dc_vals, d.dc_nvals, d.dc_present),
+                                                 (self._ac, d.ac_bits, d.ac_vals, d.ac_nvals, d.ac_present)):
+            for tid, t in tabs.items():
+                if not 0 <= tid < 4:
+                    raise JPEGPanic(_ffi.PANIC_INDEX_OOB)
+                if len(t.data_table) > 256:
+                    raise JPEGPanic(_ffi.ERR_BAD_HUFFMAN_TABLE)
+                for k in range(16):
+                    bits[tid][k] = t.size_data[k]
+                for k, v in enumerate(t.data_table):
+                    vals[tid][k] = v
+                nvals[tid] = len(t.data_table)
+                present[tid] = 1
+        d.scan = self._data.ctypes.data
+        d.scan_len = self._data.size
+        return d
+
+    def decode(self):
+        """decoder.rs:162: returns (pixels as an (H*W, 3) uint8 array, bytes_read)."""
+        d = self.descriptor()
+        ctx = context(self.device)
+        out = np.empty((d.height * d.width, 3), np.uint8)
+        br = C.c_size_t(0)
+        ctx._ck(_ffi.lib().jpgpu_decode(ctx.handle, C.byref(d), out.ctypes.data, C.byref(br)), "jpgpu_decode")
+        return out, br.value
+
+
+# ----------------------------------------------------------------------------- JPEGImage (mod.rs:59-87, 202-477)
+def parse_descriptor(data, ext=EXT_NONE, layout=LAYOUT_REF):
+    """jpgpu_parse: returns (status, ImageDesc, buffer that owns the bytes the descriptor points into)."""
+    buf = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), np.uint8).copy()
+    d = _ffi.ImageDesc()
+    st = _ffi.lib().jpgpu_parse(buf.ctypes.data, buf.size, ext, layout, C.byref(d))
+    return st, d, buf
+
+
+class JPEGImage:
+    """Result of JPEGImage::parse (mod.rs:202): dimensions and decoded pixels."""
+
+    def __init__(self):
+        self._dimensions = (0, 0)
+        self._image_data = None
+        self.bytes_read = 0
+        self.descriptor = None
+
+    @staticmethod
+    def parse(vec, ext=EXT_NONE, layout=LAYOUT_REF, device=0):
+        """mod.rs:202-465. Raises JPEGPanic where the reference panics; like the reference it
+        decodes the first scan and returns."""
+        st, d, buf = parse_descriptor(vec, ext, layout)
+        _check(st, "parse")
+        img = JPEGImage()
+        img._dimensions = (d.width, d.height)
+        img.descriptor = d
+        img._buf = buf
+        ctx = context(device)
+        out = np.empty((d.height * d.width, 3), np.uint8)
+        br = C.c_size_t(0)
+        ctx._ck(_ffi.lib().jpgpu_decode(ctx.handle, C.byref(d), out.ctypes.data, C.byref(br)), "jpgpu_decode")
+        img._image_data = out
+        img.bytes_read = br.value
+        return img
+
+    def width(self):           # mod.rs:467
+        return self._dimensions[0]
+
+    def height(self):          # mod.rs:471
+        return self._dimensions[1]
+
+    def image_data(self):      # mod.rs:475: row-major (r, g, b) triples
+        return self._image_data
+
+    def rgb(self):
+        return self._image_data.reshape(self.height(), self.width(), 3)
+
+    def write_ppm(self, path):
+        """main.rs:34-39: ASCII PPM (P3), one `r g b` line per pixel."""
+        with open(path, "w") as f:
+            f.write(f"P3\n{self.width()} {self.height()}\n255\n")
+            for r, g, b in self._image_data:
+                f.write(f"{r} {g} {b}\n")
+
+
+# ----------------------------------------------------------------------------- batches
+class Batch:
+    """Many independent images decoded with shared kernel launches (jpgpu_batch_*)."""
+
+    def __init__(self, files=None, descs=None, ext=EXT_NONE, layout=LAYOUT_SPEC, device=0, keepalive=None):
+        L = _ffi.lib()
+        self.ctx = context(device)
+        self._keep = [keepalive]
+        if descs is None:
+            n = len(files)
+            descs = (_ffi.ImageDesc * n)()
+            self.parse_status = []
+            for i, f in enumerate(files):
+                st, d, buf = parse_descriptor(f, ext, layout)
+                self.parse_status.append(st)
+                descs[i] = d
+                self._keep.append(buf)
+        else:
+            n = len(descs)
+            self.parse_status = [0] * n
+        self.n = n
+        self.descs = descs
+        self._h = C.c_void_p()
+        self.ctx._ck(L.jpgpu_batch_create(self.ctx.handle, descs, n, C.byref(self._h)), "jpgpu_batch_create")
+
+    def _call(self, name):
+        self.ctx._ck(getattr(_ffi.lib(), "jpgpu_batch_" + name)(self._h), "jpgpu_batch_" + name)
+        return self
+
+    def upload(self):
+        return self._call("upload")
+
+    def entropy(self):
+        return self._call("entropy")
+
+    def idct(self):
+        return self._call("idct")
+
+    def decode(self):
+        return self._call("decode")
+
+    def shape(self, i):
+        return (self.descs[i].height, self.descs[i].width, 3)
+
+    def download(self, outs=None):
+        """Device->host copy of every image (async on the context stream). Returns the list of arrays."""
+        if outs is None:
+            outs = [np.empty(self.shape(i), np.uint8) for i in range(self.n)]
+        ptrs = (C.c_void_p * self.n)(*[o.ctypes.data if hasattr(o, "ctypes") else int(o) for o in outs])
+        self.ctx._ck(_ffi.lib().jpgpu_batch_download(self._h, ptrs), "jpgpu_batch_download")
+        return outs
+
+    def download_ptrs(self, ptrs):
+        arr = (C.c_void_p * self.n)(*[int(p) for p in ptrs])
+        self.ctx._ck(_ffi.lib().jpgpu_batch_download(self._h, arr), "jpgpu_batch_download")
+
+    def results(self):
+        """Synchronises. Returns (statuses, bytes_read) as int lists; parse failures take precedence."""
+        st = (C.c_int32 * self.n)()
+        br = (C.c_uint64 * self.n)()
+        self.ctx._ck(_ffi.lib().jpgpu_batch_results(self._h, st, br), "jpgpu_batch_results")
+        statuses = [self.parse_status[i] if self.parse_status[i] else st[i] for i in range(self.n)]
+        return statuses, list(br)
+
+    def device_rgb(self, i):
+        nb = C.c_size_t(0)
+        p = _ffi.lib().jpgpu_batch_device_rgb(self._h, i, C.byref(nb))
+        return p, nb.value
+
+    def coefficients(self, i):
+        """Reference arrangement (decoder.rs:208-212): list of (nblocks, 64) int16 per component, zigzag, absolute DC."""
+        d = self.descs[i]
+        cap = ((d.width + 15) // 16 + 1) * ((d.height + 15) // 16 + 1) * 12 * 64
+        out = np.zeros(cap, np.int16)
+        nb = (C.c_uint32 * 4)()
+        self.ctx._ck(_ffi.lib().jpgpu_batch_coefficients(self._h, i, out.ctypes.data, cap, nb), "coefficients")
+        comps, off = [], 0
+        for c in range(d.ncomp):
+            comps.append(out[off:off + nb[c] * 64].reshape(-1, 64).copy())
+            off += nb[c] * 64
+        return comps
+
+    def stats(self):
+        s = (C.c_uint64 * 8)()
+        _check(_ffi.lib().jpgpu_batch_stats(self._h, s))
+        return {"scan_bytes": s[0], "coef_bytes": s[1], "rgb_bytes": s[2], "pixels": s[3], "blocks": s[4],
+                "sequences": s[5], "subsequences": s[6], "device_bytes": s[7]}
+
+    def launch_count(self):
+        return int(_ffi.lib().jpgpu_batch_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            _ffi.lib().jpgpu_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decode_batch(files, ext=EXT_NONE, layout=LAYOUT_SPEC, device=0):
+    """Convenience: decode a list of JPEG byte strings; returns (list of HxWx3 arrays, statuses, bytes_read)."""
+    b = Batch(files, ext=ext, layout=layout, device=device)
+    try:
+        b.upload().decode()
+        outs = b.download()
+        statuses, br = b.results()
+        return outs, statuses, br
+    finally:
+        b.close()
+
+
+def shard_range(n_items, rank, world_size):
+    """Contiguous image range of `rank`: [rank*n/world, (rank+1)*n/world)."""
+    return (rank * n_items) // world_size, ((rank + 1) * n_items) // world_size

@@ -1,0 +1,196 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle.
+
+Gate (BASELINE.json north_star): Huffman-decoded coefficients bit-exact; output samples
+within +-1 per 8-bit channel (max and mean |delta| asserted/reported below)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle_ffi as O
+from conftest import fixture_bytes
+from jpeg_rust_b200 import (EXT_DRI, EXT_NONE, EXT_SKIP_APPN, LAYOUT_REF, LAYOUT_SPEC, Batch, JPEGImage, JPEGPanic,
+                            _ffi, synth)
+
+pytestmark = pytest.mark.gpu
+
+SAMPLE_TOL = 1          # LSB per 8-bit channel
+MEAN_TOL = 0.01         # mean |delta| (observed ~1e-5)
+
+
+def assert_samples(got, want, what=""):
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert d.max() <= SAMPLE_TOL, f"{what}: max |delta| = {d.max()}"
+    assert d.mean() <= MEAN_TOL, f"{what}: mean |delta| = {d.mean()}"
+    return int(d.max()), float(d.mean())
+
+
+def run_batch(files, layout=LAYOUT_SPEC, ext=EXT_NONE):
+    b = Batch(files, ext=ext, layout=layout)
+    b.upload().decode()
+    outs = b.download()
+    statuses, br = b.results()
+    coefs = [b.coefficients(i) if statuses[i] == 0 else None for i in range(len(files))]
+    launches = b.launch_count()
+    b.close()
+    return outs, statuses, br, coefs, launches
+
+
+def compare_with_oracle(files, layout, ext=EXT_NONE, gts=None):
+    outs, statuses, br, coefs, launches = run_batch(files, layout, ext)
+    assert launches > 0
+    worst = (0, 0.0)
+    for i, f in enumerate(files):
+        o = O.decode(f, layout=layout, ext=ext)
+        assert o.status == 0, o.msg
+        assert statuses[i] == 0, _ffi.status_string(statuses[i])
+        assert len(coefs[i]) == len(o.coefs)
+        for c, (a, w) in enumerate(zip(coefs[i], o.coefs)):
+            assert a.shape == w.shape, f"image {i} comp {c}: {a.shape} vs {w.shape}"
+            assert np.array_equal(a, w), f"image {i} comp {c}: coefficients differ"
+        if gts is not None:
+            for a, w in zip(coefs[i], gts[i]):
+                assert np.array_equal(a[:len(w)], w[:len(a)])
+        if not (ext & EXT_DRI):
+            assert br[i] == o.bytes_read
+        m = assert_samples(outs[i], o.rgb, f"image {i}")
+        worst = (max(worst[0], m[0]), max(worst[1], m[1]))
+    return worst
+
+
+KNOWN = {  # SURVEY.md §4 known answers
+    "lena.jpeg": ("ba5ce1b7b3b108bb2bf354a742b7c1217138d58cefd78abe347e05255c060c06", 90694),
+    "lena-bw.jpeg": ("0fa4cc6820aa8a2d1d2448b5ad5f6b036ff007c17ef8b0369c5207655775dea2", 21494),
+}
+
+
+@pytest.mark.parametrize("name", ["lena.jpeg", "lena-bw.jpeg"])
+def test_fixture_reference_semantics(name):
+    """configs[0]/[1]: single-image decode with the reference's semantics (REF layout)."""
+    data = fixture_bytes(name)
+    img = JPEGImage.parse(data, layout=LAYOUT_REF)
+    o = O.decode(data, layout=O.LAYOUT_REF)
+    assert (img.width(), img.height()) == (o.width, o.height)
+    assert img.bytes_read == KNOWN[name][1] == o.bytes_read
+    assert_samples(img.rgb(), o.rgb, name)
+    outs, statuses, br, coefs, _ = run_batch([data], LAYOUT_REF)
+    stream = b"".join(c.astype("<i2").tobytes() for c in coefs[0])
+    assert hashlib.sha256(stream).hexdigest() == KNOWN[name][0]
+
+
+def test_huff_simple0_panics_like_the_reference_and_decodes_with_extension():
+    data = fixture_bytes("huff_simple0.jpg")
+    with pytest.raises(JPEGPanic) as e:
+        JPEGImage.parse(data, layout=LAYOUT_REF)
+    assert e.value.status == _ffi.PANIC_APP12_14          # mod.rs:446
+    img = JPEGImage.parse(data, ext=EXT_SKIP_APPN, layout=LAYOUT_REF)
+    rgb = img.rgb()
+    assert (rgb[:, :8] == 0).all() and (rgb[:, 8:] == 255).all()
+    assert img.bytes_read == 8
+
+
+def test_2x2_chroma_spec_layout():
+    """The only 4:2:0 fixture; SPEC layout (REF layout for H2V2 is covered by test_ref_layout_*)."""
+    data = fixture_bytes("2x2-chroma.jpeg")
+    outs, statuses, br, coefs, _ = run_batch([data], LAYOUT_SPEC)
+    assert statuses[0] == 0 and br[0] == 145019
+    stream = b"".join(c.astype("<i2").tobytes() for c in coefs[0])
+    assert hashlib.sha256(stream).hexdigest() == "d29cc5cc8e09c5def6a31f652905c99f00e9db477b5c91d1666a01c02fd839a7"
+    assert_samples(outs[0], O.decode(data, layout=O.LAYOUT_SPEC).rgb)
+
+
+@pytest.mark.parametrize("sub", ["420", "422", "444", "440", "gray"])
+def test_synthetic_shapes(sub):
+    """Ragged, tiny and aligned sizes in one mixed batch; encoder ground truth + oracle."""
+    shapes = [(64, 64), (17, 9), (250, 131), (1, 1), (333, 200), (8, 8), (128, 16), (640, 360)]
+    files, gts = [], []
+    for i, (w, h) in enumerate(shapes):
+        f, g = synth.synth_jpeg(100 + i, w, h, sub, want_coefs=True)
+        files.append(f)
+        gts.append(g)
+    compare_with_oracle(files, LAYOUT_SPEC, gts=gts)
+
+
+@pytest.mark.parametrize("sub,ri", [("444", 1), ("444", 7), ("420", 3), ("gray", 1), ("422", 16), ("444", 80)])
+def test_restart_intervals(sub, ri):
+    """configs[3] semantics at small size: DRI corpus + DRI-invariance (SURVEY.md §8c pin 4)."""
+    files, plain = [], []
+    for i, (w, h) in enumerate([(640, 480), (250, 131), (64, 64)]):
+        files.append(synth.synth_jpeg(200 + i, w, h, sub, restart_interval=ri))
+        plain.append(synth.synth_jpeg(200 + i, w, h, sub, restart_interval=0))
+    compare_with_oracle(files, LAYOUT_SPEC, ext=EXT_DRI)
+    a = run_batch(files, LAYOUT_SPEC, EXT_DRI)
+    b = run_batch(plain, LAYOUT_SPEC)
+    for i in range(len(files)):
+        assert all(np.array_equal(x, y) for x, y in zip(a[3][i], b[3][i]))
+        assert np.array_equal(a[0][i], b[0][i])
+
+
+def test_dri_rejected_without_extension():
+    f = synth.synth_jpeg(1, 64, 64, "444", restart_interval=4)
+    with pytest.raises(JPEGPanic) as e:
+        JPEGImage.parse(f)
+    assert e.value.status == _ffi.PANIC_DRI               # mod.rs:427
+
+
+def test_ref_layout_equals_spec_where_the_reference_is_correct():
+    files = [synth.synth_jpeg(300, 640, 480, "422"), synth.synth_jpeg(301, 320, 240, "444"),
+             synth.synth_jpeg(302, 200, 96, "gray")]
+    compare_with_oracle(files, LAYOUT_REF)
+
+
+@pytest.mark.parametrize("q", [5, 50, 95, 100])
+def test_quality_extremes(q):
+    files = [synth.synth_jpeg(400 + i, 320, 240, "420", quality=q) for i in range(2)]
+    compare_with_oracle(files, LAYOUT_SPEC)
+
+
+def test_flat_images_degenerate_sync():
+    flat = np.full((256, 256, 3), 128, np.uint8)
+    files = [synth.encode(flat, "420"), synth.encode(flat, "gray"), synth.encode(np.zeros((512, 512, 3), np.uint8), "444")]
+    compare_with_oracle(files, LAYOUT_SPEC)
+
+
+def test_1080p_420_full_size_parity():
+    """configs[2] shape at full size: one 1920x1080 4:2:0 image against the oracle and encoder ground truth."""
+    f, g = synth.synth_jpeg(0, 1920, 1080, "420", want_coefs=True)
+    worst = compare_with_oracle([f], LAYOUT_SPEC, gts=[g])
+    print("1080p 4:2:0 max/mean |delta|:", worst)
+
+
+def test_batch_is_deterministic_and_order_independent():
+    files = [synth.synth_jpeg(500 + i, 320 + 16 * i, 200, "420") for i in range(6)]
+    a = run_batch(files)
+    b = run_batch(files[::-1])
+    c = run_batch(files)
+    for i in range(len(files)):
+        assert np.array_equal(a[0][i], c[0][i])
+        assert np.array_equal(a[0][i], b[0][len(files) - 1 - i])
+
+
+def test_bad_inputs_are_reported_per_image():
+    good = synth.synth_jpeg(600, 64, 64, "420")
+    cut = good[:len(good) // 2]                       # truncated entropy data
+    outs, statuses, br, coefs, _ = run_batch([good, cut, good])
+    assert statuses[0] == 0 and statuses[2] == 0
+    assert statuses[1] != 0
+    assert np.array_equal(outs[0], outs[2])
+
+
+def test_full_size_batch_properties():
+    """Size-independent properties at batch scale (64 x 1080p): every copy of the same file decodes to
+    identical bytes, bytes_read equals the scan length minus EOI, ground-truth coefficients are exact."""
+    base = [synth.synth_jpeg(i, 1920, 1080, "420", want_coefs=True) for i in range(4)]
+    files = [base[i % 4][0] for i in range(64)]
+    b = Batch(files, layout=LAYOUT_SPEC)
+    b.upload().decode()
+    outs = b.download()
+    statuses, br = b.results()
+    assert all(s == 0 for s in statuses)
+    for i in range(64):
+        assert np.array_equal(outs[i], outs[i % 4])
+    for i in (0, 1, 2, 3, 63):
+        got = b.coefficients(i)
+        for a, w in zip(got, base[i % 4][1]):
+            assert np.array_equal(a, w)
+    b.close()
