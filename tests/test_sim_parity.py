@@ -1,0 +1,106 @@
+"""CPU simulation of the kernels' algorithm (tests/sim/jpsim.cpp: same per-thread code, same planner,
+barrier structure replayed serially) against the oracle.  This is what the not-gpu suite can say about
+the parallel decode: coefficients bit-exact, samples within +-1, bytes_read identical."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_ffi as O
+import sim_ffi as S
+from conftest import fixture_bytes
+from jpeg_rust_b200 import synth
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "known_answers.json")))
+
+
+def check(files, layout=1, ext=0, gts=None):
+    rs, diag = S.decode_batch(files, layout=layout, ext=ext)
+    for k, (f, r) in enumerate(zip(files, rs)):
+        o = O.decode(f, layout=layout, ext=ext)
+        assert o.status == 0 and r.status == 0, (k, r.status, o.msg)
+        assert len(r.coefs) == len(o.coefs)
+        for a, b in zip(r.coefs, o.coefs):
+            assert np.array_equal(a, b), f"image {k}: coefficients differ"
+        if gts:
+            for a, b in zip(r.coefs, gts[k]):
+                assert np.array_equal(a, b)
+        if not (ext & 2):
+            assert r.bytes_read == o.bytes_read
+        d = np.abs(r.rgb.astype(int) - o.rgb.astype(int))
+        assert d.max() <= 1 and d.mean() < 0.01
+    return diag
+
+
+@pytest.mark.parametrize("name,layout,ext", [("lena.jpeg", 0, 0), ("lena-bw.jpeg", 0, 0), ("huff_simple0.jpg", 0, 1),
+                                             ("2x2-chroma.jpeg", 1, 0), ("lena.jpeg", 1, 0)])
+def test_fixtures(name, layout, ext):
+    data = fixture_bytes(name)
+    diag = check([data], layout, ext)
+    assert diag["max_inter_iters"] >= 1
+    (r,), _ = S.decode_batch([data], layout=layout, ext=ext)
+    key = "SPEC" if layout else "REF"
+    stream = b"".join(c.astype("<i2").tobytes() for c in r.coefs)
+    assert hashlib.sha256(stream).hexdigest() == GOLD["oracle"]["fixtures"][name][key]["coef_sha256"]
+
+
+@pytest.mark.parametrize("sub", ["420", "422", "444", "440", "gray"])
+def test_shapes_mixed_batch(sub):
+    files, gts = [], []
+    for i, (w, h) in enumerate([(64, 64), (17, 9), (250, 131), (1, 1), (333, 200), (8, 8), (128, 16)]):
+        f, g = synth.synth_jpeg(100 + i, w, h, sub, want_coefs=True)
+        files.append(f)
+        gts.append(g)
+    check(files, gts=gts)
+
+
+@pytest.mark.parametrize("sub,ri", [("444", 1), ("444", 7), ("420", 3), ("gray", 1), ("422", 16), ("444", 80)])
+def test_restart_intervals(sub, ri):
+    files, gts = [], []
+    for i, (w, h) in enumerate([(320, 240), (250, 131), (64, 64)]):
+        f, g = synth.synth_jpeg(200 + i, w, h, sub, restart_interval=ri, want_coefs=True)
+        files.append(f)
+        gts.append(g)
+    check(files, ext=2, gts=gts)
+
+
+def test_multi_sequence_image_needs_inter_sequence_sync():
+    """An image longer than one sequence (256 subsequences) exercises the inter-sequence walkers."""
+    f, g = synth.synth_jpeg(0, 1280, 720, "420", quality=92, want_coefs=True)
+    diag = check([f], gts=[g])
+    assert diag["inter_walk"] > 0
+
+
+def test_ref_layout_classes_equal_to_spec():
+    check([synth.synth_jpeg(300, 320, 240, "422"), synth.synth_jpeg(301, 160, 120, "444"),
+           synth.synth_jpeg(302, 200, 96, "gray")], layout=0)
+
+
+@pytest.mark.parametrize("q", [5, 100])
+def test_quality_extremes(q):
+    check([synth.synth_jpeg(400 + i, 160, 120, "420", quality=q) for i in range(2)])
+
+
+def test_flat_images():
+    flat = np.full((128, 128, 3), 128, np.uint8)
+    check([synth.encode(flat, "420"), synth.encode(flat, "gray"), synth.encode(np.zeros((256, 256, 3), np.uint8), "444")])
+
+
+def test_truncated_and_unsupported_inputs_get_a_status():
+    good = synth.synth_jpeg(600, 64, 64, "420")
+    rs, _ = S.decode_batch([good, good[:len(good) // 2], good])
+    assert rs[0].status == 0 and rs[2].status == 0 and rs[1].status != 0
+    assert np.array_equal(rs[0].rgb, rs[2].rgb)
+
+
+def test_idct_factorisation_matches_the_direct_form():
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for _ in range(100):
+        blk = np.zeros(64, np.float32)
+        k = rng.integers(1, 24)
+        blk[rng.choice(64, k, replace=False)] = rng.integers(-400, 400, k)
+        worst = max(worst, float(np.abs(O.idct_8x8(blk.reshape(8, 8)) - S.idct_8x8(blk.reshape(8, 8))).max()))
+    assert worst < 2e-3
