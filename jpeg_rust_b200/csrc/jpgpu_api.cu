@@ -144,6 +144,7 @@ extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs,
     BatchDev& d = b->dev;
     d.n_images = (uint32_t)n;
     d.n_seqs = (uint32_t)p.seqs.size();
+    d.sub_bits = p.sub_bits;
 #define TRY(x) do { st = (x); if (st != JPGPU_OK) { jpgpu_batch_destroy(b); return st; } } while (0)
     TRY(dev_upload(b, &d.imgs, p.imgs));
     TRY(dev_upload(b, &d.seqs, p.seqs));

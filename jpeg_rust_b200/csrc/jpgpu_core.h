@@ -24,9 +24,15 @@ constexpr int kLutBits = 10;               // first-level Huffman LUT index widt
 constexpr int kLutSize = 1 << kLutBits;
 constexpr int kMaxBlocksPerMcu = 12;       // 3 components x (H,V in {1,2})
 constexpr int kMaxLutSlots = 6;            // distinct (DC, AC) tables one image can reference
-constexpr int kSubseqBits = 1024;          // bits per subsequence (one decode thread each)
-constexpr int kSubseqWords = kSubseqBits / 32;
-constexpr int kSeqThreads = 256;           // subsequences per sequence (= CTA size of the sync/write kernels)
+#ifndef JPGPU_SEQ_THREADS
+#define JPGPU_SEQ_THREADS 256
+#endif
+// Bits per subsequence (one decode thread each) are a per-batch plan parameter
+// (BatchDev::sub_bits): 1024, 2048 or 4096 — larger means fewer re-decodes until
+// synchronisation, smaller means more threads for small batches.
+constexpr int kMinSubseqBits = 1024;
+constexpr int kMaxSubseqBits = 4096;
+constexpr int kSeqThreads = JPGPU_SEQ_THREADS;  // subsequences per sequence (= CTA size of the sync/write kernels)
 constexpr int kStreamPadWords = 8;         // zero words readable past every image's stream
 
 // status bits accumulated per image on the device (mapped to JPGPU_* by the host)
@@ -38,12 +44,28 @@ enum : uint32_t {
 };
 
 // One Huffman table in device format.
+// Packed decode entry: bits 0-7 symbol, 8-12 code length, 13-18 total bits (code +
+// value bits), 19-25 zigzag advance (1 for DC; run+1; 16 for ZRL; 64 for EOB), 26 DC
+// size category > 16 (huffman.rs:202 assert).  With `advance`, next_block's three cases
+// (huffman.rs:164-189) collapse into nz = min(z + advance, 64).
 struct HuffLut {
-    uint16_t fast[kLutSize];  // (len << 8) | symbol for codes of len <= kLutBits, 0 otherwise
+    uint32_t fast[kLutSize];  // entry for codes of len <= kLutBits, 0 otherwise
     int32_t maxcode[18];      // largest code of length l (right aligned), -1 if none; l = 1..16
     int32_t valoff[18];       // index of first symbol of length l minus its smallest code
     uint8_t vals[256];        // HUFFVAL
+    uint32_t is_dc;
+    uint32_t pad[3];
 };
+
+JPGPU_HD uint32_t make_entry(uint32_t sym, uint32_t len, bool is_dc) {
+    uint32_t size, adv, big = 0;
+    if (is_dc) { size = sym; adv = 1; if (size > 16) { size = 16; big = 1; } }
+    else if (sym == 0x00) { size = 0; adv = 64; }
+    else if (sym == 0xf0) { size = 0; adv = 16; }
+    else { size = sym & 15; adv = (sym >> 4) + 1; }
+    return sym | (len << 8) | ((len + size) << 13) | (adv << 19) | (big << 26);
+}
+constexpr uint32_t kBadEntry = (16u << 8) | (16u << 13) | (64u << 19);  // unknown code: 16 bits, ends the block
 
 // Per-image plan, written by the host, read by every kernel.
 struct ImgDev {
@@ -148,15 +170,14 @@ struct BitReader {
     }
 };
 
-// huffman.rs:211-227 next_code as a canonical prefix decode. Returns (len << 8) | symbol, 0 if no code matches.
-JPGPU_HD uint32_t huff_lookup(const HuffLut& t, uint32_t peek32) {
-    uint32_t e = t.fast[peek32 >> (32 - kLutBits)];
-    if (e) return e;
+// huffman.rs:211-227 next_code for codes longer than kLutBits: canonical prefix decode
+// (T.81 F.2.2.3). Returns a packed entry, 0 if no code matches.
+JPGPU_HD uint32_t huff_slow(const HuffLut& t, uint32_t peek32) {
     uint32_t code16 = peek32 >> 16;
 #pragma unroll 1
     for (int l = kLutBits + 1; l <= 16; l++) {
         int32_t code = (int32_t)(code16 >> (16 - l));
-        if (code <= t.maxcode[l]) return ((uint32_t)l << 8) | t.vals[(t.valoff[l] + code) & 255];
+        if (code <= t.maxcode[l]) return make_entry(t.vals[(t.valoff[l] + code) & 255], (uint32_t)l, t.is_dc != 0);
     }
     return 0;
 }
@@ -238,11 +259,13 @@ JPGPU_HD void decode_span(const DecCtx& cx, DecState& st, uint32_t end_bit, int3
     int32_t g = st.g, c = st.c;
     int32_t dc0 = st.dc0, dc1 = st.dc1, dc2 = st.dc2;
     uint32_t seg_end = st.seg_end, flags = st.flags;
+    uint32_t p = br.pos();
     if (end_bit > cx.stream_bits) end_bit = cx.stream_bits;
+    const HuffLut* tdc = cx.luts + cx.blk_dc_slot[c];
+    const HuffLut* tac = cx.luts + cx.blk_ac_slot[c];
+    int32_t comp = cx.blk_comp[c];
 #pragma unroll 1
-    while (true) {
-        uint32_t p = br.pos();
-        if (p >= end_bit) break;
+    while (p < end_bit) {
         if (WRITE && g >= g_limit) break;
         br.refill();
         if (p + 8 > seg_end) {  // fewer than 8 bits left in this restart interval (or already past it)
@@ -254,52 +277,55 @@ JPGPU_HD void decode_span(const DecCtx& cx, DecState& st, uint32_t end_bit, int3
             if (cross) {
                 if (st.seg + 1 >= cx.nseg) {  // end of the entropy-coded data
                     br.seek(seg_end);
+                    p = seg_end;
                     break;
                 }
                 st.seg += 1;
-                uint32_t np = seg_end;
+                p = seg_end;
                 seg_end = cx.seg[st.seg + 1];
-                br.seek(np);
+                br.seek(p);
                 g = (int32_t)(st.seg * cx.seg_units);
                 c = 0;
+                tdc = cx.luts + cx.blk_dc_slot[0]; tac = cx.luts + cx.blk_ac_slot[0]; comp = cx.blk_comp[0];
                 dc0 = dc1 = dc2 = 0;
                 flags |= kCrossed;
                 continue;
             }
         }
-        uint32_t peek = br.peek();
-        int32_t z = g & 63;
-        const HuffLut& t = cx.luts[z == 0 ? cx.blk_dc_slot[c] : cx.blk_ac_slot[c]];
-        uint32_t e = huff_lookup(t, peek);
-        if (e == 0) {  // no such code: consume 16 bits as an EOB-like symbol and flag (huffman.rs:156/162 panic)
-            flags |= kStBadCode;
-            e = (16u << 8);
+        const uint32_t peek = br.peek();
+        const int32_t z = g & 63;
+        const HuffLut* t = z ? tac : tdc;
+        uint32_t e = t->fast[peek >> (32 - kLutBits)];
+        if (e == 0) {
+            e = huff_slow(*t, peek);
+            if (e == 0) { flags |= kStBadCode; e = kBadEntry; }  // huffman.rs:156/162 panic
         }
-        uint32_t len = e >> 8, sym = e & 0xff;
-        uint32_t size, run;
-        if (z == 0) { size = sym; run = 0; if (size > 16) { size = 16; flags |= kStDcSize; } }
-        else { size = sym & 15; run = sym >> 4; }
-        uint32_t v = size ? ((peek << len) >> (32 - size)) : 0u;
-        br.skip(len + size);
-        int32_t val = extend(v, size);
-        int32_t nz;  // zigzag position after this symbol
-        if (z == 0) {
-            int32_t comp = cx.blk_comp[c];
-            int32_t pred;
-            if (comp == 0) { dc0 += val; pred = dc0; } else if (comp == 1) { dc1 += val; pred = dc1; } else { dc2 += val; pred = dc2; }
-            if (WRITE && pred != 0) coefs[(g & ~63) + store_pos[0]] = (int16_t)pred;  // decoder.rs:208-210
-            nz = 1;
-        } else if (sym == 0x00) {            // EOB, huffman.rs:164-169
-            nz = 64;
-        } else if (sym == 0xf0) {            // ZRL, huffman.rs:170-175
-            nz = z + 16 < 64 ? z + 16 : 64;
-        } else {                             // huffman.rs:183-189
-            int32_t pos = z + (int32_t)run < 63 ? z + (int32_t)run : 63;
-            if (WRITE && val != 0) coefs[(g & ~63) + store_pos[pos]] = (int16_t)val;
-            nz = pos + 1;
+        const uint32_t len = (e >> 8) & 31u, tb = (e >> 13) & 63u;
+        const int32_t adv = (int32_t)((e >> 19) & 127u);
+        if (WRITE || z == 0) {
+            const uint32_t size = tb - len;
+            const uint32_t v = size ? ((peek << len) >> (32 - size)) : 0u;
+            const int32_t val = extend(v, size);
+            if (z == 0) {  // DC difference -> predictor (decoder.rs:208-210)
+                if (e & (1u << 26)) flags |= kStDcSize;
+                int32_t pred;
+                if (comp == 0) { dc0 += val; pred = dc0; } else if (comp == 1) { dc1 += val; pred = dc1; } else { dc2 += val; pred = dc2; }
+                if (WRITE && pred != 0) coefs[(g & ~63) + store_pos[0]] = (int16_t)pred;
+            } else if (WRITE && val != 0) {  // huffman.rs:183-189: min(run, 64 - len - 1) zeros, then the value
+                const int32_t pos = z + adv - 1 < 63 ? z + adv - 1 : 63;
+                coefs[(g & ~63) + store_pos[pos]] = (int16_t)val;
+            }
         }
-        g = (g & ~63) + nz;  // nz == 64 carries into the block index
-        if (nz == 64) { c += 1; if (c == cx.nblk) c = 0; }
+        br.skip(tb);
+        p += tb;
+        if (z + adv >= 64) {  // block complete (EOB, ZRL/run past the end, or coefficient 63)
+            g = (g | 63) + 1;
+            c += 1;
+            if (c == cx.nblk) c = 0;
+            tdc = cx.luts + cx.blk_dc_slot[c]; tac = cx.luts + cx.blk_ac_slot[c]; comp = cx.blk_comp[c];
+        } else {
+            g += adv;
+        }
     }
     st.br = br; st.g = g; st.c = c; st.dc0 = dc0; st.dc1 = dc1; st.dc2 = dc2;
     st.seg_end = seg_end; st.flags = flags;

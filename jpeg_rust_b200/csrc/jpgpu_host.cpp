@@ -4,6 +4,7 @@
 // Pure host code; the image data itself is only ever touched by the CUDA kernels.
 #include "jpgpu_host.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -83,8 +84,9 @@ int compute_geometry(const jpgpu_image_desc& d, Geometry& g) {
     return JPGPU_OK;
 }
 
-int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, HuffLut& out) {
+int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, bool is_dc, HuffLut& out) {
     memset(&out, 0, sizeof out);
+    out.is_dc = is_dc ? 1u : 0u;
     int total = 0;
     for (int i = 0; i < 16; i++) total += bits[i];
     if (total > 256 || total > nvals) return JPGPU_ERR_BAD_HUFFMAN_TABLE;
@@ -99,7 +101,7 @@ int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, HuffL
             if (code >= (1u << l)) return JPGPU_ERR_BAD_HUFFMAN_TABLE;  // not a prefix code
             if (l <= kLutBits) {
                 const uint32_t first = code << (kLutBits - l), cnt = 1u << (kLutBits - l);
-                for (uint32_t e = 0; e < cnt; e++) out.fast[first + e] = (uint16_t)((l << 8) | vals[k]);
+                for (uint32_t e = 0; e < cnt; e++) out.fast[first + e] = make_entry(vals[k], (uint32_t)l, is_dc);
             }
         }
         if (n) out.maxcode[l] = (int32_t)code - 1;
@@ -117,8 +119,26 @@ void build_qt_multipliers(const uint16_t qt_zigzag[64], float out[64]) {
     }
 }
 
-int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan) {
+uint32_t choose_subseq_bits(uint64_t total_scan_bytes) {
+    if (const char* e = getenv("JPGPU_SUBSEQ_BITS")) {
+        const long v = atol(e);
+        if (v == 1024 || v == 2048 || v == 4096) return (uint32_t)v;
+    }
+    // keep at least ~2 subsequences per hardware thread slot (148 SMs x 2048 threads)
+    const uint64_t bits = total_scan_bytes * 8, want = 2ull * 148 * 2048;
+    if (bits / 4096 >= want) return 4096;
+    if (bits / 2048 >= want) return 2048;
+    return 1024;
+}
+
+int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t sub_bits) {
     plan = HostPlan();
+    if (sub_bits == 0) {
+        uint64_t tot = 0;
+        for (size_t i = 0; i < n; i++) tot += descs[i].scan_len;
+        sub_bits = choose_subseq_bits(tot);
+    }
+    plan.sub_bits = sub_bits;
     plan.imgs.resize(n);
     plan.status.assign(n, JPGPU_OK);
     std::map<std::string, uint32_t> lut_ids;
@@ -146,13 +166,14 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan) {
                 const uint8_t* bits = cls == 0 ? d.dc_bits[tid] : d.ac_bits[tid];
                 const uint8_t* vals = cls == 0 ? d.dc_vals[tid] : d.ac_vals[tid];
                 const int nvals = cls == 0 ? d.dc_nvals[tid] : d.ac_nvals[tid];
-                std::string key((const char*)bits, 16);
+                std::string key(cls == 0 ? "D" : "A");
+                key.append((const char*)bits, 16);
                 key.append((const char*)vals, (size_t)std::min(nvals, 256));
                 auto it = lut_ids.find(key);
                 uint32_t id;
                 if (it == lut_ids.end()) {
                     HuffLut lut;
-                    st = build_huff_lut(bits, vals, nvals, lut);
+                    st = build_huff_lut(bits, vals, nvals, cls == 0, lut);
                     if (st != JPGPU_OK) break;
                     id = (uint32_t)plan.luts.size();
                     plan.luts.push_back(lut);
@@ -228,7 +249,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan) {
         if (im.nseg_cap == 0) im.nseg_cap = 1;
         im.seg_off = (uint32_t)plan.seg_entries;
         plan.seg_entries += im.nseg_cap + 2;
-        im.nsub_cap = std::max<uint32_t>(1u, (uint32_t)(((uint64_t)im.raw_len * 8 + kSubseqBits - 1) / kSubseqBits));
+        im.nsub_cap = std::max<uint32_t>(1u, (uint32_t)(((uint64_t)im.raw_len * 8 + sub_bits - 1) / sub_bits));
         im.sub_off = (uint32_t)plan.sub_entries;
         plan.sub_entries += im.nsub_cap;
         im.nseq = (im.nsub_cap + kSeqThreads - 1) / kSeqThreads;

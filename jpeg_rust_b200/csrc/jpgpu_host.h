@@ -26,12 +26,13 @@ struct Geometry {
 int compute_geometry(const jpgpu_image_desc& d, Geometry& g);
 
 // Builds the device Huffman table from DHT BITS/HUFFVAL (huffman.rs:37-58, 80-98).
-int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, HuffLut& out);
+int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, bool is_dc, HuffLut& out);
 
 // 64 multipliers (column-major) = q * aan[u] * aan[v] / 8 from a zigzag-order DQT table.
 void build_qt_multipliers(const uint16_t qt_zigzag[64], float out[64]);
 
 struct HostPlan {
+    uint32_t sub_bits = kMinSubseqBits;
     std::vector<ImgDev> imgs;
     std::vector<int32_t> status;  // per image: JPGPU_OK or why it is skipped
     std::vector<SeqDesc> seqs;
@@ -49,7 +50,9 @@ struct HostPlan {
     uint64_t tot_scan_bytes = 0, tot_blocks = 0, tot_pixels = 0, tot_rgb_bytes = 0;
 };
 
-int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan);
+// sub_bits: 1024/2048/4096, or 0 = choose from the batch size (env JPGPU_SUBSEQ_BITS overrides).
+uint32_t choose_subseq_bits(uint64_t total_scan_bytes);
+int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t sub_bits = 0);
 
 // Reorders one image's coefficient arena ([mcu][block][column-major]) into the
 // reference arrangement: per component, decode order, zigzag (decoder.rs:208-212).

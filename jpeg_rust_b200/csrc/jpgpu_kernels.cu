@@ -193,9 +193,10 @@ __global__ void __launch_bounds__(kSeqThreads, 3) sync_intra_kernel(BatchDev b) 
     __shared__ SubInfo s_info[kSeqThreads];
 
     const SeqDesc sd = b.seqs[blockIdx.x];
+    const uint32_t S = b.sub_bits;
     load_entropy_ctx(b, sd.img, sm, kSeqThreads);
     const ImgDyn dyn = b.dyn[sd.img];
-    const uint32_t nsub = (dyn.stream_bits + kSubseqBits - 1) / kSubseqBits;
+    const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
     const DecCtx cx = make_ctx(b, sm, dyn);
 
@@ -205,9 +206,9 @@ __global__ void __launch_bounds__(kSeqThreads, 3) sync_intra_kernel(BatchDev b) 
     DecState st;
     int32_t g_base = 0;
     if (active) {
-        init_state(cx, st, j * kSubseqBits, 0, 0, 0, 0, 0);
+        init_state(cx, st, j * S, 0, 0, 0, 0, 0);
         g_base = st.g;
-        decode_span<false>(cx, st, (j + 1) * kSubseqBits, 0, nullptr, nullptr);
+        decode_span<false>(cx, st, (j + 1) * S, 0, nullptr, nullptr);
         SubInfo mine;
         summarise(st, g_base, mine);
         mine.pad[0] = mine.pad[1] = 0;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(kSeqThreads, 3) sync_intra_kernel(BatchDev b) 
         if (active && (tgt >= kSeqThreads || j + r >= nsub)) active = false;
         if (active) {
             begin_subsequence(st, g_base);
-            decode_span<false>(cx, st, (j + r + 1) * kSubseqBits, 0, nullptr, nullptr);
+            decode_span<false>(cx, st, (j + r + 1) * S, 0, nullptr, nullptr);
             SubInfo mine;
             summarise(st, g_base, mine);
             mine.pad[0] = mine.pad[1] = 0;
@@ -245,9 +246,10 @@ __global__ void __launch_bounds__(kInterThreads) sync_inter_scan_kernel(BatchDev
     __shared__ int32_t s_agg[kInterThreads][5];
 
     const uint32_t img = blockIdx.x;
+    const uint32_t S = b.sub_bits;
     load_entropy_ctx(b, img, sm, kInterThreads);
     const ImgDyn dyn = b.dyn[img];
-    const uint32_t nsub = (dyn.stream_bits + kSubseqBits - 1) / kSubseqBits;
+    const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     const uint32_t nseq = (nsub + kSeqThreads - 1) / kSeqThreads;
     const DecCtx cx = make_ctx(b, sm, dyn);
     SubInfo* subs = b.subs + sm.img.sub_off;
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(kInterThreads) sync_inter_scan_kernel(BatchDev
                     if (!first) begin_subsequence(st, g_base);
                     else { g_base = st.g; st.dc0 = st.dc1 = st.dc2 = 0; }
                     first = false;
-                    decode_span<false>(cx, st, (jj + 1) * kSubseqBits, 0, nullptr, nullptr);
+                    decode_span<false>(cx, st, (jj + 1) * S, 0, nullptr, nullptr);
                     SubInfo mine;
                     summarise(st, g_base, mine);
                     mine.pad[0] = mine.pad[1] = 0;
@@ -331,9 +333,10 @@ __global__ void __launch_bounds__(kSeqThreads, 3) decode_write_kernel(BatchDev b
     __shared__ EntropySmem sm;
 
     const SeqDesc sd = b.seqs[blockIdx.x];
+    const uint32_t S = b.sub_bits;
     load_entropy_ctx(b, sd.img, sm, kSeqThreads);
     const ImgDyn dyn = b.dyn[sd.img];
-    const uint32_t nsub = (dyn.stream_bits + kSubseqBits - 1) / kSubseqBits;
+    const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
     const DecCtx cx = make_ctx(b, sm, dyn);
     const uint32_t j = sd.first_sub + threadIdx.x;
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(kSeqThreads, 3) decode_write_kernel(BatchDev b
     const int32_t total = (int32_t)sm.img.total_coefs;
     const int32_t g_start = st.g;
     st.flags &= ~kCrossed;
-    decode_span<true>(cx, st, (j + 1) * kSubseqBits, total, b.coefs + sm.img.coef_off, sm.store_pos);
+    decode_span<true>(cx, st, (j + 1) * S, total, b.coefs + sm.img.coef_off, sm.store_pos);
     uint32_t bits = st.flags & (kStBadCode | kStDcSize);
     if (g_start < total && st.g >= total) {  // this thread decoded the last block of the scan
         b.dyn[sd.img].bits_consumed = st.br.pos();
@@ -360,6 +363,7 @@ __global__ void __launch_bounds__(kSeqThreads, 3) decode_write_kernel(BatchDev b
 
 // ============================================ stage 2+3: dequant + IDCT + upsample + colour
 constexpr int kIdctThreads = 128;
+constexpr int kTilesPerCta = 5;      // consecutive tiles one CTA walks (amortises set-up, lets loads run ahead)
 constexpr int kScrRowPitch = 12;     // floats; 4*odd -> conflict-free 128-bit row reads
 constexpr int kScrBlkPitch = 104;    // floats; 8 mod 32 -> conflict-free column writes across the 4 blocks of a warp
 constexpr int kOutPitch = 400;       // bytes per staged output row (128 px * 3 = 384, padded)
@@ -370,14 +374,14 @@ __device__ __forceinline__ uint32_t f32_to_u8_sat(float x) {  // decoder.rs:382-
     return r;
 }
 
-// 8 lanes own one 8x8 block; lane t loads column t (16 bytes), runs the vertical pass,
-// the block is transposed through shared memory, and lane t finishes row t.
-__device__ __forceinline__ void block_idct(const int16_t* __restrict__ src, bool valid, const float* __restrict__ qt,
-                                           int t, float* __restrict__ scr, float dc_bias, float out[8]) {
-    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-    if (valid) raw = __ldg(reinterpret_cast<const uint4*>(src) + t);
-    const float4 q0 = *reinterpret_cast<const float4*>(qt + t * 8);
-    const float4 q1 = *reinterpret_cast<const float4*>(qt + t * 8 + 4);
+// 8 lanes own one 8x8 block; lane t holds column t (16 bytes = 8 coefficients), runs the
+// vertical pass, the block is transposed through shared memory, and lane t finishes row t.
+// qt points at this lane's multipliers: qt[0..3] = rows 0-3, qt[32..35] = rows 4-7.
+__device__ __forceinline__ void block_idct(const uint4 raw, const float* __restrict__ qt, int t,
+                                           float* scr_w, const float* scr_r, float dc_bias, float out[8]) {
+    // scr_w and scr_r alias the same shared scratch tile: no __restrict__ on them.
+    const float4 q0 = *reinterpret_cast<const float4*>(qt);
+    const float4 q1 = *reinterpret_cast<const float4*>(qt + 32);
     float f0 = (float)(int16_t)(raw.x & 0xffffu) * q0.x;
     float f1 = (float)(int16_t)(raw.x >> 16) * q0.y;
     float f2 = (float)(int16_t)(raw.y & 0xffffu) * q0.z;
@@ -389,12 +393,12 @@ __device__ __forceinline__ void block_idct(const int16_t* __restrict__ src, bool
     if (t == 0) f0 += dc_bias;  // level shift folded into the DC term
     idct8(f0, f1, f2, f3, f4, f5, f6, f7);  // vertical: f[y] = sample (y, column t) before the horizontal pass
     __syncwarp();                           // previous pass finished reading scr
-    scr[0 * kScrRowPitch + t] = f0; scr[1 * kScrRowPitch + t] = f1; scr[2 * kScrRowPitch + t] = f2;
-    scr[3 * kScrRowPitch + t] = f3; scr[4 * kScrRowPitch + t] = f4; scr[5 * kScrRowPitch + t] = f5;
-    scr[6 * kScrRowPitch + t] = f6; scr[7 * kScrRowPitch + t] = f7;
+    scr_w[0 * kScrRowPitch] = f0; scr_w[1 * kScrRowPitch] = f1; scr_w[2 * kScrRowPitch] = f2;
+    scr_w[3 * kScrRowPitch] = f3; scr_w[4 * kScrRowPitch] = f4; scr_w[5 * kScrRowPitch] = f5;
+    scr_w[6 * kScrRowPitch] = f6; scr_w[7 * kScrRowPitch] = f7;
     __syncwarp();
-    const float4 a = *reinterpret_cast<const float4*>(scr + t * kScrRowPitch);
-    const float4 c = *reinterpret_cast<const float4*>(scr + t * kScrRowPitch + 4);
+    const float4 a = *reinterpret_cast<const float4*>(scr_r);
+    const float4 c = *reinterpret_cast<const float4*>(scr_r + 4);
     out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = c.x; out[5] = c.y; out[6] = c.z; out[7] = c.w;
     idct8(out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]);  // horizontal: row t
 }
@@ -406,113 +410,160 @@ __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, ui
 // Tile = 128 pixels x (8*VY) rows = 16/HY MCUs.  Phase A: chroma blocks -> shared f32
 // planes.  Phase B: luma blocks; each lane ends with 8 horizontally adjacent Y samples,
 // fetches the replicated chroma, converts and stages 24 output bytes.  Phase C: the
-// staged tile is stored with 16-byte vectors.
+// staged tile is stored with 16-byte vectors.  A CTA walks kTilesPerCta consecutive
+// tiles; the coefficient loads of the next tile are issued before the current one is
+// computed.
 template <int HY, int VY, bool GRAY>
 __global__ void __launch_bounds__(kIdctThreads) idct_colour_kernel(BatchDev b, const uint32_t* __restrict__ img_list) {
-    constexpr int MW = 8 * HY, MH = 8 * VY;
-    constexpr int NM = 128 / MW;               // MCUs per tile
+    constexpr int MH = 8 * VY;
+    constexpr int NM = 128 / (8 * HY);         // MCUs per tile
     constexpr int NY = HY * VY;                // luma blocks per MCU
     constexpr int NB = GRAY ? 1 : NY + 2;      // blocks per MCU
     constexpr int CW = NM * 8;                 // chroma samples per tile row
+    constexpr int CWP = CW + 4;                // padded pitch: rows land on different banks
+    constexpr int CH_PASSES = GRAY ? 0 : (2 * NM) / 16;
+    constexpr int Y_PASSES = (NM * NY) / 16;
+    constexpr int NL = CH_PASSES + Y_PASSES;   // 16-byte loads per thread and tile
     __shared__ __align__(16) float s_scr[16 * kScrBlkPitch];
-    __shared__ __align__(16) float s_chroma[GRAY ? 4 : 2 * 8 * CW];
+    __shared__ __align__(16) float s_chroma[GRAY ? 4 : 2 * 8 * CWP];
     __shared__ __align__(16) uint8_t s_out[MH * kOutPitch];
     __shared__ __align__(16) float s_qt[3 * 64];
 
     const ImgDev& im = b.imgs[img_list[blockIdx.y]];
-    const uint32_t tile = blockIdx.x;
-    if (tile >= im.tiles_x * im.tiles_y) return;
-    const uint32_t tx = tile % im.tiles_x, ty = tile / im.tiles_x;
+    const uint32_t ntiles = im.tiles_x * im.tiles_y;
+    uint32_t tile = blockIdx.x * kTilesPerCta;
+    if (tile >= ntiles) return;
+    const uint32_t tile_end = min(ntiles, tile + kTilesPerCta);
     const int tid = threadIdx.x, t = tid & 7, bp = tid >> 3;
 
-    for (int i = tid; i < (GRAY ? 64 : 192); i += kIdctThreads) s_qt[i] = b.qt[im.qt_off[i >> 6] + (i & 63)];
-    __syncthreads();
-
-    const int16_t* __restrict__ coefs = b.coefs + im.coef_off;
-    const uint32_t mcu0 = ty * im.mcux + tx * NM;
-    const uint32_t mcus_here = min((uint32_t)NM, im.mcux - tx * NM);
-    const uint32_t units = im.units;
-    float* scr = s_scr + bp * kScrBlkPitch;
-
-    if (!GRAY) {
-        constexpr int CH_PASSES = (2 * NM) / 16;
-#pragma unroll
-        for (int a = 0; a < CH_PASSES; a++) {
-            const int cb = a * 16 + bp, m = cb >> 1, comp = 1 + (cb & 1);
-            const bool valid = (uint32_t)m < mcus_here && mcu0 + m < units;
-            const int16_t* src = coefs + ((size_t)(mcu0 + m) * NB + NY + (comp - 1)) * 64;
-            float o[8];
-            block_idct(src, valid, s_qt + comp * 64, t, scr, 0.0f, o);
-            float* dst = s_chroma + ((comp - 1) * 8 + t) * CW + m * 8;
-            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-        }
-        __syncthreads();
+    // multipliers, re-laid so that lane t's two float4 reads are conflict-free: [comp][half][t][4]
+    for (int i = tid; i < (GRAY ? 64 : 192); i += kIdctThreads) {
+        const int comp = i >> 6, r = i & 63, tt = r >> 3, v = r & 7;
+        s_qt[comp * 64 + (v >> 2) * 32 + tt * 4 + (v & 3)] = b.qt[im.qt_off[comp] + r];
     }
 
-    constexpr int Y_PASSES = (NM * NY) / 16;
+    const uint4* __restrict__ coefs = reinterpret_cast<const uint4*>(b.coefs + im.coef_off);
+    uint8_t* __restrict__ rgb = b.rgb + im.rgb_off;
+    const uint32_t W = im.width, H = im.height, mcux = im.mcux, units = im.units, tiles_x = im.tiles_x;
+    float* const scr_w = s_scr + bp * kScrBlkPitch + t;
+    const float* const scr_r = s_scr + bp * kScrBlkPitch + t * kScrRowPitch;
+    const float* const qt_l = s_qt + t * 4;
+
+    // per-thread block assignment inside a tile (in units of blocks, relative to the tile's first MCU)
+    int blk_of[NL > 0 ? NL : 1];       // index of the block this thread handles in load l
+    int mcu_of[NL > 0 ? NL : 1];
+#pragma unroll
+    for (int a = 0; a < CH_PASSES; a++) {
+        const int cb = a * 16 + bp, m = cb >> 1;
+        mcu_of[a] = m; blk_of[a] = m * NB + NY + (cb & 1);
+    }
 #pragma unroll
     for (int p = 0; p < Y_PASSES; p++) {
-        const int yb = p * 16 + bp, m = yb / NY, sub = yb % NY, by = sub / HY, bx = sub % HY;
-        const bool valid = (uint32_t)m < mcus_here && mcu0 + m < units;
-        const int16_t* src = coefs + ((size_t)(mcu0 + m) * NB + sub) * 64;
-        float y[8];
-        block_idct(src, valid, s_qt, t, scr, 128.0f, y);
-        const int px0 = (m * HY + bx) * 8, row = by * 8 + t;
-        uint32_t r8[8], g8[8], b8[8];
-        if (GRAY) {
-#pragma unroll
-            for (int x = 0; x < 8; x++) { r8[x] = f32_to_u8_sat(y[x]); g8[x] = r8[x]; b8[x] = r8[x]; }  // decoder.rs:317-324
-        } else {
-            const int crow = row / VY, cc0 = px0 / HY;
-            float cbv[8], crv[8];
-            const float* pcb = s_chroma + (0 * 8 + crow) * CW + cc0;
-            const float* pcr = s_chroma + (1 * 8 + crow) * CW + cc0;
-            if (HY == 2) {
-                const float4 u = *reinterpret_cast<const float4*>(pcb);
-                const float4 v = *reinterpret_cast<const float4*>(pcr);
-                cbv[0] = cbv[1] = u.x; cbv[2] = cbv[3] = u.y; cbv[4] = cbv[5] = u.z; cbv[6] = cbv[7] = u.w;
-                crv[0] = crv[1] = v.x; crv[2] = crv[3] = v.y; crv[4] = crv[5] = v.z; crv[6] = crv[7] = v.w;
-            } else {
-                const float4 u0 = *reinterpret_cast<const float4*>(pcb), u1 = *reinterpret_cast<const float4*>(pcb + 4);
-                const float4 v0 = *reinterpret_cast<const float4*>(pcr), v1 = *reinterpret_cast<const float4*>(pcr + 4);
-                cbv[0] = u0.x; cbv[1] = u0.y; cbv[2] = u0.z; cbv[3] = u0.w; cbv[4] = u1.x; cbv[5] = u1.y; cbv[6] = u1.z; cbv[7] = u1.w;
-                crv[0] = v0.x; crv[1] = v0.y; crv[2] = v0.z; crv[3] = v0.w; crv[4] = v1.x; crv[5] = v1.y; crv[6] = v1.z; crv[7] = v1.w;
-            }
-#pragma unroll
-            for (int x = 0; x < 8; x++) {
-                // decoder.rs:392-401 with the +128 already inside y: r = cr*(2-2*0.299) + y, b = cb*(2-2*0.114) + y,
-                // g = (y - 0.114*b - 0.299*r)/0.587 = y - 0.344136*cb - 0.714136*cr
-                const float rr = fmaf(crv[x], 1.402f, y[x]);
-                const float bb = fmaf(cbv[x], 1.772f, y[x]);
-                const float gg = fmaf(cbv[x], -0.34413629f, fmaf(crv[x], -0.71413629f, y[x]));
-                r8[x] = f32_to_u8_sat(rr); g8[x] = f32_to_u8_sat(gg); b8[x] = f32_to_u8_sat(bb);
-            }
-        }
-        uint2* dst = reinterpret_cast<uint2*>(s_out + row * kOutPitch + px0 * 3);
-        dst[0] = make_uint2(pack4(r8[0], g8[0], b8[0], r8[1]), pack4(g8[1], b8[1], r8[2], g8[2]));
-        dst[1] = make_uint2(pack4(b8[2], r8[3], g8[3], b8[3]), pack4(r8[4], g8[4], b8[4], r8[5]));
-        dst[2] = make_uint2(pack4(g8[5], b8[5], r8[6], g8[6]), pack4(b8[6], r8[7], g8[7], b8[7]));
+        const int yb = p * 16 + bp, m = yb / NY;
+        mcu_of[CH_PASSES + p] = m; blk_of[CH_PASSES + p] = m * NB + yb % NY;
     }
-    __syncthreads();
 
-    uint8_t* __restrict__ rgb = b.rgb + im.rgb_off;
-    const uint32_t W = im.width, H = im.height;
-    const uint32_t x0 = tx * 128u, y0 = ty * MH;
-    const uint32_t wpx = min(128u, W - x0), rows = min((uint32_t)MH, H - y0);
-    const uint32_t rowbytes = wpx * 3u;
-    if (((W * 3u) & 15u) == 0u && (rowbytes & 15u) == 0u) {
-        const uint32_t vpr = rowbytes >> 4;
-        for (uint32_t i = tid; i < rows * vpr; i += kIdctThreads) {
-            const uint32_t r = i / vpr, k = i - r * vpr;
-            const uint4 v = *reinterpret_cast<const uint4*>(s_out + r * kOutPitch + k * 16);
-            *reinterpret_cast<uint4*>(rgb + ((size_t)(y0 + r) * W + x0) * 3u + k * 16u) = v;
+    uint4 cur[NL], nxt[NL];
+    auto issue_loads = [&](uint32_t tl, uint4 (&dst)[NL]) {
+        const uint32_t tx = tl % tiles_x, ty = tl / tiles_x;
+        const uint32_t mcu0 = ty * mcux + tx * NM;
+        const uint32_t here = min((uint32_t)NM, mcux - tx * NM);
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+            const bool valid = (uint32_t)mcu_of[l] < here && mcu0 + mcu_of[l] < units;
+            dst[l] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) dst[l] = __ldg(coefs + ((size_t)mcu0 * NB + blk_of[l]) * 8 + t);
         }
-    } else {
-        for (uint32_t i = tid; i < rows * rowbytes; i += kIdctThreads) {
-            const uint32_t r = i / rowbytes, k = i - r * rowbytes;
-            rgb[((size_t)(y0 + r) * W + x0) * 3u + k] = s_out[r * kOutPitch + k];
+    };
+    issue_loads(tile, cur);
+    __syncthreads();  // s_qt ready
+
+#pragma unroll 1
+    for (; tile < tile_end; tile++) {
+        if (tile + 1 < tile_end) issue_loads(tile + 1, nxt);
+        const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+
+        if (!GRAY) {
+#pragma unroll
+            for (int a = 0; a < CH_PASSES; a++) {
+                const int cb = a * 16 + bp, m = cb >> 1, comp = 1 + (cb & 1);
+                float o[8];
+                block_idct(cur[a], qt_l + comp * 64, t, scr_w, scr_r, 0.0f, o);
+                float* dst = s_chroma + ((comp - 1) * 8 + t) * CWP + m * 8;
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+            __syncthreads();
         }
+
+#pragma unroll
+        for (int p = 0; p < Y_PASSES; p++) {
+            const int yb = p * 16 + bp, m = yb / NY, sub = yb % NY, by = sub / HY, bx = sub % HY;
+            float y[8];
+            block_idct(cur[CH_PASSES + p], qt_l, t, scr_w, scr_r, 128.0f, y);
+            const int px0 = (m * HY + bx) * 8, row = by * 8 + t;
+            uint32_t r8[8], g8[8], b8[8];
+            if (GRAY) {
+#pragma unroll
+                for (int x = 0; x < 8; x++) { r8[x] = f32_to_u8_sat(y[x]); g8[x] = r8[x]; b8[x] = r8[x]; }  // decoder.rs:317-324
+            } else {
+                const int crow = row / VY, cc0 = px0 / HY;
+                float cbv[8], crv[8];
+                const float* pcb = s_chroma + (0 * 8 + crow) * CWP + cc0;
+                const float* pcr = s_chroma + (1 * 8 + crow) * CWP + cc0;
+                if (HY == 2) {
+                    const float4 u = *reinterpret_cast<const float4*>(pcb);
+                    const float4 v = *reinterpret_cast<const float4*>(pcr);
+                    cbv[0] = cbv[1] = u.x; cbv[2] = cbv[3] = u.y; cbv[4] = cbv[5] = u.z; cbv[6] = cbv[7] = u.w;
+                    crv[0] = crv[1] = v.x; crv[2] = crv[3] = v.y; crv[4] = crv[5] = v.z; crv[6] = crv[7] = v.w;
+                } else {
+                    const float4 u0 = *reinterpret_cast<const float4*>(pcb), u1 = *reinterpret_cast<const float4*>(pcb + 4);
+                    const float4 v0 = *reinterpret_cast<const float4*>(pcr), v1 = *reinterpret_cast<const float4*>(pcr + 4);
+                    cbv[0] = u0.x; cbv[1] = u0.y; cbv[2] = u0.z; cbv[3] = u0.w; cbv[4] = u1.x; cbv[5] = u1.y; cbv[6] = u1.z; cbv[7] = u1.w;
+                    crv[0] = v0.x; crv[1] = v0.y; crv[2] = v0.z; crv[3] = v0.w; crv[4] = v1.x; crv[5] = v1.y; crv[6] = v1.z; crv[7] = v1.w;
+                }
+#pragma unroll
+                for (int x = 0; x < 8; x++) {
+                    // decoder.rs:392-401 with the +128 already inside y: r = cr*(2-2*0.299) + y, b = cb*(2-2*0.114) + y,
+                    // g = (y - 0.114*b - 0.299*r)/0.587 = y - 0.344136*cb - 0.714136*cr
+                    const float rr = fmaf(crv[x], 1.402f, y[x]);
+                    const float bb = fmaf(cbv[x], 1.772f, y[x]);
+                    const float gg = fmaf(cbv[x], -0.34413629f, fmaf(crv[x], -0.71413629f, y[x]));
+                    r8[x] = f32_to_u8_sat(rr); g8[x] = f32_to_u8_sat(gg); b8[x] = f32_to_u8_sat(bb);
+                }
+            }
+            uint2* dst = reinterpret_cast<uint2*>(s_out + row * kOutPitch + px0 * 3);
+            dst[0] = make_uint2(pack4(r8[0], g8[0], b8[0], r8[1]), pack4(g8[1], b8[1], r8[2], g8[2]));
+            dst[1] = make_uint2(pack4(b8[2], r8[3], g8[3], b8[3]), pack4(r8[4], g8[4], b8[4], r8[5]));
+            dst[2] = make_uint2(pack4(g8[5], b8[5], r8[6], g8[6]), pack4(b8[6], r8[7], g8[7], b8[7]));
+        }
+        __syncthreads();
+
+        const uint32_t x0 = tx * 128u, y0 = ty * MH;
+        const uint32_t wpx = min(128u, W - x0), rows = min((uint32_t)MH, H - y0);
+        const uint32_t rowbytes = wpx * 3u;
+        uint8_t* const tile_out = rgb + ((size_t)y0 * W + x0) * 3u;
+        if (((W * 3u) & 15u) == 0u && (rowbytes & 15u) == 0u) {
+            const uint32_t vpr = rowbytes >> 4;  // <= 24
+#pragma unroll
+            for (uint32_t i = tid; i < (uint32_t)MH * 24u; i += kIdctThreads) {
+                const uint32_t r = i / 24u, k = i - r * 24u;
+                if (r < rows && k < vpr) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(s_out + r * kOutPitch + k * 16);
+                    *reinterpret_cast<uint4*>(tile_out + (size_t)r * W * 3u + k * 16u) = v;
+                }
+            }
+        } else {
+            for (uint32_t i = tid; i < rows * rowbytes; i += kIdctThreads) {
+                const uint32_t r = i / rowbytes, k = i - r * rowbytes;
+                tile_out[(size_t)r * W * 3u + k] = s_out[r * kOutPitch + k];
+            }
+        }
+        // s_out / s_chroma are rewritten only after the next tile's phase-A barrier (or, for gray,
+        // after the barrier below) — every thread has left phase C by then.
+        if (GRAY) __syncthreads();
+#pragma unroll
+        for (int l = 0; l < NL; l++) cur[l] = nxt[l];
     }
 }
 
@@ -534,7 +585,7 @@ int launch_idct_colour(const BatchDev& b, cudaStream_t s) {
     int launches = 0;
     for (int k = 0; k < kNumKinds; k++) {
         if (!b.kind_count[k] || !b.kind_max_tiles[k]) continue;
-        dim3 grid(b.kind_max_tiles[k], b.kind_count[k]);
+        dim3 grid((b.kind_max_tiles[k] + kTilesPerCta - 1) / kTilesPerCta, b.kind_count[k]);
         switch (k) {
             case kKindGray: idct_colour_kernel<1, 1, true><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;
             case kKind444: idct_colour_kernel<1, 1, false><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;

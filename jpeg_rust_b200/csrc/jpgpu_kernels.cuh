@@ -28,6 +28,7 @@ struct BatchDev {        // device pointers of one planned batch
     uint8_t* rgb;
     uint32_t n_images;
     uint32_t n_seqs;
+    uint32_t sub_bits;   // bits per subsequence for this batch
     // images grouped by colour-kernel variant (ImgKind)
     const uint32_t* kind_imgs[kNumKinds];
     uint32_t kind_count[kNumKinds];

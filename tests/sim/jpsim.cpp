@@ -105,7 +105,8 @@ void sim_sync_intra(SimBatch& sb, const SeqDesc& sd) {
     load_slots(sb, sd.img, slots);
     const ImgDev& im = sb.plan.imgs[sd.img];
     const ImgDyn dyn = sb.dyn[sd.img];
-    const uint32_t nsub = (dyn.stream_bits + kSubseqBits - 1) / kSubseqBits;
+    const uint32_t S = sb.plan.sub_bits;
+    const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
     const DecCtx cx = make_ctx(sb, sd.img, slots.data());
     std::vector<DecState> st(kSeqThreads);
@@ -116,9 +117,9 @@ void sim_sync_intra(SimBatch& sb, const SeqDesc& sd) {
         const uint32_t j = sd.first_sub + tid;
         active[tid] = j < nsub;
         if (!active[tid]) continue;
-        init_state(cx, st[tid], j * kSubseqBits, 0, 0, 0, 0, 0);
+        init_state(cx, st[tid], j * S, 0, 0, 0, 0, 0);
         g_base[tid] = st[tid].g;
-        decode_span<false>(cx, st[tid], (j + 1) * kSubseqBits, 0, nullptr, nullptr);
+        decode_span<false>(cx, st[tid], (j + 1) * S, 0, nullptr, nullptr);
         SubInfo mine;
         summarise(st[tid], g_base[tid], mine);
         mine.pad[0] = mine.pad[1] = 0;
@@ -134,7 +135,7 @@ void sim_sync_intra(SimBatch& sb, const SeqDesc& sd) {
             if (active[tid] && (tgt >= (uint32_t)kSeqThreads || j + r >= nsub)) active[tid] = 0;
             if (!active[tid]) continue;
             begin_subsequence(st[tid], g_base[tid]);
-            decode_span<false>(cx, st[tid], (j + r + 1) * kSubseqBits, 0, nullptr, nullptr);
+            decode_span<false>(cx, st[tid], (j + r + 1) * S, 0, nullptr, nullptr);
             SubInfo mine;
             summarise(st[tid], g_base[tid], mine);
             mine.pad[0] = mine.pad[1] = 0;
@@ -161,7 +162,8 @@ void sim_sync_inter_scan(SimBatch& sb, size_t img) {
     load_slots(sb, img, slots);
     const ImgDev& im = sb.plan.imgs[img];
     const ImgDyn dyn = sb.dyn[img];
-    const uint32_t nsub = (dyn.stream_bits + kSubseqBits - 1) / kSubseqBits;
+    const uint32_t S = sb.plan.sub_bits;
+    const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     const uint32_t nseq = (nsub + kSeqThreads - 1) / kSeqThreads;
     const DecCtx cx = make_ctx(sb, img, slots.data());
     SubInfo* subs = sb.subs.data() + im.sub_off;
@@ -195,7 +197,7 @@ void sim_sync_inter_scan(SimBatch& sb, size_t img) {
                     if (!first) begin_subsequence(st, g_base);
                     else { g_base = st.g; st.dc0 = st.dc1 = st.dc2 = 0; }
                     first = false;
-                    decode_span<false>(cx, st, (jj + 1) * kSubseqBits, 0, nullptr, nullptr);
+                    decode_span<false>(cx, st, (jj + 1) * S, 0, nullptr, nullptr);
                     sb.inter_walk++;
                     SubInfo mine;
                     summarise(st, g_base, mine);
@@ -228,7 +230,8 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
     load_slots(sb, sd.img, slots);
     const ImgDev& im = sb.plan.imgs[sd.img];
     const ImgDyn dyn = sb.dyn[sd.img];
-    const uint32_t nsub = (dyn.stream_bits + kSubseqBits - 1) / kSubseqBits;
+    const uint32_t S = sb.plan.sub_bits;
+    const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
     const DecCtx cx = make_ctx(sb, sd.img, slots.data());
     for (uint32_t tid = 0; tid < (uint32_t)kSeqThreads; tid++) {
@@ -243,7 +246,7 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
         const int32_t total = (int32_t)im.total_coefs;
         const int32_t g_start = st.g;
         st.flags &= ~kCrossed;
-        decode_span<true>(cx, st, (j + 1) * kSubseqBits, total, sb.coefs.data() + im.coef_off, sb.store_pos);
+        decode_span<true>(cx, st, (j + 1) * S, total, sb.coefs.data() + im.coef_off, sb.store_pos);
         uint32_t bits = st.flags & (kStBadCode | kStDcSize);
         if (g_start < total && st.g >= total) { sb.dyn[sd.img].bits_consumed = st.br.pos(); bits |= kStDone; }
         sb.dyn[sd.img].status |= bits;
@@ -325,9 +328,9 @@ extern "C" {
 //   diag[4]      : max intra rounds, max inter iterations, inter walk decodes, intra decodes
 int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* rgb_out, int16_t* const* coef_out,
                        const size_t* coef_cap, uint32_t* nblocks /* n x 4 */, int32_t* statuses, uint64_t* bytes_read,
-                       uint64_t* diag) {
+                       uint64_t* diag, uint32_t sub_bits) {
     SimBatch sb;
-    int st = build_plan(descs, n, sb.plan);
+    int st = build_plan(descs, n, sb.plan, sub_bits);
     if (st != JPGPU_OK) return st;
     HostPlan& p = sb.plan;
     sb.raw.assign(p.raw_bytes + 64, 0);

@@ -26,7 +26,7 @@ def lib():
         L.jpgpu_parse.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(_ffi.ImageDesc)]
         L.jpsim_decode_batch.argtypes = [C.POINTER(_ffi.ImageDesc), C.c_size_t, C.POINTER(C.c_void_p),
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint32),
-                                         C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint32]
         L.jpsim_idct_8x8.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -36,7 +36,7 @@ class SimResult:
     pass
 
 
-def decode_batch(files, layout=_ffi.LAYOUT_SPEC, ext=_ffi.EXT_NONE):
+def decode_batch(files, layout=_ffi.LAYOUT_SPEC, ext=_ffi.EXT_NONE, sub_bits=0):
     """files: list of bytes. Returns (list of SimResult, diag)."""
     L = lib()
     n = len(files)
@@ -55,7 +55,7 @@ def decode_batch(files, layout=_ffi.LAYOUT_SPEC, ext=_ffi.EXT_NONE):
     statuses = (C.c_int32 * n)()
     bytes_read = (C.c_uint64 * n)()
     diag = (C.c_uint64 * 4)()
-    st = L.jpsim_decode_batch(descs, n, rgb_p, coef_p, caps, nblocks, statuses, bytes_read, diag)
+    st = L.jpsim_decode_batch(descs, n, rgb_p, coef_p, caps, nblocks, statuses, bytes_read, diag, sub_bits)
     assert st == 0, st
     out = []
     for i in range(n):
