@@ -155,6 +155,10 @@ extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs,
         d.kind_max_tiles[k] = p.kind_max_tiles[k];
         TRY(dev_upload(b, &d.kind_imgs[k], p.kind_imgs[k]));
     }
+    TRY(dev_upload(b, &d.gmap, p.gmap));
+    d.gather_max_blocks = p.gather_max_blocks;
+    d.gather_max_quads = p.gather_max_quads;
+    if (p.sample_floats) TRY(dev_alloc(b, &d.samples, p.sample_floats));
     uint8_t* raw = nullptr;
     TRY(dev_alloc(b, &raw, p.raw_bytes + 64));
     d.raw = raw;

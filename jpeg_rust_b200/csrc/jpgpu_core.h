@@ -96,7 +96,13 @@ struct ImgDev {
     uint32_t slot_lut[kMaxLutSlots];      // index into the global HuffLut array
     uint32_t qt_off[4];                   // per component: offset (in floats) of its 64 pre-scaled multipliers
     uint32_t tiles_x, tiles_y;            // colour-kernel tiles (128 px x 8*vmax rows)
+    // gather path only (kind == kKindGeneric): REF placement / generic sampling
+    uint64_t map_off;                     // u32 offset of this shape's placement map (ncomp planes of map_plane entries)
+    uint64_t smp_off;                     // float offset of this image's per-block IDCT samples
+    uint32_t map_plane;                   // entries per component plane (W*H rounded up to 4)
+    uint32_t pad1;
 };
+constexpr uint32_t kMapNone = 0xffffffffu;  // placement-map entry of a pixel no block was ever written to
 
 enum ImgKind : uint8_t { kKindGray = 0, kKind444 = 1, kKind422 = 2, kKind420 = 3, kKind440 = 4, kKindGeneric = 5 };
 

@@ -4,8 +4,11 @@
 // Pure host code; the image data itself is only ever touched by the CUDA kernels.
 #include "jpgpu_host.h"
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <stdio.h>
 
 #include <algorithm>
 #include <map>
@@ -143,6 +146,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
     plan.status.assign(n, JPGPU_OK);
     std::map<std::string, uint32_t> lut_ids;
     std::map<std::string, uint32_t> qt_ids;
+    std::map<std::string, uint64_t> map_ids;
     auto align_up = [](uint64_t x, uint64_t a) { return (x + a - 1) / a * a; };
 
     for (size_t i = 0; i < n; i++) {
@@ -151,7 +155,6 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         memset(&im, 0, sizeof im);
         Geometry g;
         int st = compute_geometry(d, g);
-        if (st == JPGPU_OK && !g.fused_ok) st = JPGPU_ERR_UNSUPPORTED;
         if (st == JPGPU_OK && (d.scan == nullptr || d.scan_len < 4)) st = JPGPU_PANIC_INDEX_OOB;  // huffman.rs:127-128
         if (st == JPGPU_OK && d.scan_len > 0x1ff00000ull) st = JPGPU_ERR_UNSUPPORTED;             // bit positions are 32-bit
         if (st == JPGPU_OK && (uint64_t)g.units * g.blocks_per_mcu * 64 > 0x7fffffffull) st = JPGPU_ERR_UNSUPPORTED;
@@ -187,6 +190,27 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
                 (cls == 0 ? dc_slot : ac_slot)[c] = (uint8_t)s;
             }
         }
+        // gather path: placement map per distinct shape
+        uint64_t map_off = 0;
+        const uint32_t map_plane = (uint32_t)align_up((uint64_t)d.width * d.height, 4);
+        if (st == JPGPU_OK && !g.fused_ok) {
+            if ((uint64_t)d.width * d.height > 0x3fffffffull) st = JPGPU_ERR_UNSUPPORTED;
+            char key[64];
+            const int kl = snprintf(key, sizeof key, "%u,%u,%u,%u|%u%u,%u%u,%u%u", d.width, d.height, d.ncomp, d.layout,
+                                    g.h[0], g.v[0], g.h[1], g.v[1], g.h[2], g.v[2]);
+            auto it = st == JPGPU_OK ? map_ids.find(std::string(key, kl)) : map_ids.end();
+            if (st == JPGPU_OK && it == map_ids.end()) {
+                std::vector<uint32_t> m;
+                st = build_gather_map(d, g, map_plane, m);
+                if (st == JPGPU_OK) {
+                    map_off = plan.gmap.size();
+                    plan.gmap.insert(plan.gmap.end(), m.begin(), m.end());
+                    map_ids.emplace(std::string(key, kl), map_off);
+                }
+            } else if (st == JPGPU_OK) {
+                map_off = it->second;
+            }
+        }
         plan.status[i] = st;
         if (st != JPGPU_OK) {
             // Skipped image: zero work, but its own (tiny) arena slices so that the per-image
@@ -213,7 +237,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         im.blocks_per_mcu = (uint8_t)g.blocks_per_mcu;
         im.hmax = g.hmax; im.vmax = g.vmax;
         im.mcux = g.mcux; im.mcuy = g.mcuy; im.units = g.units;
-        im.kind = g.kind; im.layout = (uint8_t)d.layout;
+        im.kind = g.fused_ok ? g.kind : (uint8_t)kKindGeneric; im.layout = (uint8_t)d.layout;
         im.restart_interval = d.restart_interval;
         im.seg_units = d.restart_interval * g.blocks_per_mcu * 64u;
         im.total_coefs = g.units * g.blocks_per_mcu * 64u;
@@ -262,8 +286,17 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         const uint32_t mcus_per_tile = 128u / (8u * g.hmax);
         im.tiles_x = (g.mcux + mcus_per_tile - 1) / mcus_per_tile;
         im.tiles_y = g.mcuy;
-        plan.kind_imgs[g.kind].push_back((uint32_t)i);
-        plan.kind_max_tiles[g.kind] = std::max(plan.kind_max_tiles[g.kind], im.tiles_x * im.tiles_y);
+        plan.kind_imgs[im.kind].push_back((uint32_t)i);
+        plan.kind_max_tiles[im.kind] = std::max(plan.kind_max_tiles[im.kind], im.tiles_x * im.tiles_y);
+        if (im.kind == kKindGeneric) {
+            const uint32_t nblk = g.units * g.blocks_per_mcu;
+            im.map_off = map_off;
+            im.map_plane = map_plane;
+            im.smp_off = plan.sample_floats;
+            plan.sample_floats += (uint64_t)nblk * 64;
+            plan.gather_max_blocks = std::max(plan.gather_max_blocks, nblk);
+            plan.gather_max_quads = std::max(plan.gather_max_quads, map_plane / 4);
+        }
 
         plan.tot_scan_bytes += im.raw_len;
         plan.tot_blocks += (uint64_t)g.units * g.blocks_per_mcu;
@@ -271,6 +304,76 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         plan.tot_rgb_bytes += (uint64_t)im.width * im.height * 3;
     }
     if (plan.sub_entries > 0xffffffffull || plan.seg_entries > 0xffffffffull) return JPGPU_ERR_UNSUPPORTED;
+    return JPGPU_OK;
+}
+
+int build_gather_map(const jpgpu_image_desc& d, const Geometry& g, uint32_t plane, std::vector<uint32_t>& out) {
+    const size_t W = d.width, H = d.height, npix = W * H;
+    out.assign((size_t)plane * d.ncomp, kMapNone);
+    uint32_t first_blk[4] = {0, 0, 0, 0};
+    for (uint32_t c = 1; c < d.ncomp; c++) first_blk[c] = first_blk[c - 1] + g.h[c - 1] * g.v[c - 1];
+    const uint32_t bpm = g.blocks_per_mcu;
+    if (d.layout == JPGPU_LAYOUT_SPEC) {
+        for (uint32_t c = 0; c < d.ncomp; c++) {
+            uint32_t* m = out.data() + (size_t)c * plane;
+            const uint32_t hc = g.h[c], vc = g.v[c], fx = g.hmax / hc, fy = g.vmax / vc;  // replication factors
+            for (size_t y = 0; y < H; y++)
+                for (size_t x = 0; x < W; x++) {
+                    const uint32_t xs = (uint32_t)x / fx, ys = (uint32_t)y / fy, bx = xs >> 3, by = ys >> 3;
+                    const uint32_t mcu = (by / vc) * g.mcux + bx / hc;
+                    if (mcu >= g.units) continue;
+                    const uint32_t blk = mcu * bpm + first_blk[c] + (by % vc) * hc + bx % hc;
+                    m[y * W + x] = (blk << 6) | ((ys & 7) << 3) | (xs & 7);
+                }
+        }
+        return JPGPU_OK;
+    }
+    // REF: decoder.rs:238-312 + 347-379 replayed on indices
+    const size_t nbx = (W + 7) / 8, nby = (H + 7) / 8;
+    for (uint32_t c = 0; c < d.ncomp; c++) {
+        uint32_t* m = out.data() + (size_t)c * plane;
+        const float x_i = ceilf((float)W * ((float)g.h[c] / (float)g.hmax));   // decoder.rs:237-243
+        const float y_i = ceilf((float)H * ((float)g.v[c] / (float)g.vmax));
+        const size_t xf = (size_t)ceilf((float)W / x_i), yf = (size_t)ceilf((float)H / y_i);  // decoder.rs:247-248
+        if (xf == 0 || yf == 0) return JPGPU_PANIC_ARITH;
+        const size_t hv = (size_t)g.h[c] * g.v[c], nblocks = (size_t)g.units * hv;
+        size_t block_i = 0;
+        for (size_t y = 0; y < nby / yf; y++)
+            for (size_t x = 0; x < nbx / xf; x++, block_i++) {
+                size_t bx = x, by = y;                                           // get_indices, decoder.rs:259-288
+                if (g.vmax > 1 && yf == 1) {
+                    if (g.hmax > 1 && xf == 1) {
+                        if ((y & 1) == 0) {
+                            if ((x / 2) & 1) { bx = x / 2 - 1 + (x & 1); by = y + 1; }
+                            else { bx = x / 2 + (x & 1); by = y; }
+                        } else {
+                            if (((x / 2) & 1) == 0) { bx = nbx / 2 + x / 2 - 1 + (x & 1); by = y; }
+                            else { bx = nbx / 2 + x / 2 + (x & 1); by = y - 1; }
+                        }
+                    } else {
+                        if ((y & 1) == 0) { bx = x / 2; by = y + (x & 1); }
+                        else { bx = x / 2 + nbx / 2; by = y - (x & 1); }
+                    }
+                }
+                if (block_i >= nblocks) return JPGPU_PANIC_INDEX_OOB;            // component_blocks[block_i], decoder.rs:303
+                const uint32_t blk = (uint32_t)((block_i / hv) * bpm + first_blk[c] + block_i % hv);
+                const size_t start_x = bx * 8 * xf;                              // fill_block_in_array, decoder.rs:347-379
+                if (W < start_x) continue;
+                for (size_t line = 0; line < 8; line++) {
+                    const size_t start_i = by * 8 * yf * W + line * W + start_x;
+                    for (size_t ind = 0; ind < 8 * xf; ind++) {
+                        const size_t i = ind + start_i;
+                        for (size_t j = 0; j < yf; j++) {
+                            if (i + j * W < npix) {                              // decoder.rs:371
+                                const size_t idx = i + j * W * 8;                // decoder.rs:372
+                                if (idx >= npix) return JPGPU_PANIC_INDEX_OOB;
+                                m[idx] = (blk << 6) | (uint32_t)(line * 8 + ind / xf);
+                            }
+                        }
+                    }
+                }
+            }
+    }
     return JPGPU_OK;
 }
 

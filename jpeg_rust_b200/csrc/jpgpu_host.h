@@ -46,6 +46,9 @@ struct HostPlan {
     uint64_t sub_entries = 0;
     uint64_t coef_elems = 0;
     uint64_t rgb_bytes = 0;
+    std::vector<uint32_t> gmap;  // placement maps of the gather path, one per distinct shape
+    uint64_t sample_floats = 0;  // per-block IDCT samples of the gather-path images
+    uint32_t gather_max_blocks = 0, gather_max_quads = 0;
     // algorithmic totals over the valid images
     uint64_t tot_scan_bytes = 0, tot_blocks = 0, tot_pixels = 0, tot_rgb_bytes = 0;
 };
@@ -53,6 +56,12 @@ struct HostPlan {
 // sub_bits: 1024/2048/4096, or 0 = choose from the batch size (env JPGPU_SUBSEQ_BITS overrides).
 uint32_t choose_subseq_bits(uint64_t total_scan_bytes);
 int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t sub_bits = 0);
+
+// Placement map of the gather path: for every component plane and pixel the (arena block index << 6 | sample index)
+// whose value the layout puts there, kMapNone where nothing is written.  REF replays decoder.rs:290-312 + 347-379 on
+// indices (last writer wins, spill past the right edge included); SPEC is T.81 A.2.3 with box replication.  Returns
+// JPGPU_OK or the panic the reference's placement would raise (index out of bounds, decoder.rs:295 / 372).
+int build_gather_map(const jpgpu_image_desc& d, const Geometry& g, uint32_t plane_entries, std::vector<uint32_t>& out);
 
 // Reorders one image's coefficient arena ([mcu][block][column-major]) into the
 // reference arrangement: per component, decode order, zigzag (decoder.rs:208-212).

@@ -377,11 +377,9 @@ __device__ __forceinline__ uint32_t f32_to_u8_sat(float x) {  // decoder.rs:382-
 // 8 lanes own one 8x8 block; lane t holds column t (16 bytes = 8 coefficients), runs the
 // vertical pass, the block is transposed through shared memory, and lane t finishes row t.
 // qt points at this lane's multipliers: qt[0..3] = rows 0-3, qt[32..35] = rows 4-7.
-__device__ __forceinline__ void block_idct(const uint4 raw, const float* __restrict__ qt, int t,
+__device__ __forceinline__ void block_idct(const uint4 raw, const float4 q0, const float4 q1, int t,
                                            float* scr_w, const float* scr_r, float dc_bias, float out[8]) {
     // scr_w and scr_r alias the same shared scratch tile: no __restrict__ on them.
-    const float4 q0 = *reinterpret_cast<const float4*>(qt);
-    const float4 q1 = *reinterpret_cast<const float4*>(qt + 32);
     float f0 = (float)(int16_t)(raw.x & 0xffffu) * q0.x;
     float f1 = (float)(int16_t)(raw.x >> 16) * q0.y;
     float f2 = (float)(int16_t)(raw.y & 0xffffu) * q0.z;
@@ -401,6 +399,12 @@ __device__ __forceinline__ void block_idct(const uint4 raw, const float* __restr
     const float4 c = *reinterpret_cast<const float4*>(scr_r + 4);
     out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = c.x; out[5] = c.y; out[6] = c.z; out[7] = c.w;
     idct8(out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]);  // horizontal: row t
+}
+
+__device__ __forceinline__ void block_idct(const uint4 raw, const float* __restrict__ qt, int t,
+                                           float* scr_w, const float* scr_r, float dc_bias, float out[8]) {
+    block_idct(raw, *reinterpret_cast<const float4*>(qt), *reinterpret_cast<const float4*>(qt + 32), t, scr_w, scr_r,
+               dc_bias, out);
 }
 
 __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -567,6 +571,80 @@ __global__ void __launch_bounds__(kIdctThreads) idct_colour_kernel(BatchDev b, c
     }
 }
 
+// ============================================ gather path: REF placement / generic sampling
+// Stage A: dequant + IDCT of every block of the image, f32 samples stored per block in
+// arena order ([block][row*8+col]); luma (component 0) carries the +128 level shift.
+__global__ void __launch_bounds__(kIdctThreads) block_idct_kernel(BatchDev b, const uint32_t* __restrict__ img_list) {
+    __shared__ __align__(16) float s_scr[16 * kScrBlkPitch];
+    const ImgDev& im = b.imgs[img_list[blockIdx.y]];
+    const uint32_t nblk = im.units * im.blocks_per_mcu;
+    const int tid = threadIdx.x, t = tid & 7, bp = tid >> 3;
+    const uint32_t blk = blockIdx.x * 16u + bp;
+    if (blockIdx.x * 16u >= nblk) return;
+    const bool valid = blk < nblk;
+    const uint32_t comp = valid ? im.blk_comp[blk % im.blocks_per_mcu] : 0u;
+    const float* __restrict__ qt = b.qt + im.qt_off[comp] + t * 8;
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) raw = __ldg(reinterpret_cast<const uint4*>(b.coefs + im.coef_off) + (size_t)blk * 8 + t);
+    float o[8];
+    block_idct(raw, __ldg(reinterpret_cast<const float4*>(qt)), __ldg(reinterpret_cast<const float4*>(qt + 4)), t,
+               s_scr + bp * kScrBlkPitch + t, s_scr + bp * kScrBlkPitch + t * kScrRowPitch, comp == 0u ? 128.0f : 0.0f, o);
+    if (valid) {
+        float4* dst = reinterpret_cast<float4*>(b.samples + im.smp_off + (size_t)blk * 64 + t * 8);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// Stage B: four pixels per thread. Per component the placement map names the sample the
+// layout's last writer put at this pixel (decoder.rs:290-312, 347-379), or nothing: the
+// reference's planes start as 0.0 (decoder.rs:253-256), i.e. 128 after the level shift for luma.
+constexpr int kGatherThreads = 256;
+__global__ void __launch_bounds__(kGatherThreads) gather_colour_kernel(BatchDev b, const uint32_t* __restrict__ img_list) {
+    const ImgDev& im = b.imgs[img_list[blockIdx.y]];
+    const uint32_t npix = im.width * im.height;
+    const uint32_t q = blockIdx.x * kGatherThreads + threadIdx.x;
+    if (q * 4u >= npix) return;
+    const uint32_t* __restrict__ map = b.gmap + im.map_off;
+    const float* __restrict__ smp = b.samples + im.smp_off;
+    const int ncomp = im.ncomp;
+    float v[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float none = c == 0 ? 128.0f : 0.0f;
+        if (c < ncomp) {
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(map + (size_t)c * im.map_plane) + q);
+            v[c][0] = m.x == kMapNone ? none : __ldg(smp + m.x);
+            v[c][1] = m.y == kMapNone ? none : __ldg(smp + m.y);
+            v[c][2] = m.z == kMapNone ? none : __ldg(smp + m.z);
+            v[c][3] = m.w == kMapNone ? none : __ldg(smp + m.w);
+        } else {
+            v[c][0] = v[c][1] = v[c][2] = v[c][3] = none;
+        }
+    }
+    uint32_t r8[4], g8[4], b8[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (ncomp == 1) {
+            r8[k] = g8[k] = b8[k] = f32_to_u8_sat(v[0][k]);  // decoder.rs:317-324
+        } else {
+            const float y = v[0][k], cb = v[1][k], cr = v[2][k];  // decoder.rs:392-401, as in idct_colour_kernel
+            r8[k] = f32_to_u8_sat(fmaf(cr, 1.402f, y));
+            g8[k] = f32_to_u8_sat(fmaf(cb, -0.34413629f, fmaf(cr, -0.71413629f, y)));
+            b8[k] = f32_to_u8_sat(fmaf(cb, 1.772f, y));
+        }
+    }
+    uint8_t* out = b.rgb + im.rgb_off + (size_t)q * 12u;
+    if (q * 4u + 4u <= npix) {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
+        o32[0] = pack4(r8[0], g8[0], b8[0], r8[1]);
+        o32[1] = pack4(g8[1], b8[1], r8[2], g8[2]);
+        o32[2] = pack4(b8[2], r8[3], g8[3], b8[3]);
+    } else {
+        for (uint32_t k = 0; q * 4u + k < npix; k++) { out[3 * k] = (uint8_t)r8[k]; out[3 * k + 1] = (uint8_t)g8[k]; out[3 * k + 2] = (uint8_t)b8[k]; }
+    }
+}
+
 // ===================================================================== launchers
 void launch_prepass(const BatchDev& b, cudaStream_t s) {
     if (b.n_images) prepass_kernel<<<b.n_images, kPreThreads, 0, s>>>(b);
@@ -595,6 +673,13 @@ int launch_idct_colour(const BatchDev& b, cudaStream_t s) {
             default: continue;
         }
         launches++;
+    }
+    if (b.kind_count[kKindGeneric] && b.gather_max_blocks) {
+        dim3 ga((b.gather_max_blocks + 15) / 16, b.kind_count[kKindGeneric]);
+        block_idct_kernel<<<ga, kIdctThreads, 0, s>>>(b, b.kind_imgs[kKindGeneric]);
+        dim3 gb((b.gather_max_quads + kGatherThreads - 1) / kGatherThreads, b.kind_count[kKindGeneric]);
+        gather_colour_kernel<<<gb, kGatherThreads, 0, s>>>(b, b.kind_imgs[kKindGeneric]);
+        launches += 2;
     }
     return launches;
 }

@@ -33,6 +33,11 @@ struct BatchDev {        // device pointers of one planned batch
     const uint32_t* kind_imgs[kNumKinds];
     uint32_t kind_count[kNumKinds];
     uint32_t kind_max_tiles[kNumKinds];
+    // gather path (images of kind kKindGeneric)
+    const uint32_t* gmap;    // placement maps: (block index << 6 | sample) per pixel and component
+    float* samples;          // per-block IDCT output, [block][row*8+col]
+    uint32_t gather_max_blocks;
+    uint32_t gather_max_quads;  // most ceil(W*H/4) of any gather image
 };
 
 cudaError_t init_constants();
@@ -46,7 +51,9 @@ void launch_sync_inter_scan(const BatchDev& b, cudaStream_t s);
 // Stage 1d: final decode, coefficients written to HBM.
 void launch_decode_write(const BatchDev& b, cudaStream_t s);
 // Stage 2+3: dequantise, IDCT, upsample, YCbCr->RGB, interleaved store (SPEC geometry).
-// Returns the number of kernels launched.
+// Images whose requested layout the fused kernel cannot produce (REF placement of 4:2:0 / ragged widths,
+// decoder.rs:259-312 + 347-379; generic sampling factors) go through block_idct_kernel +
+// gather_colour_kernel and a host-built placement map.  Returns the number of kernels launched.
 int launch_idct_colour(const BatchDev& b, cudaStream_t s);
 
 }  // namespace jpgpu

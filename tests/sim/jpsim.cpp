@@ -318,6 +318,38 @@ void sim_idct_colour(SimBatch& sb, size_t img) {
         }
 }
 
+// mirrors block_idct_kernel + gather_colour_kernel (REF placement / generic sampling)
+void sim_gather(SimBatch& sb, size_t img) {
+    const ImgDev& im = sb.plan.imgs[img];
+    const uint32_t nblk = im.units * im.blocks_per_mcu;
+    const int16_t* coefs = sb.coefs.data() + im.coef_off;
+    const float* qt = sb.plan.qt.data();
+    std::vector<float> smp((size_t)nblk * 64);
+    for (uint32_t blk = 0; blk < nblk; blk++) {
+        const int comp = im.blk_comp[blk % im.blocks_per_mcu];
+        sim_block_idct(coefs + (size_t)blk * 64, true, qt + im.qt_off[comp], comp == 0 ? 128.0f : 0.0f, smp.data() + (size_t)blk * 64);
+    }
+    const uint32_t* map = sb.plan.gmap.data() + im.map_off;
+    uint8_t* rgb = sb.rgb.data() + im.rgb_off;
+    const size_t npix = (size_t)im.width * im.height;
+    for (size_t p = 0; p < npix; p++) {
+        float v[3];
+        for (int c = 0; c < 3; c++) {
+            const float none = c == 0 ? 128.0f : 0.0f;
+            const uint32_t m = c < im.ncomp ? map[(size_t)c * im.map_plane + p] : kMapNone;
+            v[c] = m == kMapNone ? none : smp[m];
+        }
+        uint8_t* o = rgb + p * 3;
+        if (im.ncomp == 1) {
+            o[0] = o[1] = o[2] = sat_u8_trunc(v[0]);
+        } else {
+            o[0] = sat_u8_trunc(fmaf(v[2], 1.402f, v[0]));
+            o[1] = sat_u8_trunc(fmaf(v[1], -0.34413629f, fmaf(v[2], -0.71413629f, v[0])));
+            o[2] = sat_u8_trunc(fmaf(v[1], 1.772f, v[0]));
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -348,7 +380,7 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
     for (size_t i = 0; i < n; i++) sim_sync_inter_scan(sb, i);
     for (const SeqDesc& sd : p.seqs) sim_decode_write(sb, sd);
     for (size_t i = 0; i < n; i++)
-        if (p.status[i] == JPGPU_OK) sim_idct_colour(sb, i);
+        if (p.status[i] == JPGPU_OK) { if (p.imgs[i].kind == kKindGeneric) sim_gather(sb, i); else sim_idct_colour(sb, i); }
     for (size_t i = 0; i < n; i++) {
         int32_t s = p.status[i];
         uint64_t br = 0;

@@ -139,6 +139,43 @@ def test_ref_layout_equals_spec_where_the_reference_is_correct():
     compare_with_oracle(files, LAYOUT_REF)
 
 
+def test_2x2_chroma_reference_layout():
+    """configs[2]: 2x2-chroma.jpeg decoded with the reference's own 4:2:0 placement (chroma tiling, spill into the
+    next row, 1763 of 1786 MCUs: decoder.rs:191-192, 259-312, 347-379) through the single-image entry point."""
+    data = fixture_bytes("2x2-chroma.jpeg")
+    img = JPEGImage.parse(data, layout=LAYOUT_REF)
+    o = O.decode(data, layout=O.LAYOUT_REF)
+    assert img.bytes_read == o.bytes_read == 144537
+    assert_samples(img.rgb(), o.rgb, "2x2-chroma REF")
+    outs, statuses, br, coefs, _ = run_batch([data], LAYOUT_REF)
+    stream = b"".join(c.astype("<i2").tobytes() for c in coefs[0])
+    assert hashlib.sha256(stream).hexdigest() == "04cf33d3a2401666bcf9972782886d8e4418ac2eff240308ed2706b83f6379b0"
+    spec = O.decode(data, layout=O.LAYOUT_SPEC).rgb
+    assert (outs[0] != spec).any(axis=2).mean() > 0.5     # the two layouts really differ on this file (SURVEY §8)
+
+
+REF_SHAPES = [("420", 64, 64), ("420", 48, 32), ("420", 752, 592), ("420", 250, 131), ("420", 512, 64), ("444", 61, 45),
+              ("gray", 33, 17), ("422", 100, 40), ("440", 64, 48), ("420", 16, 16), ("420", 8, 8), ("444", 7, 5),
+              ("420", 1920, 1080)]
+
+
+def test_ref_layout_where_it_differs_from_spec():
+    """REF placement through the gather path, one mixed batch; shapes whose placement panics in the reference
+    (index out of bounds) must report that panic."""
+    files = [synth.synth_jpeg(700 + w + h, w, h, sub) for sub, w, h in REF_SHAPES]
+    outs, statuses, br, coefs, _ = run_batch(files, LAYOUT_REF)
+    for i, f in enumerate(files):
+        o = O.decode(f, layout=O.LAYOUT_REF)
+        if o.status != 0:
+            assert statuses[i] == o.status, (REF_SHAPES[i], statuses[i], o.msg)
+            continue
+        assert statuses[i] == 0, (REF_SHAPES[i], _ffi.status_string(statuses[i]))
+        for a, w in zip(coefs[i], o.coefs):
+            assert np.array_equal(a, w)
+        assert br[i] == o.bytes_read
+        assert_samples(outs[i], o.rgb, str(REF_SHAPES[i]))
+
+
 @pytest.mark.parametrize("q", [5, 50, 95, 100])
 def test_quality_extremes(q):
     files = [synth.synth_jpeg(400 + i, 320, 240, "420", quality=q) for i in range(2)]

@@ -78,6 +78,53 @@ def test_ref_layout_classes_equal_to_spec():
            synth.synth_jpeg(302, 200, 96, "gray")], layout=0)
 
 
+REF_SHAPES = [("420", 64, 64), ("420", 48, 32), ("420", 752, 592), ("420", 250, 131), ("420", 512, 64), ("444", 61, 45),
+              ("gray", 33, 17), ("422", 100, 40), ("440", 64, 48), ("420", 16, 16), ("420", 8, 8), ("444", 7, 5)]
+
+
+@pytest.mark.parametrize("sub,w,h", REF_SHAPES)
+def test_ref_layout_gather_path(sub, w, h):
+    """REF placement where it differs from SPEC (4:2:0, ragged widths; decoder.rs:259-312, 347-379): the
+    host-built placement map + gather arithmetic must reproduce the oracle's REF output, or raise the same panic."""
+    f = synth.synth_jpeg(700 + w + h, w, h, sub)
+    o = O.decode(f, layout=0)
+    (r,), _ = S.decode_batch([f], layout=0)
+    if o.status != 0:
+        assert r.status == o.status, (r.status, o.msg)
+        return
+    assert r.status == 0, r.status
+    for a, b in zip(r.coefs, o.coefs):
+        assert np.array_equal(a, b)
+    assert r.bytes_read == o.bytes_read
+    d = np.abs(r.rgb.astype(int) - o.rgb.astype(int))
+    assert d.max() <= 1 and d.mean() < 0.01
+
+
+def test_ref_layout_2x2_chroma_fixture():
+    """configs[2]: 2x2-chroma.jpeg with the reference's own (buggy) 4:2:0 placement, 1763 of 1786 MCUs."""
+    data = fixture_bytes("2x2-chroma.jpeg")
+    check([data], layout=0)
+    (r,), _ = S.decode_batch([data], layout=0)
+    stream = b"".join(c.astype("<i2").tobytes() for c in r.coefs)
+    assert hashlib.sha256(stream).hexdigest() == GOLD["oracle"]["fixtures"]["2x2-chroma.jpeg"]["REF"]["coef_sha256"]
+    assert r.bytes_read == 144537  # SURVEY.md §4
+
+
+def test_spec_layout_generic_sampling_goes_through_the_gather_path():
+    """Sampling the fused kernels have no variant for (gray declared as 2x2 in REF layout)."""
+    f = bytearray(synth.synth_jpeg(800, 40, 24, "gray"))
+    sof = bytes(f).index(b"\xff\xc0")
+    f[sof + 11] = 0x22
+    o = O.decode(bytes(f), layout=0)
+    (r,), _ = S.decode_batch([bytes(f)], layout=0)
+    if o.status in (9, 10):      # huffman.rs:156/162 lookup panics are reported as JPGPU_ERR_BAD_CODE
+        assert r.status in (38, 37)
+    else:
+        assert r.status == o.status
+    if o.status == 0:
+        assert np.abs(r.rgb.astype(int) - o.rgb.astype(int)).max() <= 1
+
+
 @pytest.mark.parametrize("q", [5, 100])
 def test_quality_extremes(q):
     check([synth.synth_jpeg(400 + i, 160, 120, "420", quality=q) for i in range(2)])
