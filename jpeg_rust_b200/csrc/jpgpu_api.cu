@@ -145,6 +145,9 @@ extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs,
     d.n_images = (uint32_t)n;
     d.n_seqs = (uint32_t)p.seqs.size();
     d.sub_bits = p.sub_bits;
+    d.lw = p.lw;
+    d.lookback_bits = p.lookback_bits;
+    d.max_slots = p.max_slots;
 #define TRY(x) do { st = (x); if (st != JPGPU_OK) { jpgpu_batch_destroy(b); return st; } } while (0)
     TRY(dev_upload(b, &d.imgs, p.imgs));
     TRY(dev_upload(b, &d.seqs, p.seqs));
@@ -166,7 +169,6 @@ extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs,
     TRY(dev_alloc(b, &d.stream, p.stream_words + 64));
     TRY(dev_alloc(b, &d.segtab, p.seg_entries + 8));
     TRY(dev_alloc(b, &d.subs, p.sub_entries + 1));
-    TRY(dev_alloc(b, &d.seq_flags, 2 * p.seqs.size() + 2));
     TRY(dev_alloc(b, &d.coefs, p.coef_elems + 64));
     TRY(dev_alloc(b, &d.rgb, p.rgb_bytes + 256));
 #undef TRY
@@ -175,6 +177,7 @@ extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs,
     if (cudaMemsetAsync(raw, 0, p.raw_bytes + 64, ctx->stream) != cudaSuccess ||
         cudaMemsetAsync(d.stream, 0, (p.stream_words + 64) * 4, ctx->stream) != cudaSuccess ||
         cudaMemsetAsync(d.dyn, 0, (n + 1) * sizeof(ImgDyn), ctx->stream) != cudaSuccess ||
+        cudaMemsetAsync(d.coefs, 0, (p.coef_elems + 64) * 2, ctx->stream) != cudaSuccess ||
         cudaMemsetAsync(d.segtab, 0, (p.seg_entries + 8) * 4, ctx->stream) != cudaSuccess) {
         int r = fail(ctx, cudaGetLastError(), "cudaMemsetAsync");
         jpgpu_batch_destroy(b);
@@ -215,12 +218,11 @@ extern "C" int jpgpu_batch_entropy(jpgpu_batch* b) {
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    if (b->coef_bytes) CK(cudaMemsetAsync(b->dev.coefs, 0, b->coef_bytes, s));  // decode_write stores non-zeros only
     launch_prepass(b->dev, s);
-    launch_sync_intra(b->dev, s);
-    launch_sync_inter_scan(b->dev, s);
-    launch_decode_write(b->dev, s);
-    b->launches += 5;  // memset + 4 kernels
+    launch_sync(b->dev, s);
+    launch_verify_scan(b->dev, s);
+    CK(launch_decode_write(b->dev, s));
+    b->launches += 4;
     CK(cudaGetLastError());
     return JPGPU_OK;
 }

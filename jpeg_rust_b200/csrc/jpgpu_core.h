@@ -3,11 +3,11 @@
 // CPU simulation harness under tests/ (never by the product path).
 //
 // Reference semantics restated here (file:line in martinhath/jpeg-rust):
-//   huffman.rs:146-195  next_block       -> decode_span(): DC size/EXTEND, EOB, ZRL, (run,size)
-//   huffman.rs:211-227  next_code        -> huff_lookup(): canonical prefix decode
+//   huffman.rs:146-195  next_block       -> decode_symbol(): DC size/EXTEND, EOB, ZRL, (run,size)
+//   huffman.rs:211-227  next_code        -> two-level LUT + huff_slow(): canonical prefix decode
 //   huffman.rs:256-268  value_correction -> extend()
 //   decoder.rs:195-215  MCU loop + DC prediction -> g/c bookkeeping + dc predictors
-// The parallel formulation (self-synchronising subsequences) is new; see DESIGN.md.
+// The parallel formulation (look-back synchronisation of subsequences) is new; see DESIGN.md.
 #pragma once
 #include <stdint.h>
 
@@ -20,20 +20,24 @@
 namespace jpgpu {
 
 // ------------------------------------------------------------------ constants
-constexpr int kLutBits = 10;               // first-level Huffman LUT index width
+constexpr int kLutBits = 9;                // first-level Huffman LUT index width
 constexpr int kLutSize = 1 << kLutBits;
+constexpr int kPoolSize = 256;             // second-level entries (sub-tables for codes longer than kLutBits)
 constexpr int kMaxBlocksPerMcu = 12;       // 3 components x (H,V in {1,2})
 constexpr int kMaxLutSlots = 6;            // distinct (DC, AC) tables one image can reference
 #ifndef JPGPU_SEQ_THREADS
-#define JPGPU_SEQ_THREADS 256
+#define JPGPU_SEQ_THREADS 128
 #endif
 // Bits per subsequence (one decode thread each) are a per-batch plan parameter
-// (BatchDev::sub_bits): 1024, 2048 or 4096 — larger means fewer re-decodes until
-// synchronisation, smaller means more threads for small batches.
+// (BatchDev::sub_bits), a power of two in [kMinSubseqBits, kMaxSubseqBits]: larger means less
+// look-back overhead per decoded bit, smaller means more threads for small batches.
 constexpr int kMinSubseqBits = 1024;
-constexpr int kMaxSubseqBits = 4096;
+constexpr int kMaxSubseqBits = 8192;
+constexpr int kDefaultLookbackBits = 2048; // cold-start distance before a subsequence (BatchDev::lookback_bits)
 constexpr int kSeqThreads = JPGPU_SEQ_THREADS;  // subsequences per sequence (= CTA size of the sync/write kernels)
 constexpr int kStreamPadWords = 8;         // zero words readable past every image's stream
+constexpr int kWriteBufs = 2;              // coefficient block buffers per lane in the write kernel
+constexpr int kPhaseSymbols = 12;          // symbols a lane decodes between two cooperative flushes
 
 // status bits accumulated per image on the device (mapped to JPGPU_* by the host)
 enum : uint32_t {
@@ -44,18 +48,22 @@ enum : uint32_t {
 };
 
 // One Huffman table in device format.
-// Packed decode entry: bits 0-7 symbol, 8-12 code length, 13-18 total bits (code +
-// value bits), 19-25 zigzag advance (1 for DC; run+1; 16 for ZRL; 64 for EOB), 26 DC
-// size category > 16 (huffman.rs:202 assert).  With `advance`, next_block's three cases
-// (huffman.rs:164-189) collapse into nz = min(z + advance, 64).
+// Packed decode entry: bits 0-4 code length, 5-10 total bits (code + value bits), 11-17
+// zigzag advance (1 for DC; run+1; 16 for ZRL; 64 for EOB), 18 DC size category > 16
+// (huffman.rs:202 assert).  With `advance`, next_block's three cases (huffman.rs:164-189)
+// collapse into nz = min(z + advance, 64).  A first-level entry with bit 31 set links to a
+// second-level sub-table: bits 0-8 pool offset, bits 9-11 its index width (1..7 bits after
+// the first kLutBits).  0 = no code here (walk the canonical tables).
 struct HuffLut {
-    uint32_t fast[kLutSize];  // entry for codes of len <= kLutBits, 0 otherwise
+    uint32_t fast[kLutSize];
+    uint32_t pool[kPoolSize];
     int32_t maxcode[18];      // largest code of length l (right aligned), -1 if none; l = 1..16
     int32_t valoff[18];       // index of first symbol of length l minus its smallest code
     uint8_t vals[256];        // HUFFVAL
     uint32_t is_dc;
     uint32_t pad[3];
 };
+constexpr uint32_t kLinkBit = 1u << 31;
 
 JPGPU_HD uint32_t make_entry(uint32_t sym, uint32_t len, bool is_dc) {
     uint32_t size, adv, big = 0;
@@ -63,9 +71,9 @@ JPGPU_HD uint32_t make_entry(uint32_t sym, uint32_t len, bool is_dc) {
     else if (sym == 0x00) { size = 0; adv = 64; }
     else if (sym == 0xf0) { size = 0; adv = 16; }
     else { size = sym & 15; adv = (sym >> 4) + 1; }
-    return sym | (len << 8) | ((len + size) << 13) | (adv << 19) | (big << 26);
+    return len | ((len + size) << 5) | (adv << 11) | (big << 18);
 }
-constexpr uint32_t kBadEntry = (16u << 8) | (16u << 13) | (64u << 19);  // unknown code: 16 bits, ends the block
+constexpr uint32_t kBadEntry = 16u | (16u << 5) | (64u << 11);  // unknown code: 16 bits, ends the block
 
 // Per-image plan, written by the host, read by every kernel.
 struct ImgDev {
@@ -92,6 +100,7 @@ struct ImgDev {
     uint8_t blk_comp[kMaxBlocksPerMcu];   // component of block c inside an MCU
     uint8_t blk_dc_slot[kMaxBlocksPerMcu];
     uint8_t blk_ac_slot[kMaxBlocksPerMcu];
+    uint32_t blk_info[kMaxBlocksPerMcu];  // DC slot | AC slot << 8 | component << 16 (what the decoder loads per block)
     uint8_t nslots, kind, layout, pad0;   // kind: colour kernel variant (see ImgKind)
     uint32_t slot_lut[kMaxLutSlots];      // index into the global HuffLut array
     uint32_t qt_off[4];                   // per component: offset (in floats) of its 64 pre-scaled multipliers
@@ -114,17 +123,21 @@ struct ImgDyn {
     uint32_t bits_consumed; // bit position after the last decoded MCU -> bytes_read
 };
 
-// Synchronisation record of one subsequence.
+// Synchronisation record of one subsequence j (bits [j*S, (j+1)*S) of the compacted stream).
+// A = state at the first symbol starting at or after j*S, reached from a cold start
+// lookback_bits earlier; B = state at the first symbol starting at or after (j+1)*S.
+// The chain is consistent where A(j) == B(j-1).
 struct SubInfo {
-    uint32_t p;     // bit position of the first symbol starting at or after the subsequence end
-    uint32_t czf;   // bits 0-5 z, 6-9 c (block in MCU), 16 crossed, 17 bad
-    int32_t n;      // coefficient positions advanced (relative) — or absolute position if crossed;
-                    // after the scan kernel: absolute position at the end of the subsequence
-    int32_t dc[3];  // sum of DC differences per component (relative/absolute like n)
-    uint32_t pad[2];
+    uint32_t pA, pB;   // bit positions
+    uint32_t cz;       // bits 0-5 z(A), 6-9 c(A), 10-15 z(B), 16-19 c(B), 30 absolute (a restart
+                       // interval began inside: n/dc below are absolute, not relative to A), 31 bad
+    int32_t n;         // sync pass: coefficient positions advanced A -> B (or absolute position at B);
+                       // after the scan: absolute coefficient position at A
+    int32_t dc[3];     // same for the sum of DC differences / the DC predictors per component
+    uint32_t pad;
 };
 constexpr uint32_t kCzMask = 0x3ffu;
-constexpr uint32_t kCrossed = 1u << 16;
+constexpr uint32_t kCrossed = 1u << 30;
 
 // ------------------------------------------------------------ zigzag mappings
 // decoder.rs:404-407: ZIGZAG_INDICES[k] = natural (row-major v*8+u) index of zigzag position k.
@@ -149,79 +162,100 @@ JPGPU_HD int zigzag_to_colmajor(int k, const uint8_t* zz_nat) {
 }
 
 // ------------------------------------------------------------------ bit reader
-// The compacted stream is stored as 32-bit words holding 4 stream bytes each,
-// first byte in the most significant position, so a word IS the next 32 bits.
+// The compacted stream is stored as 32-bit words holding 4 stream bytes each, first byte
+// in the most significant position, so a word IS the next 32 bits.  Words are laid out
+// LANE-INTERLEAVED: with W = S/32 words per subsequence, a group of 32 consecutive
+// subsequences (one warp of decode threads) occupies 32*W words and word k of
+// subsequence l sits at k*32 + l inside it.  When the 32 lanes of a warp refill at similar
+// depths k they touch the same one or two 128-byte lines instead of 32 different ones.
+JPGPU_HD uint32_t stream_phys(uint32_t i, uint32_t lw) {  // lw = log2(W)
+    return (i & ~((32u << lw) - 1u)) | ((i & ((1u << lw) - 1u)) << 5) | ((i >> lw) & 31u);
+}
+
 struct BitReader {
     const uint32_t* w;
-    uint32_t widx;   // next word to load
+    uint32_t lw;     // log2(words per subsequence)
+    uint32_t widx;   // next (linear) word to load
     uint32_t avail;  // valid bits at the top of buf
     uint64_t buf;
 
+    JPGPU_HD uint32_t load(uint32_t i) const { return w[stream_phys(i, lw)]; }
     JPGPU_HD void seek(uint32_t p) {
         widx = p >> 5;
-        uint32_t off = p & 31;
-        uint64_t a = w[widx], b = w[widx + 1];
+        const uint32_t off = p & 31;
+        const uint64_t a = load(widx), b = load(widx + 1);
         buf = ((a << 32) | b) << off;
         avail = 64 - off;
         widx += 2;
     }
-    JPGPU_HD uint32_t pos() const { return widx * 32 - avail; }
     JPGPU_HD uint32_t peek() const { return (uint32_t)(buf >> 32); }
     JPGPU_HD void skip(uint32_t n) { buf <<= n; avail -= n; }  // n <= 32
     JPGPU_HD void refill() {
         if (avail <= 32) {
-            buf |= (uint64_t)w[widx++] << (32 - avail);
+            buf |= (uint64_t)load(widx++) << (32 - avail);
             avail += 32;
         }
     }
 };
 
-// huffman.rs:211-227 next_code for codes longer than kLutBits: canonical prefix decode
+// huffman.rs:211-227 next_code for codes the LUT levels do not hold: canonical prefix decode
 // (T.81 F.2.2.3). Returns a packed entry, 0 if no code matches.
 JPGPU_HD uint32_t huff_slow(const HuffLut& t, uint32_t peek32) {
-    uint32_t code16 = peek32 >> 16;
+    const uint32_t code16 = peek32 >> 16;
 #pragma unroll 1
-    for (int l = kLutBits + 1; l <= 16; l++) {
-        int32_t code = (int32_t)(code16 >> (16 - l));
+    for (int l = 1; l <= 16; l++) {
+        const int32_t code = (int32_t)(code16 >> (16 - l));
         if (code <= t.maxcode[l]) return make_entry(t.vals[(t.valoff[l] + code) & 255], (uint32_t)l, t.is_dc != 0);
     }
     return 0;
 }
 
-// huffman.rs:256-268 value_correction (T.81 F.2.2.1 EXTEND)
-JPGPU_HD int32_t extend(uint32_t v, uint32_t size) {
-    return (size && v < (1u << (size - 1))) ? (int32_t)v - (int32_t)(1u << size) + 1 : (int32_t)v;
+// huffman.rs:256-268 value_correction (T.81 F.2.2.1 EXTEND).  `top` = the bits following the
+// code, left aligned; `v` = the first `size` of them.
+JPGPU_HD int32_t extend(uint32_t v, uint32_t top, uint32_t size) {
+    const uint32_t neg = (uint32_t)((int32_t)~top >> 31);   // all ones when the first value bit is 0
+    return (int32_t)v - (int32_t)(neg & ((1u << size) - 1u));
 }
 
 // ------------------------------------------------------------ decoder state
 struct DecCtx {               // per-image constants of the entropy decoder
-    const uint32_t* words;    // compacted stream of this image
+    const uint32_t* words;    // compacted stream of this image (lane-interleaved)
+    uint32_t lw;              // log2(words per subsequence)
     const uint32_t* seg;      // seg[k] = first bit of restart interval k; seg[nseg] = stream_bits
     uint32_t nseg;
     uint32_t stream_bits;
     uint32_t seg_units;
     int32_t nblk;             // blocks per MCU
     const HuffLut* luts;      // slot array
-    const uint8_t* blk_comp;
-    const uint8_t* blk_dc_slot;
-    const uint8_t* blk_ac_slot;
+    const uint32_t* blk_info; // per block of an MCU: DC slot | AC slot << 8 | component << 16
 };
 
 struct DecState {
     BitReader br;
+    uint32_t p;       // bit position of the next symbol
     int32_t g;        // coefficient position: (block index << 6) | zigzag index; relative or absolute
     int32_t c;        // block index within the MCU
     uint32_t seg;     // current restart interval
     uint32_t seg_end; // its end bit
     int32_t dc0, dc1, dc2;  // DC sums / predictors per component
     uint32_t flags;   // kCrossed | kSt* bits
+    const HuffLut* tdc;     // tables and component of block c
+    const HuffLut* tac;
+    int32_t comp;
 };
+
+JPGPU_HD void load_block_tables(const DecCtx& cx, DecState& st) {
+    const uint32_t info = cx.blk_info[st.c];
+    st.tdc = cx.luts + (info & 255u);
+    st.tac = cx.luts + ((info >> 8) & 255u);
+    st.comp = (int32_t)(info >> 16);
+}
 
 // Largest k with seg[k] <= p.
 JPGPU_HD uint32_t find_segment(const DecCtx& cx, uint32_t p) {
     uint32_t lo = 0, hi = cx.nseg;  // invariant: seg[lo] <= p < seg[hi] (seg[nseg] = stream_bits, p < stream_bits)
     while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
+        const uint32_t mid = (lo + hi) >> 1;
         if (cx.seg[mid] <= p) lo = mid; else hi = mid;
     }
     return lo;
@@ -233,17 +267,20 @@ JPGPU_HD uint32_t find_segment(const DecCtx& cx, uint32_t p) {
 JPGPU_HD void init_state(const DecCtx& cx, DecState& st, uint32_t p, int32_t g, int32_t c, int32_t d0, int32_t d1,
                          int32_t d2) {
     st.flags = 0;
+    st.br.w = cx.words;
+    st.br.lw = cx.lw;
+    st.p = p;
     if (p >= cx.stream_bits) {  // nothing to decode
         st.seg = cx.nseg ? cx.nseg - 1 : 0;
         st.seg_end = cx.stream_bits;
-        st.br.w = cx.words; st.br.widx = (p >> 5) + 2; st.br.avail = 64 - (p & 31); st.br.buf = 0;
+        st.br.widx = (p >> 5) + 2; st.br.avail = 64 - (p & 31); st.br.buf = 0;
         st.g = g; st.c = c; st.dc0 = d0; st.dc1 = d1; st.dc2 = d2;
+        load_block_tables(cx, st);
         return;
     }
-    uint32_t k = find_segment(cx, p);
+    const uint32_t k = find_segment(cx, p);
     st.seg = k;
     st.seg_end = cx.seg[k + 1];
-    st.br.w = cx.words;
     st.br.seek(p);
     if (cx.seg[k] == p) {
         st.g = (int32_t)(k * cx.seg_units);
@@ -253,108 +290,107 @@ JPGPU_HD void init_state(const DecCtx& cx, DecState& st, uint32_t p, int32_t g, 
     } else {
         st.g = g; st.c = c; st.dc0 = d0; st.dc1 = d1; st.dc2 = d2;
     }
+    load_block_tables(cx, st);
 }
 
-// Decode symbols that START before end_bit (and, when WRITE, while g < g_limit).
-// WRITE = false: synchronisation pass, only state is tracked.
-// WRITE = true : coefficients are stored to coefs[(g & ~63) + store_pos[z]] (buffer pre-zeroed).
+// Events decode_symbol reports to its caller.
+enum : uint32_t {
+    kEvBlock = 1u,   // the symbol completed a block (EOB, ZRL/run past the end, or coefficient 63)
+    kEvCross = 2u,   // no symbol decoded: moved to the start of the next restart interval
+    kEvEnd = 4u      // no symbol decoded: end of the entropy-coded data
+};
+
+// Position of coefficient `pos` (column-major, see zigzag_to_colmajor) inside a block buffer whose
+// 16-byte pieces are XOR-swizzled by `swz` (0 for plain memory).
+JPGPU_HD int buf_index(int pos, uint32_t swz) { return (int)((((uint32_t)pos >> 3) ^ swz) << 3) | (pos & 7); }
+
+// Decode ONE symbol at st.p (huffman.rs:146-195 unrolled into single steps).
+// WRITE = false: synchronisation pass, only state (and DC sums) are tracked.
+// WRITE = true : when store_on, coefficients go to blk[buf_index(store_pos[k], swz)] (buffer pre-zeroed).
 template <bool WRITE>
-JPGPU_HD void decode_span(const DecCtx& cx, DecState& st, uint32_t end_bit, int32_t g_limit, int16_t* coefs,
-                          const uint8_t* store_pos) {
-    BitReader br = st.br;
-    int32_t g = st.g, c = st.c;
-    int32_t dc0 = st.dc0, dc1 = st.dc1, dc2 = st.dc2;
-    uint32_t seg_end = st.seg_end, flags = st.flags;
-    uint32_t p = br.pos();
-    if (end_bit > cx.stream_bits) end_bit = cx.stream_bits;
-    const HuffLut* tdc = cx.luts + cx.blk_dc_slot[c];
-    const HuffLut* tac = cx.luts + cx.blk_ac_slot[c];
-    int32_t comp = cx.blk_comp[c];
-#pragma unroll 1
-    while (p < end_bit) {
-        if (WRITE && g >= g_limit) break;
-        br.refill();
-        if (p + 8 > seg_end) {  // fewer than 8 bits left in this restart interval (or already past it)
-            bool cross = p >= seg_end;
-            if (!cross) {
-                uint32_t rem = seg_end - p;  // 1..7 pad bits must all be 1 (T.81 F.1.2.3)
-                cross = (br.peek() >> (32 - rem)) == ((1u << rem) - 1u);
-            }
-            if (cross) {
-                if (st.seg + 1 >= cx.nseg) {  // end of the entropy-coded data
-                    br.seek(seg_end);
-                    p = seg_end;
-                    break;
-                }
-                st.seg += 1;
-                p = seg_end;
-                seg_end = cx.seg[st.seg + 1];
-                br.seek(p);
-                g = (int32_t)(st.seg * cx.seg_units);
-                c = 0;
-                tdc = cx.luts + cx.blk_dc_slot[0]; tac = cx.luts + cx.blk_ac_slot[0]; comp = cx.blk_comp[0];
-                dc0 = dc1 = dc2 = 0;
-                flags |= kCrossed;
-                continue;
-            }
+JPGPU_HD uint32_t decode_symbol(const DecCtx& cx, DecState& st, int16_t* blk, uint32_t swz, const uint8_t* store_pos,
+                                bool store_on) {
+    st.br.refill();
+    if (st.p + 8 > st.seg_end) {  // fewer than 8 bits left in this restart interval (or already past it)
+        bool cross = st.p >= st.seg_end;
+        if (!cross) {
+            const uint32_t rem = st.seg_end - st.p;  // 1..7 pad bits must all be 1 (T.81 F.1.2.3)
+            cross = (st.br.peek() >> (32 - rem)) == ((1u << rem) - 1u);
         }
-        const uint32_t peek = br.peek();
-        const int32_t z = g & 63;
-        const HuffLut* t = z ? tac : tdc;
-        uint32_t e = t->fast[peek >> (32 - kLutBits)];
-        if (e == 0) {
-            e = huff_slow(*t, peek);
-            if (e == 0) { flags |= kStBadCode; e = kBadEntry; }  // huffman.rs:156/162 panic
-        }
-        const uint32_t len = (e >> 8) & 31u, tb = (e >> 13) & 63u;
-        const int32_t adv = (int32_t)((e >> 19) & 127u);
-        if (WRITE || z == 0) {
-            const uint32_t size = tb - len;
-            const uint32_t v = size ? ((peek << len) >> (32 - size)) : 0u;
-            const int32_t val = extend(v, size);
-            if (z == 0) {  // DC difference -> predictor (decoder.rs:208-210)
-                if (e & (1u << 26)) flags |= kStDcSize;
-                int32_t pred;
-                if (comp == 0) { dc0 += val; pred = dc0; } else if (comp == 1) { dc1 += val; pred = dc1; } else { dc2 += val; pred = dc2; }
-                if (WRITE && pred != 0) coefs[(g & ~63) + store_pos[0]] = (int16_t)pred;
-            } else if (WRITE && val != 0) {  // huffman.rs:183-189: min(run, 64 - len - 1) zeros, then the value
-                const int32_t pos = z + adv - 1 < 63 ? z + adv - 1 : 63;
-                coefs[(g & ~63) + store_pos[pos]] = (int16_t)val;
-            }
-        }
-        br.skip(tb);
-        p += tb;
-        if (z + adv >= 64) {  // block complete (EOB, ZRL/run past the end, or coefficient 63)
-            g = (g | 63) + 1;
-            c += 1;
-            if (c == cx.nblk) c = 0;
-            tdc = cx.luts + cx.blk_dc_slot[c]; tac = cx.luts + cx.blk_ac_slot[c]; comp = cx.blk_comp[c];
-        } else {
-            g += adv;
+        if (cross) {
+            st.p = st.seg_end;
+            st.br.seek(st.p);
+            if (st.seg + 1 >= cx.nseg) return kEvEnd;  // end of the entropy-coded data
+            st.seg += 1;
+            st.seg_end = cx.seg[st.seg + 1];
+            st.g = (int32_t)(st.seg * cx.seg_units);
+            st.c = 0;
+            load_block_tables(cx, st);
+            st.dc0 = st.dc1 = st.dc2 = 0;
+            st.flags |= kCrossed;
+            return kEvCross;
         }
     }
-    st.br = br; st.g = g; st.c = c; st.dc0 = dc0; st.dc1 = dc1; st.dc2 = dc2;
-    st.seg_end = seg_end; st.flags = flags;
+    const uint32_t peek = st.br.peek();
+    const int32_t z = st.g & 63;
+    const HuffLut* t = z ? st.tac : st.tdc;
+    uint32_t e = t->fast[peek >> (32 - kLutBits)];
+    if (e & kLinkBit) e = t->pool[(e & 511u) + ((peek << kLutBits) >> (32 - ((e >> 9) & 7u)))];
+    if (e == 0) {
+        e = huff_slow(*t, peek);
+        if (e == 0) { st.flags |= kStBadCode; e = kBadEntry; }  // huffman.rs:156/162 panic
+    }
+    const uint32_t len = e & 31u, tb = (e >> 5) & 63u;
+    const int32_t adv = (int32_t)((e >> 11) & 127u);
+    if (WRITE || z == 0) {
+        const uint32_t size = tb - len;
+        const uint32_t top = peek << len;
+#ifdef __CUDA_ARCH__
+        const uint32_t v = __funnelshift_l(top, 0u, size);
+#else
+        const uint32_t v = size ? top >> (32 - size) : 0u;
+#endif
+        const int32_t val = extend(v, top, size);
+        if (z == 0) {  // DC difference -> predictor (decoder.rs:208-210)
+            if (e & (1u << 18)) st.flags |= kStDcSize;
+            int32_t pred;
+            if (st.comp == 0) { st.dc0 += val; pred = st.dc0; } else if (st.comp == 1) { st.dc1 += val; pred = st.dc1; } else { st.dc2 += val; pred = st.dc2; }
+            if (WRITE && store_on) blk[buf_index(store_pos[0], swz)] = (int16_t)pred;
+        } else if (WRITE && store_on && val != 0) {  // huffman.rs:183-189: min(run, 64 - len - 1) zeros, then the value
+            const int32_t pos = z + adv - 1 < 63 ? z + adv - 1 : 63;
+            blk[buf_index(store_pos[pos], swz)] = (int16_t)val;
+        }
+    }
+    st.br.skip(tb);
+    st.p += tb;
+    if (z + adv >= 64) {  // block complete
+        st.g = (st.g | 63) + 1;
+        st.c += 1;
+        if (st.c == cx.nblk) st.c = 0;
+        load_block_tables(cx, st);
+        return kEvBlock;
+    }
+    st.g += adv;
+    return 0u;
 }
 
-JPGPU_HD uint32_t pack_czf(const DecState& st) {
-    return (uint32_t)(st.g & 63) | ((uint32_t)st.c << 6) | (st.flags & kCrossed) | ((st.flags & kStBadCode) ? (1u << 17) : 0u);
-}
+JPGPU_HD uint32_t pack_cz(const DecState& st) { return (uint32_t)(st.g & 63) | ((uint32_t)st.c << 6); }
 
-// Prepare the per-subsequence accumulators before decoding the next subsequence
-// with a carried state: positions become relative to "now".
-JPGPU_HD void begin_subsequence(DecState& st, int32_t& g_base) {
-    st.flags &= ~kCrossed;
-    st.dc0 = st.dc1 = st.dc2 = 0;
-    g_base = st.g;
-}
-
-// Summarise the subsequence just decoded.
-JPGPU_HD void summarise(const DecState& st, int32_t g_base, SubInfo& out) {
-    out.p = st.br.pos();
-    out.czf = pack_czf(st);
+// Synchronisation decode of one subsequence record: from the state in `st` (standing at A)
+// to the first symbol at or after end_bit (B).  Fills pB, cz(B), n, dc; keeps pA/cz(A) as given.
+JPGPU_HD void sync_span(const DecCtx& cx, DecState& st, uint32_t end_bit, SubInfo& out) {
+    int32_t g_base = 0;
+    if (!(st.flags & kCrossed)) { g_base = st.g; st.dc0 = st.dc1 = st.dc2 = 0; }  // else: absolute state, keep it
+    if (end_bit > cx.stream_bits) end_bit = cx.stream_bits;
+#pragma unroll 1
+    while (st.p < end_bit) {
+        if (decode_symbol<false>(cx, st, nullptr, 0u, nullptr, false) & kEvEnd) break;
+    }
+    out.pB = st.p;
+    out.cz = (out.cz & kCzMask) | (pack_cz(st) << 10) | (st.flags & kCrossed) | ((st.flags & kStBadCode) ? (1u << 31) : 0u);
     out.n = (st.flags & kCrossed) ? st.g : st.g - g_base;
     out.dc[0] = st.dc0; out.dc[1] = st.dc1; out.dc[2] = st.dc2;
+    out.pad = 0;
 }
 
 // ------------------------------------------------------------------- IDCT

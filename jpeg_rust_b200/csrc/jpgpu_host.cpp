@@ -94,6 +94,9 @@ int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, bool 
     for (int i = 0; i < 16; i++) total += bits[i];
     if (total > 256 || total > nvals) return JPGPU_ERR_BAD_HUFFMAN_TABLE;
     memcpy(out.vals, vals, (size_t)total);
+    // canonical codes (huffman.rs:80-98 = T.81 Fig. C.2)
+    struct Code { uint32_t code; int len; uint8_t val; };
+    std::vector<Code> codes;
     uint32_t code = 0;
     int k = 0;
     for (int l = 1; l <= 16; l++) {
@@ -102,16 +105,39 @@ int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, bool 
         out.valoff[l] = k - (int32_t)code;
         for (int i = 0; i < n; i++, k++, code++) {
             if (code >= (1u << l)) return JPGPU_ERR_BAD_HUFFMAN_TABLE;  // not a prefix code
-            if (l <= kLutBits) {
-                const uint32_t first = code << (kLutBits - l), cnt = 1u << (kLutBits - l);
-                for (uint32_t e = 0; e < cnt; e++) out.fast[first + e] = make_entry(vals[k], (uint32_t)l, is_dc);
-            }
+            codes.push_back(Code{code, l, vals[k]});
         }
         if (n) out.maxcode[l] = (int32_t)code - 1;
         code <<= 1;
     }
     out.maxcode[0] = -1;
     out.maxcode[17] = 0x7fffffff;
+    // first level: codes of length <= kLutBits fill 2^(kLutBits-len) entries each
+    for (const Code& c : codes) {
+        if (c.len > kLutBits) continue;
+        const uint32_t first = c.code << (kLutBits - c.len), cnt = 1u << (kLutBits - c.len);
+        for (uint32_t e = 0; e < cnt; e++) out.fast[first + e] = make_entry(c.val, (uint32_t)c.len, is_dc);
+    }
+    // second level: one sub-table per kLutBits-prefix that starts longer codes, as wide as its longest code up to
+    // kLutBits+7 bits; what does not fit the pool (or is longer) is left to the canonical walk (entry 0).
+    uint32_t pool_used = 0;
+    for (uint32_t prefix = 0; prefix < (uint32_t)kLutSize; prefix++) {
+        int maxlen = 0;
+        for (const Code& c : codes)
+            if (c.len > kLutBits && (c.code >> (c.len - kLutBits)) == prefix) maxlen = std::max(maxlen, c.len);
+        if (!maxlen) continue;
+        const int nb = std::min(maxlen - kLutBits, 7);
+        if (pool_used + (1u << nb) > (uint32_t)kPoolSize) continue;
+        const uint32_t base = pool_used;
+        pool_used += 1u << nb;
+        for (const Code& c : codes) {
+            if (c.len <= kLutBits || (c.code >> (c.len - kLutBits)) != prefix || c.len > kLutBits + nb) continue;
+            const int rest = c.len - kLutBits;  // bits of the code inside the sub-table index
+            const uint32_t first = (c.code & ((1u << rest) - 1u)) << (nb - rest), cnt = 1u << (nb - rest);
+            for (uint32_t e = 0; e < cnt; e++) out.pool[base + first + e] = make_entry(c.val, (uint32_t)c.len, is_dc);
+        }
+        out.fast[prefix] = kLinkBit | base | ((uint32_t)nb << 9);
+    }
     return JPGPU_OK;
 }
 
@@ -125,13 +151,21 @@ void build_qt_multipliers(const uint16_t qt_zigzag[64], float out[64]) {
 uint32_t choose_subseq_bits(uint64_t total_scan_bytes) {
     if (const char* e = getenv("JPGPU_SUBSEQ_BITS")) {
         const long v = atol(e);
-        if (v == 1024 || v == 2048 || v == 4096) return (uint32_t)v;
+        if (v >= kMinSubseqBits && v <= kMaxSubseqBits && (v & (v - 1)) == 0) return (uint32_t)v;
     }
-    // keep at least ~2 subsequences per hardware thread slot (148 SMs x 2048 threads)
-    const uint64_t bits = total_scan_bytes * 8, want = 2ull * 148 * 2048;
-    if (bits / 4096 >= want) return 4096;
-    if (bits / 2048 >= want) return 2048;
-    return 1024;
+    // keep at least ~1.3 subsequences per hardware thread slot (148 SMs x 1536 threads)
+    const uint64_t bits = total_scan_bytes * 8, want = 300000;
+    uint32_t s = kMaxSubseqBits;
+    while (s > (uint32_t)kMinSubseqBits && bits / s < want) s >>= 1;
+    return s;
+}
+
+uint32_t choose_lookback_bits() {
+    if (const char* e = getenv("JPGPU_LOOKBACK_BITS")) {
+        const long v = atol(e);
+        if (v >= 0 && v <= (1 << 20)) return (uint32_t)v;
+    }
+    return kDefaultLookbackBits;
 }
 
 int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t sub_bits) {
@@ -142,6 +176,11 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         sub_bits = choose_subseq_bits(tot);
     }
     plan.sub_bits = sub_bits;
+    plan.lookback_bits = choose_lookback_bits();
+    uint32_t lw = 0;
+    while ((32u << lw) < sub_bits) lw++;
+    plan.lw = lw;
+    const uint64_t group_words = (uint64_t)32 << lw;  // one warp's 32 subsequences, lane-interleaved
     plan.imgs.resize(n);
     plan.status.assign(n, JPGPU_OK);
     std::map<std::string, uint32_t> lut_ids;
@@ -216,8 +255,8 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
             // Skipped image: zero work, but its own (tiny) arena slices so that the per-image
             // kernels, which still visit it, never touch another image's memory.
             im.stream_off = plan.stream_words;
-            im.stream_cap_words = 32;
-            plan.stream_words += 32;
+            im.stream_cap_words = (uint32_t)group_words;
+            plan.stream_words += group_words;
             im.raw_off = plan.raw_bytes;
             plan.raw_bytes += 16;
             im.nseg_cap = 1;
@@ -242,6 +281,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         im.seg_units = d.restart_interval * g.blocks_per_mcu * 64u;
         im.total_coefs = g.units * g.blocks_per_mcu * 64u;
         im.nslots = (uint8_t)nslots;
+        plan.max_slots = std::max<uint32_t>(plan.max_slots, (uint32_t)nslots);
         for (int s = 0; s < nslots; s++) im.slot_lut[s] = slot_lut[s];
         int blk = 0;
         for (uint32_t c = 0; c < d.ncomp; c++) {
@@ -250,6 +290,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
                 im.blk_comp[blk] = (uint8_t)c;
                 im.blk_dc_slot[blk] = dc_slot[c];
                 im.blk_ac_slot[blk] = ac_slot[c];
+                im.blk_info[blk] = (uint32_t)dc_slot[c] | ((uint32_t)ac_slot[c] << 8) | (c << 16);
             }
             // quantisation multipliers (deduplicated)
             const uint16_t* q = d.qt[d.comp[c].tq];
@@ -267,7 +308,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         im.raw_off = plan.raw_bytes;
         plan.raw_bytes += align_up((uint64_t)im.raw_len + 16, 16);
         im.stream_off = plan.stream_words;
-        im.stream_cap_words = (uint32_t)align_up((uint64_t)(im.raw_len + 3) / 4 + 1 + kStreamPadWords, 32);
+        im.stream_cap_words = (uint32_t)align_up((uint64_t)(im.raw_len + 3) / 4 + 1 + kStreamPadWords, group_words);
         plan.stream_words += im.stream_cap_words;
         im.nseg_cap = d.restart_interval ? (g.units + d.restart_interval - 1) / d.restart_interval : 1u;
         if (im.nseg_cap == 0) im.nseg_cap = 1;

@@ -33,6 +33,9 @@ void build_qt_multipliers(const uint16_t qt_zigzag[64], float out[64]);
 
 struct HostPlan {
     uint32_t sub_bits = kMinSubseqBits;
+    uint32_t lw = 5;             // log2(words per subsequence)
+    uint32_t lookback_bits = kDefaultLookbackBits;
+    uint32_t max_slots = 1;      // most Huffman LUT slots any image references
     std::vector<ImgDev> imgs;
     std::vector<int32_t> status;  // per image: JPGPU_OK or why it is skipped
     std::vector<SeqDesc> seqs;
@@ -53,7 +56,7 @@ struct HostPlan {
     uint64_t tot_scan_bytes = 0, tot_blocks = 0, tot_pixels = 0, tot_rgb_bytes = 0;
 };
 
-// sub_bits: 1024/2048/4096, or 0 = choose from the batch size (env JPGPU_SUBSEQ_BITS overrides).
+// sub_bits: a power of two in [1024, 8192], or 0 = choose from the batch size (env JPGPU_SUBSEQ_BITS overrides).
 uint32_t choose_subseq_bits(uint64_t total_scan_bytes);
 int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t sub_bits = 0);
 

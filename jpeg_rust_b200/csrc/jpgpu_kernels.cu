@@ -3,9 +3,9 @@
 //   prepass_kernel          mod.rs:371-385 (byte unstuffing) as a parallel stream
 //                           compaction, plus RSTn detection (no reference counterpart:
 //                           mod.rs:424-428 panics on DRI)
-//   sync_intra_kernel       |
-//   sync_inter_scan_kernel  |  huffman.rs:146-227 + decoder.rs:195-215 (serial MCU loop)
-//   decode_write_kernel     |  as self-synchronising subsequence decoding
+//   sync_kernel             |
+//   verify_scan_kernel      |  huffman.rs:146-227 + decoder.rs:195-215 (serial MCU loop)
+//   decode_write_kernel     |  as look-back synchronised subsequence decoding
 //   idct_colour_kernel      decoder.rs:227-235 (dequant, de-zigzag), transform.rs:55-87
 //                           (IDCT), decoder.rs:290-331 + 347-402 (placement, replication,
 //                           YCbCr->RGB, +128, clamp, truncation)
@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(kPreThreads) prepass_kernel(BatchDev b) {
     uint32_t* __restrict__ seg = b.segtab + im.seg_off;
     const bool dri = im.restart_interval != 0;
     const uint32_t nseg_cap = im.nseg_cap;
+    const uint32_t lw = b.lw;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t* stage_bytes = reinterpret_cast<uint8_t*>(s_stage);
     uint32_t emitted = 0, rst_total = 0;
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(kPreThreads) prepass_kernel(BatchDev b) {
         }
         __syncthreads();
         const uint32_t staged = carry + totc, nw = staged >> 2, wbase = (emitted - carry) >> 2;
-        for (uint32_t i = tid; i < nw; i += kPreThreads) out[wbase + i] = s_stage[i];
+        for (uint32_t i = tid; i < nw; i += kPreThreads) out[stream_phys(wbase + i, lw)] = s_stage[i];
         __syncthreads();
         if (tid == 0 && (staged & 3u) && nw) s_stage[0] = s_stage[nw];
         __syncthreads();
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(kPreThreads) prepass_kernel(BatchDev b) {
     if (tid == 0) {
         const uint32_t carry = emitted & 3u;
         uint32_t wbase = (emitted - carry) >> 2;
-        if (carry) { out[wbase] = s_stage[0] & (0xffffffffu << (32 - 8 * carry)); wbase++; }
-        for (int i = 0; i < kStreamPadWords; i++) out[wbase + i] = 0u;
+        if (carry) { out[stream_phys(wbase, lw)] = s_stage[0] & (0xffffffffu << (32 - 8 * carry)); wbase++; }
+        for (int i = 0; i < kStreamPadWords; i++) out[stream_phys(wbase + i, lw)] = 0u;
         uint32_t nseg = rst_total + 1;
         uint32_t st = s_status;
         if (nseg != nseg_cap && dri) st |= kStRestart;
@@ -144,24 +145,26 @@ __global__ void __launch_bounds__(kPreThreads) prepass_kernel(BatchDev b) {
 
 // ========================================================= stage 1b-1d: entropy decode
 struct EntropySmem {
-    HuffLut lut[kMaxLutSlots];
     ImgDev img;
     uint8_t store_pos[64];
+    HuffLut lut[kMaxLutSlots];   // kernels with dynamic shared memory only carve max_slots of these
 };
 
 // Cooperative load of the per-image decode context into shared memory.
-__device__ __forceinline__ void load_entropy_ctx(const BatchDev& b, uint32_t img, EntropySmem& sm, int nthreads) {
+__device__ __forceinline__ void load_entropy_img(const BatchDev& b, uint32_t img, EntropySmem& sm, int nthreads) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&b.imgs[img]);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.img);
     for (int i = threadIdx.x; i < (int)(sizeof(ImgDev) / 4); i += nthreads) dst[i] = src[i];
     if (threadIdx.x < 64) sm.store_pos[threadIdx.x] = c_store_pos[threadIdx.x];
     __syncthreads();
+}
+__device__ __forceinline__ void load_entropy_luts(const BatchDev& b, EntropySmem& sm, int nthreads) {
     const int nslots = sm.img.nslots;
-    constexpr int kLutWords = sizeof(HuffLut) / 4;
+    constexpr int kLutVecs = sizeof(HuffLut) / 16;
     for (int s = 0; s < nslots; s++) {
-        const uint32_t* ls = reinterpret_cast<const uint32_t*>(&b.luts[sm.img.slot_lut[s]]);
-        uint32_t* ld = reinterpret_cast<uint32_t*>(&sm.lut[s]);
-        for (int i = threadIdx.x; i < kLutWords; i += nthreads) ld[i] = ls[i];
+        const uint4* ls = reinterpret_cast<const uint4*>(&b.luts[sm.img.slot_lut[s]]);
+        uint4* ld = reinterpret_cast<uint4*>(&sm.lut[s]);
+        for (int i = threadIdx.x; i < kLutVecs; i += nthreads) ld[i] = __ldg(ls + i);
     }
     __syncthreads();
 }
@@ -169,146 +172,112 @@ __device__ __forceinline__ void load_entropy_ctx(const BatchDev& b, uint32_t img
 __device__ __forceinline__ DecCtx make_ctx(const BatchDev& b, const EntropySmem& sm, const ImgDyn& d) {
     DecCtx cx;
     cx.words = b.stream + sm.img.stream_off;
+    cx.lw = b.lw;
     cx.seg = b.segtab + sm.img.seg_off;
     cx.nseg = d.nseg;
     cx.stream_bits = d.stream_bits;
     cx.seg_units = sm.img.seg_units;
     cx.nblk = sm.img.blocks_per_mcu;
     cx.luts = sm.lut;
-    cx.blk_comp = sm.img.blk_comp;
-    cx.blk_dc_slot = sm.img.blk_dc_slot;
-    cx.blk_ac_slot = sm.img.blk_ac_slot;
+    cx.blk_info = sm.img.blk_info;
     return cx;
 }
 
-// One CTA per sequence (kSeqThreads consecutive subsequences of one image). Thread i
-// decodes subsequence i from a cold state, then keeps decoding the following
-// subsequences until the state it arrives with equals the state recorded there
-// (self-synchronisation), overwriting the records on its way.  In round r only thread
-// i touches record i+r and lower-numbered (more authoritative) threads arrive later,
-// so after the last round every record holds what the lowest thread that reached it
-// computed.
-__global__ void __launch_bounds__(kSeqThreads, 3) sync_intra_kernel(BatchDev b) {
+// One thread per subsequence j.  It starts cold (block 0 of an MCU, zigzag 0) lookback_bits
+// before j*S; by the time it reaches j*S it has, with high probability, fallen into step with
+// the true decode (self-synchronisation of Huffman streams).  It records the state there (A),
+// decodes its own S bits and records the state at the end (B) with the advance in coefficient
+// positions and the DC sums in between.  Whether A was right is checked afterwards against the
+// predecessor's B (verify_scan_kernel); thread 0 and threads that passed a restart marker are
+// right by construction.  All threads do the same amount of work: no rounds, no barriers.
+__global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     __shared__ EntropySmem sm;
-    __shared__ SubInfo s_info[kSeqThreads];
-
     const SeqDesc sd = b.seqs[blockIdx.x];
     const uint32_t S = b.sub_bits;
-    load_entropy_ctx(b, sd.img, sm, kSeqThreads);
+    load_entropy_img(b, sd.img, sm, kSeqThreads);
     const ImgDyn dyn = b.dyn[sd.img];
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
+    load_entropy_luts(b, sm, kSeqThreads);
     const DecCtx cx = make_ctx(b, sm, dyn);
+    const uint32_t j = sd.first_sub + threadIdx.x;
+    if (j >= nsub) return;
 
-    const uint32_t tid = threadIdx.x;
-    const uint32_t j = sd.first_sub + tid;
-    bool active = j < nsub;
+    const uint32_t own = j * S, p0 = own > b.lookback_bits ? own - b.lookback_bits : 0u;
     DecState st;
-    int32_t g_base = 0;
-    if (active) {
-        init_state(cx, st, j * S, 0, 0, 0, 0, 0);
-        g_base = st.g;
-        decode_span<false>(cx, st, (j + 1) * S, 0, nullptr, nullptr);
-        SubInfo mine;
-        summarise(st, g_base, mine);
-        mine.pad[0] = mine.pad[1] = 0;
-        s_info[tid] = mine;
-    }
-    __syncthreads();
+    init_state(cx, st, p0, 0, 0, 0, 0, 0);
 #pragma unroll 1
-    for (uint32_t r = 1; r < kSeqThreads; r++) {
-        const uint32_t tgt = tid + r;
-        if (active && (tgt >= kSeqThreads || j + r >= nsub)) active = false;
-        if (active) {
-            begin_subsequence(st, g_base);
-            decode_span<false>(cx, st, (j + r + 1) * S, 0, nullptr, nullptr);
-            SubInfo mine;
-            summarise(st, g_base, mine);
-            mine.pad[0] = mine.pad[1] = 0;
-            const SubInfo old = s_info[tgt];
-            const bool same = old.p == mine.p && ((old.czf ^ mine.czf) & kCzMask) == 0u;
-            s_info[tgt] = mine;  // n / dc must be those of the last (lowest) arriver
-            if (same) active = false;
-        }
-        if (!__syncthreads_or(active ? 1 : 0)) break;
+    while (st.p < own) {
+        if (decode_symbol<false>(cx, st, nullptr, 0u, nullptr, false) & kEvEnd) break;
     }
-    if (j < nsub) b.subs[sm.img.sub_off + j] = s_info[tid];
+    SubInfo rec;
+    rec.pA = st.p;
+    rec.cz = pack_cz(st);
+    sync_span(cx, st, own + S, rec);
+    b.subs[sm.img.sub_off + j] = rec;
 }
 
-constexpr int kInterThreads = 64;
+constexpr int kInterThreads = 128;
 
-// One CTA per image. (1) Inter-sequence synchronisation: for every sequence boundary
-// a thread continues from the final record of the previous sequence until it meets
-// an equal record; repeated while a walk ran off the end of its sequence. (2) Prefix
-// scan turning per-subsequence advances into absolute end states.
-__global__ void __launch_bounds__(kInterThreads) sync_inter_scan_kernel(BatchDev b) {
+// One CTA per image. (1) Verification: the chain is right where A(j) == B(j-1).  A broken link
+// (look-back too short for that spot) is repaired by decoding subsequence j again from B(j-1);
+// repeated until the chain holds — the lowest broken link always starts from a correct state, so
+// every iteration extends the correct prefix.  (2) Exclusive prefix scan turning per-subsequence
+// advances into the absolute state at every A (segmented where a restart interval began).
+__global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) {
     __shared__ EntropySmem sm;
     __shared__ int32_t s_agg[kInterThreads][5];
 
     const uint32_t img = blockIdx.x;
     const uint32_t S = b.sub_bits;
-    load_entropy_ctx(b, img, sm, kInterThreads);
+    load_entropy_img(b, img, sm, kInterThreads);
     const ImgDyn dyn = b.dyn[img];
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
-    const uint32_t nseq = (nsub + kSeqThreads - 1) / kSeqThreads;
     const DecCtx cx = make_ctx(b, sm, dyn);
     SubInfo* subs = b.subs + sm.img.sub_off;
-    uint32_t* need_a = b.seq_flags + sm.img.seq_first;
-    uint32_t* need_b = b.seq_flags + b.n_seqs + sm.img.seq_first;
     const uint32_t tid = threadIdx.x;
 
-    for (uint32_t q = tid; q < nseq; q += kInterThreads) { need_a[q] = q > 0 ? 1u : 0u; need_b[q] = 0u; }
-    __syncthreads();
-
+    bool loaded = false;
 #pragma unroll 1
-    for (uint32_t iter = 0; iter < nseq; iter++) {
+    for (uint32_t iter = 0; iter < nsub; iter++) {
         int any = 0;
 #pragma unroll 1
-        for (uint32_t q0 = 1; q0 < nseq; q0 += kInterThreads) {  // passes keep snapshot-before-write order
-            const uint32_t q = q0 + tid;
-            const bool work = q < nseq && need_a[q] != 0u;
-            SubInfo start;
-            if (work) start = subs[q * kSeqThreads - 1];
-            __syncthreads();
-            if (work) {
-                need_a[q] = 0u;
+        for (uint32_t j0 = 1; j0 < nsub; j0 += kInterThreads) {  // reads of a pass precede its writes
+            const uint32_t j = j0 + tid;
+            bool broken = false;
+            uint32_t start_p = 0, start_cz = 0;
+            if (j < nsub) {
+                const SubInfo prev = subs[j - 1];
+                const SubInfo mine = subs[j];
+                start_p = prev.pB;
+                start_cz = (prev.cz >> 10) & kCzMask;
+                broken = start_p != mine.pA || start_cz != (mine.cz & kCzMask);
+            }
+            if (!__syncthreads_or(broken ? 1 : 0)) continue;
+            any = 1;
+            if (!loaded) { load_entropy_luts(b, sm, kInterThreads); loaded = true; }
+            if (broken) {
                 DecState st;
-                init_state(cx, st, start.p, (int32_t)(start.czf & 63u), (int32_t)((start.czf >> 6) & 15u), 0, 0, 0);
-                int32_t g_base = st.g;
-                bool first = true;
-#pragma unroll 1
-                for (uint32_t t = 0; t < (uint32_t)kSeqThreads; t++) {
-                    const uint32_t jj = q * kSeqThreads + t;
-                    if (jj >= nsub) break;
-                    if (!first) begin_subsequence(st, g_base);
-                    else { g_base = st.g; st.dc0 = st.dc1 = st.dc2 = 0; }
-                    first = false;
-                    decode_span<false>(cx, st, (jj + 1) * S, 0, nullptr, nullptr);
-                    SubInfo mine;
-                    summarise(st, g_base, mine);
-                    mine.pad[0] = mine.pad[1] = 0;
-                    const SubInfo old = subs[jj];
-                    const bool same = old.p == mine.p && ((old.czf ^ mine.czf) & kCzMask) == 0u;
-                    subs[jj] = mine;
-                    if (same) break;
-                    if (t == (uint32_t)kSeqThreads - 1 && q + 1 < nseq) { need_b[q + 1] = 1u; any = 1; }
-                }
+                init_state(cx, st, start_p, (int32_t)(start_cz & 63u), (int32_t)(start_cz >> 6), 0, 0, 0);
+                SubInfo rec;
+                rec.pA = st.p;
+                rec.cz = start_cz;
+                sync_span(cx, st, (j + 1) * S, rec);
+                subs[j] = rec;
             }
             __syncthreads();
         }
-        if (!__syncthreads_or(any)) break;
-        for (uint32_t q = tid; q < nseq; q += kInterThreads) { need_a[q] = need_b[q]; need_b[q] = 0u; }
-        __syncthreads();
+        if (!any) break;
     }
 
-    // ---- scan: n/dc become absolute end states (segmented by `crossed`)
+    // ---- exclusive scan: n/dc become the absolute state at A (segmented by `crossed`)
     const uint32_t chunk = (nsub + kInterThreads - 1) / kInterThreads;
     const uint32_t lo = tid * chunk, hi = min(nsub, lo + chunk);
     int32_t acc[4] = {0, 0, 0, 0};
     int32_t crossed = 0;
     for (uint32_t jj = lo; jj < hi; jj++) {
         const SubInfo s = subs[jj];
-        if (s.czf & kCrossed) { acc[0] = s.n; acc[1] = s.dc[0]; acc[2] = s.dc[1]; acc[3] = s.dc[2]; crossed = 1; }
+        if (s.cz & kCrossed) { acc[0] = s.n; acc[1] = s.dc[0]; acc[2] = s.dc[1]; acc[3] = s.dc[2]; crossed = 1; }
         else { acc[0] += s.n; acc[1] += s.dc[0]; acc[2] += s.dc[1]; acc[3] += s.dc[2]; }
     }
     s_agg[tid][0] = acc[0]; s_agg[tid][1] = acc[1]; s_agg[tid][2] = acc[2]; s_agg[tid][3] = acc[3]; s_agg[tid][4] = crossed;
@@ -320,45 +289,144 @@ __global__ void __launch_bounds__(kInterThreads) sync_inter_scan_kernel(BatchDev
     }
     for (uint32_t jj = lo; jj < hi; jj++) {
         SubInfo s = subs[jj];
-        if (s.czf & kCrossed) { run[0] = s.n; run[1] = s.dc[0]; run[2] = s.dc[1]; run[3] = s.dc[2]; }
+        const int32_t at_a[4] = {run[0], run[1], run[2], run[3]};
+        if (s.cz & kCrossed) { run[0] = s.n; run[1] = s.dc[0]; run[2] = s.dc[1]; run[3] = s.dc[2]; }
         else { run[0] += s.n; run[1] += s.dc[0]; run[2] += s.dc[1]; run[3] += s.dc[2]; }
-        s.n = run[0]; s.dc[0] = run[1]; s.dc[1] = run[2]; s.dc[2] = run[3];
+        s.n = at_a[0]; s.dc[0] = at_a[1]; s.dc[1] = at_a[2]; s.dc[2] = at_a[3];
         subs[jj] = s;
     }
 }
 
-// One CTA per sequence: every thread re-decodes its subsequence from its now exact
-// start state and scatters the non-zero coefficients into the (pre-zeroed) arena.
-__global__ void __launch_bounds__(kSeqThreads, 3) decode_write_kernel(BatchDev b) {
-    __shared__ EntropySmem sm;
+// One thread per subsequence re-decodes it from its now exact start state and produces the
+// coefficients.  A lane assembles each 8x8 block in a private, pre-zeroed 128-byte buffer in
+// shared memory (kWriteBufs of them, 16-byte pieces XOR-swizzled so that both the scattered
+// 2-byte stores and the flush are nearly conflict-free).  Lanes run kPhaseSymbols symbols (or
+// until their buffers are full), then the warp flushes every completed block cooperatively:
+// 8 lanes store one block as 8 x 16 bytes, so HBM only ever sees whole 128-byte blocks, written
+// once — no memset of the arena, no read-modify-write of partial sectors.
+// A block belongs to the lane in whose subsequence it STARTS: a lane that begins inside a block
+// decodes the rest of it without storing, a lane that ends inside a block runs on until the
+// block is complete.
+struct WriteLayout {
+    uint32_t lut_bytes, buf_off, list_off, total;
+};
+__host__ __device__ inline WriteLayout write_layout(uint32_t max_slots) {
+    WriteLayout l;
+    l.lut_bytes = (uint32_t)(sizeof(EntropySmem) - (kMaxLutSlots - max_slots) * sizeof(HuffLut));
+    l.buf_off = (l.lut_bytes + 127u) & ~127u;
+    l.list_off = l.buf_off + kSeqThreads * kWriteBufs * 128u;
+    l.total = l.list_off + (kSeqThreads / 32) * 32u * kWriteBufs * 8u;
+    return l;
+}
+
+__global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
+    EntropySmem& sm = *reinterpret_cast<EntropySmem*>(dyn_smem);
+    const WriteLayout lay = write_layout(b.max_slots);
+    int16_t* const bufs = reinterpret_cast<int16_t*>(dyn_smem + lay.buf_off);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint2* const flist = reinterpret_cast<uint2*>(dyn_smem + lay.list_off) + warp * (32 * kWriteBufs);
 
     const SeqDesc sd = b.seqs[blockIdx.x];
     const uint32_t S = b.sub_bits;
-    load_entropy_ctx(b, sd.img, sm, kSeqThreads);
+    load_entropy_img(b, sd.img, sm, kSeqThreads);
     const ImgDyn dyn = b.dyn[sd.img];
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
+    load_entropy_luts(b, sm, kSeqThreads);
+    for (uint32_t i = tid; i < kSeqThreads * kWriteBufs * 8u; i += kSeqThreads)
+        reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
     const DecCtx cx = make_ctx(b, sm, dyn);
-    const uint32_t j = sd.first_sub + threadIdx.x;
-    if (j >= nsub) return;
+    const uint32_t j = sd.first_sub + tid;
+    bool active = j < nsub;
+    if (!__ballot_sync(0xffffffffu, active)) return;
 
-    DecState st;
-    if (j == 0) {
-        init_state(cx, st, 0u, 0, 0, 0, 0, 0);
-    } else {
-        const SubInfo prev = b.subs[sm.img.sub_off + j - 1];
-        init_state(cx, st, prev.p, prev.n, (int32_t)((prev.czf >> 6) & 15u), prev.dc[0], prev.dc[1], prev.dc[2]);
-    }
     const int32_t total = (int32_t)sm.img.total_coefs;
-    const int32_t g_start = st.g;
-    st.flags &= ~kCrossed;
-    decode_span<true>(cx, st, (j + 1) * S, total, b.coefs + sm.img.coef_off, sm.store_pos);
-    uint32_t bits = st.flags & (kStBadCode | kStDcSize);
-    if (g_start < total && st.g >= total) {  // this thread decoded the last block of the scan
-        b.dyn[sd.img].bits_consumed = st.br.pos();
-        bits |= kStDone;
+    int16_t* __restrict__ coefs = b.coefs + sm.img.coef_off;
+    const uint32_t end_bit = (j + 1) * S;
+    DecState st;
+    bool store_on = true;
+    if (active) {
+        const SubInfo me = b.subs[sm.img.sub_off + j];
+        init_state(cx, st, me.pA, me.n, (int32_t)((me.cz >> 6) & 15u), me.dc[0], me.dc[1], me.dc[2]);
+        st.flags &= ~kCrossed;
+        store_on = (st.g & 63) == 0;
+        if (st.g >= total) active = false;
+    } else {
+        st.p = 0; st.g = 0; st.flags = 0;
     }
-    if (bits) atomicOr(&b.dyn[sd.img].status, bits);
+    const int32_t g_start = st.g;
+    const uint32_t row0 = tid * kWriteBufs;   // this lane's first buffer row (one row = one 128-byte block)
+    uint32_t cur = 0, ndone = 0;
+    uint32_t dest[kWriteBufs];
+#pragma unroll
+    for (int i = 0; i < kWriteBufs; i++) dest[i] = 0u;
+
+#pragma unroll 1
+    while (true) {
+        // ---- phase A: every lane decodes up to kPhaseSymbols symbols into its own buffers
+#pragma unroll 1
+        for (int k = 0; k < kPhaseSymbols && active && ndone < (uint32_t)kWriteBufs; k++) {
+            if ((st.p >= end_bit && (st.g & 63) == 0) || st.g >= total) { active = false; break; }
+            const uint32_t row = row0 + cur;
+            const int32_t g_before = st.g;
+            const uint32_t ev = decode_symbol<true>(cx, st, bufs + row * 64u, row & 7u, sm.store_pos, store_on);
+            if (ev & kEvBlock) {
+                if (store_on) { dest[ndone] = (uint32_t)(g_before >> 6); ndone++; cur = cur + 1 == (uint32_t)kWriteBufs ? 0u : cur + 1; }
+                store_on = true;
+            } else if (ev & kEvCross) {
+                // a valid stream only gets here between blocks; drop a half-written block of a corrupt one
+                if ((g_before & 63) != 0 && store_on) { dest[ndone] = 0xffffffffu; ndone++; cur = cur + 1 == (uint32_t)kWriteBufs ? 0u : cur + 1; }
+                store_on = true;
+            } else if (ev & kEvEnd) {
+                active = false;
+            }
+        }
+        // ---- phase B: the warp flushes all completed blocks, 8 lanes per block
+        uint32_t offs = 0, count = 0;
+#pragma unroll
+        for (int i = 0; i < kWriteBufs; i++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, ndone > (uint32_t)i);
+            offs += __popc(m & ((1u << lane) - 1u));
+            count += __popc(m);
+        }
+        if (count == 0) {
+            if (!__ballot_sync(0xffffffffu, active)) break;
+            continue;
+        }
+        {
+            uint32_t r = cur + kWriteBufs - ndone;  // oldest completed buffer
+#pragma unroll
+            for (int i = 0; i < kWriteBufs; i++) {
+                if ((uint32_t)i < ndone) {
+                    if (r >= (uint32_t)kWriteBufs) r -= kWriteBufs;
+                    flist[offs + i] = make_uint2(row0 + r, dest[i]);
+                    r++;
+                }
+            }
+        }
+        __syncwarp();
+        const uint32_t piece = lane & 7u;
+#pragma unroll 1
+        for (uint32_t i = lane >> 3; i < count; i += 4) {
+            const uint2 e = flist[i];
+            uint4* src = reinterpret_cast<uint4*>(bufs + e.x * 64u) + (piece ^ (e.x & 7u));
+            const uint4 v = *src;
+            *src = make_uint4(0u, 0u, 0u, 0u);
+            if (e.y != 0xffffffffu) reinterpret_cast<uint4*>(coefs + (size_t)e.y * 64u)[piece] = v;
+        }
+        __syncwarp();
+        ndone = 0;
+    }
+    if (j < nsub) {
+        uint32_t bits = st.flags & (kStBadCode | kStDcSize);
+        if (g_start < total && st.g >= total) {  // this thread decoded the last block of the scan
+            b.dyn[sd.img].bits_consumed = st.p;
+            bits |= kStDone;
+        }
+        if (bits) atomicOr(&b.dyn[sd.img].status, bits);
+    }
 }
 
 // ============================================ stage 2+3: dequant + IDCT + upsample + colour
@@ -649,14 +717,23 @@ __global__ void __launch_bounds__(kGatherThreads) gather_colour_kernel(BatchDev 
 void launch_prepass(const BatchDev& b, cudaStream_t s) {
     if (b.n_images) prepass_kernel<<<b.n_images, kPreThreads, 0, s>>>(b);
 }
-void launch_sync_intra(const BatchDev& b, cudaStream_t s) {
-    if (b.n_seqs) sync_intra_kernel<<<b.n_seqs, kSeqThreads, 0, s>>>(b);
+void launch_sync(const BatchDev& b, cudaStream_t s) {
+    if (b.n_seqs) sync_kernel<<<b.n_seqs, kSeqThreads, 0, s>>>(b);
 }
-void launch_sync_inter_scan(const BatchDev& b, cudaStream_t s) {
-    if (b.n_images) sync_inter_scan_kernel<<<b.n_images, kInterThreads, 0, s>>>(b);
+void launch_verify_scan(const BatchDev& b, cudaStream_t s) {
+    if (b.n_images) verify_scan_kernel<<<b.n_images, kInterThreads, 0, s>>>(b);
 }
-void launch_decode_write(const BatchDev& b, cudaStream_t s) {
-    if (b.n_seqs) decode_write_kernel<<<b.n_seqs, kSeqThreads, 0, s>>>(b);
+cudaError_t launch_decode_write(const BatchDev& b, cudaStream_t s) {
+    if (!b.n_seqs) return cudaSuccess;
+    const WriteLayout lay = write_layout(b.max_slots);
+    static uint32_t configured = 0;
+    if (lay.total > configured) {
+        cudaError_t e = cudaFuncSetAttribute(decode_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+        if (e != cudaSuccess) return e;
+        configured = lay.total;
+    }
+    decode_write_kernel<<<b.n_seqs, kSeqThreads, lay.total, s>>>(b);
+    return cudaSuccess;
 }
 
 int launch_idct_colour(const BatchDev& b, cudaStream_t s) {

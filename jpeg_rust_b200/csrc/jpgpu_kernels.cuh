@@ -23,12 +23,14 @@ struct BatchDev {        // device pointers of one planned batch
     uint32_t* stream;
     uint32_t* segtab;
     SubInfo* subs;
-    uint32_t* seq_flags; // 2 x n_seqs scratch for the inter-sequence pass
     int16_t* coefs;
     uint8_t* rgb;
     uint32_t n_images;
     uint32_t n_seqs;
     uint32_t sub_bits;   // bits per subsequence for this batch
+    uint32_t lw;         // log2(sub_bits / 32): words per subsequence
+    uint32_t lookback_bits;
+    uint32_t max_slots;
     // images grouped by colour-kernel variant (ImgKind)
     const uint32_t* kind_imgs[kNumKinds];
     uint32_t kind_count[kNumKinds];
@@ -44,12 +46,12 @@ cudaError_t init_constants();
 
 // Stage 1a: byte-unstuffing + RSTn detection, one CTA per image.
 void launch_prepass(const BatchDev& b, cudaStream_t s);
-// Stage 1b: intra-sequence self-synchronisation, one CTA per sequence.
-void launch_sync_intra(const BatchDev& b, cudaStream_t s);
-// Stage 1c: inter-sequence synchronisation + prefix scan, one CTA per image.
-void launch_sync_inter_scan(const BatchDev& b, cudaStream_t s);
-// Stage 1d: final decode, coefficients written to HBM.
-void launch_decode_write(const BatchDev& b, cudaStream_t s);
+// Stage 1b: look-back synchronisation, one thread per subsequence.
+void launch_sync(const BatchDev& b, cudaStream_t s);
+// Stage 1c: chain verification (+ repair where look-back did not synchronise) + prefix scan, one CTA per image.
+void launch_verify_scan(const BatchDev& b, cudaStream_t s);
+// Stage 1d: final decode, whole coefficient blocks written to HBM.
+cudaError_t launch_decode_write(const BatchDev& b, cudaStream_t s);
 // Stage 2+3: dequantise, IDCT, upsample, YCbCr->RGB, interleaved store (SPEC geometry).
 // Images whose requested layout the fused kernel cannot produce (REF placement of 4:2:0 / ragged widths,
 // decoder.rs:259-312 + 347-379; generic sampling factors) go through block_idct_kernel +

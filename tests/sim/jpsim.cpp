@@ -29,10 +29,10 @@ struct SimBatch {
     std::vector<uint8_t> rgb;
     uint8_t store_pos[64];
     // diagnostics
-    uint32_t max_rounds = 0;       // most intra-sequence rounds any CTA needed
-    uint32_t inter_iters = 0;      // most inter-sequence iterations any image needed
-    uint64_t inter_walk = 0;       // total subsequences decoded by inter-sequence walkers
-    uint64_t intra_decodes = 0;    // total subsequence decodes in the intra pass
+    uint32_t repair_iters = 0;     // most repair iterations any image needed
+    uint64_t repairs = 0;          // subsequences decoded again because the look-back had not synchronised
+    uint64_t sync_decodes = 0;     // subsequences decoded by the sync pass
+    uint64_t flush_phases = 0, flushed_blocks = 0;
 };
 
 // mirrors prepass_kernel's per-byte rule (the warp/CTA scan itself is GPU plumbing)
@@ -40,6 +40,7 @@ void sim_prepass(SimBatch& sb, size_t img) {
     const ImgDev& im = sb.plan.imgs[img];
     const uint8_t* in = sb.raw.data() + im.raw_off;
     const uint32_t n = im.raw_len;
+    const uint32_t lw = sb.plan.lw;
     uint32_t* out = sb.stream.data() + im.stream_off;
     uint32_t* seg = sb.segtab.data() + im.seg_off;
     const bool dri = im.restart_interval != 0;
@@ -63,12 +64,14 @@ void sim_prepass(SimBatch& sb, size_t img) {
         }
         if (!drop) { bytes.push_back((uint8_t)cur); emitted++; }
     }
-    for (uint32_t k = 0; k < emitted; k++) {
-        if ((k & 3) == 0) out[k >> 2] = 0;
-        out[k >> 2] |= (uint32_t)bytes[k] << (24 - 8 * (k & 3));
+    const uint32_t nwords = (emitted + 3) >> 2;
+    for (uint32_t w = 0; w < nwords; w++) {
+        uint32_t v = 0;
+        for (uint32_t k = 0; k < 4; k++)
+            if (w * 4 + k < emitted) v |= (uint32_t)bytes[w * 4 + k] << (24 - 8 * k);
+        out[stream_phys(w, lw)] = v;
     }
-    uint32_t wbase = (emitted + 3) >> 2;
-    for (int i = 0; i < kStreamPadWords; i++) out[wbase + i] = 0;
+    for (int i = 0; i < kStreamPadWords; i++) out[stream_phys(nwords + i, lw)] = 0;
     uint32_t nseg = rst_total + 1;
     if (nseg != im.nseg_cap && dri) status |= kStRestart;
     if (nseg > im.nseg_cap) nseg = im.nseg_cap;
@@ -81,15 +84,14 @@ DecCtx make_ctx(const SimBatch& sb, size_t img, const HuffLut* slots) {
     const ImgDev& im = sb.plan.imgs[img];
     DecCtx cx;
     cx.words = sb.stream.data() + im.stream_off;
+    cx.lw = sb.plan.lw;
     cx.seg = sb.segtab.data() + im.seg_off;
     cx.nseg = sb.dyn[img].nseg;
     cx.stream_bits = sb.dyn[img].stream_bits;
     cx.seg_units = im.seg_units;
     cx.nblk = im.blocks_per_mcu;
     cx.luts = slots;
-    cx.blk_comp = im.blk_comp;
-    cx.blk_dc_slot = im.blk_dc_slot;
-    cx.blk_ac_slot = im.blk_ac_slot;
+    cx.blk_info = im.blk_info;
     return cx;
 }
 
@@ -99,132 +101,94 @@ void load_slots(const SimBatch& sb, size_t img, std::vector<HuffLut>& slots) {
     for (int s = 0; s < im.nslots; s++) slots[s] = sb.plan.luts[im.slot_lut[s]];
 }
 
-// mirrors sync_intra_kernel: one "CTA" per sequence, barrier-separated rounds
-void sim_sync_intra(SimBatch& sb, const SeqDesc& sd) {
+// mirrors sync_kernel: one independent thread per subsequence
+void sim_sync(SimBatch& sb, const SeqDesc& sd) {
     std::vector<HuffLut> slots;
     load_slots(sb, sd.img, slots);
     const ImgDev& im = sb.plan.imgs[sd.img];
     const ImgDyn dyn = sb.dyn[sd.img];
-    const uint32_t S = sb.plan.sub_bits;
+    const uint32_t S = sb.plan.sub_bits, L = sb.plan.lookback_bits;
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
     const DecCtx cx = make_ctx(sb, sd.img, slots.data());
-    std::vector<DecState> st(kSeqThreads);
-    std::vector<int32_t> g_base(kSeqThreads, 0);
-    std::vector<char> active(kSeqThreads, 0);
-    std::vector<SubInfo> s_info(kSeqThreads);
     for (uint32_t tid = 0; tid < (uint32_t)kSeqThreads; tid++) {
         const uint32_t j = sd.first_sub + tid;
-        active[tid] = j < nsub;
-        if (!active[tid]) continue;
-        init_state(cx, st[tid], j * S, 0, 0, 0, 0, 0);
-        g_base[tid] = st[tid].g;
-        decode_span<false>(cx, st[tid], (j + 1) * S, 0, nullptr, nullptr);
-        SubInfo mine;
-        summarise(st[tid], g_base[tid], mine);
-        mine.pad[0] = mine.pad[1] = 0;
-        s_info[tid] = mine;
-        sb.intra_decodes++;
-    }
-    uint32_t rounds = 1;
-    for (uint32_t r = 1; r < (uint32_t)kSeqThreads; r++) {
-        bool any = false;
-        // within a round every thread reads/writes only s_info[tid + r]: order is irrelevant
-        for (uint32_t tid = 0; tid < (uint32_t)kSeqThreads; tid++) {
-            const uint32_t j = sd.first_sub + tid, tgt = tid + r;
-            if (active[tid] && (tgt >= (uint32_t)kSeqThreads || j + r >= nsub)) active[tid] = 0;
-            if (!active[tid]) continue;
-            begin_subsequence(st[tid], g_base[tid]);
-            decode_span<false>(cx, st[tid], (j + r + 1) * S, 0, nullptr, nullptr);
-            SubInfo mine;
-            summarise(st[tid], g_base[tid], mine);
-            mine.pad[0] = mine.pad[1] = 0;
-            const SubInfo old = s_info[tgt];
-            const bool same = old.p == mine.p && ((old.czf ^ mine.czf) & kCzMask) == 0u;
-            s_info[tgt] = mine;
-            if (same) active[tid] = 0;
-            sb.intra_decodes++;
-            any = any || active[tid];
+        if (j >= nsub) continue;
+        const uint32_t own = j * S, p0 = own > L ? own - L : 0u;
+        DecState st;
+        init_state(cx, st, p0, 0, 0, 0, 0, 0);
+        while (st.p < own) {
+            if (decode_symbol<false>(cx, st, nullptr, 0u, nullptr, false) & kEvEnd) break;
         }
-        rounds++;
-        if (!any) break;
-    }
-    sb.max_rounds = std::max(sb.max_rounds, rounds);
-    for (uint32_t tid = 0; tid < (uint32_t)kSeqThreads; tid++) {
-        const uint32_t j = sd.first_sub + tid;
-        if (j < nsub) sb.subs[im.sub_off + j] = s_info[tid];
+        SubInfo rec;
+        rec.pA = st.p;
+        rec.cz = pack_cz(st);
+        sync_span(cx, st, own + S, rec);
+        sb.subs[im.sub_off + j] = rec;
+        sb.sync_decodes++;
     }
 }
 
-// mirrors sync_inter_scan_kernel
-void sim_sync_inter_scan(SimBatch& sb, size_t img) {
+constexpr uint32_t kSimInterThreads = 128;  // = kInterThreads of jpgpu_kernels.cu
+
+// mirrors verify_scan_kernel
+void sim_verify_scan(SimBatch& sb, size_t img) {
     std::vector<HuffLut> slots;
     load_slots(sb, img, slots);
     const ImgDev& im = sb.plan.imgs[img];
     const ImgDyn dyn = sb.dyn[img];
     const uint32_t S = sb.plan.sub_bits;
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
-    const uint32_t nseq = (nsub + kSeqThreads - 1) / kSeqThreads;
     const DecCtx cx = make_ctx(sb, img, slots.data());
     SubInfo* subs = sb.subs.data() + im.sub_off;
-    std::vector<uint32_t> need_a(nseq + 1, 0), need_b(nseq + 1, 0);
-    for (uint32_t q = 1; q < nseq; q++) need_a[q] = 1;
     uint32_t iters = 0;
-    for (uint32_t iter = 0; iter < nseq; iter++) {
+    for (uint32_t iter = 0; iter < nsub; iter++) {
         bool any = false;
-        iters++;
-        for (uint32_t q0 = 1; q0 < nseq; q0 += 64) {
-            // snapshot phase
-            std::vector<SubInfo> start(64);
-            std::vector<char> work(64, 0);
-            for (uint32_t tid = 0; tid < 64; tid++) {
-                const uint32_t q = q0 + tid;
-                work[tid] = q < nseq && need_a[q];
-                if (work[tid]) start[tid] = subs[q * kSeqThreads - 1];
+        for (uint32_t j0 = 1; j0 < nsub; j0 += kSimInterThreads) {
+            // read phase of the pass
+            struct Job { bool broken; uint32_t p, cz; };
+            Job jobs[kSimInterThreads];
+            for (uint32_t tid = 0; tid < kSimInterThreads; tid++) {
+                const uint32_t j = j0 + tid;
+                jobs[tid].broken = false;
+                if (j >= nsub) continue;
+                const SubInfo& prev = subs[j - 1];
+                const SubInfo& mine = subs[j];
+                jobs[tid].p = prev.pB;
+                jobs[tid].cz = (prev.cz >> 10) & kCzMask;
+                jobs[tid].broken = jobs[tid].p != mine.pA || jobs[tid].cz != (mine.cz & kCzMask);
             }
-            // walk phase (threads of one pass are independent except through need_b)
-            for (uint32_t tid = 0; tid < 64; tid++) {
-                if (!work[tid]) continue;
-                const uint32_t q = q0 + tid;
-                need_a[q] = 0;
+            // write phase
+            for (uint32_t tid = 0; tid < kSimInterThreads; tid++) {
+                if (!jobs[tid].broken) continue;
+                any = true;
+                const uint32_t j = j0 + tid;
                 DecState st;
-                init_state(cx, st, start[tid].p, (int32_t)(start[tid].czf & 63u), (int32_t)((start[tid].czf >> 6) & 15u), 0, 0, 0);
-                int32_t g_base = st.g;
-                bool first = true;
-                for (uint32_t t = 0; t < (uint32_t)kSeqThreads; t++) {
-                    const uint32_t jj = q * kSeqThreads + t;
-                    if (jj >= nsub) break;
-                    if (!first) begin_subsequence(st, g_base);
-                    else { g_base = st.g; st.dc0 = st.dc1 = st.dc2 = 0; }
-                    first = false;
-                    decode_span<false>(cx, st, (jj + 1) * S, 0, nullptr, nullptr);
-                    sb.inter_walk++;
-                    SubInfo mine;
-                    summarise(st, g_base, mine);
-                    mine.pad[0] = mine.pad[1] = 0;
-                    const SubInfo old = subs[jj];
-                    const bool same = old.p == mine.p && ((old.czf ^ mine.czf) & kCzMask) == 0u;
-                    subs[jj] = mine;
-                    if (same) break;
-                    if (t == (uint32_t)kSeqThreads - 1 && q + 1 < nseq) { need_b[q + 1] = 1; any = true; }
-                }
+                init_state(cx, st, jobs[tid].p, (int32_t)(jobs[tid].cz & 63u), (int32_t)(jobs[tid].cz >> 6), 0, 0, 0);
+                SubInfo rec;
+                rec.pA = st.p;
+                rec.cz = jobs[tid].cz;
+                sync_span(cx, st, (j + 1) * S, rec);
+                subs[j] = rec;
+                sb.repairs++;
             }
         }
         if (!any) break;
-        for (uint32_t q = 0; q < nseq; q++) { need_a[q] = need_b[q]; need_b[q] = 0; }
+        iters++;
     }
-    sb.inter_iters = std::max(sb.inter_iters, iters);
-    // scan (serial form of the chunked scan)
+    sb.repair_iters = std::max(sb.repair_iters, iters);
+    // exclusive scan (serial form of the chunked scan)
     int32_t run[4] = {0, 0, 0, 0};
     for (uint32_t jj = 0; jj < nsub; jj++) {
         SubInfo& s = subs[jj];
-        if (s.czf & kCrossed) { run[0] = s.n; run[1] = s.dc[0]; run[2] = s.dc[1]; run[3] = s.dc[2]; }
+        const int32_t at_a[4] = {run[0], run[1], run[2], run[3]};
+        if (s.cz & kCrossed) { run[0] = s.n; run[1] = s.dc[0]; run[2] = s.dc[1]; run[3] = s.dc[2]; }
         else { run[0] += s.n; run[1] += s.dc[0]; run[2] += s.dc[1]; run[3] += s.dc[2]; }
-        s.n = run[0]; s.dc[0] = run[1]; s.dc[1] = run[2]; s.dc[2] = run[3];
+        s.n = at_a[0]; s.dc[0] = at_a[1]; s.dc[1] = at_a[2]; s.dc[2] = at_a[3];
     }
 }
 
-// mirrors decode_write_kernel
+// mirrors decode_write_kernel: warps in lock-step phases, per-lane swizzled block buffers, cooperative flush
 void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
     std::vector<HuffLut> slots;
     load_slots(sb, sd.img, slots);
@@ -234,22 +198,87 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
     const DecCtx cx = make_ctx(sb, sd.img, slots.data());
-    for (uint32_t tid = 0; tid < (uint32_t)kSeqThreads; tid++) {
-        const uint32_t j = sd.first_sub + tid;
-        if (j >= nsub) continue;
-        DecState st;
-        if (j == 0) init_state(cx, st, 0u, 0, 0, 0, 0, 0);
-        else {
-            const SubInfo prev = sb.subs[im.sub_off + j - 1];
-            init_state(cx, st, prev.p, prev.n, (int32_t)((prev.czf >> 6) & 15u), prev.dc[0], prev.dc[1], prev.dc[2]);
+    const int32_t total = (int32_t)im.total_coefs;
+    int16_t* coefs = sb.coefs.data() + im.coef_off;
+    std::vector<int16_t> bufs((size_t)kSeqThreads * kWriteBufs * 64, 0);
+    for (uint32_t warp = 0; warp < (uint32_t)kSeqThreads / 32; warp++) {
+        struct Lane { DecState st; bool active, store_on; uint32_t j, end_bit, cur, ndone, dest[kWriteBufs]; int32_t g_start; };
+        Lane ln[32];
+        bool any_active = false;
+        for (uint32_t lane = 0; lane < 32; lane++) {
+            Lane& l = ln[lane];
+            const uint32_t tid = warp * 32 + lane;
+            l.j = sd.first_sub + tid;
+            l.active = l.j < nsub;
+            l.end_bit = (l.j + 1) * S;
+            l.cur = l.ndone = 0;
+            l.store_on = true;
+            l.st.p = 0; l.st.g = 0; l.st.flags = 0;
+            if (l.active) {
+                const SubInfo me = sb.subs[im.sub_off + l.j];
+                init_state(cx, l.st, me.pA, me.n, (int32_t)((me.cz >> 6) & 15u), me.dc[0], me.dc[1], me.dc[2]);
+                l.st.flags &= ~kCrossed;
+                l.store_on = (l.st.g & 63) == 0;
+                if (l.st.g >= total) l.active = false;
+            }
+            l.g_start = l.st.g;
+            any_active = any_active || l.active;
         }
-        const int32_t total = (int32_t)im.total_coefs;
-        const int32_t g_start = st.g;
-        st.flags &= ~kCrossed;
-        decode_span<true>(cx, st, (j + 1) * S, total, sb.coefs.data() + im.coef_off, sb.store_pos);
-        uint32_t bits = st.flags & (kStBadCode | kStDcSize);
-        if (g_start < total && st.g >= total) { sb.dyn[sd.img].bits_consumed = st.br.pos(); bits |= kStDone; }
-        sb.dyn[sd.img].status |= bits;
+        if (!any_active) {
+            bool any_j = false;
+            for (auto& l : ln) any_j = any_j || l.j < nsub;
+            if (!any_j) continue;
+        }
+        while (true) {
+            for (uint32_t lane = 0; lane < 32; lane++) {
+                Lane& l = ln[lane];
+                const uint32_t row0 = (warp * 32 + lane) * kWriteBufs;
+                for (int k = 0; k < kPhaseSymbols && l.active && l.ndone < (uint32_t)kWriteBufs; k++) {
+                    if ((l.st.p >= l.end_bit && (l.st.g & 63) == 0) || l.st.g >= total) { l.active = false; break; }
+                    const uint32_t row = row0 + l.cur;
+                    const int32_t g_before = l.st.g;
+                    const uint32_t ev = decode_symbol<true>(cx, l.st, bufs.data() + (size_t)row * 64, row & 7u, sb.store_pos, l.store_on);
+                    if (ev & kEvBlock) {
+                        if (l.store_on) { l.dest[l.ndone++] = (uint32_t)(g_before >> 6); l.cur = l.cur + 1 == (uint32_t)kWriteBufs ? 0u : l.cur + 1; }
+                        l.store_on = true;
+                    } else if (ev & kEvCross) {
+                        if ((g_before & 63) != 0 && l.store_on) { l.dest[l.ndone++] = 0xffffffffu; l.cur = l.cur + 1 == (uint32_t)kWriteBufs ? 0u : l.cur + 1; }
+                        l.store_on = true;
+                    } else if (ev & kEvEnd) {
+                        l.active = false;
+                    }
+                }
+            }
+            uint32_t count = 0;
+            bool act = false;
+            for (auto& l : ln) { count += l.ndone; act = act || l.active; }
+            if (count == 0) { if (!act) break; continue; }
+            for (uint32_t lane = 0; lane < 32; lane++) {
+                Lane& l = ln[lane];
+                const uint32_t row0 = (warp * 32 + lane) * kWriteBufs;
+                uint32_t r = l.cur + kWriteBufs - l.ndone;
+                for (uint32_t i = 0; i < l.ndone; i++, r++) {
+                    if (r >= (uint32_t)kWriteBufs) r -= kWriteBufs;
+                    const uint32_t row = row0 + r;
+                    int16_t* src = bufs.data() + (size_t)row * 64;
+                    for (uint32_t piece = 0; piece < 8; piece++)
+                        for (int e = 0; e < 8; e++) {
+                            int16_t& v = src[((piece ^ (row & 7u)) << 3) + e];
+                            if (l.dest[i] != 0xffffffffu) coefs[(size_t)l.dest[i] * 64 + piece * 8 + e] = v;
+                            v = 0;
+                        }
+                    sb.flushed_blocks++;
+                }
+                l.ndone = 0;
+            }
+            sb.flush_phases++;
+        }
+        for (auto& l : ln) {
+            if (l.j >= nsub) continue;
+            uint32_t bits = l.st.flags & (kStBadCode | kStDcSize);
+            if (l.g_start < total && l.st.g >= total) { sb.dyn[sd.img].bits_consumed = l.st.p; bits |= kStDone; }
+            sb.dyn[sd.img].status |= bits;
+        }
     }
 }
 
@@ -357,7 +386,7 @@ extern "C" {
 // Runs the whole simulated pipeline on a batch of descriptors.
 //   rgb_out[i]   : W*H*3 bytes (may be NULL)
 //   coef_out[i]  : reference-order coefficients (may be NULL), coef_cap[i] int16 each
-//   diag[4]      : max intra rounds, max inter iterations, inter walk decodes, intra decodes
+//   diag[4]      : max repair iterations, repaired subsequences, sync-pass subsequences, flush phases
 int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* rgb_out, int16_t* const* coef_out,
                        const size_t* coef_cap, uint32_t* nblocks /* n x 4 */, int32_t* statuses, uint64_t* bytes_read,
                        uint64_t* diag, uint32_t sub_bits) {
@@ -370,14 +399,14 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
     sb.segtab.assign(p.seg_entries + 8, 0);
     sb.subs.assign(p.sub_entries + 1, SubInfo());
     sb.dyn.assign(n + 1, ImgDyn());
-    sb.coefs.assign(p.coef_elems + 64, 0);
+    sb.coefs.assign(p.coef_elems + 64, 0x5555);  // the write pass must produce every coefficient itself
     sb.rgb.assign(p.rgb_bytes + 256, 0);
     for (int k = 0; k < 64; k++) sb.store_pos[k] = (uint8_t)zigzag_to_colmajor(k, kZigzagNaturalHost);
     for (size_t i = 0; i < n; i++)
         if (p.status[i] == JPGPU_OK) memcpy(sb.raw.data() + p.imgs[i].raw_off, descs[i].scan, p.imgs[i].raw_len);
     for (size_t i = 0; i < n; i++) sim_prepass(sb, i);
-    for (const SeqDesc& sd : p.seqs) sim_sync_intra(sb, sd);
-    for (size_t i = 0; i < n; i++) sim_sync_inter_scan(sb, i);
+    for (const SeqDesc& sd : p.seqs) sim_sync(sb, sd);
+    for (size_t i = 0; i < n; i++) sim_verify_scan(sb, i);
     for (const SeqDesc& sd : p.seqs) sim_decode_write(sb, sd);
     for (size_t i = 0; i < n; i++)
         if (p.status[i] == JPGPU_OK) { if (p.imgs[i].kind == kKindGeneric) sim_gather(sb, i); else sim_idct_colour(sb, i); }
@@ -398,7 +427,7 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
         if (statuses) statuses[i] = s;
         if (bytes_read) bytes_read[i] = br;
     }
-    if (diag) { diag[0] = sb.max_rounds; diag[1] = sb.inter_iters; diag[2] = sb.inter_walk; diag[3] = sb.intra_decodes; }
+    if (diag) { diag[0] = sb.repair_iters; diag[1] = sb.repairs; diag[2] = sb.sync_decodes; diag[3] = sb.flush_phases; }
     return JPGPU_OK;
 }
 

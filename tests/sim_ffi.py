@@ -72,7 +72,7 @@ def decode_batch(files, layout=_ffi.LAYOUT_SPEC, ext=_ffi.EXT_NONE, sub_bits=0):
             r.coefs.append(coefs[i][off:off + nb[c] * 64].reshape(-1, 64))
             off += nb[c] * 64
         out.append(r)
-    return out, {"max_intra_rounds": diag[0], "max_inter_iters": diag[1], "inter_walk": diag[2], "intra_decodes": diag[3]}
+    return out, {"repair_iters": diag[0], "repairs": diag[1], "sync_decodes": diag[2], "flush_phases": diag[3]}
 
 
 def idct_8x8(block_natural):
