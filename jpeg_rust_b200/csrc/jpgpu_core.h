@@ -48,8 +48,8 @@ enum : uint32_t {
 };
 
 // One Huffman table in device format.
-// Packed decode entry: bits 0-4 code length, 5-10 total bits (code + value bits), 11-17
-// zigzag advance (1 for DC; run+1; 16 for ZRL; 64 for EOB), 18 DC size category > 16
+// Packed decode entry: byte 0 total bits (code + value bits), byte 1 code length, byte 2
+// zigzag advance (1 for DC; run+1; 16 for ZRL; 64 for EOB), bit 24 DC size category > 16
 // (huffman.rs:202 assert).  With `advance`, next_block's three cases (huffman.rs:164-189)
 // collapse into nz = min(z + advance, 64).  A first-level entry with bit 31 set links to a
 // second-level sub-table: bits 0-8 pool offset, bits 9-11 its index width (1..7 bits after
@@ -71,9 +71,9 @@ JPGPU_HD uint32_t make_entry(uint32_t sym, uint32_t len, bool is_dc) {
     else if (sym == 0x00) { size = 0; adv = 64; }
     else if (sym == 0xf0) { size = 0; adv = 16; }
     else { size = sym & 15; adv = (sym >> 4) + 1; }
-    return len | ((len + size) << 5) | (adv << 11) | (big << 18);
+    return (len + size) | (len << 8) | (adv << 16) | (big << 24);
 }
-constexpr uint32_t kBadEntry = 16u | (16u << 5) | (64u << 11);  // unknown code: 16 bits, ends the block
+constexpr uint32_t kBadEntry = 16u | (16u << 8) | (64u << 16);  // unknown code: 16 bits, ends the block
 
 // Per-image plan, written by the host, read by every kernel.
 struct ImgDev {
@@ -101,6 +101,7 @@ struct ImgDev {
     uint8_t blk_dc_slot[kMaxBlocksPerMcu];
     uint8_t blk_ac_slot[kMaxBlocksPerMcu];
     uint32_t blk_info[kMaxBlocksPerMcu];  // DC slot | AC slot << 8 | component << 16 (what the decoder loads per block)
+    uint32_t blk_info_g[kMaxBlocksPerMcu];// same with indices into the batch-wide LUT array instead of slots (< 256 LUTs)
     uint8_t nslots, kind, layout, pad0;   // kind: colour kernel variant (see ImgKind)
     uint32_t slot_lut[kMaxLutSlots];      // index into the global HuffLut array
     uint32_t qt_off[4];                   // per component: offset (in floats) of its 64 pre-scaled multipliers
@@ -127,6 +128,10 @@ struct ImgDyn {
 // A = state at the first symbol starting at or after j*S, reached from a cold start
 // lookback_bits earlier; B = state at the first symbol starting at or after (j+1)*S.
 // The chain is consistent where A(j) == B(j-1).
+struct RepairJob {     // a broken link found by verify_list_kernel: decode subsequence `sub` of `img` again from (p, cz)
+    uint32_t img, sub, p, cz;
+};
+
 struct SubInfo {
     uint32_t pA, pB;   // bit positions
     uint32_t cz;       // bits 0-5 z(A), 6-9 c(A), 10-15 z(B), 16-19 c(B), 30 absolute (a restart
@@ -340,8 +345,8 @@ JPGPU_HD uint32_t decode_symbol(const DecCtx& cx, DecState& st, int16_t* blk, ui
         e = huff_slow(*t, peek);
         if (e == 0) { st.flags |= kStBadCode; e = kBadEntry; }  // huffman.rs:156/162 panic
     }
-    const uint32_t len = e & 31u, tb = (e >> 5) & 63u;
-    const int32_t adv = (int32_t)((e >> 11) & 127u);
+    const uint32_t tb = e & 255u, len = (e >> 8) & 255u;
+    const int32_t adv = (int32_t)((e >> 16) & 255u);
     if (WRITE || z == 0) {
         const uint32_t size = tb - len;
         const uint32_t top = peek << len;
@@ -352,7 +357,7 @@ JPGPU_HD uint32_t decode_symbol(const DecCtx& cx, DecState& st, int16_t* blk, ui
 #endif
         const int32_t val = extend(v, top, size);
         if (z == 0) {  // DC difference -> predictor (decoder.rs:208-210)
-            if (e & (1u << 18)) st.flags |= kStDcSize;
+            if (e & (1u << 24)) st.flags |= kStDcSize;
             int32_t pred;
             if (st.comp == 0) { st.dc0 += val; pred = st.dc0; } else if (st.comp == 1) { st.dc1 += val; pred = st.dc1; } else { st.dc2 += val; pred = st.dc2; }
             if (WRITE && store_on) blk[buf_index(store_pos[0], swz)] = (int16_t)pred;

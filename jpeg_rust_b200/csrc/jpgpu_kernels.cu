@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kPreThreads) prepass_kernel(BatchDev b) {
     uint8_t* stage_bytes = reinterpret_cast<uint8_t*>(s_stage);
     uint32_t emitted = 0, rst_total = 0;
     if (tid == 0) s_status = 0;
+    if (blockIdx.x == 0 && tid < 2) b.repair_count[tid] = 0u;
     __syncthreads();
 
     for (uint32_t base = 0; base < n; base += kPreChunk) {
@@ -183,15 +184,275 @@ __device__ __forceinline__ DecCtx make_ctx(const BatchDev& b, const EntropySmem&
     return cx;
 }
 
+// ------------------------------------------------------------------ fast decode step
+// decode_symbol() of jpgpu_core.h (the form the CPU simulation and the repair kernels execute)
+// restated for the two bulk kernels with everything on the per-symbol path branch-free or a
+// short forward branch: predicated stream refill, Huffman tables / block buffers / DC
+// predictors addressed as 32-bit shared-memory offsets, the DC predictor of the current
+// component held in a register and swapped through shared memory at block boundaries.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds32v(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32v(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16_if(uint32_t a, uint32_t v, bool p) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.shared.u16 [%0], %1;\n}" :: "r"(a), "r"(v), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ uint32_t ldg_if(const uint32_t* a, bool p) {
+    uint32_t v;
+    asm("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n mov.u32 %0, 0;\n @q ld.global.nc.u32 %0, [%1];\n}" : "=r"(v) : "l"(a), "r"((uint32_t)p));
+    return v;
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+#define JPGPU_PIN32(x) asm volatile("" : "+r"(x))
+#define JPGPU_PIN64(x) asm volatile("" : "+l"(x))
+
+struct FastCtx {
+    const uint32_t* words;   // lane-interleaved stream of the image (global)
+    uint32_t lw, wmask5, gmask_inv;
+    const uint32_t* seg;
+    uint32_t nseg, stream_bits, seg_units;
+    uint32_t info_addr;      // shared: FastTables::info
+    uint32_t dc_addr;        // shared: this lane's DC slots (component k at dc_addr + k * 4 * kSeqThreads)
+    uint32_t sp_addr;        // shared: byte offset of zigzag position k inside an unswizzled block buffer
+    const HuffLut* luts;     // generic pointer to the shared LUT slots (rare paths)
+    uint32_t lut0_addr;
+};
+
+struct FastState {
+    uint32_t hi, lo, avail, widx, p, nextw;
+    int32_t g;
+    uint32_t info_ptr;       // shared address of the FastTables::info entry of the current block-in-MCU
+    uint32_t lut_dc, lut_ac, dc_off;
+    int32_t dcur;
+    uint32_t seg, seg_end, seg_lim, flags;   // seg_lim = seg_end - 7 (0 if shorter): at or past it a step must look at the interval end
+};
+
+// per-CTA tables the fast path reads (filled once after the LUTs are loaded)
+struct FastTables {
+    uint4 info[kMaxBlocksPerMcu];  // per block of an MCU: {dc lut addr | ac lut addr << 16, DC slot offset, address of the next entry, c}
+    uint32_t dc[3 * kSeqThreads];
+    uint8_t sp[64];
+};
+
+__device__ __forceinline__ void fast_tables_init(FastTables& ft, const EntropySmem& sm, int nthreads) {
+    const uint32_t lut0 = smem_addr(&sm.lut[0]), info0 = smem_addr(ft.info);
+    const int nblk = sm.img.blocks_per_mcu;
+    for (int i = threadIdx.x; i < kMaxBlocksPerMcu; i += nthreads) {
+        const uint32_t info = sm.img.blk_info[i < nblk ? i : 0];
+        const uint32_t a_dc = lut0 + (info & 255u) * (uint32_t)sizeof(HuffLut), a_ac = lut0 + ((info >> 8) & 255u) * (uint32_t)sizeof(HuffLut);
+        ft.info[i] = make_uint4(a_dc | (a_ac << 16), (info >> 16) * 4u * kSeqThreads, info0 + (i + 1 < nblk ? i + 1 : 0) * 16u, (uint32_t)i);
+    }
+    for (int i = threadIdx.x; i < 64; i += nthreads) {
+        const uint32_t pos = sm.store_pos[i];
+        ft.sp[i] = (uint8_t)(((pos >> 3) << 4) | ((pos & 7u) << 1));
+    }
+}
+
+__device__ __forceinline__ const uint32_t* fast_word_ptr(const FastCtx& cx, uint32_t i) {
+    const uint32_t phys = (i & cx.gmask_inv) | ((i << 5) & cx.wmask5) | ((i >> cx.lw) & 31u);
+    return cx.words + phys;
+}
+__device__ __forceinline__ void fast_seek(const FastCtx& cx, FastState& st, uint32_t p) {
+    st.p = p;
+    st.widx = p >> 5;
+    const uint32_t off = p & 31u;
+    const uint32_t a = __ldg(fast_word_ptr(cx, st.widx)), b2 = __ldg(fast_word_ptr(cx, st.widx + 1));
+    st.hi = __funnelshift_l(b2, a, off);
+    st.lo = b2 << off;
+    st.avail = 64u - off;
+    st.widx += 2;
+    st.nextw = __ldg(fast_word_ptr(cx, st.widx));
+}
+__device__ __forceinline__ uint32_t fast_c(const FastState& st) { return lds32(st.info_ptr + 12u); }
+__device__ __forceinline__ void fast_load_block(const FastCtx& cx, FastState& st) {  // st.info_ptr changed: tables + DC slot
+    uint4 info;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(info.x), "=r"(info.y), "=r"(info.z), "=r"(info.w) : "r"(st.info_ptr));
+    sts32v(cx.dc_addr + st.dc_off, (uint32_t)st.dcur);
+    st.dc_off = info.y;
+    st.dcur = (int32_t)lds32v(cx.dc_addr + st.dc_off);
+    st.lut_dc = info.x & 0xffffu;
+    st.lut_ac = info.x >> 16;
+}
+__device__ __forceinline__ void fast_set_dc(const FastCtx& cx, FastState& st, int32_t d0, int32_t d1, int32_t d2) {
+    sts32v(cx.dc_addr, (uint32_t)d0);
+    sts32v(cx.dc_addr + 4u * kSeqThreads, (uint32_t)d1);
+    sts32v(cx.dc_addr + 8u * kSeqThreads, (uint32_t)d2);
+    st.dcur = (int32_t)lds32v(cx.dc_addr + st.dc_off);
+}
+__device__ __forceinline__ void fast_get_dc(const FastCtx& cx, const FastState& st, int32_t dc[3]) {
+    sts32v(cx.dc_addr + st.dc_off, (uint32_t)st.dcur);
+    dc[0] = (int32_t)lds32v(cx.dc_addr);
+    dc[1] = (int32_t)lds32v(cx.dc_addr + 4u * kSeqThreads);
+    dc[2] = (int32_t)lds32v(cx.dc_addr + 8u * kSeqThreads);
+}
+__device__ __forceinline__ void fast_set_segment(const FastCtx& cx, FastState& st, uint32_t k) {
+    st.seg = k;
+    st.seg_end = cx.seg[k + 1];
+    st.seg_lim = st.seg_end >= 7u ? st.seg_end - 7u : 0u;
+}
+
+// init_state() of jpgpu_core.h
+__device__ __forceinline__ void fast_init(const FastCtx& cx, FastState& st, uint32_t p, int32_t g, uint32_t c, int32_t d0,
+                                          int32_t d1, int32_t d2) {
+    st.flags = 0;
+    st.dc_off = 0;
+    st.dcur = 0;
+    if (p >= cx.stream_bits) {
+        st.seg = cx.nseg ? cx.nseg - 1 : 0;
+        st.seg_end = cx.stream_bits;
+        st.seg_lim = st.seg_end >= 7u ? st.seg_end - 7u : 0u;
+        st.p = p; st.widx = (p >> 5) + 2; st.avail = 64u - (p & 31u); st.hi = st.lo = st.nextw = 0u;
+        st.g = g;
+    } else {
+        uint32_t lo = 0, hi = cx.nseg;  // find_segment
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (cx.seg[mid] <= p) lo = mid; else hi = mid;
+        }
+        fast_set_segment(cx, st, lo);
+        fast_seek(cx, st, p);
+        if (cx.seg[lo] == p) {
+            st.g = (int32_t)(lo * cx.seg_units);
+            c = 0;
+            d0 = d1 = d2 = 0;
+            st.flags = kCrossed;
+        } else {
+            st.g = g;
+        }
+    }
+    st.info_ptr = cx.info_addr + c * 16u;
+    const uint4 info = *reinterpret_cast<const uint4*>(__cvta_shared_to_generic(st.info_ptr));
+    st.dc_off = info.y;
+    st.lut_dc = info.x & 0xffffu;
+    st.lut_ac = info.x >> 16;
+    fast_set_dc(cx, st, d0, d1, d2);
+}
+
+// Rare part of a step: fewer than 8 bits left in the restart interval. Returns 0 when decoding simply goes on.
+__device__ __forceinline__ uint32_t fast_interval_end(const FastCtx& cx, FastState& st) {
+    bool cross = st.p >= st.seg_end;
+    if (!cross) {
+        const uint32_t rem = st.seg_end - st.p;  // 1..7 pad bits must all be 1 (T.81 F.1.2.3)
+        cross = (st.hi >> (32u - rem)) == ((1u << rem) - 1u);
+    }
+    if (!cross) return 0u;
+    fast_seek(cx, st, st.seg_end);
+    if (st.seg + 1 >= cx.nseg) return kEvEnd;
+    fast_set_segment(cx, st, st.seg + 1);
+    st.g = (int32_t)(st.seg * cx.seg_units);
+    st.info_ptr = cx.info_addr;
+    fast_load_block(cx, st);
+    fast_set_dc(cx, st, 0, 0, 0);
+    st.flags |= kCrossed;
+    return kEvCross;
+}
+
+// Second-level LUT or canonical walk (huffman.rs:211-227) for codes longer than kLutBits.
+__device__ __forceinline__ uint32_t fast_long_code(const FastCtx& cx, FastState& st, uint32_t lut, uint32_t e) {
+    if (e != 0u) e = lds32(lut + (uint32_t)(kLutSize * 4) + (((e & 511u) + ((st.hi << kLutBits) >> (32u - ((e >> 9) & 7u)))) << 2));
+    if (e == 0u) {
+        e = huff_slow(cx.luts[(lut - cx.lut0_addr) / (uint32_t)sizeof(HuffLut)], st.hi);
+        if (e == 0u) { st.flags |= kStBadCode; e = kBadEntry; }
+    }
+    return e;
+}
+
+// CHECK = false: the caller guarantees st.p < st.seg_lim (no look at the interval end needed).
+template <bool WRITE, bool CHECK>
+__device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, uint32_t row_addr, uint32_t swz16, bool store_on) {
+    {   // refill: one word when 32 or fewer bits are left; the word was fetched one refill ago (predicated, no branch)
+        const bool need = st.avail <= 32u;
+        const uint32_t w = need ? st.nextw : 0u;
+        st.hi |= __funnelshift_rc(w, 0u, st.avail);
+        st.lo |= __funnelshift_lc(0u, w, 32u - st.avail);
+        st.avail += need ? 32u : 0u;
+        st.widx += need ? 1u : 0u;
+        const uint32_t* np = fast_word_ptr(cx, st.widx);
+        asm("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q ld.global.nc.u32 %0, [%1];\n}" : "+r"(st.nextw) : "l"(np), "r"((uint32_t)need));
+    }
+    if (CHECK && st.p >= st.seg_lim) {
+        const uint32_t ev = fast_interval_end(cx, st);
+        if (ev) return ev;
+    }
+    const uint32_t z = (uint32_t)st.g & 63u;
+    const uint32_t lut = z ? st.lut_ac : st.lut_dc;
+    uint32_t e = lds32(lut + ((st.hi >> (32 - kLutBits)) << 2));
+    if ((int32_t)e <= 0) e = fast_long_code(cx, st, lut, e);
+    const uint32_t tb = e & 255u, len = __byte_perm(e, 0u, 0x4441), adv = __byte_perm(e, 0u, 0x4442);
+    st.flags |= (e >> 21) & kStDcSize;            // bit 24 -> kStDcSize (8)
+    const uint32_t size = tb - len;
+    const uint32_t top = st.hi << len;            // len <= 16
+    const uint32_t v = __funnelshift_l(top, 0u, size);
+    const int32_t val = (int32_t)v - (int32_t)((uint32_t)((int32_t)~top >> 31) & ((1u << size) - 1u));
+    const bool is_dc = z == 0u;
+    st.dcur += is_dc ? val : 0;                   // decoder.rs:208-210
+    const uint32_t nz = z + adv;
+    if (WRITE) {
+        const uint32_t off = lds8(cx.sp_addr + min(nz - 1u, 63u));   // huffman.rs:183-189
+        sts16_if(row_addr + (off ^ swz16), (uint32_t)(is_dc ? st.dcur : val), store_on && (is_dc || val != 0));
+    }
+    st.hi = __funnelshift_lc(st.lo, st.hi, tb);
+    st.lo = __funnelshift_lc(0u, st.lo, tb);
+    st.avail -= tb;
+    st.p += tb;
+    if (nz >= 64u) {  // block complete
+        st.g = (st.g | 63) + 1;
+        st.info_ptr = lds32(st.info_ptr + 8u);
+        fast_load_block(cx, st);
+        return kEvBlock;
+    }
+    st.g += (int32_t)adv;
+    return 0u;
+}
+
+// Decode every symbol that starts before end_bit (sync pass form: the interval-end test is hoisted out of the loop).
+__device__ __forceinline__ void fast_run_to(const FastCtx& cx, FastState& st, uint32_t end_bit) {
+#pragma unroll 1
+    while (true) {
+        const uint32_t lim = min(end_bit, st.seg_lim);
+#pragma unroll 1
+        while (st.p < lim) fast_step<false, false>(cx, st, 0u, 0u, false);
+        if (st.p >= end_bit) return;
+        const uint32_t ev = fast_interval_end(cx, st);
+        if (ev & kEvEnd) return;
+        if (ev == 0u) fast_step<false, false>(cx, st, 0u, 0u, false);
+    }
+}
+
+__device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const EntropySmem& sm, const ImgDyn& d, const FastTables& ft) {
+    FastCtx cx;
+    cx.words = b.stream + sm.img.stream_off;
+    cx.lw = b.lw;
+    cx.wmask5 = ((1u << b.lw) - 1u) << 5;
+    cx.gmask_inv = ~((32u << b.lw) - 1u);
+    cx.seg = b.segtab + sm.img.seg_off;
+    cx.nseg = d.nseg;
+    cx.stream_bits = d.stream_bits;
+    cx.seg_units = sm.img.seg_units;
+    cx.info_addr = smem_addr(ft.info);
+    cx.dc_addr = smem_addr(ft.dc) + threadIdx.x * 4u;
+    cx.sp_addr = smem_addr(ft.sp);
+    cx.luts = sm.lut;
+    cx.lut0_addr = smem_addr(&sm.lut[0]);
+    // keep the per-symbol operands in registers instead of re-deriving them from the parameter bank every step
+    JPGPU_PIN64(cx.words);
+    JPGPU_PIN32(cx.lw); JPGPU_PIN32(cx.wmask5); JPGPU_PIN32(cx.gmask_inv);
+    JPGPU_PIN32(cx.dc_addr); JPGPU_PIN32(cx.sp_addr);
+    return cx;
+}
+
 // One thread per subsequence j.  It starts cold (block 0 of an MCU, zigzag 0) lookback_bits
 // before j*S; by the time it reaches j*S it has, with high probability, fallen into step with
 // the true decode (self-synchronisation of Huffman streams).  It records the state there (A),
 // decodes its own S bits and records the state at the end (B) with the advance in coefficient
 // positions and the DC sums in between.  Whether A was right is checked afterwards against the
-// predecessor's B (verify_scan_kernel); thread 0 and threads that passed a restart marker are
+// predecessor's B (verify kernels); thread 0 and threads that passed a restart marker are
 // right by construction.  All threads do the same amount of work: no rounds, no barriers.
 __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     __shared__ EntropySmem sm;
+    __shared__ FastTables ft;
     const SeqDesc sd = b.seqs[blockIdx.x];
     const uint32_t S = b.sub_bits;
     load_entropy_img(b, sd.img, sm, kSeqThreads);
@@ -199,22 +460,72 @@ __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
     load_entropy_luts(b, sm, kSeqThreads);
-    const DecCtx cx = make_ctx(b, sm, dyn);
+    fast_tables_init(ft, sm, kSeqThreads);
+    __syncthreads();
+    const FastCtx cx = make_fast_ctx(b, sm, dyn, ft);
     const uint32_t j = sd.first_sub + threadIdx.x;
     if (j >= nsub) return;
 
     const uint32_t own = j * S, p0 = own > b.lookback_bits ? own - b.lookback_bits : 0u;
-    DecState st;
-    init_state(cx, st, p0, 0, 0, 0, 0, 0);
-#pragma unroll 1
-    while (st.p < own) {
-        if (decode_symbol<false>(cx, st, nullptr, 0u, nullptr, false) & kEvEnd) break;
-    }
+    FastState st;
+    fast_init(cx, st, p0, 0, 0u, 0, 0, 0);
+    fast_run_to(cx, st, own);
     SubInfo rec;
     rec.pA = st.p;
-    rec.cz = pack_cz(st);
-    sync_span(cx, st, own + S, rec);
+    rec.cz = ((uint32_t)st.g & 63u) | (fast_c(st) << 6);
+    int32_t g_base = 0;                      // sync_span() of jpgpu_core.h
+    if (!(st.flags & kCrossed)) { g_base = st.g; fast_set_dc(cx, st, 0, 0, 0); }
+    fast_run_to(cx, st, min(own + S, cx.stream_bits));
+    rec.pB = st.p;
+    rec.cz |= ((((uint32_t)st.g & 63u) | (fast_c(st) << 6)) << 10) | (st.flags & kCrossed) | ((st.flags & kStBadCode) ? (1u << 31) : 0u);
+    rec.n = (st.flags & kCrossed) ? st.g : st.g - g_base;
+    fast_get_dc(cx, st, rec.dc);
+    rec.pad = 0;
     b.subs[sm.img.sub_off + j] = rec;
+}
+
+// Batch-wide verification: one thread per link; a broken link becomes a RepairJob carrying the state it has to
+// start from (a snapshot, so the repair never reads records another repair is writing).
+__global__ void __launch_bounds__(kSeqThreads) verify_list_kernel(BatchDev b, int round) {
+    const SeqDesc sd = b.seqs[blockIdx.x];
+    const ImgDev& im = b.imgs[sd.img];
+    const uint32_t S = b.sub_bits;
+    const uint32_t nsub = (b.dyn[sd.img].stream_bits + S - 1) / S;
+    const uint32_t j = sd.first_sub + threadIdx.x;
+    if (j == 0 || j >= nsub) return;
+    const SubInfo* subs = b.subs + im.sub_off;
+    const uint32_t start_p = subs[j - 1].pB, start_cz = (subs[j - 1].cz >> 10) & kCzMask;
+    if (start_p != subs[j].pA || start_cz != (subs[j].cz & kCzMask)) {
+        const uint32_t k = atomicAdd(b.repair_count + round, 1u);
+        b.repair_list[(size_t)round * b.n_subs + k] = RepairJob{sd.img, j, start_p, start_cz};
+    }
+}
+
+// One thread per broken link, full warps whatever image the links belong to: Huffman tables are read from
+// the batch-wide array in global memory (L1-resident) instead of a per-image copy in shared memory.
+__global__ void __launch_bounds__(kSeqThreads) repair_kernel(BatchDev b, int round) {
+    const uint32_t i = blockIdx.x * kSeqThreads + threadIdx.x;
+    if (i >= b.repair_count[round]) return;
+    const RepairJob job = b.repair_list[(size_t)round * b.n_subs + i];
+    const ImgDev& im = b.imgs[job.img];
+    const ImgDyn dyn = b.dyn[job.img];
+    DecCtx cx;
+    cx.words = b.stream + im.stream_off;
+    cx.lw = b.lw;
+    cx.seg = b.segtab + im.seg_off;
+    cx.nseg = dyn.nseg;
+    cx.stream_bits = dyn.stream_bits;
+    cx.seg_units = im.seg_units;
+    cx.nblk = im.blocks_per_mcu;
+    cx.luts = b.luts;
+    cx.blk_info = im.blk_info_g;
+    DecState st;
+    init_state(cx, st, job.p, (int32_t)(job.cz & 63u), (int32_t)(job.cz >> 6), 0, 0, 0);
+    SubInfo rec;
+    rec.pA = st.p;
+    rec.cz = job.cz;
+    sync_span(cx, st, (job.sub + 1) * b.sub_bits, rec);
+    b.subs[im.sub_off + job.sub] = rec;
 }
 
 constexpr int kInterThreads = 128;
@@ -308,12 +619,13 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
 // decodes the rest of it without storing, a lane that ends inside a block runs on until the
 // block is complete.
 struct WriteLayout {
-    uint32_t lut_bytes, buf_off, list_off, total;
+    uint32_t lut_bytes, ft_off, buf_off, list_off, total;
 };
 __host__ __device__ inline WriteLayout write_layout(uint32_t max_slots) {
     WriteLayout l;
     l.lut_bytes = (uint32_t)(sizeof(EntropySmem) - (kMaxLutSlots - max_slots) * sizeof(HuffLut));
-    l.buf_off = (l.lut_bytes + 127u) & ~127u;
+    l.ft_off = (l.lut_bytes + 15u) & ~15u;
+    l.buf_off = (l.ft_off + (uint32_t)sizeof(FastTables) + 127u) & ~127u;
     l.list_off = l.buf_off + kSeqThreads * kWriteBufs * 128u;
     l.total = l.list_off + (kSeqThreads / 32) * 32u * kWriteBufs * 8u;
     return l;
@@ -323,6 +635,7 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     EntropySmem& sm = *reinterpret_cast<EntropySmem*>(dyn_smem);
     const WriteLayout lay = write_layout(b.max_slots);
+    FastTables& ft = *reinterpret_cast<FastTables*>(dyn_smem + lay.ft_off);
     int16_t* const bufs = reinterpret_cast<int16_t*>(dyn_smem + lay.buf_off);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint2* const flist = reinterpret_cast<uint2*>(dyn_smem + lay.list_off) + warp * (32 * kWriteBufs);
@@ -334,10 +647,11 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
     load_entropy_luts(b, sm, kSeqThreads);
+    fast_tables_init(ft, sm, kSeqThreads);
     for (uint32_t i = tid; i < kSeqThreads * kWriteBufs * 8u; i += kSeqThreads)
         reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    const DecCtx cx = make_ctx(b, sm, dyn);
+    const FastCtx cx = make_fast_ctx(b, sm, dyn, ft);
     const uint32_t j = sd.first_sub + tid;
     bool active = j < nsub;
     if (!__ballot_sync(0xffffffffu, active)) return;
@@ -345,19 +659,21 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
     const int32_t total = (int32_t)sm.img.total_coefs;
     int16_t* __restrict__ coefs = b.coefs + sm.img.coef_off;
     const uint32_t end_bit = (j + 1) * S;
-    DecState st;
+    FastState st;
     bool store_on = true;
     if (active) {
         const SubInfo me = b.subs[sm.img.sub_off + j];
-        init_state(cx, st, me.pA, me.n, (int32_t)((me.cz >> 6) & 15u), me.dc[0], me.dc[1], me.dc[2]);
+        fast_init(cx, st, me.pA, me.n, (me.cz >> 6) & 15u, me.dc[0], me.dc[1], me.dc[2]);
         st.flags &= ~kCrossed;
         store_on = (st.g & 63) == 0;
         if (st.g >= total) active = false;
     } else {
-        st.p = 0; st.g = 0; st.flags = 0;
+        st.p = 0; st.g = 0; st.flags = 0; st.info_ptr = cx.info_addr; st.avail = 64; st.hi = st.lo = st.nextw = 0; st.widx = 0;
+        st.seg = 0; st.seg_end = st.seg_lim = 0; st.dcur = 0; st.dc_off = 0; st.lut_dc = st.lut_ac = cx.lut0_addr;
     }
     const int32_t g_start = st.g;
     const uint32_t row0 = tid * kWriteBufs;   // this lane's first buffer row (one row = one 128-byte block)
+    const uint32_t bufs_addr = smem_addr(bufs);
     uint32_t cur = 0, ndone = 0;
     uint32_t dest[kWriteBufs];
 #pragma unroll
@@ -371,7 +687,7 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
             if ((st.p >= end_bit && (st.g & 63) == 0) || st.g >= total) { active = false; break; }
             const uint32_t row = row0 + cur;
             const int32_t g_before = st.g;
-            const uint32_t ev = decode_symbol<true>(cx, st, bufs + row * 64u, row & 7u, sm.store_pos, store_on);
+            const uint32_t ev = fast_step<true, true>(cx, st, bufs_addr + row * 128u, (row & 7u) << 4, store_on);
             if (ev & kEvBlock) {
                 if (store_on) { dest[ndone] = (uint32_t)(g_before >> 6); ndone++; cur = cur + 1 == (uint32_t)kWriteBufs ? 0u : cur + 1; }
                 store_on = true;
@@ -719,6 +1035,11 @@ void launch_prepass(const BatchDev& b, cudaStream_t s) {
 }
 void launch_sync(const BatchDev& b, cudaStream_t s) {
     if (b.n_seqs) sync_kernel<<<b.n_seqs, kSeqThreads, 0, s>>>(b);
+}
+void launch_verify_repair(const BatchDev& b, cudaStream_t s, int round) {
+    if (!b.n_seqs || !b.flat_repair) return;
+    verify_list_kernel<<<b.n_seqs, kSeqThreads, 0, s>>>(b, round);
+    repair_kernel<<<(b.n_subs + kSeqThreads - 1) / kSeqThreads, kSeqThreads, 0, s>>>(b, round);
 }
 void launch_verify_scan(const BatchDev& b, cudaStream_t s) {
     if (b.n_images) verify_scan_kernel<<<b.n_images, kInterThreads, 0, s>>>(b);
