@@ -169,10 +169,8 @@ extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs,
     TRY(dev_alloc(b, &d.stream, p.stream_words + 64));
     TRY(dev_alloc(b, &d.segtab, p.seg_entries + 8));
     TRY(dev_alloc(b, &d.subs, p.sub_entries + 1));
-    d.n_subs = (uint32_t)p.sub_entries;
-    d.flat_repair = p.many_luts ? 0u : 1u;
-    TRY(dev_alloc(b, &d.repair_list, 2 * p.sub_entries + 2));
-    TRY(dev_alloc(b, &d.repair_count, 64));
+    d.seg_bits = p.seg_bits;
+    TRY(dev_alloc(b, &d.segs, p.sub_entries * (p.sub_bits / p.seg_bits) + 1));
     TRY(dev_alloc(b, &d.coefs, p.coef_elems + 64));
     TRY(dev_alloc(b, &d.rgb, p.rgb_bytes + 256));
 #undef TRY
@@ -224,11 +222,9 @@ extern "C" int jpgpu_batch_entropy(jpgpu_batch* b) {
     cudaStream_t s = ctx->stream;
     launch_prepass(b->dev, s);
     launch_sync(b->dev, s);
-    launch_verify_repair(b->dev, s, 0);
-    launch_verify_repair(b->dev, s, 1);
     launch_verify_scan(b->dev, s);
     CK(launch_decode_write(b->dev, s));
-    b->launches += 4 + (b->dev.flat_repair ? 4 : 0);
+    b->launches += 4;
     CK(cudaGetLastError());
     return JPGPU_OK;
 }

@@ -33,7 +33,8 @@ constexpr int kMaxLutSlots = 6;            // distinct (DC, AC) tables one image
 // look-back overhead per decoded bit, smaller means more threads for small batches.
 constexpr int kMinSubseqBits = 1024;
 constexpr int kMaxSubseqBits = 8192;
-constexpr int kDefaultLookbackBits = 2048; // cold-start distance before a subsequence (BatchDev::lookback_bits)
+constexpr int kDefaultLookbackBits = 2048;
+constexpr int kMinSegBits = 512;           // smallest checkpoint distance inside a subsequence (BatchDev::seg_bits) // cold-start distance before a subsequence (BatchDev::lookback_bits)
 constexpr int kSeqThreads = JPGPU_SEQ_THREADS;  // subsequences per sequence (= CTA size of the sync/write kernels)
 constexpr int kStreamPadWords = 8;         // zero words readable past every image's stream
 constexpr int kWriteBufs = 2;              // coefficient block buffers per lane in the write kernel
@@ -128,8 +129,20 @@ struct ImgDyn {
 // A = state at the first symbol starting at or after j*S, reached from a cold start
 // lookback_bits earlier; B = state at the first symbol starting at or after (j+1)*S.
 // The chain is consistent where A(j) == B(j-1).
-struct RepairJob {     // a broken link found by verify_list_kernel: decode subsequence `sub` of `img` again from (p, cz)
-    uint32_t img, sub, p, cz;
+struct RepairJob {     // a broken link: decode subsequence `sub` again from (p, cz) = B of its predecessor
+    uint32_t sub, p, cz;
+};
+
+// A subsequence is recorded in S/C segments of C bits (C = BatchDev::seg_bits): the state at
+// the first symbol at or after each C-bit boundary plus what was counted inside the segment.
+// A repair walker that reaches a boundary in the recorded state can stop there: from that
+// point on the recorded decode was already the true one.
+struct SegRec {
+    uint32_t p;        // bit position at the end of the segment
+    uint32_t cz;       // bits 0-5 z, 6-9 c at the end; bit 30: a restart interval began inside (n/dc absolute)
+    int32_t n;         // coefficient positions advanced inside the segment (or absolute position at its end)
+    int32_t dc[3];     // sum of DC differences per component inside the segment (or absolute predictors)
+    uint32_t pad[2];
 };
 
 struct SubInfo {
@@ -381,21 +394,50 @@ JPGPU_HD uint32_t decode_symbol(const DecCtx& cx, DecState& st, int16_t* blk, ui
 
 JPGPU_HD uint32_t pack_cz(const DecState& st) { return (uint32_t)(st.g & 63) | ((uint32_t)st.c << 6); }
 
-// Synchronisation decode of one subsequence record: from the state in `st` (standing at A)
-// to the first symbol at or after end_bit (B).  Fills pB, cz(B), n, dc; keeps pA/cz(A) as given.
-JPGPU_HD void sync_span(const DecCtx& cx, DecState& st, uint32_t end_bit, SubInfo& out) {
-    int32_t g_base = 0;
-    if (!(st.flags & kCrossed)) { g_base = st.g; st.dc0 = st.dc1 = st.dc2 = 0; }  // else: absolute state, keep it
+// Synchronisation decode of one segment: from the state in `st` to the first symbol at or after end_bit.
+JPGPU_HD void sync_segment(const DecCtx& cx, DecState& st, uint32_t end_bit, SegRec& r) {
+    const int32_t g_base = st.g;
+    st.dc0 = st.dc1 = st.dc2 = 0;
+    st.flags &= ~kCrossed;
     if (end_bit > cx.stream_bits) end_bit = cx.stream_bits;
 #pragma unroll 1
     while (st.p < end_bit) {
         if (decode_symbol<false>(cx, st, nullptr, 0u, nullptr, false) & kEvEnd) break;
     }
-    out.pB = st.p;
-    out.cz = (out.cz & kCzMask) | (pack_cz(st) << 10) | (st.flags & kCrossed) | ((st.flags & kStBadCode) ? (1u << 31) : 0u);
-    out.n = (st.flags & kCrossed) ? st.g : st.g - g_base;
-    out.dc[0] = st.dc0; out.dc[1] = st.dc1; out.dc[2] = st.dc2;
-    out.pad = 0;
+    r.p = st.p;
+    r.cz = pack_cz(st) | (st.flags & kCrossed);
+    r.n = (st.flags & kCrossed) ? st.g : st.g - g_base;
+    r.dc[0] = st.dc0; r.dc[1] = st.dc1; r.dc[2] = st.dc2;
+    r.pad[0] = r.pad[1] = 0;
+}
+
+// Accumulate segment / subsequence advances: a restart interval makes the values absolute.
+JPGPU_HD void fold_advance(int32_t acc[4], uint32_t& crossed, uint32_t cz, int32_t n, const int32_t dc[3]) {
+    if (cz & kCrossed) { acc[0] = n; acc[1] = dc[0]; acc[2] = dc[1]; acc[3] = dc[2]; crossed = kCrossed; }
+    else { acc[0] += n; acc[1] += dc[0]; acc[2] += dc[1]; acc[3] += dc[2]; }
+}
+
+// Decode subsequence [own, own + S) from the state in `st` (standing at A; rec.pA / rec.cz(A) set by the
+// caller), segment by segment.  compare = false: first decode, every segment is recorded.  compare = true:
+// repair walk; stops at the first segment end where it meets the recorded state.  Fills the rest of rec.
+JPGPU_HD void sync_subsequence(const DecCtx& cx, DecState& st, uint32_t own, uint32_t S, uint32_t C, SegRec* segs,
+                               bool compare, SubInfo& rec) {
+    const uint32_t nsegs = S / C;
+#pragma unroll 1
+    for (uint32_t k = 0; k < nsegs; k++) {
+        SegRec r;
+        sync_segment(cx, st, own + (k + 1) * C, r);
+        const bool met = compare && segs[k].p == r.p && ((segs[k].cz ^ r.cz) & kCzMask) == 0u;
+        segs[k] = r;
+        if (met) break;
+    }
+    int32_t acc[4] = {0, 0, 0, 0};
+    uint32_t crossed = 0;
+    for (uint32_t k = 0; k < nsegs; k++) fold_advance(acc, crossed, segs[k].cz, segs[k].n, segs[k].dc);
+    rec.pB = segs[nsegs - 1].p;
+    rec.cz = (rec.cz & kCzMask) | ((segs[nsegs - 1].cz & kCzMask) << 10) | crossed;
+    rec.n = acc[0]; rec.dc[0] = acc[1]; rec.dc[1] = acc[2]; rec.dc[2] = acc[3];
+    rec.pad = 0;
 }
 
 // ------------------------------------------------------------------- IDCT

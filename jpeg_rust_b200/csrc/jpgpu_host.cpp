@@ -177,6 +177,11 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
     }
     plan.sub_bits = sub_bits;
     plan.lookback_bits = choose_lookback_bits();
+    plan.seg_bits = std::max<uint32_t>(kMinSegBits, sub_bits / 8);
+    if (const char* e = getenv("JPGPU_SEG_BITS")) {
+        const long v = atol(e);
+        if (v >= 64 && v <= (long)sub_bits && (v & (v - 1)) == 0) plan.seg_bits = (uint32_t)v;
+    }
     uint32_t lw = 0;
     while ((32u << lw) < sub_bits) lw++;
     plan.lw = lw;

@@ -35,6 +35,7 @@ struct HostPlan {
     uint32_t sub_bits = kMinSubseqBits;
     uint32_t lw = 5;             // log2(words per subsequence)
     uint32_t lookback_bits = kDefaultLookbackBits;
+    uint32_t seg_bits = kMinSegBits;  // checkpoint distance inside a subsequence
     uint32_t max_slots = 1;      // most Huffman LUT slots any image references
     bool many_luts = false;      // more than 256 distinct LUTs in the batch: the flat repair kernel is skipped
     std::vector<ImgDev> imgs;

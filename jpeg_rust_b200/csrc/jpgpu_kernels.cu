@@ -46,7 +46,6 @@ __global__ void __launch_bounds__(kPreThreads) prepass_kernel(BatchDev b) {
     uint8_t* stage_bytes = reinterpret_cast<uint8_t*>(s_stage);
     uint32_t emitted = 0, rst_total = 0;
     if (tid == 0) s_status = 0;
-    if (blockIdx.x == 0 && tid < 2) b.repair_count[tid] = 0u;
     __syncthreads();
 
     for (uint32_t base = 0; base < n; base += kPreChunk) {
@@ -443,13 +442,62 @@ __device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const Entrop
     return cx;
 }
 
+// sync_segment() / sync_subsequence() of jpgpu_core.h on the fast step.
+__device__ __forceinline__ void fast_sync_segment(const FastCtx& cx, FastState& st, uint32_t end_bit, SegRec& r) {
+    const int32_t g_base = st.g;
+    fast_set_dc(cx, st, 0, 0, 0);
+    st.flags &= ~kCrossed;
+    fast_run_to(cx, st, min(end_bit, cx.stream_bits));
+    r.p = st.p;
+    r.cz = ((uint32_t)st.g & 63u) | (fast_c(st) << 6) | (st.flags & kCrossed);
+    r.n = (st.flags & kCrossed) ? st.g : st.g - g_base;
+    fast_get_dc(cx, st, r.dc);
+    r.pad[0] = r.pad[1] = 0;
+}
+__device__ __forceinline__ void store_segrec(SegRec* dst, const SegRec& r) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4(r.p, r.cz, (uint32_t)r.n, (uint32_t)r.dc[0]);
+    d[1] = make_uint4((uint32_t)r.dc[1], (uint32_t)r.dc[2], 0u, 0u);
+}
+__device__ __forceinline__ void fast_sync_subsequence(const FastCtx& cx, FastState& st, uint32_t own, uint32_t S, uint32_t C,
+                                                      SegRec* segs, bool compare, SubInfo& rec) {
+    const uint32_t nsegs = S / C;
+    int32_t acc[4] = {0, 0, 0, 0};
+    uint32_t crossed = 0, k = 0, last_p = st.p, last_cz = 0;
+#pragma unroll 1
+    for (; k < nsegs; k++) {
+        SegRec r;
+        fast_sync_segment(cx, st, own + (k + 1) * C, r);
+        bool met = false;
+        if (compare) {
+            const uint2 old = *reinterpret_cast<const uint2*>(segs + k);
+            met = old.x == r.p && ((old.y ^ r.cz) & kCzMask) == 0u;
+        }
+        store_segrec(segs + k, r);
+        fold_advance(acc, crossed, r.cz, r.n, r.dc);
+        last_p = r.p; last_cz = r.cz;
+        if (met) { k++; break; }
+    }
+#pragma unroll 1
+    for (; k < nsegs; k++) {  // met the recorded decode: the remaining segments stand as they are
+        const SegRec r = segs[k];
+        fold_advance(acc, crossed, r.cz, r.n, r.dc);
+        last_p = r.p; last_cz = r.cz;
+    }
+    rec.pB = last_p;
+    rec.cz = (rec.cz & kCzMask) | ((last_cz & kCzMask) << 10) | crossed;
+    rec.n = acc[0]; rec.dc[0] = acc[1]; rec.dc[1] = acc[2]; rec.dc[2] = acc[3];
+    rec.pad = 0;
+}
+
 // One thread per subsequence j.  It starts cold (block 0 of an MCU, zigzag 0) lookback_bits
 // before j*S; by the time it reaches j*S it has, with high probability, fallen into step with
 // the true decode (self-synchronisation of Huffman streams).  It records the state there (A),
 // decodes its own S bits and records the state at the end (B) with the advance in coefficient
-// positions and the DC sums in between.  Whether A was right is checked afterwards against the
-// predecessor's B (verify kernels); thread 0 and threads that passed a restart marker are
-// right by construction.  All threads do the same amount of work: no rounds, no barriers.
+// positions and the DC sums in between, segment by segment.  Whether A was right is checked
+// afterwards against the predecessor's B (verify_scan_kernel); thread 0 and threads that
+// passed a restart marker are right by construction.  All threads do the same amount of
+// work: no rounds, no barriers.
 __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     __shared__ EntropySmem sm;
     __shared__ FastTables ft;
@@ -473,125 +521,80 @@ __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     SubInfo rec;
     rec.pA = st.p;
     rec.cz = ((uint32_t)st.g & 63u) | (fast_c(st) << 6);
-    int32_t g_base = 0;                      // sync_span() of jpgpu_core.h
-    if (!(st.flags & kCrossed)) { g_base = st.g; fast_set_dc(cx, st, 0, 0, 0); }
-    fast_run_to(cx, st, min(own + S, cx.stream_bits));
-    rec.pB = st.p;
-    rec.cz |= ((((uint32_t)st.g & 63u) | (fast_c(st) << 6)) << 10) | (st.flags & kCrossed) | ((st.flags & kStBadCode) ? (1u << 31) : 0u);
-    rec.n = (st.flags & kCrossed) ? st.g : st.g - g_base;
-    fast_get_dc(cx, st, rec.dc);
-    rec.pad = 0;
+    fast_sync_subsequence(cx, st, own, S, b.seg_bits, b.segs + (size_t)(sm.img.sub_off + j) * (S / b.seg_bits), false, rec);
     b.subs[sm.img.sub_off + j] = rec;
 }
 
-// Batch-wide verification: one thread per link; a broken link becomes a RepairJob carrying the state it has to
-// start from (a snapshot, so the repair never reads records another repair is writing).
-__global__ void __launch_bounds__(kSeqThreads) verify_list_kernel(BatchDev b, int round) {
-    const SeqDesc sd = b.seqs[blockIdx.x];
-    const ImgDev& im = b.imgs[sd.img];
-    const uint32_t S = b.sub_bits;
-    const uint32_t nsub = (b.dyn[sd.img].stream_bits + S - 1) / S;
-    const uint32_t j = sd.first_sub + threadIdx.x;
-    if (j == 0 || j >= nsub) return;
-    const SubInfo* subs = b.subs + im.sub_off;
-    const uint32_t start_p = subs[j - 1].pB, start_cz = (subs[j - 1].cz >> 10) & kCzMask;
-    if (start_p != subs[j].pA || start_cz != (subs[j].cz & kCzMask)) {
-        const uint32_t k = atomicAdd(b.repair_count + round, 1u);
-        b.repair_list[(size_t)round * b.n_subs + k] = RepairJob{sd.img, j, start_p, start_cz};
-    }
-}
+constexpr int kInterThreads = kSeqThreads;
+constexpr int kRepairJobs = 2 * kInterThreads;
 
-// One thread per broken link, full warps whatever image the links belong to: Huffman tables are read from
-// the batch-wide array in global memory (L1-resident) instead of a per-image copy in shared memory.
-__global__ void __launch_bounds__(kSeqThreads) repair_kernel(BatchDev b, int round) {
-    const uint32_t i = blockIdx.x * kSeqThreads + threadIdx.x;
-    if (i >= b.repair_count[round]) return;
-    const RepairJob job = b.repair_list[(size_t)round * b.n_subs + i];
-    const ImgDev& im = b.imgs[job.img];
-    const ImgDyn dyn = b.dyn[job.img];
-    DecCtx cx;
-    cx.words = b.stream + im.stream_off;
-    cx.lw = b.lw;
-    cx.seg = b.segtab + im.seg_off;
-    cx.nseg = dyn.nseg;
-    cx.stream_bits = dyn.stream_bits;
-    cx.seg_units = im.seg_units;
-    cx.nblk = im.blocks_per_mcu;
-    cx.luts = b.luts;
-    cx.blk_info = im.blk_info_g;
-    DecState st;
-    init_state(cx, st, job.p, (int32_t)(job.cz & 63u), (int32_t)(job.cz >> 6), 0, 0, 0);
-    SubInfo rec;
-    rec.pA = st.p;
-    rec.cz = job.cz;
-    sync_span(cx, st, (job.sub + 1) * b.sub_bits, rec);
-    b.subs[im.sub_off + job.sub] = rec;
-}
-
-constexpr int kInterThreads = 128;
-
-// One CTA per image. (1) Verification: the chain is right where A(j) == B(j-1).  A broken link
-// (look-back too short for that spot) is repaired by decoding subsequence j again from B(j-1);
-// repeated until the chain holds — the lowest broken link always starts from a correct state, so
-// every iteration extends the correct prefix.  (2) Exclusive prefix scan turning per-subsequence
-// advances into the absolute state at every A (segmented where a restart interval began).
+// One CTA per image. (1) Verification: the chain is right where A(j) == B(j-1).  The broken links
+// (look-back too short for that spot) are collected and each is decoded again from B(j-1) by one
+// thread, segment by segment, until the walk meets the decode recorded for subsequence j — from
+// there on that record was already the true one.  Repeated until the chain holds: the lowest
+// broken link always starts from a correct state, so every iteration extends the correct prefix.
+// (2) Exclusive prefix scan turning per-subsequence advances into the absolute state at every A
+// (segmented where a restart interval began).
 __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) {
     __shared__ EntropySmem sm;
+    __shared__ FastTables ft;
     __shared__ int32_t s_agg[kInterThreads][5];
+    __shared__ RepairJob s_jobs[kRepairJobs];
+    __shared__ uint32_t s_count;
 
     const uint32_t img = blockIdx.x;
     const uint32_t S = b.sub_bits;
     load_entropy_img(b, img, sm, kInterThreads);
     const ImgDyn dyn = b.dyn[img];
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
-    const DecCtx cx = make_ctx(b, sm, dyn);
     SubInfo* subs = b.subs + sm.img.sub_off;
     const uint32_t tid = threadIdx.x;
 
     bool loaded = false;
 #pragma unroll 1
-    for (uint32_t iter = 0; iter < nsub; iter++) {
-        int any = 0;
-#pragma unroll 1
-        for (uint32_t j0 = 1; j0 < nsub; j0 += kInterThreads) {  // reads of a pass precede its writes
-            const uint32_t j = j0 + tid;
-            bool broken = false;
-            uint32_t start_p = 0, start_cz = 0;
-            if (j < nsub) {
-                const SubInfo prev = subs[j - 1];
-                const SubInfo mine = subs[j];
-                start_p = prev.pB;
-                start_cz = (prev.cz >> 10) & kCzMask;
-                broken = start_p != mine.pA || start_cz != (mine.cz & kCzMask);
+    for (uint32_t iter = 0; iter <= nsub; iter++) {
+        if (tid == 0) s_count = 0u;
+        __syncthreads();
+        for (uint32_t j = 1 + tid; j < nsub; j += kInterThreads) {
+            const uint32_t start_p = subs[j - 1].pB, start_cz = (subs[j - 1].cz >> 10) & kCzMask;
+            if (start_p != subs[j].pA || start_cz != (subs[j].cz & kCzMask)) {
+                const uint32_t k = atomicAdd(&s_count, 1u);
+                if (k < (uint32_t)kRepairJobs) s_jobs[k] = RepairJob{j, start_p, start_cz};  // the rest waits for the next iteration
             }
-            if (!__syncthreads_or(broken ? 1 : 0)) continue;
-            any = 1;
-            if (!loaded) { load_entropy_luts(b, sm, kInterThreads); loaded = true; }
-            if (broken) {
-                DecState st;
-                init_state(cx, st, start_p, (int32_t)(start_cz & 63u), (int32_t)(start_cz >> 6), 0, 0, 0);
-                SubInfo rec;
-                rec.pA = st.p;
-                rec.cz = start_cz;
-                sync_span(cx, st, (j + 1) * S, rec);
-                subs[j] = rec;
-            }
-            __syncthreads();
         }
-        if (!any) break;
+        __syncthreads();
+        const uint32_t njobs = min(s_count, (uint32_t)kRepairJobs);
+        if (njobs == 0u) break;
+        if (!loaded) {
+            load_entropy_luts(b, sm, kInterThreads);
+            fast_tables_init(ft, sm, kInterThreads);
+            __syncthreads();
+            loaded = true;
+        }
+        const FastCtx cx = make_fast_ctx(b, sm, dyn, ft);
+        for (uint32_t i = tid; i < njobs; i += kInterThreads) {
+            const RepairJob job = s_jobs[i];
+            FastState st;
+            fast_init(cx, st, job.p, (int32_t)(job.cz & 63u), job.cz >> 6, 0, 0, 0);
+            SubInfo rec;
+            rec.pA = st.p;
+            rec.cz = job.cz;
+            fast_sync_subsequence(cx, st, job.sub * S, S, b.seg_bits, b.segs + (size_t)(sm.img.sub_off + job.sub) * (S / b.seg_bits), true, rec);
+            subs[job.sub] = rec;
+        }
+        __syncthreads();
     }
 
     // ---- exclusive scan: n/dc become the absolute state at A (segmented by `crossed`)
     const uint32_t chunk = (nsub + kInterThreads - 1) / kInterThreads;
     const uint32_t lo = tid * chunk, hi = min(nsub, lo + chunk);
     int32_t acc[4] = {0, 0, 0, 0};
-    int32_t crossed = 0;
+    uint32_t crossed = 0;
     for (uint32_t jj = lo; jj < hi; jj++) {
         const SubInfo s = subs[jj];
-        if (s.cz & kCrossed) { acc[0] = s.n; acc[1] = s.dc[0]; acc[2] = s.dc[1]; acc[3] = s.dc[2]; crossed = 1; }
-        else { acc[0] += s.n; acc[1] += s.dc[0]; acc[2] += s.dc[1]; acc[3] += s.dc[2]; }
+        fold_advance(acc, crossed, s.cz, s.n, s.dc);
     }
-    s_agg[tid][0] = acc[0]; s_agg[tid][1] = acc[1]; s_agg[tid][2] = acc[2]; s_agg[tid][3] = acc[3]; s_agg[tid][4] = crossed;
+    s_agg[tid][0] = acc[0]; s_agg[tid][1] = acc[1]; s_agg[tid][2] = acc[2]; s_agg[tid][3] = acc[3]; s_agg[tid][4] = (int32_t)crossed;
     __syncthreads();
     int32_t run[4] = {0, 0, 0, 0};
     for (uint32_t k = 0; k < tid; k++) {  // exclusive prefix over the preceding chunks
@@ -601,8 +604,8 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
     for (uint32_t jj = lo; jj < hi; jj++) {
         SubInfo s = subs[jj];
         const int32_t at_a[4] = {run[0], run[1], run[2], run[3]};
-        if (s.cz & kCrossed) { run[0] = s.n; run[1] = s.dc[0]; run[2] = s.dc[1]; run[3] = s.dc[2]; }
-        else { run[0] += s.n; run[1] += s.dc[0]; run[2] += s.dc[1]; run[3] += s.dc[2]; }
+        uint32_t dummy = 0;
+        fold_advance(run, dummy, s.cz, s.n, s.dc);
         s.n = at_a[0]; s.dc[0] = at_a[1]; s.dc[1] = at_a[2]; s.dc[2] = at_a[3];
         subs[jj] = s;
     }
@@ -1035,11 +1038,6 @@ void launch_prepass(const BatchDev& b, cudaStream_t s) {
 }
 void launch_sync(const BatchDev& b, cudaStream_t s) {
     if (b.n_seqs) sync_kernel<<<b.n_seqs, kSeqThreads, 0, s>>>(b);
-}
-void launch_verify_repair(const BatchDev& b, cudaStream_t s, int round) {
-    if (!b.n_seqs || !b.flat_repair) return;
-    verify_list_kernel<<<b.n_seqs, kSeqThreads, 0, s>>>(b, round);
-    repair_kernel<<<(b.n_subs + kSeqThreads - 1) / kSeqThreads, kSeqThreads, 0, s>>>(b, round);
 }
 void launch_verify_scan(const BatchDev& b, cudaStream_t s) {
     if (b.n_images) verify_scan_kernel<<<b.n_images, kInterThreads, 0, s>>>(b);

@@ -31,10 +31,8 @@ struct BatchDev {        // device pointers of one planned batch
     uint32_t lw;         // log2(sub_bits / 32): words per subsequence
     uint32_t lookback_bits;
     uint32_t max_slots;
-    uint32_t n_subs;          // total subsequence capacity of the batch
-    uint32_t flat_repair;     // 1 = run the batch-wide verify/repair rounds (needs < 256 distinct LUTs)
-    RepairJob* repair_list;   // 2 rounds x n_subs entries
-    uint32_t* repair_count;   // 2 counters, zeroed by the pre-pass
+    uint32_t seg_bits;        // checkpoint distance inside a subsequence (divides sub_bits)
+    SegRec* segs;             // sub_bits / seg_bits records per subsequence
     // images grouped by colour-kernel variant (ImgKind)
     const uint32_t* kind_imgs[kNumKinds];
     uint32_t kind_count[kNumKinds];
@@ -52,9 +50,7 @@ cudaError_t init_constants();
 void launch_prepass(const BatchDev& b, cudaStream_t s);
 // Stage 1b: look-back synchronisation, one thread per subsequence.
 void launch_sync(const BatchDev& b, cudaStream_t s);
-// Stage 1c: chain verification; broken links of the whole batch are collected and decoded again by full warps
-// (two rounds), what is still broken after that is mended by the per-image CTA that also runs the prefix scan.
-void launch_verify_repair(const BatchDev& b, cudaStream_t s, int round);
+// Stage 1c: chain verification, repair of the links the look-back did not synchronise, prefix scan; one CTA per image.
 void launch_verify_scan(const BatchDev& b, cudaStream_t s);
 // Stage 1d: final decode, whole coefficient blocks written to HBM.
 cudaError_t launch_decode_write(const BatchDev& b, cudaStream_t s);

@@ -24,6 +24,7 @@ struct SimBatch {
     std::vector<uint32_t> stream;
     std::vector<uint32_t> segtab;
     std::vector<SubInfo> subs;
+    std::vector<SegRec> segs;
     std::vector<ImgDyn> dyn;
     std::vector<int16_t> coefs;
     std::vector<uint8_t> rgb;
@@ -123,57 +124,43 @@ void sim_sync(SimBatch& sb, const SeqDesc& sd) {
         SubInfo rec;
         rec.pA = st.p;
         rec.cz = pack_cz(st);
-        sync_span(cx, st, own + S, rec);
+        const uint32_t C = sb.plan.seg_bits;
+        sync_subsequence(cx, st, own, S, C, sb.segs.data() + (size_t)(im.sub_off + j) * (S / C), false, rec);
         sb.subs[im.sub_off + j] = rec;
         sb.sync_decodes++;
     }
 }
 
-constexpr uint32_t kSimInterThreads = 128;  // = kInterThreads of jpgpu_kernels.cu
-
-// mirrors verify_scan_kernel
+// mirrors verify_scan_kernel (the order in which the broken links of one iteration are repaired does not matter:
+// every repair starts from a snapshot taken before any of them writes)
 void sim_verify_scan(SimBatch& sb, size_t img) {
     std::vector<HuffLut> slots;
     load_slots(sb, img, slots);
     const ImgDev& im = sb.plan.imgs[img];
     const ImgDyn dyn = sb.dyn[img];
-    const uint32_t S = sb.plan.sub_bits;
+    const uint32_t S = sb.plan.sub_bits, C = sb.plan.seg_bits;
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     const DecCtx cx = make_ctx(sb, img, slots.data());
     SubInfo* subs = sb.subs.data() + im.sub_off;
     uint32_t iters = 0;
-    for (uint32_t iter = 0; iter < nsub; iter++) {
-        bool any = false;
-        for (uint32_t j0 = 1; j0 < nsub; j0 += kSimInterThreads) {
-            // read phase of the pass
-            struct Job { bool broken; uint32_t p, cz; };
-            Job jobs[kSimInterThreads];
-            for (uint32_t tid = 0; tid < kSimInterThreads; tid++) {
-                const uint32_t j = j0 + tid;
-                jobs[tid].broken = false;
-                if (j >= nsub) continue;
-                const SubInfo& prev = subs[j - 1];
-                const SubInfo& mine = subs[j];
-                jobs[tid].p = prev.pB;
-                jobs[tid].cz = (prev.cz >> 10) & kCzMask;
-                jobs[tid].broken = jobs[tid].p != mine.pA || jobs[tid].cz != (mine.cz & kCzMask);
-            }
-            // write phase
-            for (uint32_t tid = 0; tid < kSimInterThreads; tid++) {
-                if (!jobs[tid].broken) continue;
-                any = true;
-                const uint32_t j = j0 + tid;
-                DecState st;
-                init_state(cx, st, jobs[tid].p, (int32_t)(jobs[tid].cz & 63u), (int32_t)(jobs[tid].cz >> 6), 0, 0, 0);
-                SubInfo rec;
-                rec.pA = st.p;
-                rec.cz = jobs[tid].cz;
-                sync_span(cx, st, (j + 1) * S, rec);
-                subs[j] = rec;
-                sb.repairs++;
-            }
+    for (uint32_t iter = 0; iter <= nsub; iter++) {
+        std::vector<RepairJob> jobs;
+        for (uint32_t j = 1; j < nsub; j++) {
+            const uint32_t start_p = subs[j - 1].pB, start_cz = (subs[j - 1].cz >> 10) & kCzMask;
+            if (start_p != subs[j].pA || start_cz != (subs[j].cz & kCzMask)) jobs.push_back(RepairJob{j, start_p, start_cz});
         }
-        if (!any) break;
+        if (jobs.size() > 256) jobs.resize(256);  // kRepairJobs
+        if (jobs.empty()) break;
+        for (const RepairJob& job : jobs) {
+            DecState st;
+            init_state(cx, st, job.p, (int32_t)(job.cz & 63u), (int32_t)(job.cz >> 6), 0, 0, 0);
+            SubInfo rec;
+            rec.pA = st.p;
+            rec.cz = job.cz;
+            sync_subsequence(cx, st, job.sub * S, S, C, sb.segs.data() + (size_t)(im.sub_off + job.sub) * (S / C), true, rec);
+            subs[job.sub] = rec;
+            sb.repairs++;
+        }
         iters++;
     }
     sb.repair_iters = std::max(sb.repair_iters, iters);
@@ -182,8 +169,8 @@ void sim_verify_scan(SimBatch& sb, size_t img) {
     for (uint32_t jj = 0; jj < nsub; jj++) {
         SubInfo& s = subs[jj];
         const int32_t at_a[4] = {run[0], run[1], run[2], run[3]};
-        if (s.cz & kCrossed) { run[0] = s.n; run[1] = s.dc[0]; run[2] = s.dc[1]; run[3] = s.dc[2]; }
-        else { run[0] += s.n; run[1] += s.dc[0]; run[2] += s.dc[1]; run[3] += s.dc[2]; }
+        uint32_t dummy = 0;
+        fold_advance(run, dummy, s.cz, s.n, s.dc);
         s.n = at_a[0]; s.dc[0] = at_a[1]; s.dc[1] = at_a[2]; s.dc[2] = at_a[3];
     }
 }
@@ -398,6 +385,7 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
     sb.stream.assign(p.stream_words + 64, 0);
     sb.segtab.assign(p.seg_entries + 8, 0);
     sb.subs.assign(p.sub_entries + 1, SubInfo());
+    sb.segs.assign(p.sub_entries * (p.sub_bits / p.seg_bits) + 1, SegRec());
     sb.dyn.assign(n + 1, ImgDyn());
     sb.coefs.assign(p.coef_elems + 64, 0x5555);  // the write pass must produce every coefficient itself
     sb.rgb.assign(p.rgb_bytes + 256, 0);
