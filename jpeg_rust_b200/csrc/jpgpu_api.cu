@@ -3,6 +3,7 @@
 // without a usable sm_100 device every entry point returns JPGPU_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -170,6 +171,7 @@ extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs,
     TRY(dev_alloc(b, &d.segtab, p.seg_entries + 8));
     TRY(dev_alloc(b, &d.subs, p.sub_entries + 1));
     d.seg_bits = p.seg_bits;
+    d.write_mode = getenv("JPGPU_WRITE_MODE") ? (uint32_t)atoi(getenv("JPGPU_WRITE_MODE")) : 0u;
     TRY(dev_alloc(b, &d.segs, p.sub_entries * (p.sub_bits / p.seg_bits) + 1));
     TRY(dev_alloc(b, &d.coefs, p.coef_elems + 64));
     TRY(dev_alloc(b, &d.rgb, p.rgb_bytes + 256));

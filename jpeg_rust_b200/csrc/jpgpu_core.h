@@ -33,12 +33,12 @@ constexpr int kMaxLutSlots = 6;            // distinct (DC, AC) tables one image
 // look-back overhead per decoded bit, smaller means more threads for small batches.
 constexpr int kMinSubseqBits = 1024;
 constexpr int kMaxSubseqBits = 8192;
-constexpr int kDefaultLookbackBits = 2048;
+constexpr int kDefaultLookbackBits = 1024;
 constexpr int kMinSegBits = 512;           // smallest checkpoint distance inside a subsequence (BatchDev::seg_bits) // cold-start distance before a subsequence (BatchDev::lookback_bits)
 constexpr int kSeqThreads = JPGPU_SEQ_THREADS;  // subsequences per sequence (= CTA size of the sync/write kernels)
 constexpr int kStreamPadWords = 8;         // zero words readable past every image's stream
-constexpr int kWriteBufs = 2;              // coefficient block buffers per lane in the write kernel
-constexpr int kPhaseSymbols = 12;          // symbols a lane decodes between two cooperative flushes
+constexpr int kWriteBufs = 1;              // coefficient block buffers per lane in the write kernel
+constexpr int kPhaseSymbols = 5;           // symbols a lane decodes between two cooperative flushes
 
 // status bits accumulated per image on the device (mapped to JPGPU_* by the host)
 enum : uint32_t {

@@ -358,9 +358,39 @@ __device__ __forceinline__ uint32_t fast_long_code(const FastCtx& cx, FastState&
     return e;
 }
 
+// Per-lane output state of the write kernel: NBUF block buffers (rows of 128 bytes in shared memory) used as a ring.
+template <int NBUF>
+struct WriteLane {
+    static_assert(NBUF >= 1 && NBUF <= 2, "two completion slots");
+    uint32_t row_addr, swz16;  // shared address / piece swizzle of the buffer being filled
+    uint32_t rows_addr, row0;  // address of this lane's first row, its row number
+    uint32_t cur, ndone;       // ring position, completed (unflushed) buffers
+    uint32_t dest0, dest1;     // arena block index of each completed buffer, oldest first (0xffffffff = discard); NBUF <= 2
+    uint32_t end_bit;
+    int32_t total;
+    bool store_on, active, run;
+    __device__ __forceinline__ void select(uint32_t c) {
+        cur = c;
+        row_addr = rows_addr + c * 128u;
+        swz16 = ((row0 + c) & 7u) << 4;
+    }
+    // the buffer being filled is complete (block index d) or to be discarded; z == 0 now
+    __device__ __forceinline__ void close_block(uint32_t d, uint32_t p, int32_t g) {
+        if (store_on) {
+            if (ndone == 0u) dest0 = d; else dest1 = d;
+            ndone++;
+            select(cur + 1 == (uint32_t)NBUF ? 0u : cur + 1);
+        }
+        store_on = true;
+        if (p >= end_bit || g >= total) { active = false; run = false; }   // finished: block boundary past the subsequence / scan
+        else if (ndone == (uint32_t)NBUF) run = false;                         // out of buffers until the next flush
+    }
+};
+struct NoLane {};
+
 // CHECK = false: the caller guarantees st.p < st.seg_lim (no look at the interval end needed).
-template <bool WRITE, bool CHECK>
-__device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, uint32_t row_addr, uint32_t swz16, bool store_on) {
+template <bool WRITE, bool CHECK, typename LANE>
+__device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, LANE& wl) {
     {   // refill: one word when 32 or fewer bits are left; the word was fetched one refill ago (predicated, no branch)
         const bool need = st.avail <= 32u;
         const uint32_t w = need ? st.nextw : 0u;
@@ -388,9 +418,9 @@ __device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, 
     const bool is_dc = z == 0u;
     st.dcur += is_dc ? val : 0;                   // decoder.rs:208-210
     const uint32_t nz = z + adv;
-    if (WRITE) {
+    if constexpr (WRITE) {
         const uint32_t off = lds8(cx.sp_addr + min(nz - 1u, 63u));   // huffman.rs:183-189
-        sts16_if(row_addr + (off ^ swz16), (uint32_t)(is_dc ? st.dcur : val), store_on && (is_dc || val != 0));
+        sts16_if(wl.row_addr + (off ^ wl.swz16), (uint32_t)(is_dc ? st.dcur : val), wl.store_on && (is_dc || val != 0));
     }
     st.hi = __funnelshift_lc(st.lo, st.hi, tb);
     st.lo = __funnelshift_lc(0u, st.lo, tb);
@@ -400,6 +430,7 @@ __device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, 
         st.g = (st.g | 63) + 1;
         st.info_ptr = lds32(st.info_ptr + 8u);
         fast_load_block(cx, st);
+        if constexpr (WRITE) wl.close_block((uint32_t)(st.g >> 6) - 1u, st.p, st.g);
         return kEvBlock;
     }
     st.g += (int32_t)adv;
@@ -408,15 +439,16 @@ __device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, 
 
 // Decode every symbol that starts before end_bit (sync pass form: the interval-end test is hoisted out of the loop).
 __device__ __forceinline__ void fast_run_to(const FastCtx& cx, FastState& st, uint32_t end_bit) {
+    NoLane nl;
 #pragma unroll 1
     while (true) {
         const uint32_t lim = min(end_bit, st.seg_lim);
 #pragma unroll 1
-        while (st.p < lim) fast_step<false, false>(cx, st, 0u, 0u, false);
+        while (st.p < lim) fast_step<false, false>(cx, st, nl);
         if (st.p >= end_bit) return;
         const uint32_t ev = fast_interval_end(cx, st);
         if (ev & kEvEnd) return;
-        if (ev == 0u) fast_step<false, false>(cx, st, 0u, 0u, false);
+        if (ev == 0u) fast_step<false, false>(cx, st, nl);
     }
 }
 
@@ -624,24 +656,25 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
 struct WriteLayout {
     uint32_t lut_bytes, ft_off, buf_off, list_off, total;
 };
-__host__ __device__ inline WriteLayout write_layout(uint32_t max_slots) {
+__host__ __device__ inline WriteLayout write_layout(uint32_t max_slots, uint32_t nbuf) {
     WriteLayout l;
     l.lut_bytes = (uint32_t)(sizeof(EntropySmem) - (kMaxLutSlots - max_slots) * sizeof(HuffLut));
     l.ft_off = (l.lut_bytes + 15u) & ~15u;
     l.buf_off = (l.ft_off + (uint32_t)sizeof(FastTables) + 127u) & ~127u;
-    l.list_off = l.buf_off + kSeqThreads * kWriteBufs * 128u;
-    l.total = l.list_off + (kSeqThreads / 32) * 32u * kWriteBufs * 8u;
+    l.list_off = l.buf_off + kSeqThreads * nbuf * 128u;
+    l.total = l.list_off + (kSeqThreads / 32) * 32u * nbuf * 8u;
     return l;
 }
 
+template <int NBUF, int PHASE>
 __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     EntropySmem& sm = *reinterpret_cast<EntropySmem*>(dyn_smem);
-    const WriteLayout lay = write_layout(b.max_slots);
+    const WriteLayout lay = write_layout(b.max_slots, NBUF);
     FastTables& ft = *reinterpret_cast<FastTables*>(dyn_smem + lay.ft_off);
     int16_t* const bufs = reinterpret_cast<int16_t*>(dyn_smem + lay.buf_off);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint2* const flist = reinterpret_cast<uint2*>(dyn_smem + lay.list_off) + warp * (32 * kWriteBufs);
+    uint2* const flist = reinterpret_cast<uint2*>(dyn_smem + lay.list_off) + warp * (32 * NBUF);
 
     const SeqDesc sd = b.seqs[blockIdx.x];
     const uint32_t S = b.sub_bits;
@@ -651,7 +684,7 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
     if (sd.first_sub >= nsub) return;
     load_entropy_luts(b, sm, kSeqThreads);
     fast_tables_init(ft, sm, kSeqThreads);
-    for (uint32_t i = tid; i < kSeqThreads * kWriteBufs * 8u; i += kSeqThreads)
+    for (uint32_t i = tid; i < kSeqThreads * NBUF * 8u; i += kSeqThreads)
         reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const FastCtx cx = make_fast_ctx(b, sm, dyn, ft);
@@ -669,43 +702,48 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
         fast_init(cx, st, me.pA, me.n, (me.cz >> 6) & 15u, me.dc[0], me.dc[1], me.dc[2]);
         st.flags &= ~kCrossed;
         store_on = (st.g & 63) == 0;
-        if (st.g >= total) active = false;
+        if (st.g >= total || (st.p >= end_bit && store_on)) active = false;
     } else {
         st.p = 0; st.g = 0; st.flags = 0; st.info_ptr = cx.info_addr; st.avail = 64; st.hi = st.lo = st.nextw = 0; st.widx = 0;
         st.seg = 0; st.seg_end = st.seg_lim = 0; st.dcur = 0; st.dc_off = 0; st.lut_dc = st.lut_ac = cx.lut0_addr;
     }
     const int32_t g_start = st.g;
-    const uint32_t row0 = tid * kWriteBufs;   // this lane's first buffer row (one row = one 128-byte block)
-    const uint32_t bufs_addr = smem_addr(bufs);
-    uint32_t cur = 0, ndone = 0;
-    uint32_t dest[kWriteBufs];
-#pragma unroll
-    for (int i = 0; i < kWriteBufs; i++) dest[i] = 0u;
+    WriteLane<NBUF> wl;
+    wl.row0 = tid * NBUF;   // this lane's first buffer row (one row = one 128-byte block)
+    wl.rows_addr = smem_addr(bufs) + wl.row0 * 128u;
+    wl.select(0u);
+    wl.ndone = 0;
+    wl.dest0 = wl.dest1 = 0u;
+    wl.end_bit = end_bit;
+    wl.total = total;
+    wl.store_on = store_on;
+    wl.active = active;
 
 #pragma unroll 1
     while (true) {
-        // ---- phase A: every lane decodes up to kPhaseSymbols symbols into its own buffers
+        // ---- phase A: every lane decodes up to PHASE symbols into its own buffers.  Whether a lane is finished
+        // (block boundary at or past the end of its subsequence, or past the last block of the scan) or out of
+        // buffers can only change when a block completes, so it is only looked at there (WriteLane::close_block).
+        wl.run = wl.active;
 #pragma unroll 1
-        for (int k = 0; k < kPhaseSymbols && active && ndone < (uint32_t)kWriteBufs; k++) {
-            if ((st.p >= end_bit && (st.g & 63) == 0) || st.g >= total) { active = false; break; }
-            const uint32_t row = row0 + cur;
-            const int32_t g_before = st.g;
-            const uint32_t ev = fast_step<true, true>(cx, st, bufs_addr + row * 128u, (row & 7u) << 4, store_on);
-            if (ev & kEvBlock) {
-                if (store_on) { dest[ndone] = (uint32_t)(g_before >> 6); ndone++; cur = cur + 1 == (uint32_t)kWriteBufs ? 0u : cur + 1; }
-                store_on = true;
-            } else if (ev & kEvCross) {
-                // a valid stream only gets here between blocks; drop a half-written block of a corrupt one
-                if ((g_before & 63) != 0 && store_on) { dest[ndone] = 0xffffffffu; ndone++; cur = cur + 1 == (uint32_t)kWriteBufs ? 0u : cur + 1; }
-                store_on = true;
-            } else if (ev & kEvEnd) {
-                active = false;
+        for (int k = 0; k < PHASE; k++) {
+            if (wl.run) {
+                const int32_t g_before = st.g;
+                const uint32_t ev = fast_step<true, true>(cx, st, wl);
+                if (ev & (kEvCross | kEvEnd)) {  // rare: restart interval / end of data
+                    if (ev & kEvEnd) { wl.active = false; wl.run = false; }
+                    // a valid stream only changes interval between blocks; drop a half-written block of a corrupt one
+                    else if ((g_before & 63) != 0) wl.close_block(0xffffffffu, st.p, st.g);
+                    else { wl.store_on = true; if (st.p >= end_bit || st.g >= total) { wl.active = false; wl.run = false; } }
+                }
             }
         }
+        const uint32_t ndone = wl.ndone, cur = wl.cur, row0 = wl.row0;
+        active = wl.active;
         // ---- phase B: the warp flushes all completed blocks, 8 lanes per block
         uint32_t offs = 0, count = 0;
 #pragma unroll
-        for (int i = 0; i < kWriteBufs; i++) {
+        for (int i = 0; i < NBUF; i++) {
             const uint32_t m = __ballot_sync(0xffffffffu, ndone > (uint32_t)i);
             offs += __popc(m & ((1u << lane) - 1u));
             count += __popc(m);
@@ -715,12 +753,12 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
             continue;
         }
         {
-            uint32_t r = cur + kWriteBufs - ndone;  // oldest completed buffer
+            uint32_t r = cur + NBUF - ndone;  // oldest completed buffer
 #pragma unroll
-            for (int i = 0; i < kWriteBufs; i++) {
+            for (int i = 0; i < NBUF; i++) {
                 if ((uint32_t)i < ndone) {
-                    if (r >= (uint32_t)kWriteBufs) r -= kWriteBufs;
-                    flist[offs + i] = make_uint2(row0 + r, dest[i]);
+                    if (r >= (uint32_t)NBUF) r -= NBUF;
+                    flist[offs + i] = make_uint2(row0 + r, i == 0 ? wl.dest0 : wl.dest1);
                     r++;
                 }
             }
@@ -736,7 +774,7 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
             if (e.y != 0xffffffffu) reinterpret_cast<uint4*>(coefs + (size_t)e.y * 64u)[piece] = v;
         }
         __syncwarp();
-        ndone = 0;
+        wl.ndone = 0;
     }
     if (j < nsub) {
         uint32_t bits = st.flags & (kStBadCode | kStDcSize);
@@ -1042,17 +1080,27 @@ void launch_sync(const BatchDev& b, cudaStream_t s) {
 void launch_verify_scan(const BatchDev& b, cudaStream_t s) {
     if (b.n_images) verify_scan_kernel<<<b.n_images, kInterThreads, 0, s>>>(b);
 }
-cudaError_t launch_decode_write(const BatchDev& b, cudaStream_t s) {
-    if (!b.n_seqs) return cudaSuccess;
-    const WriteLayout lay = write_layout(b.max_slots);
+template <int NBUF, int PHASE>
+static cudaError_t launch_write_variant(const BatchDev& b, cudaStream_t s) {
+    const WriteLayout lay = write_layout(b.max_slots, NBUF);
     static uint32_t configured = 0;
     if (lay.total > configured) {
-        cudaError_t e = cudaFuncSetAttribute(decode_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+        cudaError_t e = cudaFuncSetAttribute(decode_write_kernel<NBUF, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
         if (e != cudaSuccess) return e;
         configured = lay.total;
     }
-    decode_write_kernel<<<b.n_seqs, kSeqThreads, lay.total, s>>>(b);
+    decode_write_kernel<NBUF, PHASE><<<b.n_seqs, kSeqThreads, lay.total, s>>>(b);
     return cudaSuccess;
+}
+cudaError_t launch_decode_write(const BatchDev& b, cudaStream_t s) {
+    if (!b.n_seqs) return cudaSuccess;
+    switch (b.write_mode) {   // experiment switch (env JPGPU_WRITE_MODE); 0 is the tuned default
+        case 1: return launch_write_variant<1, 4>(b, s);
+        case 2: return launch_write_variant<1, 6>(b, s);
+        case 3: return launch_write_variant<2, 8>(b, s);
+        case 4: return launch_write_variant<2, 12>(b, s);
+        default: return launch_write_variant<kWriteBufs, kPhaseSymbols>(b, s);
+    }
 }
 
 int launch_idct_colour(const BatchDev& b, cudaStream_t s) {

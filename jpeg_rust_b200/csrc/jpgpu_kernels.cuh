@@ -31,6 +31,7 @@ struct BatchDev {        // device pointers of one planned batch
     uint32_t lw;         // log2(sub_bits / 32): words per subsequence
     uint32_t lookback_bits;
     uint32_t max_slots;
+    uint32_t write_mode;      // decode_write_kernel variant (experiments)
     uint32_t seg_bits;        // checkpoint distance inside a subsequence (divides sub_bits)
     SegRec* segs;             // sub_bits / seg_bits records per subsequence
     // images grouped by colour-kernel variant (ImgKind)
