@@ -793,9 +793,11 @@ constexpr int kScrRowPitch = 12;     // floats; 4*odd -> conflict-free 128-bit r
 constexpr int kScrBlkPitch = 104;    // floats; 8 mod 32 -> conflict-free column writes across the 4 blocks of a warp
 constexpr int kOutPitch = 400;       // bytes per staged output row (128 px * 3 = 384, padded)
 
-__device__ __forceinline__ uint32_t f32_to_u8_sat(float x) {  // decoder.rs:382-390: clamp to [0,255], truncate
-    uint32_t r;
-    asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(x));
+// decoder.rs:382-390 (clamp to [0,255], truncate) in two steps: truncation to s32 here, the clamp in pack4's
+// saturating byte pack (I2IP) - 6 instructions per 4 output bytes.
+__device__ __forceinline__ int32_t f32_to_u8_sat(float x) {
+    int32_t r;
+    asm("cvt.rzi.s32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
 
@@ -832,8 +834,11 @@ __device__ __forceinline__ void block_idct(const uint4 raw, const float* __restr
                dc_bias, out);
 }
 
-__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    return a | (b << 8) | (c << 16) | (d << 24);
+__device__ __forceinline__ uint32_t pack4(int32_t a, int32_t b, int32_t c, int32_t d) {  // bytes a (lowest) .. d, each clamped
+    uint32_t t, r;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(d), "r"(c), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(t));
+    return r;
 }
 
 // Tile = 128 pixels x (8*VY) rows = 16/HY MCUs.  Phase A: chroma blocks -> shared f32
@@ -892,6 +897,18 @@ __global__ void __launch_bounds__(kIdctThreads) idct_colour_kernel(BatchDev b, c
         mcu_of[CH_PASSES + p] = m; blk_of[CH_PASSES + p] = m * NB + yb % NY;
     }
 
+    // copy-out plan of this thread: which 16-byte vectors of the staged tile it stores (tile-invariant)
+    constexpr int NV = (MH * 24 + kIdctThreads - 1) / kIdctThreads;
+    const bool vec_ok = ((W * 3u) & 15u) == 0u;
+    uint32_t co_rk[NV], co_s[NV], co_g[NV];
+#pragma unroll
+    for (int n = 0; n < NV; n++) {
+        const uint32_t i = (uint32_t)tid + (uint32_t)n * kIdctThreads, r = i / 24u, k = i - r * 24u;
+        co_rk[n] = i < (uint32_t)MH * 24u ? (r | (k << 8)) : 255u;   // row 255 never passes the bounds test
+        co_s[n] = r * kOutPitch + k * 16u;
+        co_g[n] = r * W * 3u + k * 16u;
+    }
+
     uint4 cur[NL], nxt[NL];
     auto issue_loads = [&](uint32_t tl, uint4 (&dst)[NL]) {
         const uint32_t tx = tl % tiles_x, ty = tl / tiles_x;
@@ -931,7 +948,7 @@ __global__ void __launch_bounds__(kIdctThreads) idct_colour_kernel(BatchDev b, c
             float y[8];
             block_idct(cur[CH_PASSES + p], qt_l, t, scr_w, scr_r, 128.0f, y);
             const int px0 = (m * HY + bx) * 8, row = by * 8 + t;
-            uint32_t r8[8], g8[8], b8[8];
+            int32_t r8[8], g8[8], b8[8];
             if (GRAY) {
 #pragma unroll
                 for (int x = 0; x < 8; x++) { r8[x] = f32_to_u8_sat(y[x]); g8[x] = r8[x]; b8[x] = r8[x]; }  // decoder.rs:317-324
@@ -972,14 +989,14 @@ __global__ void __launch_bounds__(kIdctThreads) idct_colour_kernel(BatchDev b, c
         const uint32_t wpx = min(128u, W - x0), rows = min((uint32_t)MH, H - y0);
         const uint32_t rowbytes = wpx * 3u;
         uint8_t* const tile_out = rgb + ((size_t)y0 * W + x0) * 3u;
-        if (((W * 3u) & 15u) == 0u && (rowbytes & 15u) == 0u) {
+        if (vec_ok && (rowbytes & 15u) == 0u) {
             const uint32_t vpr = rowbytes >> 4;  // <= 24
 #pragma unroll
-            for (uint32_t i = tid; i < (uint32_t)MH * 24u; i += kIdctThreads) {
-                const uint32_t r = i / 24u, k = i - r * 24u;
+            for (int n = 0; n < NV; n++) {
+                const uint32_t r = co_rk[n] & 255u, k = co_rk[n] >> 8;
                 if (r < rows && k < vpr) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(s_out + r * kOutPitch + k * 16);
-                    *reinterpret_cast<uint4*>(tile_out + (size_t)r * W * 3u + k * 16u) = v;
+                    const uint4 v = *reinterpret_cast<const uint4*>(s_out + co_s[n]);
+                    *reinterpret_cast<uint4*>(tile_out + co_g[n]) = v;
                 }
             }
         } else {
@@ -1047,7 +1064,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_colour_kernel(BatchDev 
             v[c][0] = v[c][1] = v[c][2] = v[c][3] = none;
         }
     }
-    uint32_t r8[4], g8[4], b8[4];
+    int32_t r8[4], g8[4], b8[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         if (ncomp == 1) {
@@ -1066,7 +1083,9 @@ __global__ void __launch_bounds__(kGatherThreads) gather_colour_kernel(BatchDev 
         o32[1] = pack4(g8[1], b8[1], r8[2], g8[2]);
         o32[2] = pack4(b8[2], r8[3], g8[3], b8[3]);
     } else {
-        for (uint32_t k = 0; q * 4u + k < npix; k++) { out[3 * k] = (uint8_t)r8[k]; out[3 * k + 1] = (uint8_t)g8[k]; out[3 * k + 2] = (uint8_t)b8[k]; }
+        for (uint32_t k = 0; q * 4u + k < npix; k++) {
+            out[3 * k] = (uint8_t)min(max(r8[k], 0), 255); out[3 * k + 1] = (uint8_t)min(max(g8[k], 0), 255); out[3 * k + 2] = (uint8_t)min(max(b8[k], 0), 255);
+        }
     }
 }
 
