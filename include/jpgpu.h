@@ -157,12 +157,21 @@ int jpgpu_decode_file(jpgpu_ctx *ctx, const uint8_t *file, size_t len, uint32_t 
  * A batch may be uploaded/decoded repeatedly (buffers are reused). */
 int jpgpu_batch_create(jpgpu_ctx *ctx, const jpgpu_image_desc *descs, size_t n, jpgpu_batch **out);
 void jpgpu_batch_destroy(jpgpu_batch *b);
+/* Plans a different set of images on an existing batch object: device arenas are kept and only grow, so a long
+ * job runs wave after wave through one batch (replan -> upload -> decode -> download).  Synchronises the stream. */
+int jpgpu_batch_replan(jpgpu_batch *b, const jpgpu_image_desc *descs, size_t n);
 /* Host->device copy of every image's scan bytes (async on the context stream).
  * desc.scan memory must stay valid until the stream has passed this point. */
 int jpgpu_batch_upload(jpgpu_batch *b);
 /* Alternative to upload: the raw scan bytes of all images are already in device
  * memory, image i at dev_base + offsets[i] (length = descs[i].scan_len). */
 int jpgpu_batch_set_device_scans(jpgpu_batch *b, const void *dev_base, const uint64_t *offsets);
+/* Wave decoding (16 384 x 1080p do not fit one GPU at once): direct the RGB output of the next
+ * decode to caller-owned device memory instead of the batch's own arena — image i goes to dev_base + the same
+ * 256-byte aligned offsets jpgpu_batch_device_rgb() reports relative to image 0.  One planned batch (coefficient
+ * and bitstream arenas sized for one wave) then serves wave after wave: set_device_scans / upload, set_device_output,
+ * decode.  NULL restores the batch's own arena.  `capacity` is checked against jpgpu_batch_stats()[2] rounded up. */
+int jpgpu_batch_set_device_output(jpgpu_batch *b, void *dev_base, size_t capacity);
 int jpgpu_batch_entropy(jpgpu_batch *b); /* stage 1: unstuff/RST pre-pass, self-synchronising Huffman decode */
 int jpgpu_batch_idct(jpgpu_batch *b);    /* stage 2+3: dequant, IDCT, upsample, YCbCr->RGB, interleaved store */
 int jpgpu_batch_decode(jpgpu_batch *b);  /* entropy + idct */

@@ -7,8 +7,9 @@ JPEGImage / JPEGDecoder interface, and the offline synthetic-input generator.
 from . import _ffi
 from ._ffi import EXT_DRI, EXT_NONE, EXT_SKIP_APPN, LAYOUT_REF, LAYOUT_SPEC, JpgpuError
 from .jpeg import (Batch, Context, FrameComponentHeader, FrameHeader, HuffmanTable, JPEGDecoder, JPEGImage,
-                   JPEGPanic, ScanComponentHeader, ScanHeader, context, decode_batch, parse_descriptor, shard_range)
+                   JPEGPanic, ScanComponentHeader, ScanHeader, context, decode_batch, decode_waves, parse_descriptor,
+                   shard_range)
 
 __all__ = ["_ffi", "EXT_DRI", "EXT_NONE", "EXT_SKIP_APPN", "LAYOUT_REF", "LAYOUT_SPEC", "JpgpuError", "Batch",
            "Context", "FrameComponentHeader", "FrameHeader", "HuffmanTable", "JPEGDecoder", "JPEGImage", "JPEGPanic",
-           "ScanComponentHeader", "ScanHeader", "context", "decode_batch", "parse_descriptor", "shard_range"]
+           "ScanComponentHeader", "ScanHeader", "context", "decode_batch", "decode_waves", "parse_descriptor", "shard_range"]

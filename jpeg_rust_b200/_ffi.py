@@ -78,11 +78,13 @@ def lib():
         L.jpgpu_decode_file.argtypes = [vp, vp, sz, C.c_uint32, C.c_uint32, vp, sz, C.POINTER(C.c_uint32),
                                         C.POINTER(C.c_uint32), C.POINTER(sz)]
         L.jpgpu_batch_create.argtypes = [vp, C.POINTER(ImageDesc), sz, C.POINTER(vp)]
+        L.jpgpu_batch_replan.argtypes = [vp, C.POINTER(ImageDesc), sz]
         L.jpgpu_batch_destroy.argtypes = [vp]
         L.jpgpu_batch_destroy.restype = None
         for name in ("upload", "entropy", "idct", "decode"):
             getattr(L, "jpgpu_batch_" + name).argtypes = [vp]
         L.jpgpu_batch_set_device_scans.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+        L.jpgpu_batch_set_device_output.argtypes = [vp, vp, sz]
         L.jpgpu_batch_download.argtypes = [vp, C.POINTER(vp)]
         L.jpgpu_batch_device_rgb.restype = vp
         L.jpgpu_batch_device_rgb.argtypes = [vp, sz, C.POINTER(sz)]
@@ -108,7 +110,7 @@ EXPORTED_SYMBOLS = [
     "jpgpu_parse", "jpgpu_geometry", "jpgpu_status_string", "jpgpu_abi_version",
     "jpgpu_create", "jpgpu_destroy", "jpgpu_last_error", "jpgpu_set_stream", "jpgpu_sync",
     "jpgpu_decode", "jpgpu_decode_file",
-    "jpgpu_batch_create", "jpgpu_batch_destroy", "jpgpu_batch_upload", "jpgpu_batch_set_device_scans",
+    "jpgpu_batch_create", "jpgpu_batch_replan", "jpgpu_batch_destroy", "jpgpu_batch_upload", "jpgpu_batch_set_device_scans", "jpgpu_batch_set_device_output",
     "jpgpu_batch_entropy", "jpgpu_batch_idct", "jpgpu_batch_decode", "jpgpu_batch_download",
     "jpgpu_batch_device_rgb", "jpgpu_batch_results", "jpgpu_batch_coefficients", "jpgpu_batch_stats",
     "jpgpu_batch_launch_count",

@@ -28,9 +28,13 @@ struct jpgpu_batch {
     std::vector<const uint8_t*> host_scan;
     std::vector<size_t> host_scan_len;
     BatchDev dev;
-    std::vector<void*> allocs;
+    struct Arena { void* p = nullptr; size_t cap = 0; };
+    enum { kImgs, kSeqs, kLuts, kQt, kKind0, kGmap = kKind0 + kNumKinds, kSamples, kRaw, kDyn, kStream, kSegtab, kSubs, kSegs, kCoefs,
+           kRgb, kNumArenas };
+    Arena arena[kNumArenas];   // device allocations, grown on demand by jpgpu_batch_replan()
     uint64_t launches = 0;
     size_t coef_bytes = 0;
+    uint8_t* own_rgb = nullptr;
     bool decoded = false;
 };
 
@@ -51,21 +55,31 @@ int fail(jpgpu_ctx* c, cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return fail(ctx, e_, #call);   \
     } while (0)
 
+// Makes arena `which` at least `count` elements of T large (contents undefined after growth).
 template <typename T>
-int dev_alloc(jpgpu_batch* b, T** out, size_t count) {
+int dev_ensure(jpgpu_batch* b, int which, T** out, size_t count) {
     jpgpu_ctx* ctx = b->ctx;
-    void* p = nullptr;
-    CK(cudaMalloc(&p, std::max<size_t>(count * sizeof(T), 256)));
-    b->allocs.push_back(p);
-    *out = reinterpret_cast<T*>(p);
+    jpgpu_batch::Arena& a = b->arena[which];
+    const size_t need = std::max<size_t>(count * sizeof(T), 256);
+    if (a.cap < need) {
+        if (a.p) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaFree(a.p));
+            a.p = nullptr;
+            a.cap = 0;
+        }
+        CK(cudaMalloc(&a.p, need));
+        a.cap = need;
+    }
+    *out = reinterpret_cast<T*>(a.p);
     return JPGPU_OK;
 }
 
 template <typename T>
-int dev_upload(jpgpu_batch* b, const T** out, const std::vector<T>& v) {
+int dev_upload(jpgpu_batch* b, int which, const T** out, const std::vector<T>& v) {
     jpgpu_ctx* ctx = b->ctx;
     T* p = nullptr;
-    int st = dev_alloc(b, &p, v.size());
+    int st = dev_ensure(b, which, &p, v.size());
     if (st != JPGPU_OK) return st;
     if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     *out = p;
@@ -124,23 +138,25 @@ extern "C" void jpgpu_batch_destroy(jpgpu_batch* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    for (void* p : b->allocs) cudaFree(p);
+    for (auto& a : b->arena) if (a.p) cudaFree(a.p);
     delete b;
 }
 
-extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs, size_t n, jpgpu_batch** out) {
-    if (!ctx || !out || (!descs && n)) return JPGPU_ERR_INVALID_ARG;
-    *out = nullptr;
+extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs, size_t n) {
+    if (!b || (!descs && n)) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
-    jpgpu_batch* b = new jpgpu_batch();
-    b->ctx = ctx;
+    // the previous plan's host vectors may still be the source of an asynchronous upload
+    CK(cudaStreamSynchronize(ctx->stream));
     b->n = n;
     int st = build_plan(descs, n, b->plan);
-    if (st != JPGPU_OK) { delete b; return st; }
+    if (st != JPGPU_OK) return st;
     b->host_scan.resize(n);
     b->host_scan_len.resize(n);
     for (size_t i = 0; i < n; i++) { b->host_scan[i] = descs[i].scan; b->host_scan_len[i] = descs[i].scan_len; }
     HostPlan& p = b->plan;
+    const bool external_rgb = b->dev.rgb && b->dev.rgb != b->own_rgb;
+    uint8_t* const ext_rgb = b->dev.rgb;
     memset(&b->dev, 0, sizeof b->dev);
     BatchDev& d = b->dev;
     d.n_images = (uint32_t)n;
@@ -149,44 +165,56 @@ extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs,
     d.lw = p.lw;
     d.lookback_bits = p.lookback_bits;
     d.max_slots = p.max_slots;
-#define TRY(x) do { st = (x); if (st != JPGPU_OK) { jpgpu_batch_destroy(b); return st; } } while (0)
-    TRY(dev_upload(b, &d.imgs, p.imgs));
-    TRY(dev_upload(b, &d.seqs, p.seqs));
-    TRY(dev_upload(b, &d.luts, p.luts));
-    TRY(dev_upload(b, &d.qt, p.qt));
+    d.seg_bits = p.seg_bits;
+    d.write_mode = getenv("JPGPU_WRITE_MODE") ? (uint32_t)atoi(getenv("JPGPU_WRITE_MODE")) : 0u;
+#define TRY(x) do { st = (x); if (st != JPGPU_OK) return st; } while (0)
+    TRY(dev_upload(b, jpgpu_batch::kImgs, &d.imgs, p.imgs));
+    TRY(dev_upload(b, jpgpu_batch::kSeqs, &d.seqs, p.seqs));
+    TRY(dev_upload(b, jpgpu_batch::kLuts, &d.luts, p.luts));
+    TRY(dev_upload(b, jpgpu_batch::kQt, &d.qt, p.qt));
     for (int k = 0; k < kNumKinds; k++) {
         d.kind_count[k] = (uint32_t)p.kind_imgs[k].size();
         d.kind_max_tiles[k] = p.kind_max_tiles[k];
-        TRY(dev_upload(b, &d.kind_imgs[k], p.kind_imgs[k]));
+        TRY(dev_upload(b, jpgpu_batch::kKind0 + k, &d.kind_imgs[k], p.kind_imgs[k]));
     }
-    TRY(dev_upload(b, &d.gmap, p.gmap));
+    TRY(dev_upload(b, jpgpu_batch::kGmap, &d.gmap, p.gmap));
     d.gather_max_blocks = p.gather_max_blocks;
     d.gather_max_quads = p.gather_max_quads;
-    if (p.sample_floats) TRY(dev_alloc(b, &d.samples, p.sample_floats));
+    if (p.sample_floats) TRY(dev_ensure(b, jpgpu_batch::kSamples, &d.samples, p.sample_floats));
     uint8_t* raw = nullptr;
-    TRY(dev_alloc(b, &raw, p.raw_bytes + 64));
+    TRY(dev_ensure(b, jpgpu_batch::kRaw, &raw, p.raw_bytes + 64));
     d.raw = raw;
-    TRY(dev_alloc(b, &d.dyn, n + 1));
-    TRY(dev_alloc(b, &d.stream, p.stream_words + 64));
-    TRY(dev_alloc(b, &d.segtab, p.seg_entries + 8));
-    TRY(dev_alloc(b, &d.subs, p.sub_entries + 1));
-    d.seg_bits = p.seg_bits;
-    d.write_mode = getenv("JPGPU_WRITE_MODE") ? (uint32_t)atoi(getenv("JPGPU_WRITE_MODE")) : 0u;
-    TRY(dev_alloc(b, &d.segs, p.sub_entries * (p.sub_bits / p.seg_bits) + 1));
-    TRY(dev_alloc(b, &d.coefs, p.coef_elems + 64));
-    TRY(dev_alloc(b, &d.rgb, p.rgb_bytes + 256));
+    TRY(dev_ensure(b, jpgpu_batch::kDyn, &d.dyn, n + 1));
+    TRY(dev_ensure(b, jpgpu_batch::kStream, &d.stream, p.stream_words + 64));
+    TRY(dev_ensure(b, jpgpu_batch::kSegtab, &d.segtab, p.seg_entries + 8));
+    TRY(dev_ensure(b, jpgpu_batch::kSubs, &d.subs, p.sub_entries + 1));
+    TRY(dev_ensure(b, jpgpu_batch::kSegs, &d.segs, p.sub_entries * (p.sub_bits / p.seg_bits) + 1));
+    TRY(dev_ensure(b, jpgpu_batch::kCoefs, &d.coefs, p.coef_elems + 64));
+    if (external_rgb) {
+        d.rgb = ext_rgb;   // stays where jpgpu_batch_set_device_output() pointed it; the caller sized it
+    } else {
+        TRY(dev_ensure(b, jpgpu_batch::kRgb, &d.rgb, p.rgb_bytes + 256));
+    }
+    b->own_rgb = static_cast<uint8_t*>(b->arena[jpgpu_batch::kRgb].p);
 #undef TRY
     b->coef_bytes = p.coef_elems * sizeof(int16_t);
     // defined contents for everything a speculative decoder may read
-    if (cudaMemsetAsync(raw, 0, p.raw_bytes + 64, ctx->stream) != cudaSuccess ||
-        cudaMemsetAsync(d.stream, 0, (p.stream_words + 64) * 4, ctx->stream) != cudaSuccess ||
-        cudaMemsetAsync(d.dyn, 0, (n + 1) * sizeof(ImgDyn), ctx->stream) != cudaSuccess ||
-        cudaMemsetAsync(d.coefs, 0, (p.coef_elems + 64) * 2, ctx->stream) != cudaSuccess ||
-        cudaMemsetAsync(d.segtab, 0, (p.seg_entries + 8) * 4, ctx->stream) != cudaSuccess) {
-        int r = fail(ctx, cudaGetLastError(), "cudaMemsetAsync");
-        jpgpu_batch_destroy(b);
-        return r;
-    }
+    CK(cudaMemsetAsync(raw, 0, p.raw_bytes + 64, ctx->stream));
+    CK(cudaMemsetAsync(d.stream, 0, (p.stream_words + 64) * 4, ctx->stream));
+    CK(cudaMemsetAsync(d.dyn, 0, (n + 1) * sizeof(ImgDyn), ctx->stream));
+    CK(cudaMemsetAsync(d.coefs, 0, (p.coef_elems + 64) * 2, ctx->stream));
+    CK(cudaMemsetAsync(d.segtab, 0, (p.seg_entries + 8) * 4, ctx->stream));
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs, size_t n, jpgpu_batch** out) {
+    if (!ctx || !out || (!descs && n)) return JPGPU_ERR_INVALID_ARG;
+    *out = nullptr;
+    jpgpu_batch* b = new jpgpu_batch();
+    b->ctx = ctx;
+    memset(&b->dev, 0, sizeof b->dev);
+    const int st = jpgpu_batch_replan(b, descs, n);
+    if (st != JPGPU_OK) { jpgpu_batch_destroy(b); return st; }
     *out = b;
     return JPGPU_OK;
 }
@@ -214,6 +242,23 @@ extern "C" int jpgpu_batch_set_device_scans(jpgpu_batch* b, const void* dev_base
         CK(cudaMemcpyAsync(raw + b->plan.imgs[i].raw_off, (const uint8_t*)dev_base + offsets[i], b->plan.imgs[i].raw_len,
                            cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_batch_set_device_output(jpgpu_batch* b, void* dev_base, size_t capacity) {
+    if (!b) return JPGPU_ERR_INVALID_ARG;
+    if (!dev_base) {
+        jpgpu_ctx* ctx = b->ctx;
+        CK(cudaSetDevice(ctx->device));
+        if (!b->own_rgb) {
+            int st = dev_ensure(b, jpgpu_batch::kRgb, &b->own_rgb, b->plan.rgb_bytes + 256);
+            if (st != JPGPU_OK) return st;
+        }
+        b->dev.rgb = b->own_rgb;
+        return JPGPU_OK;
+    }
+    if (capacity < b->plan.rgb_bytes || (reinterpret_cast<uintptr_t>(dev_base) & 255u)) return JPGPU_ERR_INVALID_ARG;
+    b->dev.rgb = static_cast<uint8_t*>(dev_base);
     return JPGPU_OK;
 }
 
@@ -316,6 +361,7 @@ extern "C" int jpgpu_batch_stats(jpgpu_batch* b, uint64_t stats[8]) {
     stats[5] = p.seqs.size();
     stats[6] = p.sub_entries;
     stats[7] = p.raw_bytes + p.stream_words * 4 + p.coef_elems * 2 + p.rgb_bytes + p.sub_entries * sizeof(SubInfo);
+    stats[2] = p.tot_rgb_bytes;
     return JPGPU_OK;
 }
 

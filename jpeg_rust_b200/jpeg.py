@@ -286,9 +286,9 @@ class JPEGImage:
 class Batch:
     """Many independent images decoded with shared kernel launches (jpgpu_batch_*)."""
 
-    def __init__(self, files=None, descs=None, ext=EXT_NONE, layout=LAYOUT_SPEC, device=0, keepalive=None):
+    def __init__(self, files=None, descs=None, ext=EXT_NONE, layout=LAYOUT_SPEC, device=0, keepalive=None, ctx=None):
         L = _ffi.lib()
-        self.ctx = context(device)
+        self.ctx = ctx if ctx is not None else context(device)  # pass an own Context to overlap batches on its stream
         self._keep = [keepalive]
         if descs is None:
             n = len(files)
@@ -306,6 +306,26 @@ class Batch:
         self.descs = descs
         self._h = C.c_void_p()
         self.ctx._ck(L.jpgpu_batch_create(self.ctx.handle, descs, n, C.byref(self._h)), "jpgpu_batch_create")
+
+    def replan(self, files=None, descs=None, ext=EXT_NONE, layout=LAYOUT_SPEC, keepalive=None):
+        """Plan another wave of images on this batch object (device arenas are reused and only grow)."""
+        self._keep = [keepalive]
+        if descs is None:
+            n = len(files)
+            descs = (_ffi.ImageDesc * n)()
+            self.parse_status = []
+            for i, f in enumerate(files):
+                st, d, buf = parse_descriptor(f, ext, layout)
+                self.parse_status.append(st)
+                descs[i] = d
+                self._keep.append(buf)
+        else:
+            n = len(descs)
+            self.parse_status = [0] * n
+        self.n = n
+        self.descs = descs
+        self.ctx._ck(_ffi.lib().jpgpu_batch_replan(self._h, descs, n), "jpgpu_batch_replan")
+        return self
 
     def _call(self, name):
         self.ctx._ck(getattr(_ffi.lib(), "jpgpu_batch_" + name)(self._h), "jpgpu_batch_" + name)
@@ -345,6 +365,39 @@ class Batch:
         self.ctx._ck(_ffi.lib().jpgpu_batch_results(self._h, st, br), "jpgpu_batch_results")
         statuses = [self.parse_status[i] if self.parse_status[i] else st[i] for i in range(self.n)]
         return statuses, list(br)
+
+    def set_device_scans(self, dev_base, offsets):
+        """The raw scan bytes are already in device memory: image i at dev_base + offsets[i]."""
+        offs = (C.c_uint64 * self.n)(*[int(o) for o in offsets])
+        self.ctx._ck(_ffi.lib().jpgpu_batch_set_device_scans(self._h, C.c_void_p(int(dev_base)), offs), "set_device_scans")
+        return self
+
+    def set_device_output(self, dev_base, capacity):
+        """Wave decoding: RGB of the next decode goes to caller-owned device memory (None = own arena)."""
+        self.ctx._ck(_ffi.lib().jpgpu_batch_set_device_output(self._h, C.c_void_p(int(dev_base) if dev_base else 0), capacity),
+                     "set_device_output")
+        return self
+
+    def output_bytes(self):
+        """Bytes one wave of RGB output occupies (images at 256-byte aligned offsets)."""
+        p_last, nb = self.device_rgb(self.n - 1)
+        p_first, _ = self.device_rgb(0)
+        return (p_last - p_first) + (nb + 255) // 256 * 256
+
+    def rgb_offset(self, i):
+        p_i, nb = self.device_rgb(i)
+        p_0, _ = self.device_rgb(0)
+        return p_i - p_0, nb
+
+    def device_tensor(self, i):
+        """Zero-copy torch view (H, W, 3) uint8 of image i's RGB output in device memory."""
+        import torch
+        ptr, nb = self.device_rgb(i)
+        h, w, _ = self.shape(i)
+
+        class _Cai:
+            __cuda_array_interface__ = {"shape": (h, w, 3), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(_Cai(), device=f"cuda:{self.ctx.device}")
 
     def device_rgb(self, i):
         nb = C.c_size_t(0)
@@ -395,6 +448,45 @@ def decode_batch(files, ext=EXT_NONE, layout=LAYOUT_SPEC, device=0):
         return outs, statuses, br
     finally:
         b.close()
+
+
+def decode_waves(files, wave, ext=EXT_NONE, layout=LAYOUT_SPEC, device=0):
+    """Decode a long list of JPEG byte strings in waves of `wave` images through ONE batch object (its bitstream and
+    coefficient arenas are reused), keeping every RGB output resident in one device arena.
+    Returns (list of zero-copy (H, W, 3) uint8 CUDA tensors, statuses, bytes_read)."""
+    import torch
+    descs_all, bufs, pstat = [], [], []
+    for f in files:
+        st, d, buf = parse_descriptor(f, ext, layout)
+        descs_all.append(d); bufs.append(buf); pstat.append(st)
+    sizes = [(d.width * d.height * 3 + 255) // 256 * 256 if st == 0 else 0 for d, st in zip(descs_all, pstat)]
+    arena = torch.empty(sum(sizes) + 256, dtype=torch.uint8, device=f"cuda:{device}")
+    base = (arena.data_ptr() + 255) // 256 * 256
+    outs, statuses, bytes_read = [], [], []
+    batch, off = None, 0
+    for i0 in range(0, len(files), wave):
+        ds = descs_all[i0:i0 + wave]
+        arr = (_ffi.ImageDesc * len(ds))(*ds)
+        if batch is None:
+            batch = Batch(descs=arr, device=device, keepalive=bufs)
+        else:
+            batch.replan(descs=arr, keepalive=bufs)
+        batch.parse_status = pstat[i0:i0 + wave]
+        nbytes = batch.output_bytes() if any(s == 0 for s in batch.parse_status) else 0
+        batch.set_device_output(base + off, max(nbytes, 256))
+        batch.upload().decode()
+        st, br = batch.results()
+        statuses += st; bytes_read += br
+        for i in range(len(ds)):
+            outs.append(batch.device_tensor(i) if st[i] == 0 else None)
+        off += (nbytes + 255) // 256 * 256
+    if batch is not None:
+        batch.set_device_output(None, 0)
+        batch.close()
+    for t in outs:
+        if t is not None:
+            t._jpgpu_arena = arena   # keep the arena alive as long as any view is
+    return outs, statuses, bytes_read
 
 
 def shard_range(n_items, rank, world_size):

@@ -231,3 +231,33 @@ def test_full_size_batch_properties():
         for a, w in zip(got, base[i % 4][1]):
             assert np.array_equal(a, w)
     b.close()
+
+
+def test_waves_through_one_batch_object():
+    """a job larger than one GPU's memory runs wave after wave through one planned batch whose
+    arenas are reused (jpgpu_batch_replan), outputs kept in one caller-owned device arena (set_device_output)."""
+    from jpeg_rust_b200 import decode_waves
+    files = [synth.synth_jpeg(800 + i, 160 + 16 * (i % 3), 120 + 8 * (i % 2), ["420", "444", "gray", "422"][i % 4]) for i in range(11)]
+    files[4] = files[4][:len(files[4]) // 2]                     # one broken image in the middle of a wave
+    outs, statuses, br = decode_waves(files, 4)
+    ref, ref_st, ref_br = run_batch(files)[:3]
+    assert statuses == ref_st and statuses[4] != 0
+    for i in range(len(files)):
+        if statuses[i] == 0:
+            assert br[i] == ref_br[i]
+            assert np.array_equal(outs[i].cpu().numpy(), ref[i]), i
+
+
+def test_replan_grows_and_shrinks():
+    small = [synth.synth_jpeg(820, 64, 64, "420")]
+    big = [synth.synth_jpeg(821 + i, 640, 480, "420") for i in range(3)]
+    b = Batch(small, layout=LAYOUT_SPEC)
+    for files in (small, big, small, big):
+        b.replan(files)
+        b.upload().decode()
+        outs = b.download()
+        statuses, _ = b.results()
+        assert all(s == 0 for s in statuses)
+        for f, o in zip(files, outs):
+            assert_samples(o, O.decode(f, layout=O.LAYOUT_SPEC).rgb)
+    b.close()
