@@ -191,6 +191,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
     std::map<std::string, uint32_t> lut_ids;
     std::map<std::string, uint32_t> qt_ids;
     std::map<std::string, uint64_t> map_ids;
+    std::string cur_lutset;
     auto align_up = [](uint64_t x, uint64_t a) { return (x + a - 1) / a * a; };
 
     for (size_t i = 0; i < n; i++) {
@@ -324,9 +325,18 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         im.nsub_cap = std::max<uint32_t>(1u, (uint32_t)(((uint64_t)im.raw_len * 8 + sub_bits - 1) / sub_bits));
         im.sub_off = (uint32_t)plan.sub_entries;
         plan.sub_entries += im.nsub_cap;
-        im.nseq = (im.nsub_cap + kSeqThreads - 1) / kSeqThreads;
+        // warp jobs: 32 consecutive subsequences each; a CTA takes kSeqThreads/32 consecutive jobs, which may belong
+        // to different images as long as those use the same Huffman tables (the CTA keeps one copy in shared memory)
+        {
+            std::string lutset((const char*)slot_lut, sizeof(uint32_t) * (size_t)nslots);
+            constexpr uint32_t kJobsPerCta = kSeqThreads / 32;
+            if (lutset != cur_lutset && plan.seqs.size() % kJobsPerCta != 0)
+                while (plan.seqs.size() % kJobsPerCta != 0) plan.seqs.push_back(SeqDesc{0xffffffffu, 0u});
+            cur_lutset = lutset;
+        }
+        im.nseq = (im.nsub_cap + 31) / 32;
         im.seq_first = (uint32_t)plan.seqs.size();
-        for (uint32_t q = 0; q < im.nseq; q++) plan.seqs.push_back(SeqDesc{(uint32_t)i, q * kSeqThreads});
+        for (uint32_t q = 0; q < im.nseq; q++) plan.seqs.push_back(SeqDesc{(uint32_t)i, q * 32u});
         im.coef_off = plan.coef_elems;
         plan.coef_elems += im.total_coefs;
         im.rgb_off = plan.rgb_bytes;
@@ -351,6 +361,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         plan.tot_pixels += (uint64_t)im.width * im.height;
         plan.tot_rgb_bytes += (uint64_t)im.width * im.height * 3;
     }
+    while (plan.seqs.size() % (kSeqThreads / 32) != 0) plan.seqs.push_back(SeqDesc{0xffffffffu, 0u});
     if (plan.sub_entries > 0xffffffffull || plan.seg_entries > 0xffffffffull) return JPGPU_ERR_UNSUPPORTED;
     return JPGPU_OK;
 }

@@ -144,43 +144,35 @@ __global__ void __launch_bounds__(kPreThreads) prepass_kernel(BatchDev b) {
 }
 
 // ========================================================= stage 1b-1d: entropy decode
+constexpr int kJobsPerCta = kSeqThreads / 32;
 struct EntropySmem {
-    ImgDev img;
+    ImgDev img[kJobsPerCta];     // per warp job (verify_scan_kernel: [0] only)
     uint8_t store_pos[64];
     HuffLut lut[kMaxLutSlots];   // kernels with dynamic shared memory only carve max_slots of these
 };
 
-// Cooperative load of the per-image decode context into shared memory.
-__device__ __forceinline__ void load_entropy_img(const BatchDev& b, uint32_t img, EntropySmem& sm, int nthreads) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&b.imgs[img]);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.img);
-    for (int i = threadIdx.x; i < (int)(sizeof(ImgDev) / 4); i += nthreads) dst[i] = src[i];
+// Cooperative load of the per-image decode context into shared memory: every group of `group` threads loads the
+// image of its own job into sm.img[threadIdx.x / group] (kNoImage: nothing).
+__device__ __forceinline__ void load_entropy_img(const BatchDev& b, uint32_t img, EntropySmem& sm, int group) {
+    const int slot = threadIdx.x / group, t = threadIdx.x % group;
+    if (img != kNoImage) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&b.imgs[img]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.img[slot]);
+        for (int i = t; i < (int)(sizeof(ImgDev) / 4); i += group) dst[i] = src[i];
+    }
     if (threadIdx.x < 64) sm.store_pos[threadIdx.x] = c_store_pos[threadIdx.x];
     __syncthreads();
 }
+// The Huffman tables of the CTA: those of job 0 (all jobs of a CTA use the same set, see build_plan).
 __device__ __forceinline__ void load_entropy_luts(const BatchDev& b, EntropySmem& sm, int nthreads) {
-    const int nslots = sm.img.nslots;
+    const int nslots = sm.img[0].nslots;
     constexpr int kLutVecs = sizeof(HuffLut) / 16;
     for (int s = 0; s < nslots; s++) {
-        const uint4* ls = reinterpret_cast<const uint4*>(&b.luts[sm.img.slot_lut[s]]);
+        const uint4* ls = reinterpret_cast<const uint4*>(&b.luts[sm.img[0].slot_lut[s]]);
         uint4* ld = reinterpret_cast<uint4*>(&sm.lut[s]);
         for (int i = threadIdx.x; i < kLutVecs; i += nthreads) ld[i] = __ldg(ls + i);
     }
     __syncthreads();
-}
-
-__device__ __forceinline__ DecCtx make_ctx(const BatchDev& b, const EntropySmem& sm, const ImgDyn& d) {
-    DecCtx cx;
-    cx.words = b.stream + sm.img.stream_off;
-    cx.lw = b.lw;
-    cx.seg = b.segtab + sm.img.seg_off;
-    cx.nseg = d.nseg;
-    cx.stream_bits = d.stream_bits;
-    cx.seg_units = sm.img.seg_units;
-    cx.nblk = sm.img.blocks_per_mcu;
-    cx.luts = sm.lut;
-    cx.blk_info = sm.img.blk_info;
-    return cx;
 }
 
 // ------------------------------------------------------------------ fast decode step
@@ -230,18 +222,22 @@ struct FastState {
 
 // per-CTA tables the fast path reads (filled once after the LUTs are loaded)
 struct FastTables {
-    uint4 info[kMaxBlocksPerMcu];  // per block of an MCU: {dc lut addr | ac lut addr << 16, DC slot offset, address of the next entry, c}
+    uint4 info[kJobsPerCta][kMaxBlocksPerMcu];  // per job and block of an MCU: {dc lut addr | ac lut addr << 16, DC slot offset, address of the next entry, c}
     uint32_t dc[3 * kSeqThreads];
     uint8_t sp[64];
 };
 
-__device__ __forceinline__ void fast_tables_init(FastTables& ft, const EntropySmem& sm, int nthreads) {
-    const uint32_t lut0 = smem_addr(&sm.lut[0]), info0 = smem_addr(ft.info);
-    const int nblk = sm.img.blocks_per_mcu;
-    for (int i = threadIdx.x; i < kMaxBlocksPerMcu; i += nthreads) {
-        const uint32_t info = sm.img.blk_info[i < nblk ? i : 0];
-        const uint32_t a_dc = lut0 + (info & 255u) * (uint32_t)sizeof(HuffLut), a_ac = lut0 + ((info >> 8) & 255u) * (uint32_t)sizeof(HuffLut);
-        ft.info[i] = make_uint4(a_dc | (a_ac << 16), (info >> 16) * 4u * kSeqThreads, info0 + (i + 1 < nblk ? i + 1 : 0) * 16u, (uint32_t)i);
+// `group` threads fill the table of job threadIdx.x / group (its image must be loaded; kNoImage jobs skip).
+__device__ __forceinline__ void fast_tables_init(FastTables& ft, const EntropySmem& sm, bool valid, int group, int nthreads) {
+    const int slot = threadIdx.x / group, t = threadIdx.x % group;
+    const uint32_t lut0 = smem_addr(&sm.lut[0]), info0 = smem_addr(ft.info[slot]);
+    if (valid) {
+        const int nblk = sm.img[slot].blocks_per_mcu;
+        for (int i = t; i < kMaxBlocksPerMcu; i += group) {
+            const uint32_t info = sm.img[slot].blk_info[i < nblk ? i : 0];
+            const uint32_t a_dc = lut0 + (info & 255u) * (uint32_t)sizeof(HuffLut), a_ac = lut0 + ((info >> 8) & 255u) * (uint32_t)sizeof(HuffLut);
+            ft.info[slot][i] = make_uint4(a_dc | (a_ac << 16), (info >> 16) * 4u * kSeqThreads, info0 + (i + 1 < nblk ? i + 1 : 0) * 16u, (uint32_t)i);
+        }
     }
     for (int i = threadIdx.x; i < 64; i += nthreads) {
         const uint32_t pos = sm.store_pos[i];
@@ -452,17 +448,18 @@ __device__ __forceinline__ void fast_run_to(const FastCtx& cx, FastState& st, ui
     }
 }
 
-__device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const EntropySmem& sm, const ImgDyn& d, const FastTables& ft) {
+__device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const EntropySmem& sm, int slot, const ImgDyn& d, const FastTables& ft) {
+    const ImgDev& im = sm.img[slot];
     FastCtx cx;
-    cx.words = b.stream + sm.img.stream_off;
+    cx.words = b.stream + im.stream_off;
     cx.lw = b.lw;
     cx.wmask5 = ((1u << b.lw) - 1u) << 5;
     cx.gmask_inv = ~((32u << b.lw) - 1u);
-    cx.seg = b.segtab + sm.img.seg_off;
+    cx.seg = b.segtab + im.seg_off;
     cx.nseg = d.nseg;
     cx.stream_bits = d.stream_bits;
-    cx.seg_units = sm.img.seg_units;
-    cx.info_addr = smem_addr(ft.info);
+    cx.seg_units = im.seg_units;
+    cx.info_addr = smem_addr(ft.info[slot]);
     cx.dc_addr = smem_addr(ft.dc) + threadIdx.x * 4u;
     cx.sp_addr = smem_addr(ft.sp);
     cx.luts = sm.lut;
@@ -533,17 +530,19 @@ __device__ __forceinline__ void fast_sync_subsequence(const FastCtx& cx, FastSta
 __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     __shared__ EntropySmem sm;
     __shared__ FastTables ft;
-    const SeqDesc sd = b.seqs[blockIdx.x];
+    const int warp = threadIdx.x >> 5;
+    const SeqDesc sd = b.seqs[blockIdx.x * kJobsPerCta + warp];
     const uint32_t S = b.sub_bits;
-    load_entropy_img(b, sd.img, sm, kSeqThreads);
+    load_entropy_img(b, sd.img, sm, 32);
+    load_entropy_luts(b, sm, kSeqThreads);
+    fast_tables_init(ft, sm, sd.img != kNoImage, 32, kSeqThreads);
+    __syncthreads();
+    if (sd.img == kNoImage) return;
+    const ImgDev& img = sm.img[warp];
     const ImgDyn dyn = b.dyn[sd.img];
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
-    if (sd.first_sub >= nsub) return;
-    load_entropy_luts(b, sm, kSeqThreads);
-    fast_tables_init(ft, sm, kSeqThreads);
-    __syncthreads();
-    const FastCtx cx = make_fast_ctx(b, sm, dyn, ft);
-    const uint32_t j = sd.first_sub + threadIdx.x;
+    const FastCtx cx = make_fast_ctx(b, sm, warp, dyn, ft);
+    const uint32_t j = sd.first_sub + (threadIdx.x & 31u);
     if (j >= nsub) return;
 
     const uint32_t own = j * S, p0 = own > b.lookback_bits ? own - b.lookback_bits : 0u;
@@ -553,8 +552,8 @@ __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     SubInfo rec;
     rec.pA = st.p;
     rec.cz = ((uint32_t)st.g & 63u) | (fast_c(st) << 6);
-    fast_sync_subsequence(cx, st, own, S, b.seg_bits, b.segs + (size_t)(sm.img.sub_off + j) * (S / b.seg_bits), false, rec);
-    b.subs[sm.img.sub_off + j] = rec;
+    fast_sync_subsequence(cx, st, own, S, b.seg_bits, b.segs + (size_t)(img.sub_off + j) * (S / b.seg_bits), false, rec);
+    b.subs[img.sub_off + j] = rec;
 }
 
 constexpr int kInterThreads = kSeqThreads;
@@ -576,10 +575,11 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
 
     const uint32_t img = blockIdx.x;
     const uint32_t S = b.sub_bits;
-    load_entropy_img(b, img, sm, kInterThreads);
+    load_entropy_img(b, threadIdx.x < 32 ? img : kNoImage, sm, 32);
+    const ImgDev& im = sm.img[0];
     const ImgDyn dyn = b.dyn[img];
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
-    SubInfo* subs = b.subs + sm.img.sub_off;
+    SubInfo* subs = b.subs + im.sub_off;
     const uint32_t tid = threadIdx.x;
 
     bool loaded = false;
@@ -599,11 +599,11 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
         if (njobs == 0u) break;
         if (!loaded) {
             load_entropy_luts(b, sm, kInterThreads);
-            fast_tables_init(ft, sm, kInterThreads);
+            fast_tables_init(ft, sm, threadIdx.x < 32, 32, kInterThreads);
             __syncthreads();
             loaded = true;
         }
-        const FastCtx cx = make_fast_ctx(b, sm, dyn, ft);
+        const FastCtx cx = make_fast_ctx(b, sm, 0, dyn, ft);
         for (uint32_t i = tid; i < njobs; i += kInterThreads) {
             const RepairJob job = s_jobs[i];
             FastState st;
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
             SubInfo rec;
             rec.pA = st.p;
             rec.cz = job.cz;
-            fast_sync_subsequence(cx, st, job.sub * S, S, b.seg_bits, b.segs + (size_t)(sm.img.sub_off + job.sub) * (S / b.seg_bits), true, rec);
+            fast_sync_subsequence(cx, st, job.sub * S, S, b.seg_bits, b.segs + (size_t)(im.sub_off + job.sub) * (S / b.seg_bits), true, rec);
             subs[job.sub] = rec;
         }
         __syncthreads();
@@ -676,29 +676,30 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint2* const flist = reinterpret_cast<uint2*>(dyn_smem + lay.list_off) + warp * (32 * NBUF);
 
-    const SeqDesc sd = b.seqs[blockIdx.x];
+    const SeqDesc sd = b.seqs[blockIdx.x * kJobsPerCta + warp];
     const uint32_t S = b.sub_bits;
-    load_entropy_img(b, sd.img, sm, kSeqThreads);
-    const ImgDyn dyn = b.dyn[sd.img];
-    const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
-    if (sd.first_sub >= nsub) return;
+    load_entropy_img(b, sd.img, sm, 32);
     load_entropy_luts(b, sm, kSeqThreads);
-    fast_tables_init(ft, sm, kSeqThreads);
+    fast_tables_init(ft, sm, sd.img != kNoImage, 32, kSeqThreads);
     for (uint32_t i = tid; i < kSeqThreads * NBUF * 8u; i += kSeqThreads)
         reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    const FastCtx cx = make_fast_ctx(b, sm, dyn, ft);
-    const uint32_t j = sd.first_sub + tid;
+    if (sd.img == kNoImage) return;
+    const ImgDev& img = sm.img[warp];
+    const ImgDyn dyn = b.dyn[sd.img];
+    const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
+    const FastCtx cx = make_fast_ctx(b, sm, warp, dyn, ft);
+    const uint32_t j = sd.first_sub + lane;
     bool active = j < nsub;
     if (!__ballot_sync(0xffffffffu, active)) return;
 
-    const int32_t total = (int32_t)sm.img.total_coefs;
-    int16_t* __restrict__ coefs = b.coefs + sm.img.coef_off;
+    const int32_t total = (int32_t)img.total_coefs;
+    int16_t* __restrict__ coefs = b.coefs + img.coef_off;
     const uint32_t end_bit = (j + 1) * S;
     FastState st;
     bool store_on = true;
     if (active) {
-        const SubInfo me = b.subs[sm.img.sub_off + j];
+        const SubInfo me = b.subs[img.sub_off + j];
         fast_init(cx, st, me.pA, me.n, (me.cz >> 6) & 15u, me.dc[0], me.dc[1], me.dc[2]);
         st.flags &= ~kCrossed;
         store_on = (st.g & 63) == 0;
@@ -1094,7 +1095,7 @@ void launch_prepass(const BatchDev& b, cudaStream_t s) {
     if (b.n_images) prepass_kernel<<<b.n_images, kPreThreads, 0, s>>>(b);
 }
 void launch_sync(const BatchDev& b, cudaStream_t s) {
-    if (b.n_seqs) sync_kernel<<<b.n_seqs, kSeqThreads, 0, s>>>(b);
+    if (b.n_seqs) sync_kernel<<<b.n_seqs / kJobsPerCta, kSeqThreads, 0, s>>>(b);
 }
 void launch_verify_scan(const BatchDev& b, cudaStream_t s) {
     if (b.n_images) verify_scan_kernel<<<b.n_images, kInterThreads, 0, s>>>(b);
@@ -1108,7 +1109,7 @@ static cudaError_t launch_write_variant(const BatchDev& b, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         configured = lay.total;
     }
-    decode_write_kernel<NBUF, PHASE><<<b.n_seqs, kSeqThreads, lay.total, s>>>(b);
+    decode_write_kernel<NBUF, PHASE><<<b.n_seqs / kJobsPerCta, kSeqThreads, lay.total, s>>>(b);
     return cudaSuccess;
 }
 cudaError_t launch_decode_write(const BatchDev& b, cudaStream_t s) {

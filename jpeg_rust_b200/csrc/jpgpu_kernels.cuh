@@ -6,10 +6,11 @@
 
 namespace jpgpu {
 
-struct SeqDesc {
-    uint32_t img;        // image index
-    uint32_t first_sub;  // first subsequence of this sequence within the image
+struct SeqDesc {         // one warp job of the sync / write kernels: 32 consecutive subsequences of one image
+    uint32_t img;        // image index, 0xffffffff = padding (a CTA's jobs must share their Huffman tables)
+    uint32_t first_sub;  // first subsequence of the job within the image
 };
+constexpr uint32_t kNoImage = 0xffffffffu;
 
 constexpr int kNumKinds = 6;
 

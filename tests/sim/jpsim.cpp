@@ -104,6 +104,7 @@ void load_slots(const SimBatch& sb, size_t img, std::vector<HuffLut>& slots) {
 
 // mirrors sync_kernel: one independent thread per subsequence
 void sim_sync(SimBatch& sb, const SeqDesc& sd) {
+    if (sd.img == kNoImage) return;
     std::vector<HuffLut> slots;
     load_slots(sb, sd.img, slots);
     const ImgDev& im = sb.plan.imgs[sd.img];
@@ -112,7 +113,7 @@ void sim_sync(SimBatch& sb, const SeqDesc& sd) {
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
     const DecCtx cx = make_ctx(sb, sd.img, slots.data());
-    for (uint32_t tid = 0; tid < (uint32_t)kSeqThreads; tid++) {
+    for (uint32_t tid = 0; tid < 32u; tid++) {  // one warp job
         const uint32_t j = sd.first_sub + tid;
         if (j >= nsub) continue;
         const uint32_t own = j * S, p0 = own > L ? own - L : 0u;
@@ -177,6 +178,7 @@ void sim_verify_scan(SimBatch& sb, size_t img) {
 
 // mirrors decode_write_kernel: warps in lock-step phases, per-lane swizzled block buffers, cooperative flush
 void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
+    if (sd.img == kNoImage) return;
     std::vector<HuffLut> slots;
     load_slots(sb, sd.img, slots);
     const ImgDev& im = sb.plan.imgs[sd.img];
@@ -187,8 +189,8 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
     const DecCtx cx = make_ctx(sb, sd.img, slots.data());
     const int32_t total = (int32_t)im.total_coefs;
     int16_t* coefs = sb.coefs.data() + im.coef_off;
-    std::vector<int16_t> bufs((size_t)kSeqThreads * kWriteBufs * 64, 0);
-    for (uint32_t warp = 0; warp < (uint32_t)kSeqThreads / 32; warp++) {
+    std::vector<int16_t> bufs((size_t)32 * kWriteBufs * 64, 0);
+    for (uint32_t warp = 0; warp < 1u; warp++) {  // one warp job
         struct Lane { DecState st; bool active, store_on; uint32_t j, end_bit, cur, ndone, dest[kWriteBufs]; int32_t g_start; };
         Lane ln[32];
         bool any_active = false;
