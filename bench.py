@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--subsampling", default="420")
     ap.add_argument("--quality", type=int, default=85)
+    ap.add_argument("--restart-interval", type=int, default=0, help="MCUs per restart interval (0 = none; needs the DRI "
+                    "extension the reference panics on: BASELINE configs[3], e.g. 3840x2160 444 with 480/16/1)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample (0 = 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -184,7 +186,8 @@ def main():
     # ---- inputs: `distinct` synthetic images (different per rank), cycled to `images`, each copy with its own
     # host region and its own device buffers
     files = synth.synth_corpus(args.distinct, args.width, args.height, args.subsampling, args.quality,
-                               first_index=rank * args.distinct)
+                               restart_interval=args.restart_interval, first_index=rank * args.distinct)
+    ext = _ffi.EXT_DRI if args.restart_interval else _ffi.EXT_NONE
     n = args.images
     sizes = [len(files[i % args.distinct]) for i in range(n)]
     offs = np.zeros(n + 1, np.int64)
@@ -195,7 +198,7 @@ def main():
         hin[offs[i]:offs[i] + sizes[i]] = np.frombuffer(files[i % args.distinct], np.uint8)
     descs = (_ffi.ImageDesc * n)()
     for i in range(n):
-        st, d, _ = parse_descriptor(hin[offs[i]:offs[i] + sizes[i]], _ffi.EXT_NONE, LAYOUT_SPEC)
+        st, d, _ = parse_descriptor(hin[offs[i]:offs[i] + sizes[i]], ext, LAYOUT_SPEC)
         assert st == 0, st
         descs[i] = d
     ctx = context(local_rank)
@@ -262,7 +265,9 @@ def main():
             traffic = t["dram_bytes_per_image"] * n
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "idct_colour_kernel<2,2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kname = {"420": "idct_colour_kernel<2,2,false>", "422": "idct_colour_kernel<2,1,false>", "444": "idct_colour_kernel<1,1,false>",
+             "440": "idct_colour_kernel<1,2,false>", "gray": "idct_colour_kernel<1,1,true>"}[args.subsampling]
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "ms_per_launch": idct_ms,
                 "algorithmic_bytes_per_launch": idct_bytes,
                 "entropy_stage": {"ms": ent_ms, "bitstream_GBps": stats["scan_bytes"] / (ent_ms * 1e-3) / 1e9,
@@ -349,7 +354,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (IDCT/colour), i16/u8 (entropy)", "data": "synthetic",
             "config": {"workload": f"{n} synthetic {args.width}x{args.height} {args.subsampling} q{args.quality} baseline "
-                                   f"JPEGs per GPU ({args.distinct} distinct, own buffers per copy), SPEC layout",
+                                   f"JPEGs per GPU ({args.distinct} distinct, own buffers per copy), SPEC layout"
+                                   + (f", restart interval {args.restart_interval} MCUs" if args.restart_interval else ""),
                        "images_per_gpu": n, "l2": "inputs larger than L2 (no flush needed): "
                        f"{stats['scan_bytes'] / 1e6:.0f} MB bitstream, {stats['coef_bytes'] / 1e9:.2f} GB coefficients",
                        "parallelism": f"images sharded over {world} GPU(s), no collective"},

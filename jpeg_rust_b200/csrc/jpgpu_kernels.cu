@@ -911,8 +911,7 @@ __global__ void __launch_bounds__(kIdctThreads) idct_colour_kernel(BatchDev b, c
     }
 
     uint4 cur[NL], nxt[NL];
-    auto issue_loads = [&](uint32_t tl, uint4 (&dst)[NL]) {
-        const uint32_t tx = tl % tiles_x, ty = tl / tiles_x;
+    auto issue_loads = [&](uint32_t tx, uint32_t ty, uint4 (&dst)[NL]) {
         const uint32_t mcu0 = ty * mcux + tx * NM;
         const uint32_t here = min((uint32_t)NM, mcux - tx * NM);
 #pragma unroll
@@ -922,13 +921,14 @@ __global__ void __launch_bounds__(kIdctThreads) idct_colour_kernel(BatchDev b, c
             if (valid) dst[l] = __ldg(coefs + ((size_t)mcu0 * NB + blk_of[l]) * 8 + t);
         }
     };
-    issue_loads(tile, cur);
+    uint32_t tx = tile % tiles_x, ty = tile / tiles_x;   // tile coordinates, advanced incrementally
+    issue_loads(tx, ty, cur);
     __syncthreads();  // s_qt ready
 
 #pragma unroll 1
     for (; tile < tile_end; tile++) {
-        if (tile + 1 < tile_end) issue_loads(tile + 1, nxt);
-        const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+        const uint32_t ntx = tx + 1u == tiles_x ? 0u : tx + 1u, nty = ty + (tx + 1u == tiles_x ? 1u : 0u);
+        if (tile + 1 < tile_end) issue_loads(ntx, nty, nxt);
 
         if (!GRAY) {
 #pragma unroll
@@ -1009,6 +1009,7 @@ __global__ void __launch_bounds__(kIdctThreads) idct_colour_kernel(BatchDev b, c
         // s_out / s_chroma are rewritten only after the next tile's phase-A barrier (or, for gray,
         // after the barrier below) — every thread has left phase C by then.
         if (GRAY) __syncthreads();
+        tx = ntx; ty = nty;
 #pragma unroll
         for (int l = 0; l < NL; l++) cur[l] = nxt[l];
     }

@@ -261,3 +261,17 @@ def test_replan_grows_and_shrinks():
         for f, o in zip(files, outs):
             assert_samples(o, O.decode(f, layout=O.LAYOUT_SPEC).rgb)
     b.close()
+
+
+@pytest.mark.parametrize("ri", [240, 16, 1])
+def test_4k_444_dense_restart_intervals_full_size(ri):
+    """configs[3]: synthetic 3840x2160 4:4:4 with dense restart intervals (intra-image parallelism from RSTn):
+    coefficients against the encoder's ground truth and the oracle, samples within 1 LSB, and identical to the
+    same image without restart markers (DRI-invariance, SURVEY.md §8c pin 4)."""
+    f, g = synth.synth_jpeg(3, 3840, 2160, "444", restart_interval=ri, want_coefs=True)
+    plain = synth.synth_jpeg(3, 3840, 2160, "444")
+    worst = compare_with_oracle([f], LAYOUT_SPEC, ext=EXT_DRI, gts=[g])
+    a = run_batch([f], LAYOUT_SPEC, EXT_DRI)
+    b = run_batch([plain], LAYOUT_SPEC)
+    assert np.array_equal(a[0][0], b[0][0])
+    print("4K 4:4:4 Ri =", ri, "max/mean |delta|:", worst)
