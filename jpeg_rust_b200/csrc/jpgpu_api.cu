@@ -29,7 +29,7 @@ struct jpgpu_batch {
     std::vector<size_t> host_scan_len;
     BatchDev dev;
     struct Arena { void* p = nullptr; size_t cap = 0; };
-    enum { kImgs, kSeqs, kLuts, kQt, kKind0, kGmap = kKind0 + kNumKinds, kSamples, kRaw, kDyn, kStream, kSegtab, kSubs, kSegs, kCoefs,
+    enum { kImgs, kSeqs, kLuts, kQt, kKind0, kGmap = kKind0 + kNumKinds, kSamples, kRaw, kDyn, kStream, kSegtab, kSubs, kSegs, kChunks, kCoefs,
            kRgb, kNumArenas };
     Arena arena[kNumArenas];   // device allocations, grown on demand by jpgpu_batch_replan()
     uint64_t launches = 0;
@@ -189,6 +189,8 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     TRY(dev_ensure(b, jpgpu_batch::kSegtab, &d.segtab, p.seg_entries + 8));
     TRY(dev_ensure(b, jpgpu_batch::kSubs, &d.subs, p.sub_entries + 1));
     TRY(dev_ensure(b, jpgpu_batch::kSegs, &d.segs, p.sub_entries * (p.sub_bits / p.seg_bits) + 1));
+    TRY(dev_ensure(b, jpgpu_batch::kChunks, &d.chunk_counts, p.chunk_entries + 1));
+    d.max_chunks = p.max_chunks;
     TRY(dev_ensure(b, jpgpu_batch::kCoefs, &d.coefs, p.coef_elems + 64));
     if (external_rgb) {
         d.rgb = ext_rgb;   // stays where jpgpu_batch_set_device_output() pointed it; the caller sized it
@@ -271,7 +273,7 @@ extern "C" int jpgpu_batch_entropy(jpgpu_batch* b) {
     launch_sync(b->dev, s);
     launch_verify_scan(b->dev, s);
     CK(launch_decode_write(b->dev, s));
-    b->launches += 4;
+    b->launches += 6;
     CK(cudaGetLastError());
     return JPGPU_OK;
 }

@@ -89,6 +89,8 @@ struct ImgDev {
     uint32_t nseg_cap;        // expected number of intervals (1 without DRI)
     uint32_t sub_off;         // offset into the subsequence-info array
     uint32_t nsub_cap;        // capacity in subsequences (from raw_len)
+    uint32_t chunk_off;       // offset of this image's entries in the pre-pass chunk table
+    uint32_t pad2;
     uint32_t seq_first;       // index of this image's first sequence in the global sequence list
     uint32_t nseq;
     uint32_t mcux, mcuy;      // MCU grid (SPEC geometry)

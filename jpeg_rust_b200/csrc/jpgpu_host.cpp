@@ -322,6 +322,12 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         if (im.nseg_cap == 0) im.nseg_cap = 1;
         im.seg_off = (uint32_t)plan.seg_entries;
         plan.seg_entries += im.nseg_cap + 2;
+        {
+            const uint32_t nchunks = (im.raw_len + 4095u) / 4096u;   // kPreChunk of jpgpu_kernels.cu
+            im.chunk_off = (uint32_t)plan.chunk_entries;
+            plan.chunk_entries += nchunks;
+            plan.max_chunks = std::max(plan.max_chunks, nchunks);
+        }
         im.nsub_cap = std::max<uint32_t>(1u, (uint32_t)(((uint64_t)im.raw_len * 8 + sub_bits - 1) / sub_bits));
         im.sub_off = (uint32_t)plan.sub_entries;
         plan.sub_entries += im.nsub_cap;

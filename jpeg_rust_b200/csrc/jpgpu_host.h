@@ -49,6 +49,8 @@ struct HostPlan {
     uint64_t stream_words = 0;
     uint64_t seg_entries = 0;
     uint64_t sub_entries = 0;
+    uint64_t chunk_entries = 0;  // pre-pass chunk table
+    uint32_t max_chunks = 0;
     uint64_t coef_elems = 0;
     uint64_t rgb_bytes = 0;
     std::vector<uint32_t> gmap;  // placement maps of the gather path, one per distinct shape

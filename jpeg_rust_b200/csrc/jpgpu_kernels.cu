@@ -1,6 +1,6 @@
 // jpgpu_kernels.cu — hand-written sm_100a kernels of the JPEG decode hot path.
 //
-//   prepass_kernel          mod.rs:371-385 (byte unstuffing) as a parallel stream
+//   prepass_*_kernel        mod.rs:371-385 (byte unstuffing) as a parallel stream
 //                           compaction, plus RSTn detection (no reference counterpart:
 //                           mod.rs:424-428 panics on DRI)
 //   sync_kernel             |
@@ -26,120 +26,182 @@ cudaError_t init_constants() {
 }
 
 // =============================================================== stage 1a: pre-pass
+// mod.rs:371-385 (drop the 00 after every FF) as a parallel stream compaction in three small kernels, so that
+// no CTA walks an image serially: (1) every 4 KiB chunk counts the bytes it keeps and the RSTn markers it
+// holds, (2) one CTA per image turns the counts into offsets and writes the per-image results, (3) every chunk
+// compacts its bytes to its final position in the lane-interleaved word stream.
 constexpr int kPreThreads = 256;
-constexpr int kPreChunk = kPreThreads * 16;  // raw bytes per CTA iteration
+constexpr int kPreChunk = kPreThreads * 16;  // raw bytes per CTA
 
-__global__ void __launch_bounds__(kPreThreads) prepass_kernel(BatchDev b) {
+// Classification of the 16 raw bytes at offset o (thread-private): which are kept, which start an RSTn marker.
+struct PreBytes {
+    uint32_t w[4];
+    uint32_t keep, rstm, next;
+};
+// Per-byte masks of a 32-bit word (4 raw bytes, little endian): 0x80 in every byte that fulfils the predicate.
+__device__ __forceinline__ uint32_t bytes_eq(uint32_t w, uint32_t pattern) {   // byte == pattern byte
+    const uint32_t x = w ^ pattern;                       // 0 where equal
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+}
+// Gathers the 0x80 marks of four word masks into a 16-bit mask (bit k = byte k of the 16).
+__device__ __forceinline__ uint32_t marks16(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    auto pack = [](uint32_t m) { return ((m >> 7) * 0x00204081u >> 21) & 0xfu; };  // bits 7,15,23,31 -> 0..3
+    return pack(m0) | (pack(m1) << 4) | (pack(m2) << 8) | (pack(m3) << 12);
+}
+__device__ __forceinline__ PreBytes pre_classify(const uint8_t* __restrict__ in, uint32_t n, uint32_t o, bool dri) {
+    PreBytes r;
+    r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0u;
+    r.keep = r.rstm = r.next = 0u;
+    if (o >= n) return r;
+    uint32_t prev = 0;
+    {
+        const uint4 v = *reinterpret_cast<const uint4*>(in + o);  // raw arena is 16-byte padded
+        r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+        if (o > 0) prev = in[o - 1];
+        if (o + 16 < n) r.next = in[o + 16];
+    }
+    const uint32_t valid = n - o >= 16u ? 0xffffu : (1u << (n - o)) - 1u;
+    // byte k is 0xff / 0x00 (bit k), four bytes per word at a time
+    const uint32_t ff = marks16(bytes_eq(r.w[0], 0xffffffffu), bytes_eq(r.w[1], 0xffffffffu), bytes_eq(r.w[2], 0xffffffffu),
+                                bytes_eq(r.w[3], 0xffffffffu));
+    const uint32_t zz = marks16(bytes_eq(r.w[0], 0u), bytes_eq(r.w[1], 0u), bytes_eq(r.w[2], 0u), bytes_eq(r.w[3], 0u));
+    const uint32_t prev_ff = ((ff << 1) | (prev == 0xffu ? 1u : 0u)) & 0xffffu;   // the byte before k is 0xff
+    uint32_t drop = zz & prev_ff;                            // stuffed zero (mod.rs:378-382)
+    if (dri) {  // restart-interval extension: RSTn markers and fill bytes leave the stream
+        const uint32_t dx = marks16(bytes_eq(r.w[0] & 0xf8f8f8f8u, 0xd0d0d0d0u), bytes_eq(r.w[1] & 0xf8f8f8f8u, 0xd0d0d0d0u),
+                                    bytes_eq(r.w[2] & 0xf8f8f8f8u, 0xd0d0d0d0u), bytes_eq(r.w[3] & 0xf8f8f8f8u, 0xd0d0d0d0u));
+        const uint32_t has_next = n - o > 16u ? 0xffffu : valid >> 1;               // byte k+1 exists
+        const uint32_t next_dx = ((dx >> 1) | ((r.next & 0xf8u) == 0xd0u ? 0x8000u : 0u)) & has_next;
+        const uint32_t next_ff = ((ff >> 1) | (r.next == 0xffu ? 0x8000u : 0u)) & has_next;
+        const uint32_t r1 = ff & next_dx;                    // FF of a marker
+        const uint32_t r2 = dx & prev_ff;                    // its Dn byte
+        const uint32_t fill = ff & next_ff;                  // FF FF: fill byte
+        drop |= r1 | r2 | fill;
+        r.rstm = r1 & valid;
+    }
+    r.keep = ~drop & valid;
+    return r;
+}
+
+// CTA-wide exclusive scan of two counters (kept bytes, markers). Returns the exclusive prefixes and the totals.
+__device__ __forceinline__ void pre_scan(uint32_t cnt, uint32_t nr, uint32_t (*s_wsum)[kPreThreads / 32], uint32_t& exc,
+                                         uint32_t& exr, uint32_t& totc, uint32_t& totr) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t ic = cnt, ir = nr;  // warp-inclusive scans
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t tc = __shfl_up_sync(0xffffffffu, ic, d);
+        const uint32_t tr = __shfl_up_sync(0xffffffffu, ir, d);
+        if (lane >= (uint32_t)d) { ic += tc; ir += tr; }
+    }
+    if (lane == 31) { s_wsum[0][warp] = ic; s_wsum[1][warp] = ir; }
+    __syncthreads();
+    uint32_t wc = 0, wr = 0;
+    totc = totr = 0;
+#pragma unroll
+    for (int i = 0; i < kPreThreads / 32; i++) {
+        const uint32_t a = s_wsum[0][i], r = s_wsum[1][i];
+        if ((uint32_t)i < warp) { wc += a; wr += r; }
+        totc += a; totr += r;
+    }
+    exc = wc + ic - cnt;
+    exr = wr + ir - nr;
+}
+
+// (1) grid (max chunks of any image, images): counts per chunk.
+__global__ void __launch_bounds__(kPreThreads) prepass_count_kernel(BatchDev b) {
+    __shared__ uint32_t s_wsum[2][kPreThreads / 32];
+    const ImgDev& im = b.imgs[blockIdx.y];
+    const uint32_t n = im.raw_len, base = blockIdx.x * kPreChunk;
+    if (base >= n) return;
+    const PreBytes pb = pre_classify(b.raw + im.raw_off, n, base + threadIdx.x * 16, im.restart_interval != 0);
+    uint32_t exc, exr, totc, totr;
+    pre_scan(__popc(pb.keep), __popc(pb.rstm), s_wsum, exc, exr, totc, totr);
+    if (threadIdx.x == 0) b.chunk_counts[im.chunk_off + blockIdx.x] = make_uint2(totc, totr);
+}
+
+// (2) one CTA per image: exclusive scan of its chunk counts; stream length, interval count, padding.
+__global__ void __launch_bounds__(kPreThreads) prepass_scan_kernel(BatchDev b) {
+    __shared__ uint32_t s_wsum[2][kPreThreads / 32];
+    const ImgDev& im = b.imgs[blockIdx.x];
+    const uint32_t nchunks = (im.raw_len + kPreChunk - 1) / kPreChunk;
+    uint2* counts = b.chunk_counts + im.chunk_off;
+    const uint32_t per = (nchunks + kPreThreads - 1) / kPreThreads;
+    const uint32_t lo = threadIdx.x * per, hi = min(nchunks, lo + per);
+    uint32_t c = 0, r = 0;
+    for (uint32_t i = lo; i < hi; i++) { const uint2 v = counts[i]; c += v.x; r += v.y; }
+    uint32_t exc, exr, totc, totr;
+    pre_scan(c, r, s_wsum, exc, exr, totc, totr);
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint2 v = counts[i];
+        counts[i] = make_uint2(exc, exr);
+        exc += v.x; exr += v.y;
+    }
+    if (threadIdx.x == 0) {
+        uint32_t* out = b.stream + im.stream_off;
+        uint32_t* seg = b.segtab + im.seg_off;
+        const uint32_t wend = (totc + 3u) >> 2;
+        for (int i = 0; i < kStreamPadWords; i++) out[stream_phys(wend + i, b.lw)] = 0u;
+        const bool dri = im.restart_interval != 0;
+        uint32_t nseg = totr + 1, st = 0;
+        if (nseg != im.nseg_cap && dri) st |= kStRestart;
+        if (nseg > im.nseg_cap) nseg = im.nseg_cap;
+        seg[0] = 0u;
+        seg[nseg] = totc * 8u;
+        ImgDyn d;
+        d.stream_bits = totc * 8u; d.nseg = nseg; d.status = st; d.bits_consumed = 0u;
+        b.dyn[blockIdx.x] = d;
+    }
+}
+
+// (3) grid as (1): every chunk writes its kept bytes at its offset. A stream word IS the next 32 bits (first byte
+// in the most significant position); words a chunk only partly covers are written byte by byte, since the
+// neighbouring chunk owns the other bytes.
+__global__ void __launch_bounds__(kPreThreads) prepass_write_kernel(BatchDev b) {
     __shared__ uint32_t s_stage[kPreChunk / 4 + 8];
     __shared__ uint32_t s_wsum[2][kPreThreads / 32];
-    __shared__ uint32_t s_status;
-
-    const ImgDev& im = b.imgs[blockIdx.x];
-    const uint8_t* __restrict__ in = b.raw + im.raw_off;
-    const uint32_t n = im.raw_len;
-    uint32_t* __restrict__ out = b.stream + im.stream_off;
-    uint32_t* __restrict__ seg = b.segtab + im.seg_off;
-    const bool dri = im.restart_interval != 0;
-    const uint32_t nseg_cap = im.nseg_cap;
-    const uint32_t lw = b.lw;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ImgDev& im = b.imgs[blockIdx.y];
+    const uint32_t n = im.raw_len, base = blockIdx.x * kPreChunk;
+    if (base >= n) return;
+    const uint32_t lw = b.lw, tid = threadIdx.x;
+    const PreBytes pb = pre_classify(b.raw + im.raw_off, n, base + tid * 16, im.restart_interval != 0);
+    const uint2 start = b.chunk_counts[im.chunk_off + blockIdx.x];   // bytes / markers before this chunk
+    uint32_t exc, exr, totc, totr;
+    pre_scan(__popc(pb.keep), __popc(pb.rstm), s_wsum, exc, exr, totc, totr);
     uint8_t* stage_bytes = reinterpret_cast<uint8_t*>(s_stage);
-    uint32_t emitted = 0, rst_total = 0;
-    if (tid == 0) s_status = 0;
-    __syncthreads();
-
-    for (uint32_t base = 0; base < n; base += kPreChunk) {
-        const uint32_t o = base + tid * 16;
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        uint32_t prev = 0, next = 0;
-        if (o < n) {
-            const uint4 v = *reinterpret_cast<const uint4*>(in + o);  // raw arena is 16-byte padded
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            if (o > 0) prev = in[o - 1];
-            if (o + 16 < n) next = in[o + 16];
-        }
-        uint32_t keep = 0, rstm = 0;
-        uint32_t p = prev;
+    const uint32_t carry = start.x & 3u;
+    uint32_t pos = carry + exc;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const uint32_t cur = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
-            const uint32_t nxt = k < 15 ? ((w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu) : next;
-            const bool valid = o + k < n;
-            const bool has_next = o + k + 1 < n;
-            bool drop = (cur == 0u && p == 0xffu);  // stuffed zero (mod.rs:378-382)
-            bool r1 = false;
-            if (dri) {  // restart-interval extension: RSTn markers and fill bytes leave the stream
-                r1 = cur == 0xffu && has_next && (nxt & 0xf8u) == 0xd0u;
-                const bool r2 = p == 0xffu && (cur & 0xf8u) == 0xd0u;
-                const bool fill = cur == 0xffu && has_next && nxt == 0xffu;
-                drop = drop || r1 || r2 || fill;
-            }
-            if (valid && !drop) keep |= 1u << k;
-            if (valid && r1) rstm |= 1u << k;
-            p = cur;
+    for (int k = 0; k < 16; k++) {
+        if (pb.keep & (1u << k)) {
+            stage_bytes[pos ^ 3u] = (uint8_t)((pb.w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+            pos++;
         }
-        const uint32_t cnt = __popc(keep), nr = __popc(rstm);
-        uint32_t ic = cnt, ir = nr;  // warp-inclusive scans
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t tc = __shfl_up_sync(0xffffffffu, ic, d);
-            const uint32_t tr = __shfl_up_sync(0xffffffffu, ir, d);
-            if (lane >= (uint32_t)d) { ic += tc; ir += tr; }
-        }
-        if (lane == 31) { s_wsum[0][warp] = ic; s_wsum[1][warp] = ir; }
-        __syncthreads();
-        uint32_t wc = 0, wr = 0, totc = 0, totr = 0;
-#pragma unroll
-        for (int i = 0; i < kPreThreads / 32; i++) {
-            const uint32_t a = s_wsum[0][i], r = s_wsum[1][i];
-            if ((uint32_t)i < warp) { wc += a; wr += r; }
-            totc += a; totr += r;
-        }
-        const uint32_t exc = wc + ic - cnt, exr = wr + ir - nr;
-        const uint32_t carry = emitted & 3u;
-        uint32_t pos = carry + exc;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if (keep & (1u << k)) {
-                stage_bytes[pos ^ 3u] = (uint8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xffu);  // first byte = MSB of the word
-                pos++;
-            }
-        }
-        if (rstm) {
-            uint32_t r = rst_total + exr;
-#pragma unroll 1
-            for (int k = 0; k < 16; k++) {
-                if (!(rstm & (1u << k))) continue;
-                const uint32_t idx = emitted + exc + __popc(keep & ((1u << k) - 1u));
-                if (r + 1 < nseg_cap) seg[r + 1] = idx * 8u;
-                const uint32_t mk = k < 15 ? ((w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu) : next;
-                if ((mk & 7u) != (r & 7u)) atomicOr(&s_status, kStRestart);
-                r++;
-            }
-        }
-        __syncthreads();
-        const uint32_t staged = carry + totc, nw = staged >> 2, wbase = (emitted - carry) >> 2;
-        for (uint32_t i = tid; i < nw; i += kPreThreads) out[stream_phys(wbase + i, lw)] = s_stage[i];
-        __syncthreads();
-        if (tid == 0 && (staged & 3u) && nw) s_stage[0] = s_stage[nw];
-        __syncthreads();
-        emitted += totc;
-        rst_total += totr;
     }
-    if (tid == 0) {
-        const uint32_t carry = emitted & 3u;
-        uint32_t wbase = (emitted - carry) >> 2;
-        if (carry) { out[stream_phys(wbase, lw)] = s_stage[0] & (0xffffffffu << (32 - 8 * carry)); wbase++; }
-        for (int i = 0; i < kStreamPadWords; i++) out[stream_phys(wbase + i, lw)] = 0u;
-        uint32_t nseg = rst_total + 1;
-        uint32_t st = s_status;
-        if (nseg != nseg_cap && dri) st |= kStRestart;
-        if (nseg > nseg_cap) nseg = nseg_cap;
-        seg[0] = 0u;
-        seg[nseg] = emitted * 8u;
-        ImgDyn d;
-        d.stream_bits = emitted * 8u; d.nseg = nseg; d.status = st; d.bits_consumed = 0u;
-        b.dyn[blockIdx.x] = d;
+    if (pb.rstm) {
+        uint32_t* seg = b.segtab + im.seg_off;
+        uint32_t r = start.y + exr;
+#pragma unroll 1
+        for (int k = 0; k < 16; k++) {
+            if (!(pb.rstm & (1u << k))) continue;
+            const uint32_t idx = start.x + exc + __popc(pb.keep & ((1u << k) - 1u));
+            if (r + 1 < im.nseg_cap) seg[r + 1] = idx * 8u;
+            const uint32_t mk = k < 15 ? ((pb.w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu) : pb.next;
+            if ((mk & 7u) != (r & 7u)) atomicOr(&b.dyn[blockIdx.y].status, kStRestart);
+            r++;
+        }
+    }
+    __syncthreads();
+    uint32_t* out = b.stream + im.stream_off;
+    const uint32_t staged = carry + totc, w0 = start.x >> 2, nw = (staged + 3u) >> 2;
+    for (uint32_t i = tid; i < nw; i += kPreThreads) {
+        const uint32_t lo = max(4u * i, carry), hi = min(4u * i + 4u, staged);
+        if (hi - lo == 4u) {
+            out[stream_phys(w0 + i, lw)] = s_stage[i];
+        } else {
+            uint8_t* wb = reinterpret_cast<uint8_t*>(out + stream_phys(w0 + i, lw));
+            for (uint32_t q = lo; q < hi; q++) wb[3u - (q & 3u)] = stage_bytes[q ^ 3u];
+        }
     }
 }
 
@@ -358,13 +420,15 @@ __device__ __forceinline__ uint32_t fast_long_code(const FastCtx& cx, FastState&
 template <int NBUF>
 struct WriteLane {
     static_assert(NBUF >= 1 && NBUF <= 2, "two completion slots");
+    enum : uint32_t { kRun = 0, kBlocked = 1, kFinished = 2 };
     uint32_t row_addr, swz16;  // shared address / piece swizzle of the buffer being filled
     uint32_t rows_addr, row0;  // address of this lane's first row, its row number
     uint32_t cur, ndone;       // ring position, completed (unflushed) buffers
-    uint32_t dest0, dest1;     // arena block index of each completed buffer, oldest first (0xffffffff = discard); NBUF <= 2
+    uint32_t dest0, dest1;     // arena block index of each completed buffer, oldest first (0xffffffff = discard)
     uint32_t end_bit;
     int32_t total;
-    bool store_on, active, run;
+    uint32_t store_on;         // 0 while finishing a block that started in the previous subsequence
+    uint32_t state;            // kRun / kBlocked (out of buffers until the next flush) / kFinished
     __device__ __forceinline__ void select(uint32_t c) {
         cur = c;
         row_addr = rows_addr + c * 128u;
@@ -373,13 +437,13 @@ struct WriteLane {
     // the buffer being filled is complete (block index d) or to be discarded; z == 0 now
     __device__ __forceinline__ void close_block(uint32_t d, uint32_t p, int32_t g) {
         if (store_on) {
-            if (ndone == 0u) dest0 = d; else dest1 = d;
+            if (NBUF == 1 || ndone == 0u) dest0 = d; else dest1 = d;
             ndone++;
-            select(cur + 1 == (uint32_t)NBUF ? 0u : cur + 1);
+            if (NBUF > 1) select(cur + 1 == (uint32_t)NBUF ? 0u : cur + 1);
         }
-        store_on = true;
-        if (p >= end_bit || g >= total) { active = false; run = false; }   // finished: block boundary past the subsequence / scan
-        else if (ndone == (uint32_t)NBUF) run = false;                         // out of buffers until the next flush
+        store_on = 1u;
+        // finished: block boundary past the subsequence / scan; blocked: no free buffer
+        state = (p >= end_bit || g >= total) ? (uint32_t)kFinished : (ndone == (uint32_t)NBUF ? (uint32_t)kBlocked : (uint32_t)kRun);
     }
 };
 struct NoLane {};
@@ -416,7 +480,7 @@ __device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, 
     const uint32_t nz = z + adv;
     if constexpr (WRITE) {
         const uint32_t off = lds8(cx.sp_addr + min(nz - 1u, 63u));   // huffman.rs:183-189
-        sts16_if(wl.row_addr + (off ^ wl.swz16), (uint32_t)(is_dc ? st.dcur : val), wl.store_on && (is_dc || val != 0));
+        sts16_if(wl.row_addr + (off ^ wl.swz16), (uint32_t)(is_dc ? st.dcur : val), wl.store_on != 0u && (is_dc || val != 0));
     }
     st.hi = __funnelshift_lc(st.lo, st.hi, tb);
     st.lo = __funnelshift_lc(0u, st.lo, tb);
@@ -717,30 +781,30 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
     wl.dest0 = wl.dest1 = 0u;
     wl.end_bit = end_bit;
     wl.total = total;
-    wl.store_on = store_on;
-    wl.active = active;
+    wl.store_on = store_on ? 1u : 0u;
+    wl.state = active ? (uint32_t)WriteLane<NBUF>::kRun : (uint32_t)WriteLane<NBUF>::kFinished;
 
 #pragma unroll 1
     while (true) {
         // ---- phase A: every lane decodes up to PHASE symbols into its own buffers.  Whether a lane is finished
         // (block boundary at or past the end of its subsequence, or past the last block of the scan) or out of
         // buffers can only change when a block completes, so it is only looked at there (WriteLane::close_block).
-        wl.run = wl.active;
 #pragma unroll 1
         for (int k = 0; k < PHASE; k++) {
-            if (wl.run) {
+            if (wl.state == WriteLane<NBUF>::kRun) {
                 const int32_t g_before = st.g;
                 const uint32_t ev = fast_step<true, true>(cx, st, wl);
                 if (ev & (kEvCross | kEvEnd)) {  // rare: restart interval / end of data
-                    if (ev & kEvEnd) { wl.active = false; wl.run = false; }
+                    if (ev & kEvEnd) wl.state = WriteLane<NBUF>::kFinished;
                     // a valid stream only changes interval between blocks; drop a half-written block of a corrupt one
                     else if ((g_before & 63) != 0) wl.close_block(0xffffffffu, st.p, st.g);
-                    else { wl.store_on = true; if (st.p >= end_bit || st.g >= total) { wl.active = false; wl.run = false; } }
+                    else { wl.store_on = 1u; if (st.p >= end_bit || st.g >= total) wl.state = WriteLane<NBUF>::kFinished; }
                 }
             }
         }
+        if (wl.state == WriteLane<NBUF>::kBlocked) wl.state = WriteLane<NBUF>::kRun;
+        active = wl.state != WriteLane<NBUF>::kFinished;
         const uint32_t ndone = wl.ndone, cur = wl.cur, row0 = wl.row0;
-        active = wl.active;
         // ---- phase B: the warp flushes all completed blocks, 8 lanes per block
         uint32_t offs = 0, count = 0;
 #pragma unroll
@@ -1093,7 +1157,11 @@ __global__ void __launch_bounds__(kGatherThreads) gather_colour_kernel(BatchDev 
 
 // ===================================================================== launchers
 void launch_prepass(const BatchDev& b, cudaStream_t s) {
-    if (b.n_images) prepass_kernel<<<b.n_images, kPreThreads, 0, s>>>(b);
+    if (!b.n_images || !b.max_chunks) return;
+    const dim3 grid(b.max_chunks, b.n_images);
+    prepass_count_kernel<<<grid, kPreThreads, 0, s>>>(b);
+    prepass_scan_kernel<<<b.n_images, kPreThreads, 0, s>>>(b);
+    prepass_write_kernel<<<grid, kPreThreads, 0, s>>>(b);
 }
 void launch_sync(const BatchDev& b, cudaStream_t s) {
     if (b.n_seqs) sync_kernel<<<b.n_seqs / kJobsPerCta, kSeqThreads, 0, s>>>(b);

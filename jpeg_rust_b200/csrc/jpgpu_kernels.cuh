@@ -32,6 +32,8 @@ struct BatchDev {        // device pointers of one planned batch
     uint32_t lw;         // log2(sub_bits / 32): words per subsequence
     uint32_t lookback_bits;
     uint32_t max_slots;
+    uint32_t max_chunks;      // most 4 KiB raw chunks any image has
+    uint2* chunk_counts;      // per chunk: kept bytes / RSTn markers, then (after the scan) those before the chunk
     uint32_t write_mode;      // decode_write_kernel variant (experiments)
     uint32_t seg_bits;        // checkpoint distance inside a subsequence (divides sub_bits)
     SegRec* segs;             // sub_bits / seg_bits records per subsequence
@@ -48,7 +50,7 @@ struct BatchDev {        // device pointers of one planned batch
 
 cudaError_t init_constants();
 
-// Stage 1a: byte-unstuffing + RSTn detection, one CTA per image.
+// Stage 1a: byte-unstuffing + RSTn detection: count per 4 KiB chunk, scan per image, compact per chunk.
 void launch_prepass(const BatchDev& b, cudaStream_t s);
 // Stage 1b: look-back synchronisation, one thread per subsequence.
 void launch_sync(const BatchDev& b, cudaStream_t s);
