@@ -236,8 +236,17 @@ def main():
     barrier()
     t_wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ent_ev, idct_ev = [], []
     e0.record(stream)
+    for k in range(args.steps):
+        batch.decode()            # the call a user makes: image groups pipelined over two streams inside the library
+    e1.record(stream)
+    barrier()
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = batch.launch_count() - launches0
+    ms_per_step = total_ms / args.steps
+    value = world * pixels / (ms_per_step * 1e-3) / 1e6
+    # stage breakdown and the IDCT/colour kernel's own duration: the same work, stage after stage on one stream
+    ent_ev, idct_ev = [], []
     for k in range(args.steps):
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record(stream)
@@ -247,12 +256,7 @@ def main():
         c.record(stream)
         ent_ev.append((a, b))
         idct_ev.append((b, c))
-    e1.record(stream)
     barrier()
-    total_ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = batch.launch_count() - launches0
-    ms_per_step = total_ms / args.steps
-    value = world * pixels / (ms_per_step * 1e-3) / 1e6
     idct_ms = sum(a.elapsed_time(b) for a, b in idct_ev) / args.steps
     ent_ms = sum(a.elapsed_time(b) for a, b in ent_ev) / args.steps
     peak, peak_src = measured_peak()
@@ -360,7 +364,8 @@ def main():
                        f"{stats['scan_bytes'] / 1e6:.0f} MB bitstream, {stats['coef_bytes'] / 1e9:.2f} GB coefficients",
                        "parallelism": f"images sharded over {world} GPU(s), no collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "stage_ms": {"entropy": ent_ms, "idct_colour": idct_ms},
+            "stage_ms": {"entropy": ent_ms, "idct_colour": idct_ms, "note": "stages run one after the other on one stream; "
+                         "`value` is timed over jpgpu_batch_decode, which overlaps the image groups of a batch"},
         }
         print(json.dumps(line), flush=True)
     batch.close()

@@ -18,6 +18,11 @@ struct jpgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // auxiliary streams on which jpgpu_batch_decode runs every other group of a batch (fork/join around the
+    // caller's stream, so the call keeps its stream semantics)
+    static constexpr int kAux = 3;
+    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[kAux] = {nullptr, nullptr, nullptr};
     std::string err;
 };
 
@@ -112,6 +117,11 @@ extern "C" int jpgpu_create(int device, jpgpu_ctx** out) {
 extern "C" void jpgpu_destroy(jpgpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (int i = 0; i < jpgpu_ctx::kAux; i++) {
+        if (c->aux[i]) { cudaStreamSynchronize(c->aux[i]); cudaStreamDestroy(c->aux[i]); }
+        if (c->join[i]) cudaEventDestroy(c->join[i]);
+    }
+    if (c->fork) cudaEventDestroy(c->fork);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -288,10 +298,66 @@ extern "C" int jpgpu_batch_idct(jpgpu_batch* b) {
     return JPGPU_OK;
 }
 
+namespace {
+
+BatchDev group_dev(const jpgpu_batch* b, const GroupPlan& g) {
+    BatchDev d = b->dev;
+    d.img0 = g.img0; d.n_images = g.nimg;
+    d.job0 = g.job0; d.n_seqs = g.njobs;
+    d.max_chunks = g.max_chunks;
+    for (int k = 0; k < kNumKinds; k++) {
+        d.kind_imgs[k] = b->dev.kind_imgs[k] + g.kind_lo[k];
+        d.kind_count[k] = g.kind_hi[k] - g.kind_lo[k];
+        d.kind_max_tiles[k] = g.kind_max_tiles[k];
+    }
+    d.gather_max_blocks = g.gather_max_blocks;
+    d.gather_max_quads = g.gather_max_quads;
+    return d;
+}
+
+int ensure_aux(jpgpu_ctx* ctx) {
+    for (int i = 0; i < jpgpu_ctx::kAux; i++) {
+        if (!ctx->aux[i]) CK(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+        if (!ctx->join[i]) CK(cudaEventCreateWithFlags(&ctx->join[i], cudaEventDisableTiming));
+    }
+    if (!ctx->fork) CK(cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming));
+    return JPGPU_OK;
+}
+
+}  // namespace
+
+// entropy + idct.  A large batch is cut into groups of images (HostPlan::groups) whose kernel chains alternate
+// between two auxiliary streams: the low-occupancy ends of one group's kernels (repair walks, last waves) overlap
+// the next group's work.  Forked from and joined back into the context stream.
 extern "C" int jpgpu_batch_decode(jpgpu_batch* b) {
-    int st = jpgpu_batch_entropy(b);
+    if (!b) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    if (b->plan.groups.size() <= 1) {
+        int st = jpgpu_batch_entropy(b);
+        if (st != JPGPU_OK) return st;
+        return jpgpu_batch_idct(b);
+    }
+    CK(cudaSetDevice(ctx->device));
+    int st = ensure_aux(ctx);
     if (st != JPGPU_OK) return st;
-    return jpgpu_batch_idct(b);
+    CK(cudaEventRecord(ctx->fork, ctx->stream));
+    for (int i = 0; i < jpgpu_ctx::kAux; i++) CK(cudaStreamWaitEvent(ctx->aux[i], ctx->fork, 0));
+    for (size_t g = 0; g < b->plan.groups.size(); g++) {
+        cudaStream_t s = ctx->aux[g % jpgpu_ctx::kAux];
+        const BatchDev d = group_dev(b, b->plan.groups[g]);
+        launch_prepass(d, s);
+        launch_sync(d, s);
+        launch_verify_scan(d, s);
+        CK(launch_decode_write(d, s));
+        b->launches += 6 + (uint64_t)launch_idct_colour(d, s);
+    }
+    for (int i = 0; i < jpgpu_ctx::kAux; i++) {
+        CK(cudaEventRecord(ctx->join[i], ctx->aux[i]));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->join[i], 0));
+    }
+    CK(cudaGetLastError());
+    b->decoded = true;
+    return JPGPU_OK;
 }
 
 extern "C" int jpgpu_batch_download(jpgpu_batch* b, uint8_t* const* outs) {

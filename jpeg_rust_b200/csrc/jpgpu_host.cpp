@@ -192,12 +192,44 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
     std::map<std::string, uint32_t> qt_ids;
     std::map<std::string, uint64_t> map_ids;
     std::string cur_lutset;
+    // groups: contiguous image ranges of about equal scan bytes
+    uint64_t tot_bytes = 0;
+    for (size_t i = 0; i < n; i++) tot_bytes += descs[i].scan_len;
+    uint32_t want_groups = n >= 192 ? 3u : (n >= 128 ? 2u : 1u);   // few, large groups: small kernels lose more in their tails than overlap wins
+    if (const char* e = getenv("JPGPU_GROUPS")) { const long v = atol(e); if (v >= 1 && v <= 64) want_groups = (uint32_t)v; }
+    if (want_groups > n) want_groups = n ? (uint32_t)n : 1u;
+    const uint64_t group_bytes = tot_bytes / want_groups + 1;
+    uint64_t acc_bytes = 0;
+    constexpr uint32_t kJobsPerCta = kSeqThreads / 32;
+    auto close_group = [&](size_t next_img) {
+        while (plan.seqs.size() % kJobsPerCta != 0) plan.seqs.push_back(SeqDesc{0xffffffffu, 0u});
+        if (!plan.groups.empty()) {
+            GroupPlan& g = plan.groups.back();
+            g.nimg = (uint32_t)next_img - g.img0;
+            g.njobs = (uint32_t)plan.seqs.size() - g.job0;
+            for (int k = 0; k < kNumKinds; k++) g.kind_hi[k] = (uint32_t)plan.kind_imgs[k].size();
+        }
+    };
+    auto open_group = [&](size_t img) {
+        GroupPlan g;
+        g.img0 = (uint32_t)img;
+        g.job0 = (uint32_t)plan.seqs.size();
+        for (int k = 0; k < kNumKinds; k++) g.kind_lo[k] = (uint32_t)plan.kind_imgs[k].size();
+        plan.groups.push_back(g);
+        cur_lutset.clear();
+    };
+    open_group(0);
     auto align_up = [](uint64_t x, uint64_t a) { return (x + a - 1) / a * a; };
 
     for (size_t i = 0; i < n; i++) {
         const jpgpu_image_desc& d = descs[i];
         ImgDev& im = plan.imgs[i];
         memset(&im, 0, sizeof im);
+        if (i > 0 && acc_bytes >= (uint64_t)plan.groups.size() * group_bytes && plan.groups.size() < want_groups) {
+            close_group(i);
+            open_group(i);
+        }
+        acc_bytes += d.scan_len;
         Geometry g;
         int st = compute_geometry(d, g);
         if (st == JPGPU_OK && (d.scan == nullptr || d.scan_len < 4)) st = JPGPU_PANIC_INDEX_OOB;  // huffman.rs:127-128
@@ -327,6 +359,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
             im.chunk_off = (uint32_t)plan.chunk_entries;
             plan.chunk_entries += nchunks;
             plan.max_chunks = std::max(plan.max_chunks, nchunks);
+            plan.groups.back().max_chunks = std::max(plan.groups.back().max_chunks, nchunks);
         }
         im.nsub_cap = std::max<uint32_t>(1u, (uint32_t)(((uint64_t)im.raw_len * 8 + sub_bits - 1) / sub_bits));
         im.sub_off = (uint32_t)plan.sub_entries;
@@ -335,7 +368,6 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         // to different images as long as those use the same Huffman tables (the CTA keeps one copy in shared memory)
         {
             std::string lutset((const char*)slot_lut, sizeof(uint32_t) * (size_t)nslots);
-            constexpr uint32_t kJobsPerCta = kSeqThreads / 32;
             if (lutset != cur_lutset && plan.seqs.size() % kJobsPerCta != 0)
                 while (plan.seqs.size() % kJobsPerCta != 0) plan.seqs.push_back(SeqDesc{0xffffffffu, 0u});
             cur_lutset = lutset;
@@ -352,6 +384,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         im.tiles_y = g.mcuy;
         plan.kind_imgs[im.kind].push_back((uint32_t)i);
         plan.kind_max_tiles[im.kind] = std::max(plan.kind_max_tiles[im.kind], im.tiles_x * im.tiles_y);
+        plan.groups.back().kind_max_tiles[im.kind] = std::max(plan.groups.back().kind_max_tiles[im.kind], im.tiles_x * im.tiles_y);
         if (im.kind == kKindGeneric) {
             const uint32_t nblk = g.units * g.blocks_per_mcu;
             im.map_off = map_off;
@@ -360,6 +393,8 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
             plan.sample_floats += (uint64_t)nblk * 64;
             plan.gather_max_blocks = std::max(plan.gather_max_blocks, nblk);
             plan.gather_max_quads = std::max(plan.gather_max_quads, map_plane / 4);
+            plan.groups.back().gather_max_blocks = std::max(plan.groups.back().gather_max_blocks, nblk);
+            plan.groups.back().gather_max_quads = std::max(plan.groups.back().gather_max_quads, map_plane / 4);
         }
 
         plan.tot_scan_bytes += im.raw_len;
@@ -367,7 +402,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         plan.tot_pixels += (uint64_t)im.width * im.height;
         plan.tot_rgb_bytes += (uint64_t)im.width * im.height * 3;
     }
-    while (plan.seqs.size() % (kSeqThreads / 32) != 0) plan.seqs.push_back(SeqDesc{0xffffffffu, 0u});
+    close_group(n);
     if (plan.sub_entries > 0xffffffffull || plan.seg_entries > 0xffffffffull) return JPGPU_ERR_UNSUPPORTED;
     return JPGPU_OK;
 }

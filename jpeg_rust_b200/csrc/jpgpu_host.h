@@ -31,7 +31,17 @@ int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, bool 
 // 64 multipliers (column-major) = q * aan[u] * aan[v] / 8 from a zigzag-order DQT table.
 void build_qt_multipliers(const uint16_t qt_zigzag[64], float out[64]);
 
+// A contiguous range of images whose kernels are launched together; the groups of a batch run on alternating
+// streams so that the tail of one kernel overlaps the next group's work (jpgpu_batch_decode).
+struct GroupPlan {
+    uint32_t img0 = 0, nimg = 0, job0 = 0, njobs = 0, max_chunks = 0;
+    uint32_t kind_lo[kNumKinds] = {0, 0, 0, 0, 0, 0}, kind_hi[kNumKinds] = {0, 0, 0, 0, 0, 0};
+    uint32_t kind_max_tiles[kNumKinds] = {0, 0, 0, 0, 0, 0};
+    uint32_t gather_max_blocks = 0, gather_max_quads = 0;
+};
+
 struct HostPlan {
+    std::vector<GroupPlan> groups;
     uint32_t sub_bits = kMinSubseqBits;
     uint32_t lw = 5;             // log2(words per subsequence)
     uint32_t lookback_bits = kDefaultLookbackBits;

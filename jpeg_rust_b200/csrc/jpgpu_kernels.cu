@@ -111,7 +111,7 @@ __device__ __forceinline__ void pre_scan(uint32_t cnt, uint32_t nr, uint32_t (*s
 // (1) grid (max chunks of any image, images): counts per chunk.
 __global__ void __launch_bounds__(kPreThreads) prepass_count_kernel(BatchDev b) {
     __shared__ uint32_t s_wsum[2][kPreThreads / 32];
-    const ImgDev& im = b.imgs[blockIdx.y];
+    const ImgDev& im = b.imgs[b.img0 + blockIdx.y];
     const uint32_t n = im.raw_len, base = blockIdx.x * kPreChunk;
     if (base >= n) return;
     const PreBytes pb = pre_classify(b.raw + im.raw_off, n, base + threadIdx.x * 16, im.restart_interval != 0);
@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(kPreThreads) prepass_count_kernel(BatchDev b) 
 // (2) one CTA per image: exclusive scan of its chunk counts; stream length, interval count, padding.
 __global__ void __launch_bounds__(kPreThreads) prepass_scan_kernel(BatchDev b) {
     __shared__ uint32_t s_wsum[2][kPreThreads / 32];
-    const ImgDev& im = b.imgs[blockIdx.x];
+    const uint32_t img = b.img0 + blockIdx.x;
+    const ImgDev& im = b.imgs[img];
     const uint32_t nchunks = (im.raw_len + kPreChunk - 1) / kPreChunk;
     uint2* counts = b.chunk_counts + im.chunk_off;
     const uint32_t per = (nchunks + kPreThreads - 1) / kPreThreads;
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kPreThreads) prepass_scan_kernel(BatchDev b) {
         seg[nseg] = totc * 8u;
         ImgDyn d;
         d.stream_bits = totc * 8u; d.nseg = nseg; d.status = st; d.bits_consumed = 0u;
-        b.dyn[blockIdx.x] = d;
+        b.dyn[img] = d;
     }
 }
 
@@ -160,7 +161,8 @@ __global__ void __launch_bounds__(kPreThreads) prepass_scan_kernel(BatchDev b) {
 __global__ void __launch_bounds__(kPreThreads) prepass_write_kernel(BatchDev b) {
     __shared__ uint32_t s_stage[kPreChunk / 4 + 8];
     __shared__ uint32_t s_wsum[2][kPreThreads / 32];
-    const ImgDev& im = b.imgs[blockIdx.y];
+    const uint32_t img = b.img0 + blockIdx.y;
+    const ImgDev& im = b.imgs[img];
     const uint32_t n = im.raw_len, base = blockIdx.x * kPreChunk;
     if (base >= n) return;
     const uint32_t lw = b.lw, tid = threadIdx.x;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(kPreThreads) prepass_write_kernel(BatchDev b) 
             const uint32_t idx = start.x + exc + __popc(pb.keep & ((1u << k) - 1u));
             if (r + 1 < im.nseg_cap) seg[r + 1] = idx * 8u;
             const uint32_t mk = k < 15 ? ((pb.w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu) : pb.next;
-            if ((mk & 7u) != (r & 7u)) atomicOr(&b.dyn[blockIdx.y].status, kStRestart);
+            if ((mk & 7u) != (r & 7u)) atomicOr(&b.dyn[img].status, kStRestart);
             r++;
         }
     }
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     __shared__ EntropySmem sm;
     __shared__ FastTables ft;
     const int warp = threadIdx.x >> 5;
-    const SeqDesc sd = b.seqs[blockIdx.x * kJobsPerCta + warp];
+    const SeqDesc sd = b.seqs[b.job0 + blockIdx.x * kJobsPerCta + warp];
     const uint32_t S = b.sub_bits;
     load_entropy_img(b, sd.img, sm, 32);
     load_entropy_luts(b, sm, kSeqThreads);
@@ -637,7 +639,7 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
     __shared__ RepairJob s_jobs[kRepairJobs];
     __shared__ uint32_t s_count;
 
-    const uint32_t img = blockIdx.x;
+    const uint32_t img = b.img0 + blockIdx.x;
     const uint32_t S = b.sub_bits;
     load_entropy_img(b, threadIdx.x < 32 ? img : kNoImage, sm, 32);
     const ImgDev& im = sm.img[0];
@@ -740,7 +742,7 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint2* const flist = reinterpret_cast<uint2*>(dyn_smem + lay.list_off) + warp * (32 * NBUF);
 
-    const SeqDesc sd = b.seqs[blockIdx.x * kJobsPerCta + warp];
+    const SeqDesc sd = b.seqs[b.job0 + blockIdx.x * kJobsPerCta + warp];
     const uint32_t S = b.sub_bits;
     load_entropy_img(b, sd.img, sm, 32);
     load_entropy_luts(b, sm, kSeqThreads);

@@ -26,8 +26,9 @@ struct BatchDev {        // device pointers of one planned batch
     SubInfo* subs;
     int16_t* coefs;
     uint8_t* rgb;
-    uint32_t n_images;
-    uint32_t n_seqs;
+    uint32_t n_images;   // images this launch covers, starting at img0 (a whole batch or one group of it)
+    uint32_t n_seqs;     // warp jobs this launch covers, starting at job0
+    uint32_t img0, job0;
     uint32_t sub_bits;   // bits per subsequence for this batch
     uint32_t lw;         // log2(sub_bits / 32): words per subsequence
     uint32_t lookback_bits;
