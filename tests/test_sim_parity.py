@@ -160,3 +160,27 @@ def test_idct_factorisation_matches_the_direct_form():
         blk[rng.choice(64, k, replace=False)] = rng.integers(-400, 400, k)
         worst = max(worst, float(np.abs(O.idct_8x8(blk.reshape(8, 8)) - S.idct_8x8(blk.reshape(8, 8))).max()))
     assert worst < 2e-3
+
+
+def test_corrupted_scans_never_derail_the_batch():
+    """Random damage inside the entropy-coded data: every image gets a status, undamaged neighbours are unaffected,
+    and where the oracle still decodes (damage that keeps the stream decodable) the coefficients agree."""
+    rng = np.random.default_rng(7)
+    good = [synth.synth_jpeg(950 + i, 96, 64, s, restart_interval=ri) for i, (s, ri) in enumerate([("420", 0), ("444", 3), ("gray", 0)])]
+    files = []
+    for k in range(24):
+        f = bytearray(good[k % 3])
+        sos = bytes(f).index(b"\xff\xda") + 14
+        for _ in range(1 + k % 4):
+            pos = int(rng.integers(sos, len(f) - 2))
+            f[pos] ^= 1 << int(rng.integers(0, 8))
+        files.append(bytes(f))
+    files += good
+    rs, _ = S.decode_batch(files, ext=2)
+    for r, f in zip(rs[-3:], good):
+        o = O.decode(f, layout=1, ext=2)
+        assert r.status == 0 and np.abs(r.rgb.astype(int) - o.rgb.astype(int)).max() <= 1
+    for r, f in zip(rs[:-3], files[:-3]):
+        o = O.decode(f, layout=1, ext=2)
+        if r.status == 0 and o.status == 0:
+            assert all(np.array_equal(a, b) for a, b in zip(r.coefs, o.coefs))
