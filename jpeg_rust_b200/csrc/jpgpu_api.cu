@@ -394,7 +394,8 @@ extern "C" int jpgpu_batch_results(jpgpu_batch* b, int32_t* statuses, uint64_t* 
             const uint32_t f = dyn[i].status;
             if (f & kStDcSize) st = JPGPU_PANIC_READ_BITS_ASSERT;
             else if (f & kStBadCode) st = JPGPU_ERR_BAD_CODE;
-            else if (!(f & kStDone)) st = (f & kStRestart) ? JPGPU_ERR_RESTART : JPGPU_ERR_TRUNCATED;
+            else if (f & kStRestart) st = JPGPU_ERR_RESTART;
+            else if (!(f & kStDone)) st = JPGPU_ERR_TRUNCATED;
             br = ((uint64_t)dyn[i].bits_consumed + 7) / 8;  // decoder.rs:336-340
         }
         if (statuses) statuses[i] = st;

@@ -429,7 +429,8 @@ struct WriteLane {
     uint32_t dest0, dest1;     // arena block index of each completed buffer, oldest first (0xffffffff = discard)
     uint32_t end_bit;
     int32_t total;
-    uint32_t store_on;         // 0 while finishing a block that started in the previous subsequence
+    int32_t seg_limit;         // first coefficient position past the current restart interval (= total without DRI)
+    uint32_t store_on;         // 0 while finishing a block that started in the previous subsequence, and past seg_limit
     uint32_t state;            // kRun / kBlocked (out of buffers until the next flush) / kFinished
     __device__ __forceinline__ void select(uint32_t c) {
         cur = c;
@@ -443,7 +444,7 @@ struct WriteLane {
             ndone++;
             if (NBUF > 1) select(cur + 1 == (uint32_t)NBUF ? 0u : cur + 1);
         }
-        store_on = 1u;
+        store_on = g < seg_limit ? 1u : 0u;   // a damaged interval holding more MCUs than it should is decoded, not stored
         // finished: block boundary past the subsequence / scan; blocked: no free buffer
         state = (p >= end_bit || g >= total) ? (uint32_t)kFinished : (ndone == (uint32_t)NBUF ? (uint32_t)kBlocked : (uint32_t)kRun);
     }
@@ -783,7 +784,8 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
     wl.dest0 = wl.dest1 = 0u;
     wl.end_bit = end_bit;
     wl.total = total;
-    wl.store_on = store_on ? 1u : 0u;
+    wl.seg_limit = cx.seg_units ? min(total, (int32_t)((st.seg + 1u) * cx.seg_units)) : total;
+    wl.store_on = store_on && st.g < wl.seg_limit ? 1u : 0u;
     wl.state = active ? (uint32_t)WriteLane<NBUF>::kRun : (uint32_t)WriteLane<NBUF>::kFinished;
 
 #pragma unroll 1
@@ -797,10 +799,25 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
                 const int32_t g_before = st.g;
                 const uint32_t ev = fast_step<true, true>(cx, st, wl);
                 if (ev & (kEvCross | kEvEnd)) {  // rare: restart interval / end of data
-                    if (ev & kEvEnd) wl.state = WriteLane<NBUF>::kFinished;
-                    // a valid stream only changes interval between blocks; drop a half-written block of a corrupt one
-                    else if ((g_before & 63) != 0) wl.close_block(0xffffffffu, st.p, st.g);
-                    else { wl.store_on = 1u; if (st.p >= end_bit || st.g >= total) wl.state = WriteLane<NBUF>::kFinished; }
+                    if (ev & kEvEnd) {
+                        wl.state = WriteLane<NBUF>::kFinished;
+                    } else {
+                        // A valid stream changes interval exactly where the previous one is complete.  A damaged one may
+                        // come short (the missing blocks, a half-written one included, become zeros) or long (the excess
+                        // was decoded without being stored); both are reported (kStRestart).
+                        const int32_t old_limit = wl.seg_limit, gap_from = g_before & ~63;
+                        wl.seg_limit = min(total, st.g + (int32_t)cx.seg_units);
+                        if (g_before != old_limit) st.flags |= kStRestart;
+                        if ((g_before & 63) != 0 && wl.store_on) wl.close_block(0xffffffffu, st.p, st.g);
+                        for (int32_t g = gap_from; g < old_limit && g < st.g; g += 64) {
+                            uint4* dst = reinterpret_cast<uint4*>(coefs + (size_t)g);
+#pragma unroll
+                            for (int i = 0; i < 8; i++) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        wl.store_on = 1u;
+                        if (st.p >= end_bit || st.g >= total) wl.state = WriteLane<NBUF>::kFinished;
+                        else if (wl.state != WriteLane<NBUF>::kBlocked) wl.state = WriteLane<NBUF>::kRun;
+                    }
                 }
             }
         }
@@ -844,7 +861,7 @@ __global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
         wl.ndone = 0;
     }
     if (j < nsub) {
-        uint32_t bits = st.flags & (kStBadCode | kStDcSize);
+        uint32_t bits = st.flags & (kStBadCode | kStDcSize | kStRestart);
         if (g_start < total && st.g >= total) {  // this thread decoded the last block of the scan
             b.dyn[sd.img].bits_consumed = st.p;
             bits |= kStDone;

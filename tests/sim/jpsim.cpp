@@ -191,7 +191,7 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
     int16_t* coefs = sb.coefs.data() + im.coef_off;
     std::vector<int16_t> bufs((size_t)32 * kWriteBufs * 64, 0);
     for (uint32_t warp = 0; warp < 1u; warp++) {  // one warp job
-        struct Lane { DecState st; bool active, store_on; uint32_t j, end_bit, cur, ndone, dest[kWriteBufs]; int32_t g_start; };
+        struct Lane { DecState st; bool active, store_on; uint32_t j, end_bit, cur, ndone, dest[kWriteBufs]; int32_t g_start, seg_limit; };
         Lane ln[32];
         bool any_active = false;
         for (uint32_t lane = 0; lane < 32; lane++) {
@@ -207,8 +207,9 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
                 const SubInfo me = sb.subs[im.sub_off + l.j];
                 init_state(cx, l.st, me.pA, me.n, (int32_t)((me.cz >> 6) & 15u), me.dc[0], me.dc[1], me.dc[2]);
                 l.st.flags &= ~kCrossed;
-                l.store_on = (l.st.g & 63) == 0;
-                if (l.st.g >= total) l.active = false;
+                l.seg_limit = cx.seg_units ? std::min(total, (int32_t)((l.st.seg + 1u) * cx.seg_units)) : total;
+                l.store_on = (l.st.g & 63) == 0 && l.st.g < l.seg_limit;
+                if (l.st.g >= total || (l.st.p >= l.end_bit && (l.st.g & 63) == 0)) l.active = false;
             }
             l.g_start = l.st.g;
             any_active = any_active || l.active;
@@ -229,9 +230,14 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
                     const uint32_t ev = decode_symbol<true>(cx, l.st, bufs.data() + (size_t)row * 64, row & 7u, sb.store_pos, l.store_on);
                     if (ev & kEvBlock) {
                         if (l.store_on) { l.dest[l.ndone++] = (uint32_t)(g_before >> 6); l.cur = l.cur + 1 == (uint32_t)kWriteBufs ? 0u : l.cur + 1; }
-                        l.store_on = true;
+                        l.store_on = l.st.g < l.seg_limit;
                     } else if (ev & kEvCross) {
+                        const int32_t old_limit = l.seg_limit, gap_from = g_before & ~63;
+                        l.seg_limit = std::min(total, l.st.g + (int32_t)cx.seg_units);
+                        if (g_before != old_limit) l.st.flags |= kStRestart;
                         if ((g_before & 63) != 0 && l.store_on) { l.dest[l.ndone++] = 0xffffffffu; l.cur = l.cur + 1 == (uint32_t)kWriteBufs ? 0u : l.cur + 1; }
+                        for (int32_t g = gap_from; g < old_limit && g < l.st.g; g += 64)
+                            for (int e = 0; e < 64; e++) coefs[(size_t)g + e] = 0;
                         l.store_on = true;
                     } else if (ev & kEvEnd) {
                         l.active = false;
@@ -264,7 +270,7 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
         }
         for (auto& l : ln) {
             if (l.j >= nsub) continue;
-            uint32_t bits = l.st.flags & (kStBadCode | kStDcSize);
+            uint32_t bits = l.st.flags & (kStBadCode | kStDcSize | kStRestart);
             if (l.g_start < total && l.st.g >= total) { sb.dyn[sd.img].bits_consumed = l.st.p; bits |= kStDone; }
             sb.dyn[sd.img].status |= bits;
         }
@@ -407,7 +413,8 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
             const uint32_t f = sb.dyn[i].status;
             if (f & kStDcSize) s = JPGPU_PANIC_READ_BITS_ASSERT;
             else if (f & kStBadCode) s = JPGPU_ERR_BAD_CODE;
-            else if (!(f & kStDone)) s = (f & kStRestart) ? JPGPU_ERR_RESTART : JPGPU_ERR_TRUNCATED;
+            else if (f & kStRestart) s = JPGPU_ERR_RESTART;
+            else if (!(f & kStDone)) s = JPGPU_ERR_TRUNCATED;
             br = ((uint64_t)sb.dyn[i].bits_consumed + 7) / 8;
             const ImgDev& im = p.imgs[i];
             if (rgb_out && rgb_out[i]) memcpy(rgb_out[i], sb.rgb.data() + im.rgb_off, (size_t)im.width * im.height * 3);
