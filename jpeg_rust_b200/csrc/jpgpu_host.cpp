@@ -200,7 +200,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
     if (want_groups > n) want_groups = n ? (uint32_t)n : 1u;
     const uint64_t group_bytes = tot_bytes / want_groups + 1;
     uint64_t acc_bytes = 0;
-    constexpr uint32_t kJobsPerCta = kSeqThreads / 32;
+    constexpr uint32_t kJobsPerCta = 8;   // write kernel CTAs take 8 warp jobs, sync kernel CTAs 4: pad to the larger
     auto close_group = [&](size_t next_img) {
         while (plan.seqs.size() % kJobsPerCta != 0) plan.seqs.push_back(SeqDesc{0xffffffffu, 0u});
         if (!plan.groups.empty()) {

@@ -208,16 +208,21 @@ __global__ void __launch_bounds__(kPreThreads) prepass_write_kernel(BatchDev b) 
 }
 
 // ========================================================= stage 1b-1d: entropy decode
-constexpr int kJobsPerCta = kSeqThreads / 32;
-struct EntropySmem {
-    ImgDev img[kJobsPerCta];     // per warp job (verify_scan_kernel: [0] only)
+constexpr int kJobsPerCta = kSeqThreads / 32;      // sync kernel
+constexpr int kWriteThreads = 256;                 // write kernel: more warps share one copy of the Huffman tables
+constexpr int kWriteJobsPerCta = kWriteThreads / 32;
+template <int JOBS>
+struct EntropySmemT {
+    ImgDev img[JOBS];            // per warp job (verify_scan_kernel: [0] only)
     uint8_t store_pos[64];
     HuffLut lut[kMaxLutSlots];   // kernels with dynamic shared memory only carve max_slots of these
 };
+using EntropySmem = EntropySmemT<kJobsPerCta>;
 
 // Cooperative load of the per-image decode context into shared memory: every group of `group` threads loads the
 // image of its own job into sm.img[threadIdx.x / group] (kNoImage: nothing).
-__device__ __forceinline__ void load_entropy_img(const BatchDev& b, uint32_t img, EntropySmem& sm, int group) {
+template <class SM>
+__device__ __forceinline__ void load_entropy_img(const BatchDev& b, uint32_t img, SM& sm, int group) {
     const int slot = threadIdx.x / group, t = threadIdx.x % group;
     if (img != kNoImage) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&b.imgs[img]);
@@ -228,7 +233,8 @@ __device__ __forceinline__ void load_entropy_img(const BatchDev& b, uint32_t img
     __syncthreads();
 }
 // The Huffman tables of the CTA: those of job 0 (all jobs of a CTA use the same set, see build_plan).
-__device__ __forceinline__ void load_entropy_luts(const BatchDev& b, EntropySmem& sm, int nthreads) {
+template <class SM>
+__device__ __forceinline__ void load_entropy_luts(const BatchDev& b, SM& sm, int nthreads) {
     const int nslots = sm.img[0].nslots;
     constexpr int kLutVecs = sizeof(HuffLut) / 16;
     for (int s = 0; s < nslots; s++) {
@@ -269,7 +275,8 @@ struct FastCtx {
     const uint32_t* seg;
     uint32_t nseg, stream_bits, seg_units;
     uint32_t info_addr;      // shared: FastTables::info
-    uint32_t dc_addr;        // shared: this lane's DC slots (component k at dc_addr + k * 4 * kSeqThreads)
+    uint32_t dc_addr;        // shared: this lane's DC slots (component k at dc_addr + k * dc_stride)
+    uint32_t dc_stride;      // 4 * threads of the CTA
     uint32_t sp_addr;        // shared: byte offset of zigzag position k inside an unswizzled block buffer
     const HuffLut* luts;     // generic pointer to the shared LUT slots (rare paths)
     uint32_t lut0_addr;
@@ -285,14 +292,18 @@ struct FastState {
 };
 
 // per-CTA tables the fast path reads (filled once after the LUTs are loaded)
-struct FastTables {
-    uint4 info[kJobsPerCta][kMaxBlocksPerMcu];  // per job and block of an MCU: {dc lut addr | ac lut addr << 16, DC slot offset, address of the next entry, c}
-    uint32_t dc[3 * kSeqThreads];
+template <int THREADS>
+struct FastTablesT {
+    static constexpr int kThreads = THREADS;
+    uint4 info[THREADS / 32][kMaxBlocksPerMcu];  // per job and block of an MCU: {dc lut addr | ac lut addr << 16, DC slot offset, address of the next entry, c}
+    uint32_t dc[3 * THREADS];
     uint8_t sp[64];
 };
+using FastTables = FastTablesT<kSeqThreads>;
 
 // `group` threads fill the table of job threadIdx.x / group (its image must be loaded; kNoImage jobs skip).
-__device__ __forceinline__ void fast_tables_init(FastTables& ft, const EntropySmem& sm, bool valid, int group, int nthreads) {
+template <class FT, class SM>
+__device__ __forceinline__ void fast_tables_init(FT& ft, const SM& sm, bool valid, int group, int nthreads) {
     const int slot = threadIdx.x / group, t = threadIdx.x % group;
     const uint32_t lut0 = smem_addr(&sm.lut[0]), info0 = smem_addr(ft.info[slot]);
     if (valid) {
@@ -300,7 +311,7 @@ __device__ __forceinline__ void fast_tables_init(FastTables& ft, const EntropySm
         for (int i = t; i < kMaxBlocksPerMcu; i += group) {
             const uint32_t info = sm.img[slot].blk_info[i < nblk ? i : 0];
             const uint32_t a_dc = lut0 + (info & 255u) * (uint32_t)sizeof(HuffLut), a_ac = lut0 + ((info >> 8) & 255u) * (uint32_t)sizeof(HuffLut);
-            ft.info[slot][i] = make_uint4(a_dc | (a_ac << 16), (info >> 16) * 4u * kSeqThreads, info0 + (i + 1 < nblk ? i + 1 : 0) * 16u, (uint32_t)i);
+            ft.info[slot][i] = make_uint4(a_dc | (a_ac << 16), (info >> 16) * 4u * FT::kThreads, info0 + (i + 1 < nblk ? i + 1 : 0) * 16u, (uint32_t)i);
         }
     }
     for (int i = threadIdx.x; i < 64; i += nthreads) {
@@ -336,15 +347,15 @@ __device__ __forceinline__ void fast_load_block(const FastCtx& cx, FastState& st
 }
 __device__ __forceinline__ void fast_set_dc(const FastCtx& cx, FastState& st, int32_t d0, int32_t d1, int32_t d2) {
     sts32v(cx.dc_addr, (uint32_t)d0);
-    sts32v(cx.dc_addr + 4u * kSeqThreads, (uint32_t)d1);
-    sts32v(cx.dc_addr + 8u * kSeqThreads, (uint32_t)d2);
+    sts32v(cx.dc_addr + cx.dc_stride, (uint32_t)d1);
+    sts32v(cx.dc_addr + 2u * cx.dc_stride, (uint32_t)d2);
     st.dcur = (int32_t)lds32v(cx.dc_addr + st.dc_off);
 }
 __device__ __forceinline__ void fast_get_dc(const FastCtx& cx, const FastState& st, int32_t dc[3]) {
     sts32v(cx.dc_addr + st.dc_off, (uint32_t)st.dcur);
     dc[0] = (int32_t)lds32v(cx.dc_addr);
-    dc[1] = (int32_t)lds32v(cx.dc_addr + 4u * kSeqThreads);
-    dc[2] = (int32_t)lds32v(cx.dc_addr + 8u * kSeqThreads);
+    dc[1] = (int32_t)lds32v(cx.dc_addr + cx.dc_stride);
+    dc[2] = (int32_t)lds32v(cx.dc_addr + 2u * cx.dc_stride);
 }
 __device__ __forceinline__ void fast_set_segment(const FastCtx& cx, FastState& st, uint32_t k) {
     st.seg = k;
@@ -515,7 +526,8 @@ __device__ __forceinline__ void fast_run_to(const FastCtx& cx, FastState& st, ui
     }
 }
 
-__device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const EntropySmem& sm, int slot, const ImgDyn& d, const FastTables& ft) {
+template <class SM, class FT>
+__device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const SM& sm, int slot, const ImgDyn& d, const FT& ft) {
     const ImgDev& im = sm.img[slot];
     FastCtx cx;
     cx.words = b.stream + im.stream_off;
@@ -528,6 +540,7 @@ __device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const Entrop
     cx.seg_units = im.seg_units;
     cx.info_addr = smem_addr(ft.info[slot]);
     cx.dc_addr = smem_addr(ft.dc) + threadIdx.x * 4u;
+    cx.dc_stride = 4u * FT::kThreads;
     cx.sp_addr = smem_addr(ft.sp);
     cx.luts = sm.lut;
     cx.lut0_addr = smem_addr(&sm.lut[0]);
@@ -598,6 +611,7 @@ __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     __shared__ EntropySmem sm;
     __shared__ FastTables ft;
     const int warp = threadIdx.x >> 5;
+    if (b.seqs[b.job0 + blockIdx.x * kJobsPerCta].img == kNoImage) return;   // a CTA of padding jobs only
     const SeqDesc sd = b.seqs[b.job0 + blockIdx.x * kJobsPerCta + warp];
     const uint32_t S = b.sub_bits;
     load_entropy_img(b, sd.img, sm, 32);
@@ -725,30 +739,34 @@ struct WriteLayout {
 };
 __host__ __device__ inline WriteLayout write_layout(uint32_t max_slots, uint32_t nbuf) {
     WriteLayout l;
-    l.lut_bytes = (uint32_t)(sizeof(EntropySmem) - (kMaxLutSlots - max_slots) * sizeof(HuffLut));
+    l.lut_bytes = (uint32_t)(sizeof(EntropySmemT<kWriteJobsPerCta>) - (kMaxLutSlots - max_slots) * sizeof(HuffLut));
     l.ft_off = (l.lut_bytes + 15u) & ~15u;
-    l.buf_off = (l.ft_off + (uint32_t)sizeof(FastTables) + 127u) & ~127u;
-    l.list_off = l.buf_off + kSeqThreads * nbuf * 128u;
-    l.total = l.list_off + (kSeqThreads / 32) * 32u * nbuf * 8u;
+    l.buf_off = (l.ft_off + (uint32_t)sizeof(FastTablesT<kWriteThreads>) + 127u) & ~127u;
+    l.list_off = l.buf_off + kWriteThreads * nbuf * 128u;
+    l.total = l.list_off + kWriteJobsPerCta * 32u * nbuf * 8u;
     return l;
 }
 
 template <int NBUF, int PHASE>
-__global__ void __launch_bounds__(kSeqThreads) decode_write_kernel(BatchDev b) {
+__global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
-    EntropySmem& sm = *reinterpret_cast<EntropySmem*>(dyn_smem);
+    using Smem = EntropySmemT<kWriteJobsPerCta>;
+    using Tables = FastTablesT<kWriteThreads>;
+    Smem& sm = *reinterpret_cast<Smem*>(dyn_smem);
     const WriteLayout lay = write_layout(b.max_slots, NBUF);
-    FastTables& ft = *reinterpret_cast<FastTables*>(dyn_smem + lay.ft_off);
+    Tables& ft = *reinterpret_cast<Tables*>(dyn_smem + lay.ft_off);
     int16_t* const bufs = reinterpret_cast<int16_t*>(dyn_smem + lay.buf_off);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint2* const flist = reinterpret_cast<uint2*>(dyn_smem + lay.list_off) + warp * (32 * NBUF);
 
-    const SeqDesc sd = b.seqs[b.job0 + blockIdx.x * kJobsPerCta + warp];
+    if (b.seqs[b.job0 + blockIdx.x * kWriteJobsPerCta].img == kNoImage) return;   // a CTA of padding jobs only
+    const uint32_t job = blockIdx.x * kWriteJobsPerCta + warp;
+    const SeqDesc sd = job < b.n_seqs ? b.seqs[b.job0 + job] : SeqDesc{kNoImage, 0u};
     const uint32_t S = b.sub_bits;
     load_entropy_img(b, sd.img, sm, 32);
-    load_entropy_luts(b, sm, kSeqThreads);
-    fast_tables_init(ft, sm, sd.img != kNoImage, 32, kSeqThreads);
-    for (uint32_t i = tid; i < kSeqThreads * NBUF * 8u; i += kSeqThreads)
+    load_entropy_luts(b, sm, kWriteThreads);
+    fast_tables_init(ft, sm, sd.img != kNoImage, 32, kWriteThreads);
+    for (uint32_t i = tid; i < kWriteThreads * NBUF * 8u; i += kWriteThreads)
         reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     if (sd.img == kNoImage) return;
@@ -1197,7 +1215,7 @@ static cudaError_t launch_write_variant(const BatchDev& b, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         configured = lay.total;
     }
-    decode_write_kernel<NBUF, PHASE><<<b.n_seqs / kJobsPerCta, kSeqThreads, lay.total, s>>>(b);
+    decode_write_kernel<NBUF, PHASE><<<(b.n_seqs + kWriteJobsPerCta - 1) / kWriteJobsPerCta, kWriteThreads, lay.total, s>>>(b);
     return cudaSuccess;
 }
 cudaError_t launch_decode_write(const BatchDev& b, cudaStream_t s) {
