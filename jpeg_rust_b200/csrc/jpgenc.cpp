@@ -3,7 +3,8 @@
 // asks for: files restricted to the feature subset the reference decoder accepts
 // (SOI, APP0, DQT, SOF0, DHT, SOS, EOI; 8-bit; H,V in {1,2}; one interleaved scan;
 // Annex-K Huffman tables, which contain no 1-bit code — reference huffman.rs:61,212),
-// plus, optionally, DRI/RSTn for the restart-interval extension corpus.
+// plus, optionally, DRI/RSTn for the restart-interval extension corpus, image-specific
+// ("optimised") Huffman tables built by T.81 K.2, and 16-bit quantisation tables.
 //
 // It also returns the quantised coefficients it entropy-coded (zigzag order,
 // absolute DC, per component in decode order), which is decoder-independent ground
@@ -120,12 +121,12 @@ void put_marker_seg(std::vector<uint8_t>& o, uint8_t m, const std::vector<uint8_
     o.insert(o.end(), payload.begin(), payload.end());
 }
 
-void scaled_qtable(const uint8_t* base, int quality, uint16_t out[64]) {
+void scaled_qtable(const uint8_t* base, int quality, uint16_t out[64], bool wide = false) {
     quality = std::max(1, std::min(100, quality));
     int scale = quality < 50 ? 5000 / quality : 200 - 2 * quality;  // libjpeg's jpeg_quality_scaling
     for (int i = 0; i < 64; i++) {
         int v = (base[i] * scale + 50) / 100;
-        out[i] = (uint16_t)std::max(1, std::min(255, v));
+        out[i] = (uint16_t)std::max(1, std::min(wide ? 32767 : 255, v));  // 8-bit tables clamp at 255 (baseline)
     }
 }
 
@@ -173,6 +174,46 @@ struct Rng {
         return std::sqrt(-2.0 * std::log(u1)) * std::cos(2.0 * M_PI * u2);
     }
 };
+
+// T.81 K.2 (as in libjpeg's jpeg_gen_optimal_table): code lengths from symbol frequencies, limited to 16 bits,
+// with one reserved code point so that no code is all ones.  vals gets the symbols in order of code length.
+void gen_optimal_table(const long freq_in[256], uint8_t bits_out[16], std::vector<uint8_t>& vals) {
+    long freq[257];
+    int codesize[257], others[257];
+    for (int i = 0; i < 256; i++) freq[i] = freq_in[i];
+    freq[256] = 1;
+    for (int i = 0; i < 257; i++) { codesize[i] = 0; others[i] = -1; }
+    for (;;) {
+        int c1 = -1, c2 = -1;
+        long v = 1000000000L;
+        for (int i = 0; i <= 256; i++) if (freq[i] && freq[i] <= v) { v = freq[i]; c1 = i; }
+        v = 1000000000L;
+        for (int i = 0; i <= 256; i++) if (freq[i] && freq[i] <= v && i != c1) { v = freq[i]; c2 = i; }
+        if (c2 < 0) break;
+        freq[c1] += freq[c2];
+        freq[c2] = 0;
+        codesize[c1]++;
+        while (others[c1] >= 0) { c1 = others[c1]; codesize[c1]++; }
+        others[c1] = c2;
+        codesize[c2]++;
+        while (others[c2] >= 0) { c2 = others[c2]; codesize[c2]++; }
+    }
+    int bits[33] = {0};
+    for (int i = 0; i <= 256; i++) if (codesize[i]) bits[std::min(codesize[i], 32)]++;
+    for (int i = 32; i > 16; i--)
+        while (bits[i] > 0) {
+            int j = i - 2;
+            while (bits[j] == 0) j--;
+            bits[i] -= 2; bits[i - 1]++; bits[j + 1] += 2; bits[j]--;
+        }
+    int i = 16;
+    while (bits[i] == 0) i--;
+    bits[i]--;  // the reserved code point
+    for (int l = 1; l <= 16; l++) bits_out[l - 1] = (uint8_t)bits[l];
+    vals.clear();
+    for (int l = 1; l <= 32; l++)
+        for (int sym = 0; sym < 256; sym++) if (codesize[sym] == l) vals.push_back((uint8_t)sym);
+}
 
 }  // namespace
 
@@ -234,9 +275,11 @@ size_t jpgenc_max_size(int width, int height) {
 //   coef_dump (optional): ncomp consecutive arrays, component c holding nblocks[c]*64 int16
 //   (zigzag order, absolute DC) in decode order; coef_cap in int16 units.
 // Returns the number of bytes written, or 0 if out_cap / coef_cap is too small.
-size_t jpgenc_encode(const uint8_t* rgb, int width, int height, int gray, int hy, int vy, int quality,
-                     int restart_interval, uint8_t* out, size_t out_cap, int16_t* coef_dump, size_t coef_cap,
-                     size_t* nblocks /*[3]*/) {
+// flags: 1 = image-specific Huffman tables (T.81 K.2; may contain 1-bit codes, which the reference cannot decode),
+//        2 = 16-bit quantisation tables (Pq = 1) with unclamped libjpeg scaling.
+size_t jpgenc_encode_ex(const uint8_t* rgb, int width, int height, int gray, int hy, int vy, int quality,
+                        int restart_interval, int flags, uint8_t* out, size_t out_cap, int16_t* coef_dump,
+                        size_t coef_cap, size_t* nblocks /*[3]*/) {
     const int ncomp = gray ? 1 : 3;
     if (gray) { hy = 1; vy = 1; }
     const int H[3] = {hy, 1, 1}, V[3] = {vy, 1, 1};
@@ -279,23 +322,89 @@ size_t jpgenc_encode(const uint8_t* rgb, int width, int height, int gray, int hy
             }
     }
 
+    const bool optimise = (flags & 1) != 0, dqt16 = (flags & 2) != 0;
     uint16_t qt[2][64];
-    scaled_qtable(kQLum, quality, qt[0]);
-    scaled_qtable(kQChr, quality, qt[1]);
-    EncTable dcl, dcc, acl, acc_;
-    make_enc_table(kDcLumBits, kDcVals, &dcl);
-    make_enc_table(kDcChrBits, kDcVals, &dcc);
-    make_enc_table(kAcLumBits, kAcLumVals, &acl);
-    make_enc_table(kAcChrBits, kAcChrVals, &acc_);
+    scaled_qtable(kQLum, quality, qt[0], dqt16);
+    scaled_qtable(kQChr, quality, qt[1], dqt16);
+
+    // ---- pass 1: quantised coefficients of every block, in decode (MCU) order
+    const float* planes[3] = {Y.data(), cbs.data(), crs.data()};
+    const int pstride[3] = {pw, cw, cw};
+    const int bpm = hy * vy + (gray ? 0 : 2);
+    std::vector<int16_t> blocks((size_t)mcux * mcuy * bpm * 64);
+    {
+        size_t bi = 0;
+        for (int my = 0; my < mcuy; my++)
+            for (int mx = 0; mx < mcux; mx++)
+                for (int c = 0; c < ncomp; c++) {
+                    const uint16_t* q = qt[c == 0 ? 0 : 1];
+                    for (int by = 0; by < V[c]; by++)
+                        for (int bx = 0; bx < H[c]; bx++, bi++) {
+                            double in[64], coef[64];
+                            int x0 = (mx * H[c] + bx) * 8, y0 = (my * V[c] + by) * 8;
+                            for (int yy = 0; yy < 8; yy++)
+                                for (int xx = 0; xx < 8; xx++)
+                                    in[yy * 8 + xx] = (double)planes[c][(size_t)(y0 + yy) * pstride[c] + x0 + xx] - 128.0;
+                            fdct8x8(in, coef);
+                            int16_t* zz = blocks.data() + bi * 64;
+                            for (int k = 0; k < 64; k++) {
+                                int nat = kZigzag[k];
+                                int v = (int)std::lround(coef[nat] / (double)q[nat]);
+                                zz[k] = (int16_t)std::max(-1023, std::min(1023, v));  // baseline ranges
+                            }
+                        }
+                }
+    }
+
+    // ---- Huffman tables: Annex K, or built from this image's symbol statistics (T.81 K.2)
+    uint8_t tbits[4][16];                // [DC lum, AC lum, DC chr, AC chr]
+    std::vector<uint8_t> tvals[4];
+    std::memcpy(tbits[0], kDcLumBits, 16); tvals[0].assign(kDcVals, kDcVals + 12);
+    std::memcpy(tbits[1], kAcLumBits, 16); tvals[1].assign(kAcLumVals, kAcLumVals + 162);
+    std::memcpy(tbits[2], kDcChrBits, 16); tvals[2].assign(kDcVals, kDcVals + 12);
+    std::memcpy(tbits[3], kAcChrBits, 16); tvals[3].assign(kAcChrVals, kAcChrVals + 162);
+    if (optimise) {
+        long freq[4][256];
+        std::memset(freq, 0, sizeof freq);
+        int pred[3] = {0, 0, 0}, in_interval = 0;
+        size_t bi = 0;
+        for (int m = 0; m < mcux * mcuy; m++) {
+            if (restart_interval > 0 && in_interval == restart_interval) { in_interval = 0; pred[0] = pred[1] = pred[2] = 0; }
+            for (int c = 0; c < ncomp; c++)
+                for (int k2 = 0; k2 < H[c] * V[c]; k2++, bi++) {
+                    const int16_t* zz = blocks.data() + bi * 64;
+                    long* fd = freq[c == 0 ? 0 : 2];
+                    long* fa = freq[c == 0 ? 1 : 3];
+                    fd[bit_size(zz[0] - pred[c])]++;
+                    pred[c] = zz[0];
+                    int run = 0;
+                    for (int k = 1; k < 64; k++) {
+                        if (zz[k] == 0) { run++; continue; }
+                        while (run > 15) { fa[0xf0]++; run -= 16; }
+                        fa[(run << 4) | bit_size(zz[k])]++;
+                        run = 0;
+                    }
+                    if (run > 0) fa[0x00]++;
+                }
+            in_interval++;
+        }
+        for (int t = 0; t < (gray ? 2 : 4); t++) gen_optimal_table(freq[t], tbits[t], tvals[t]);
+    }
+    EncTable enc[4];
+    for (int t = 0; t < 4; t++) make_enc_table(tbits[t], tvals[t].data(), &enc[t]);
 
     std::vector<uint8_t> o;
     o.reserve((size_t)width * height / 2 + 4096);
     o.push_back(0xff); o.push_back(0xd8);  // SOI
     put_marker_seg(o, 0xe0, {'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0});  // APP0 JFIF 1.01
-    for (int t = 0; t < (gray ? 1 : 2); t++) {  // DQT, 8-bit precision, zigzag order
+    for (int t = 0; t < (gray ? 1 : 2); t++) {  // DQT, zigzag order, 8- or 16-bit entries
         std::vector<uint8_t> p;
-        p.push_back((uint8_t)t);
-        for (int k = 0; k < 64; k++) p.push_back((uint8_t)qt[t][kZigzag[k]]);
+        p.push_back((uint8_t)((dqt16 ? 0x10 : 0x00) | t));
+        for (int k = 0; k < 64; k++) {
+            const uint16_t v = qt[t][kZigzag[k]];
+            if (dqt16) p.push_back((uint8_t)(v >> 8));
+            p.push_back((uint8_t)v);
+        }
         put_marker_seg(o, 0xdb, p);
     }
     {  // SOF0
@@ -308,18 +417,12 @@ size_t jpgenc_encode(const uint8_t* rgb, int width, int height, int gray, int hy
         }
         put_marker_seg(o, 0xc0, p);
     }
-    auto put_dht = [&](int tc, int th, const uint8_t* bits, const uint8_t* vals, int nvals) {
+    for (int t = 0; t < (gray ? 2 : 4); t++) {  // DHT: Tc = t & 1, Th = t >> 1
         std::vector<uint8_t> p;
-        p.push_back((uint8_t)((tc << 4) | th));
-        p.insert(p.end(), bits, bits + 16);
-        p.insert(p.end(), vals, vals + nvals);
+        p.push_back((uint8_t)(((t & 1) << 4) | (t >> 1)));
+        p.insert(p.end(), tbits[t], tbits[t] + 16);
+        p.insert(p.end(), tvals[t].begin(), tvals[t].end());
         put_marker_seg(o, 0xc4, p);
-    };
-    put_dht(0, 0, kDcLumBits, kDcVals, 12);
-    put_dht(1, 0, kAcLumBits, kAcLumVals, 162);
-    if (!gray) {
-        put_dht(0, 1, kDcChrBits, kDcVals, 12);
-        put_dht(1, 1, kAcChrBits, kAcChrVals, 162);
     }
     if (restart_interval > 0)
         put_marker_seg(o, 0xdd, {(uint8_t)(restart_interval >> 8), (uint8_t)restart_interval});
@@ -342,68 +445,50 @@ size_t jpgenc_encode(const uint8_t* rgb, int width, int height, int gray, int hy
     size_t dump_n[3] = {0, 0, 0};
     if (nblocks) for (int c = 0; c < 3; c++) nblocks[c] = c < ncomp ? nb[c] : 0;
 
+    // ---- pass 2: entropy coding
     BitWriter bw(o);
     int pred[3] = {0, 0, 0};
     int rst_count = 0, mcus_in_interval = 0;
-    const float* planes[3] = {Y.data(), cbs.data(), crs.data()};
-    const int pstride[3] = {pw, cw, cw};
-    for (int my = 0; my < mcuy; my++) {
-        for (int mx = 0; mx < mcux; mx++) {
-            if (restart_interval > 0 && mcus_in_interval == restart_interval) {
-                bw.flush_ones();
-                o.push_back(0xff);
-                o.push_back((uint8_t)(0xd0 + (rst_count & 7)));
-                rst_count++;
-                mcus_in_interval = 0;
-                pred[0] = pred[1] = pred[2] = 0;
-            }
-            for (int c = 0; c < ncomp; c++) {
-                const EncTable& dct = c == 0 ? dcl : dcc;
-                const EncTable& act = c == 0 ? acl : acc_;
-                const uint16_t* q = qt[c == 0 ? 0 : 1];
-                for (int by = 0; by < V[c]; by++)
-                    for (int bx = 0; bx < H[c]; bx++) {
-                        double in[64], coef[64];
-                        int x0 = (mx * H[c] + bx) * 8, y0 = (my * V[c] + by) * 8;
-                        for (int yy = 0; yy < 8; yy++)
-                            for (int xx = 0; xx < 8; xx++)
-                                in[yy * 8 + xx] = (double)planes[c][(size_t)(y0 + yy) * pstride[c] + x0 + xx] - 128.0;
-                        fdct8x8(in, coef);
-                        int zz[64];
-                        for (int k = 0; k < 64; k++) {
-                            int nat = kZigzag[k];
-                            zz[k] = (int)std::lround(coef[nat] / (double)q[nat]);
-                        }
-                        // clamp to the baseline ranges (DC diff <= 11 bits, AC <= 10 bits)
-                        zz[0] = std::max(-1023, std::min(1023, zz[0]));
-                        for (int k = 1; k < 64; k++) zz[k] = std::max(-1023, std::min(1023, zz[k]));
-                        if (coef_dump) {
-                            int16_t* d = coef_dump + dump_off[c] + dump_n[c] * 64;
-                            for (int k = 0; k < 64; k++) d[k] = (int16_t)zz[k];
-                            dump_n[c]++;
-                        }
-                        // DC
-                        int diff = zz[0] - pred[c];
-                        pred[c] = zz[0];
-                        int s = bit_size(diff);
-                        bw.put(dct.code[s], dct.size[s]);
-                        if (s) bw.put((uint32_t)(diff < 0 ? diff - 1 : diff), s);
-                        // AC
-                        int run = 0;
-                        for (int k = 1; k < 64; k++) {
-                            if (zz[k] == 0) { run++; continue; }
-                            while (run > 15) { bw.put(act.code[0xf0], act.size[0xf0]); run -= 16; }
-                            int sz = bit_size(zz[k]);
-                            int sym = (run << 4) | sz;
-                            bw.put(act.code[sym], act.size[sym]);
-                            bw.put((uint32_t)(zz[k] < 0 ? zz[k] - 1 : zz[k]), sz);
-                            run = 0;
-                        }
-                        if (run > 0) bw.put(act.code[0x00], act.size[0x00]);
-                    }
-            }
-            mcus_in_interval++;
+    size_t bi = 0;
+    for (int m = 0; m < mcux * mcuy; m++) {
+        if (restart_interval > 0 && mcus_in_interval == restart_interval) {
+            bw.flush_ones();
+            o.push_back(0xff);
+            o.push_back((uint8_t)(0xd0 + (rst_count & 7)));
+            rst_count++;
+            mcus_in_interval = 0;
+            pred[0] = pred[1] = pred[2] = 0;
         }
+        for (int c = 0; c < ncomp; c++) {
+            const EncTable& dct = enc[c == 0 ? 0 : 2];
+            const EncTable& act = enc[c == 0 ? 1 : 3];
+            for (int k2 = 0; k2 < H[c] * V[c]; k2++, bi++) {
+                const int16_t* zz = blocks.data() + bi * 64;
+                if (coef_dump) {
+                    std::memcpy(coef_dump + dump_off[c] + dump_n[c] * 64, zz, 64 * sizeof(int16_t));
+                    dump_n[c]++;
+                }
+                // DC
+                int diff = zz[0] - pred[c];
+                pred[c] = zz[0];
+                int sz0 = bit_size(diff);
+                bw.put(dct.code[sz0], dct.size[sz0]);
+                if (sz0) bw.put((uint32_t)(diff < 0 ? diff - 1 : diff), sz0);
+                // AC
+                int run = 0;
+                for (int k = 1; k < 64; k++) {
+                    if (zz[k] == 0) { run++; continue; }
+                    while (run > 15) { bw.put(act.code[0xf0], act.size[0xf0]); run -= 16; }
+                    int sz = bit_size(zz[k]);
+                    int sym = (run << 4) | sz;
+                    bw.put(act.code[sym], act.size[sym]);
+                    bw.put((uint32_t)(zz[k] < 0 ? zz[k] - 1 : zz[k]), sz);
+                    run = 0;
+                }
+                if (run > 0) bw.put(act.code[0x00], act.size[0x00]);
+            }
+        }
+        mcus_in_interval++;
     }
     bw.flush_ones();
     o.push_back(0xff); o.push_back(0xd9);  // EOI
@@ -412,14 +497,28 @@ size_t jpgenc_encode(const uint8_t* rgb, int width, int height, int gray, int hy
     return o.size();
 }
 
+size_t jpgenc_encode(const uint8_t* rgb, int width, int height, int gray, int hy, int vy, int quality,
+                     int restart_interval, uint8_t* out, size_t out_cap, int16_t* coef_dump, size_t coef_cap,
+                     size_t* nblocks /*[3]*/) {
+    return jpgenc_encode_ex(rgb, width, height, gray, hy, vy, quality, restart_interval, 0, out, out_cap, coef_dump,
+                            coef_cap, nblocks);
+}
+
 // synth + encode in one call (used by the batch generators; thread-safe)
+size_t jpgenc_synth_encode_ex(uint32_t seed, int width, int height, double noise_sigma, int gray, int hy, int vy,
+                              int quality, int restart_interval, int flags, uint8_t* out, size_t out_cap,
+                              int16_t* coef_dump, size_t coef_cap, size_t* nblocks) {
+    std::vector<uint8_t> rgb((size_t)width * height * 3);
+    jpgenc_synth_rgb(seed, width, height, noise_sigma, rgb.data());
+    return jpgenc_encode_ex(rgb.data(), width, height, gray, hy, vy, quality, restart_interval, flags, out, out_cap,
+                            coef_dump, coef_cap, nblocks);
+}
+
 size_t jpgenc_synth_encode(uint32_t seed, int width, int height, double noise_sigma, int gray, int hy, int vy,
                            int quality, int restart_interval, uint8_t* out, size_t out_cap, int16_t* coef_dump,
                            size_t coef_cap, size_t* nblocks) {
-    std::vector<uint8_t> rgb((size_t)width * height * 3);
-    jpgenc_synth_rgb(seed, width, height, noise_sigma, rgb.data());
-    return jpgenc_encode(rgb.data(), width, height, gray, hy, vy, quality, restart_interval, out, out_cap, coef_dump,
-                         coef_cap, nblocks);
+    return jpgenc_synth_encode_ex(seed, width, height, noise_sigma, gray, hy, vy, quality, restart_interval, 0, out, out_cap,
+                                  coef_dump, coef_cap, nblocks);
 }
 
 }  // extern "C"

@@ -28,6 +28,13 @@ def lib():
         L.jpgenc_encode.restype = C.c_size_t
         L.jpgenc_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.jpgenc_encode_ex.restype = C.c_size_t
+        L.jpgenc_encode_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.jpgenc_synth_encode_ex.restype = C.c_size_t
+        L.jpgenc_synth_encode_ex.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                             C.c_void_p]
         L.jpgenc_synth_encode.restype = C.c_size_t
         L.jpgenc_synth_encode.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -45,8 +52,14 @@ def _coef_capacity(width, height):
     return ((width + 15) // 16) * ((height + 15) // 16) * 12 * 64
 
 
-def encode(rgb, subsampling="420", quality=85, restart_interval=0, want_coefs=False):
-    """Encode an HxWx3 uint8 array. Returns bytes, or (bytes, [per-component (nblocks,64) int16]) with want_coefs."""
+def _flags(optimize, dqt16):
+    return (1 if optimize else 0) | (2 if dqt16 else 0)
+
+
+def encode(rgb, subsampling="420", quality=85, restart_interval=0, want_coefs=False, optimize=False, dqt16=False):
+    """Encode an HxWx3 uint8 array. Returns bytes, or (bytes, [per-component (nblocks,64) int16]) with want_coefs.
+    optimize: image-specific Huffman tables (T.81 K.2; may hold 1-bit codes the reference cannot decode);
+    dqt16: 16-bit quantisation tables with unclamped scaling."""
     gray, hy, vy = SUBSAMPLING[subsampling]
     rgb = np.ascontiguousarray(rgb, np.uint8)
     h, w = rgb.shape[:2]
@@ -54,8 +67,9 @@ def encode(rgb, subsampling="420", quality=85, restart_interval=0, want_coefs=Fa
     out = np.empty(cap, np.uint8)
     nb = (C.c_size_t * 3)()
     coef = np.zeros(_coef_capacity(w, h), np.int16) if want_coefs else None
-    n = lib().jpgenc_encode(rgb.ctypes.data, w, h, gray, hy, vy, quality, restart_interval, out.ctypes.data, cap,
-                            coef.ctypes.data if want_coefs else None, coef.size if want_coefs else 0, nb)
+    n = lib().jpgenc_encode_ex(rgb.ctypes.data, w, h, gray, hy, vy, quality, restart_interval, _flags(optimize, dqt16),
+                               out.ctypes.data, cap, coef.ctypes.data if want_coefs else None,
+                               coef.size if want_coefs else 0, nb)
     if n == 0:
         raise RuntimeError("jpgenc_encode failed")
     data = out[:n].tobytes()
@@ -69,16 +83,16 @@ def encode(rgb, subsampling="420", quality=85, restart_interval=0, want_coefs=Fa
 
 
 def synth_jpeg(index, width, height, subsampling="420", quality=85, restart_interval=0, noise_sigma=6.0,
-               want_coefs=False):
+               want_coefs=False, optimize=False, dqt16=False):
     """Synthetic image `index` (seed 0x5EED0000 + index) as a baseline JPEG."""
     gray, hy, vy = SUBSAMPLING[subsampling]
     cap = lib().jpgenc_max_size(width, height)
     out = np.empty(cap, np.uint8)
     nb = (C.c_size_t * 3)()
     coef = np.zeros(_coef_capacity(width, height), np.int16) if want_coefs else None
-    n = lib().jpgenc_synth_encode(SEED_BASE + index, width, height, noise_sigma, gray, hy, vy, quality,
-                                  restart_interval, out.ctypes.data, cap,
-                                  coef.ctypes.data if want_coefs else None, coef.size if want_coefs else 0, nb)
+    n = lib().jpgenc_synth_encode_ex(SEED_BASE + index, width, height, noise_sigma, gray, hy, vy, quality,
+                                     restart_interval, _flags(optimize, dqt16), out.ctypes.data, cap,
+                                     coef.ctypes.data if want_coefs else None, coef.size if want_coefs else 0, nb)
     if n == 0:
         raise RuntimeError("jpgenc_synth_encode failed")
     data = out[:n].tobytes()

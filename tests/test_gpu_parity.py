@@ -305,3 +305,43 @@ def test_corrupted_scans_never_derail_the_batch():
             assert all(np.array_equal(a, b) for a, b in zip(coefs[i], o.coefs)), i
             agree += 1
     print("damaged images still decodable by both:", agree, "of 96")
+
+
+def test_image_specific_huffman_tables_and_16bit_dqt():
+    """Files the reference accepts but the Annex-K corpus does not cover: optimised (T.81 K.2) Huffman tables, a
+    different set per image (many LUT sets in one batch), and 16-bit quantisation tables (mod.rs:245-256)."""
+    files, gts = [], []
+    for i, (sub, q, opt, wide) in enumerate([("420", 85, True, False), ("444", 30, True, False), ("gray", 95, True, False),
+                                             ("422", 8, False, True), ("420", 3, True, True), ("440", 60, True, False)]):
+        f, g = synth.synth_jpeg(1000 + i, 200 + 8 * i, 136, sub, quality=q, want_coefs=True, optimize=opt, dqt16=wide)
+        files.append(f)
+        gts.append(g)
+    outs, statuses, br, coefs, _ = run_batch(files)
+    n_oracle = 0
+    for i, (f, g) in enumerate(zip(files, gts)):
+        assert statuses[i] == 0, _ffi.status_string(statuses[i])
+        assert all(np.array_equal(a, b) for a, b in zip(coefs[i], g))
+        o = O.decode(f, layout=O.LAYOUT_SPEC)
+        if o.status == 0:               # within the reference's subset (no 1-bit code in any table)
+            n_oracle += 1
+            assert all(np.array_equal(a, b) for a, b in zip(coefs[i], o.coefs)) and br[i] == o.bytes_read
+            assert_samples(outs[i], o.rgb, f"image {i}")
+        else:
+            assert o.status in (9, 10)  # huffman.rs:156/162: a table holds a 1-bit code
+    assert n_oracle >= 3
+
+
+def test_one_bit_huffman_codes_decode_although_the_reference_cannot():
+    """A table with a single symbol gets a 1-bit code; the reference cannot decode those (huffman.rs:61, 212 -> the
+    oracle reports the panic).  The GPU path decodes them: coefficients equal the encoder's, pixels equal those of the
+    same image coded with the Annex-K tables."""
+    flat = np.full((72, 104, 3), 77, np.uint8)
+    grad = np.tile(np.arange(104, dtype=np.uint8)[None, :, None] * 2, (72, 1, 3))
+    for img, sub in ((flat, "420"), (flat, "gray"), (grad, "444")):
+        f, g = synth.encode(img, sub, want_coefs=True, optimize=True)
+        plain = synth.encode(img, sub)
+        assert O.decode(f, layout=1).status != 0 or sub == "444"
+        outs, statuses, br, coefs, _ = run_batch([f, plain])
+        assert statuses == [0, 0]
+        assert all(np.array_equal(a, b) for a, b in zip(coefs[0], g))
+        assert np.array_equal(outs[0], outs[1])

@@ -184,3 +184,44 @@ def test_corrupted_scans_never_derail_the_batch():
         o = O.decode(f, layout=1, ext=2)
         if r.status == 0 and o.status == 0:
             assert all(np.array_equal(a, b) for a, b in zip(r.coefs, o.coefs))
+
+
+def test_image_specific_huffman_tables_and_16bit_dqt():
+    """Files the reference accepts but the Annex-K corpus does not cover: optimised (T.81 K.2) Huffman tables, a
+    different set per image (many LUT sets in one batch), and 16-bit quantisation tables (mod.rs:245-256)."""
+    files, gts = [], []
+    for i, (sub, q, opt, wide) in enumerate([("420", 85, True, False), ("444", 30, True, False), ("gray", 95, True, False),
+                                             ("422", 8, False, True), ("420", 3, True, True), ("440", 60, True, False)]):
+        f, g = synth.synth_jpeg(1000 + i, 200 + 8 * i, 136, sub, quality=q, want_coefs=True, optimize=opt, dqt16=wide)
+        files.append(f)
+        gts.append(g)
+    rs, _ = S.decode_batch(files)
+    n_oracle = 0
+    for f, g, r in zip(files, gts, rs):
+        assert r.status == 0
+        assert all(np.array_equal(a, b) for a, b in zip(r.coefs, g))
+        o = O.decode(f, layout=1)
+        if o.status == 0:               # within the reference's subset (no 1-bit code in any table)
+            n_oracle += 1
+            assert all(np.array_equal(a, b) for a, b in zip(r.coefs, o.coefs)) and r.bytes_read == o.bytes_read
+            assert np.abs(r.rgb.astype(int) - o.rgb.astype(int)).max() <= 1
+        else:
+            assert o.status in (9, 10)  # huffman.rs:156/162: a table holds a 1-bit code
+    assert n_oracle >= 3
+
+
+def test_one_bit_huffman_codes_decode_although_the_reference_cannot():
+    """A table with a single symbol gets a 1-bit code; the reference cannot decode those (huffman.rs:61, 212 -> the
+    oracle reports the panic).  The GPU path decodes them: coefficients equal the encoder's, pixels equal those of the
+    same image coded with the Annex-K tables."""
+    flat = np.full((72, 104, 3), 77, np.uint8)
+    grad = np.tile(np.arange(104, dtype=np.uint8)[None, :, None] * 2, (72, 1, 3))
+    for img, sub in ((flat, "420"), (flat, "gray"), (grad, "444")):
+        f, g = synth.encode(img, sub, want_coefs=True, optimize=True)
+        plain = synth.encode(img, sub)
+        assert O.decode(f, layout=1).status != 0 or sub == "444"
+        (r,), _ = S.decode_batch([f])
+        (rp,), _ = S.decode_batch([plain])
+        assert r.status == 0 and rp.status == 0
+        assert all(np.array_equal(a, b) for a, b in zip(r.coefs, g))
+        assert np.array_equal(r.rgb, rp.rgb)
