@@ -104,7 +104,6 @@ struct ImgDev {
     uint8_t blk_dc_slot[kMaxBlocksPerMcu];
     uint8_t blk_ac_slot[kMaxBlocksPerMcu];
     uint32_t blk_info[kMaxBlocksPerMcu];  // DC slot | AC slot << 8 | component << 16 (what the decoder loads per block)
-    uint32_t blk_info_g[kMaxBlocksPerMcu];// same with indices into the batch-wide LUT array instead of slots (< 256 LUTs)
     uint8_t nslots, kind, layout, pad0;   // kind: colour kernel variant (see ImgKind)
     uint32_t slot_lut[kMaxLutSlots];      // index into the global HuffLut array
     uint32_t qt_off[4];                   // per component: offset (in floats) of its 64 pre-scaled multipliers

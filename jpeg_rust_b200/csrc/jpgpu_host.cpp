@@ -329,8 +329,6 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
                 im.blk_dc_slot[blk] = dc_slot[c];
                 im.blk_ac_slot[blk] = ac_slot[c];
                 im.blk_info[blk] = (uint32_t)dc_slot[c] | ((uint32_t)ac_slot[c] << 8) | (c << 16);
-                im.blk_info_g[blk] = (slot_lut[dc_slot[c]] & 255u) | ((slot_lut[ac_slot[c]] & 255u) << 8) | (c << 16);
-                if (slot_lut[dc_slot[c]] > 255u || slot_lut[ac_slot[c]] > 255u) plan.many_luts = true;
             }
             // quantisation multipliers (deduplicated)
             const uint16_t* q = d.qt[d.comp[c].tq];

@@ -47,7 +47,6 @@ struct HostPlan {
     uint32_t lookback_bits = kDefaultLookbackBits;
     uint32_t seg_bits = kMinSegBits;  // checkpoint distance inside a subsequence
     uint32_t max_slots = 1;      // most Huffman LUT slots any image references
-    bool many_luts = false;      // more than 256 distinct LUTs in the batch: the flat repair kernel is skipped
     std::vector<ImgDev> imgs;
     std::vector<int32_t> status;  // per image: JPGPU_OK or why it is skipped
     std::vector<SeqDesc> seqs;

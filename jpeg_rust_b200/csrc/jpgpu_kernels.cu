@@ -259,11 +259,6 @@ __device__ __forceinline__ void sts32v(uint32_t a, uint32_t v) { asm volatile("s
 __device__ __forceinline__ void sts16_if(uint32_t a, uint32_t v, bool p) {
     asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.shared.u16 [%0], %1;\n}" :: "r"(a), "r"(v), "r"((uint32_t)p) : "memory");
 }
-__device__ __forceinline__ uint32_t ldg_if(const uint32_t* a, bool p) {
-    uint32_t v;
-    asm("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n mov.u32 %0, 0;\n @q ld.global.nc.u32 %0, [%1];\n}" : "=r"(v) : "l"(a), "r"((uint32_t)p));
-    return v;
-}
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 #define JPGPU_PIN32(x) asm volatile("" : "+r"(x))
