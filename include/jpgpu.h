@@ -189,6 +189,11 @@ int jpgpu_batch_coefficients(jpgpu_batch *b, size_t i, int16_t *out, size_t cap,
 /* Algorithmic byte counts of the last plan (for roofline arithmetic):
  * [0] raw scan bytes, [1] coefficient bytes (blocks*128), [2] RGB bytes, [3] pixels, [4] blocks. */
 int jpgpu_batch_stats(jpgpu_batch *b, uint64_t stats[8]);
+/* Measurement aid: runs the decode once, kernel after kernel on the context stream, with a CUDA event between
+ * every two launches, and returns the device time of each in milliseconds:
+ * [0] prepass_count [1] prepass_scan [2] prepass_write [3] sync [4] verify_scan [5] decode_write
+ * [6] idct/colour (all sampling modes and the gather path together).  Synchronises. */
+int jpgpu_batch_profile(jpgpu_batch *b, float ms[8]);
 /* Number of kernel launches enqueued by this batch object so far. */
 uint64_t jpgpu_batch_launch_count(const jpgpu_batch *b);
 

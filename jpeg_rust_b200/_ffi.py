@@ -91,6 +91,7 @@ def lib():
         L.jpgpu_batch_results.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
         L.jpgpu_batch_coefficients.argtypes = [vp, sz, vp, sz, C.POINTER(C.c_uint32)]
         L.jpgpu_batch_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.jpgpu_batch_profile.argtypes = [vp, C.POINTER(C.c_float)]
         L.jpgpu_batch_launch_count.restype = C.c_uint64
         L.jpgpu_batch_launch_count.argtypes = [vp]
         _lib = L
@@ -113,5 +114,5 @@ EXPORTED_SYMBOLS = [
     "jpgpu_batch_create", "jpgpu_batch_replan", "jpgpu_batch_destroy", "jpgpu_batch_upload", "jpgpu_batch_set_device_scans", "jpgpu_batch_set_device_output",
     "jpgpu_batch_entropy", "jpgpu_batch_idct", "jpgpu_batch_decode", "jpgpu_batch_download",
     "jpgpu_batch_device_rgb", "jpgpu_batch_results", "jpgpu_batch_coefficients", "jpgpu_batch_stats",
-    "jpgpu_batch_launch_count",
+    "jpgpu_batch_profile", "jpgpu_batch_launch_count",
 ]

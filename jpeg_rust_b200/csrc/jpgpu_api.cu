@@ -434,6 +434,32 @@ extern "C" int jpgpu_batch_stats(jpgpu_batch* b, uint64_t stats[8]) {
     return JPGPU_OK;
 }
 
+extern "C" int jpgpu_batch_profile(jpgpu_batch* b, float ms[8]) {
+    if (!b || !ms) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    cudaEvent_t ev[8];
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(ev[0], s));
+    for (int step = 0; step < 3; step++) { launch_prepass_step(b->dev, s, step); CK(cudaEventRecord(ev[1 + step], s)); }
+    launch_sync(b->dev, s);
+    CK(cudaEventRecord(ev[4], s));
+    launch_verify_scan(b->dev, s);
+    CK(cudaEventRecord(ev[5], s));
+    CK(launch_decode_write(b->dev, s));
+    CK(cudaEventRecord(ev[6], s));
+    b->launches += 6 + (uint64_t)launch_idct_colour(b->dev, s);
+    CK(cudaEventRecord(ev[7], s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    for (int i = 0; i < 7; i++) CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    ms[7] = 0.0f;
+    for (auto& e : ev) cudaEventDestroy(e);
+    b->decoded = true;
+    return JPGPU_OK;
+}
+
 extern "C" uint64_t jpgpu_batch_launch_count(const jpgpu_batch* b) { return b ? b->launches : 0; }
 
 extern "C" int jpgpu_decode(jpgpu_ctx* ctx, const jpgpu_image_desc* desc, uint8_t* rgb_out, size_t* bytes_read) {

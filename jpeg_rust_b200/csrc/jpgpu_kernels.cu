@@ -1188,12 +1188,15 @@ __global__ void __launch_bounds__(kGatherThreads) gather_colour_kernel(BatchDev 
 }
 
 // ===================================================================== launchers
-void launch_prepass(const BatchDev& b, cudaStream_t s) {
+void launch_prepass_step(const BatchDev& b, cudaStream_t s, int step) {
     if (!b.n_images || !b.max_chunks) return;
     const dim3 grid(b.max_chunks, b.n_images);
-    prepass_count_kernel<<<grid, kPreThreads, 0, s>>>(b);
-    prepass_scan_kernel<<<b.n_images, kPreThreads, 0, s>>>(b);
-    prepass_write_kernel<<<grid, kPreThreads, 0, s>>>(b);
+    if (step == 0) prepass_count_kernel<<<grid, kPreThreads, 0, s>>>(b);
+    else if (step == 1) prepass_scan_kernel<<<b.n_images, kPreThreads, 0, s>>>(b);
+    else prepass_write_kernel<<<grid, kPreThreads, 0, s>>>(b);
+}
+void launch_prepass(const BatchDev& b, cudaStream_t s) {
+    for (int step = 0; step < 3; step++) launch_prepass_step(b, s, step);
 }
 void launch_sync(const BatchDev& b, cudaStream_t s) {
     if (b.n_seqs) sync_kernel<<<b.n_seqs / kJobsPerCta, kSeqThreads, 0, s>>>(b);

@@ -53,6 +53,7 @@ cudaError_t init_constants();
 
 // Stage 1a: byte-unstuffing + RSTn detection: count per 4 KiB chunk, scan per image, compact per chunk.
 void launch_prepass(const BatchDev& b, cudaStream_t s);
+void launch_prepass_step(const BatchDev& b, cudaStream_t s, int step);  // 0 count, 1 scan, 2 write (profiling)
 // Stage 1b: look-back synchronisation, one thread per subsequence.
 void launch_sync(const BatchDev& b, cudaStream_t s);
 // Stage 1c: chain verification, repair of the links the look-back did not synchronise, prefix scan; one CTA per image.

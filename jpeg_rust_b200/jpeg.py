@@ -423,6 +423,13 @@ class Batch:
         return {"scan_bytes": s[0], "coef_bytes": s[1], "rgb_bytes": s[2], "pixels": s[3], "blocks": s[4],
                 "sequences": s[5], "subsequences": s[6], "device_bytes": s[7]}
 
+    def profile(self):
+        """Device time (ms) of every kernel of one decode, run one after the other (jpgpu_batch_profile)."""
+        ms = (C.c_float * 8)()
+        self.ctx._ck(_ffi.lib().jpgpu_batch_profile(self._h, ms), "jpgpu_batch_profile")
+        names = ["prepass_count", "prepass_scan", "prepass_write", "sync", "verify_scan", "decode_write", "idct_colour"]
+        return {n: float(ms[i]) for i, n in enumerate(names)}
+
     def launch_count(self):
         return int(_ffi.lib().jpgpu_batch_launch_count(self._h))
 
