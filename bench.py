@@ -370,6 +370,27 @@ def main():
                "sample": f"{cnt} of the batch's images, one per thread, {dt:.1f} s wall; oracle = C restatement of the "
                          "reference decoder (not the Rust binary: no rustc in the image)"}
 
+    # ---- BASELINE configs[0]: one lena.jpeg through the single-image entry point (JPEGImage.parse = parse + H2D +
+    # decode + D2H, synchronous), next to the reference's algorithm on one host core
+    config0 = None
+    lena_path = os.path.join(ROOT, "tests", "golden", "fixtures", "lena.jpeg")
+    if rank == 0 and os.path.exists(lena_path):
+        from jpeg_rust_b200 import JPEGImage, LAYOUT_REF
+        lena = open(lena_path, "rb").read()
+        for _ in range(3):
+            JPEGImage.parse(lena, layout=LAYOUT_REF, device=local_rank)
+        t0 = time.perf_counter()
+        reps = 20
+        for _ in range(reps):
+            JPEGImage.parse(lena, layout=LAYOUT_REF, device=local_rank)
+        gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+        config0 = {"workload": "lena.jpeg 512x512 4:2:2, one image per call, host bytes in, host RGB out, REF layout",
+                   "gpu_ms_per_image": gpu_ms, "gpu_mpixel_per_s": 512 * 512 / gpu_ms / 1e3}
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle_ffi as O
+            cpu_s = O.time_decode(lena, O.LAYOUT_REF, O.EXT_NONE, O.COS_CALL, 1)
+            config0["cpu_ms_per_image_1_core"] = cpu_s * 1e3
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -382,6 +403,7 @@ def main():
                        f"{stats['scan_bytes'] / 1e6:.0f} MB bitstream, {stats['coef_bytes'] / 1e9:.2f} GB coefficients",
                        "parallelism": f"images sharded over {world} GPU(s), no collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "config0_single_image": config0,
             "stage_ms": {"entropy": ent_ms, "idct_colour": idct_ms, "note": "stages run one after the other on one stream; "
                          "`value` is timed over jpgpu_batch_decode, which overlaps the image groups of a batch"},
         }

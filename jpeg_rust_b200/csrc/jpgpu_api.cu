@@ -23,6 +23,7 @@ struct jpgpu_ctx {
     static constexpr int kAux = 3;
     cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};
     cudaEvent_t fork = nullptr, join[kAux] = {nullptr, nullptr, nullptr};
+    jpgpu_batch* single = nullptr;   // batch object jpgpu_decode() reuses from call to call (arenas only grow)
     std::string err;
 };
 
@@ -117,6 +118,7 @@ extern "C" int jpgpu_create(int device, jpgpu_ctx** out) {
 extern "C" void jpgpu_destroy(jpgpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->single) { jpgpu_batch_destroy(c->single); c->single = nullptr; }
     for (int i = 0; i < jpgpu_ctx::kAux; i++) {
         if (c->aux[i]) { cudaStreamSynchronize(c->aux[i]); cudaStreamDestroy(c->aux[i]); }
         if (c->join[i]) cudaEventDestroy(c->join[i]);
@@ -143,6 +145,8 @@ extern "C" int jpgpu_sync(jpgpu_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     return JPGPU_OK;
 }
+
+extern "C" void jpgpu_batch_destroy(jpgpu_batch* b);
 
 extern "C" void jpgpu_batch_destroy(jpgpu_batch* b) {
     if (!b) return;
@@ -464,9 +468,11 @@ extern "C" uint64_t jpgpu_batch_launch_count(const jpgpu_batch* b) { return b ? 
 
 extern "C" int jpgpu_decode(jpgpu_ctx* ctx, const jpgpu_image_desc* desc, uint8_t* rgb_out, size_t* bytes_read) {
     if (!ctx || !desc || !rgb_out) return JPGPU_ERR_INVALID_ARG;
-    jpgpu_batch* b = nullptr;
-    int st = jpgpu_batch_create(ctx, desc, 1, &b);
+    int st;
+    if (!ctx->single) st = jpgpu_batch_create(ctx, desc, 1, &ctx->single);
+    else st = jpgpu_batch_replan(ctx->single, desc, 1);
     if (st != JPGPU_OK) return st;
+    jpgpu_batch* b = ctx->single;
     int32_t ist = JPGPU_OK;
     uint64_t br = 0;
     uint8_t* outs[1] = {rgb_out};
@@ -474,7 +480,6 @@ extern "C" int jpgpu_decode(jpgpu_ctx* ctx, const jpgpu_image_desc* desc, uint8_
     if (st == JPGPU_OK) st = jpgpu_batch_decode(b);
     if (st == JPGPU_OK) st = jpgpu_batch_download(b, outs);
     if (st == JPGPU_OK) st = jpgpu_batch_results(b, &ist, &br);
-    jpgpu_batch_destroy(b);
     if (st != JPGPU_OK) return st;
     if (bytes_read) *bytes_read = (size_t)br;
     return ist;
