@@ -1207,24 +1207,23 @@ void launch_verify_scan(const BatchDev& b, cudaStream_t s) {
 template <int NBUF, int PHASE>
 static cudaError_t launch_write_variant(const BatchDev& b, cudaStream_t s) {
     const WriteLayout lay = write_layout(b.max_slots, NBUF);
-    static uint32_t configured = 0;
-    if (lay.total > configured) {
-        cudaError_t e = cudaFuncSetAttribute(decode_write_kernel<NBUF, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    static uint32_t configured[64] = {0};   // the opt-in shared-memory size is a per-device attribute of the kernel
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || lay.total > configured[dev]) {
+        e = cudaFuncSetAttribute(decode_write_kernel<NBUF, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
         if (e != cudaSuccess) return e;
-        configured = lay.total;
+        if (dev >= 0 && dev < 64) configured[dev] = lay.total;
     }
     decode_write_kernel<NBUF, PHASE><<<(b.n_seqs + kWriteJobsPerCta - 1) / kWriteJobsPerCta, kWriteThreads, lay.total, s>>>(b);
     return cudaSuccess;
 }
 cudaError_t launch_decode_write(const BatchDev& b, cudaStream_t s) {
     if (!b.n_seqs) return cudaSuccess;
-    switch (b.write_mode) {   // experiment switch (env JPGPU_WRITE_MODE); 0 is the tuned default
-        case 1: return launch_write_variant<1, 4>(b, s);
-        case 2: return launch_write_variant<1, 6>(b, s);
-        case 3: return launch_write_variant<2, 8>(b, s);
-        case 4: return launch_write_variant<2, 12>(b, s);
-        default: return launch_write_variant<kWriteBufs, kPhaseSymbols>(b, s);
-    }
+    // one block buffer per lane and 5-symbol phases measured best on B200 (2 buffers / 8-12 symbols: fewer flushes, but
+    // half the resident warps); see DESIGN.md 4.2
+    return launch_write_variant<kWriteBufs, kPhaseSymbols>(b, s);
 }
 
 int launch_idct_colour(const BatchDev& b, cudaStream_t s) {

@@ -35,7 +35,6 @@ struct BatchDev {        // device pointers of one planned batch
     uint32_t max_slots;
     uint32_t max_chunks;      // most 4 KiB raw chunks any image has
     uint2* chunk_counts;      // per chunk: kept bytes / RSTn markers, then (after the scan) those before the chunk
-    uint32_t write_mode;      // decode_write_kernel variant (experiments)
     uint32_t seg_bits;        // checkpoint distance inside a subsequence (divides sub_bits)
     SegRec* segs;             // sub_bits / seg_bits records per subsequence
     // images grouped by colour-kernel variant (ImgKind)
