@@ -198,7 +198,9 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     TRY(dev_ensure(b, jpgpu_batch::kRaw, &raw, p.raw_bytes + 64));
     d.raw = raw;
     TRY(dev_ensure(b, jpgpu_batch::kDyn, &d.dyn, n + 1));
-    TRY(dev_ensure(b, jpgpu_batch::kStream, &d.stream, p.stream_words + 64));
+    // slack: the decoders' window prefetch may read one warp group past an image's last word (see fast_advance)
+    const size_t stream_alloc_words = p.stream_words + 64 + ((size_t)32 << p.lw);
+    TRY(dev_ensure(b, jpgpu_batch::kStream, &d.stream, stream_alloc_words));
     TRY(dev_ensure(b, jpgpu_batch::kSegtab, &d.segtab, p.seg_entries + 8));
     TRY(dev_ensure(b, jpgpu_batch::kSubs, &d.subs, p.sub_entries + 1));
     TRY(dev_ensure(b, jpgpu_batch::kSegs, &d.segs, p.sub_entries * (p.sub_bits / p.seg_bits) + 1));
@@ -215,7 +217,7 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     b->coef_bytes = p.coef_elems * sizeof(int16_t);
     // defined contents for everything a speculative decoder may read
     CK(cudaMemsetAsync(raw, 0, p.raw_bytes + 64, ctx->stream));
-    CK(cudaMemsetAsync(d.stream, 0, (p.stream_words + 64) * 4, ctx->stream));
+    CK(cudaMemsetAsync(d.stream, 0, stream_alloc_words * 4, ctx->stream));
     CK(cudaMemsetAsync(d.dyn, 0, (n + 1) * sizeof(ImgDyn), ctx->stream));
     CK(cudaMemsetAsync(d.coefs, 0, (p.coef_elems + 64) * 2, ctx->stream));
     CK(cudaMemsetAsync(d.segtab, 0, (p.seg_entries + 8) * 4, ctx->stream));

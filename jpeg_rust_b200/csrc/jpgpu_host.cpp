@@ -112,6 +112,9 @@ int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, bool 
     }
     out.maxcode[0] = -1;
     out.maxcode[17] = 0x7fffffff;
+    // DC symbols naming a size category > 16 (huffman.rs:202 assert) stay out of both LUT levels: the canonical
+    // walk finds them and reports them, so the per-symbol path never has to look at that flag.
+    if (is_dc) codes.erase(std::remove_if(codes.begin(), codes.end(), [](const Code& c) { return c.val > 16; }), codes.end());
     // first level: codes of length <= kLutBits fill 2^(kLutBits-len) entries each
     for (const Code& c : codes) {
         if (c.len > kLutBits) continue;

@@ -266,7 +266,7 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 
 struct FastCtx {
     const uint32_t* words;   // lane-interleaved stream of the image (global)
-    uint32_t lw, wmask5, gmask_inv;
+    uint32_t lw, wmask5, gmask_inv;   // wmask5 = row bits of a physical word offset: ((words per subsequence) - 1) << 5
     const uint32_t* seg;
     uint32_t nseg, stream_bits, seg_units;
     uint32_t info_addr;      // shared: FastTables::info
@@ -278,12 +278,15 @@ struct FastCtx {
 };
 
 struct FastState {
-    uint32_t hi, lo, avail, widx, p, nextw;
+    uint32_t w0, w1, w2;     // stream words p>>5, +1, +2: the next 32 bits are funnelshift_l(w1, w0, p & 31)
+    uint32_t off;            // physical word offset of w2 in the lane-interleaved stream
+    uint32_t p;
     int32_t g;
     uint32_t info_ptr;       // shared address of the FastTables::info entry of the current block-in-MCU
     uint32_t lut_dc, lut_ac, dc_off;
     int32_t dcur;
     uint32_t seg, seg_end, seg_lim, flags;   // seg_lim = seg_end - 7 (0 if shorter): at or past it a step must look at the interval end
+    uint32_t wrap_lim, lim;                  // wrap_lim: see fast_advance(); lim = min(seg_lim, wrap_lim)
 };
 
 // per-CTA tables the fast path reads (filled once after the LUTs are loaded)
@@ -319,16 +322,40 @@ __device__ __forceinline__ const uint32_t* fast_word_ptr(const FastCtx& cx, uint
     const uint32_t phys = (i & cx.gmask_inv) | ((i << 5) & cx.wmask5) | ((i >> cx.lw) & 31u);
     return cx.words + phys;
 }
+__device__ __forceinline__ uint32_t fast_peek(const FastState& st) { return __funnelshift_l(st.w1, st.w0, st.p); }
+__device__ __forceinline__ void fast_set_lim(FastState& st) { st.lim = min(st.seg_lim, st.wrap_lim); }
 __device__ __forceinline__ void fast_seek(const FastCtx& cx, FastState& st, uint32_t p) {
     st.p = p;
-    st.widx = p >> 5;
-    const uint32_t off = p & 31u;
-    const uint32_t a = __ldg(fast_word_ptr(cx, st.widx)), b2 = __ldg(fast_word_ptr(cx, st.widx + 1));
-    st.hi = __funnelshift_l(b2, a, off);
-    st.lo = b2 << off;
-    st.avail = 64u - off;
-    st.widx += 2;
-    st.nextw = __ldg(fast_word_ptr(cx, st.widx));
+    const uint32_t i = p >> 5;
+    const uint32_t* p2 = fast_word_ptr(cx, i + 2);
+    st.w0 = __ldg(fast_word_ptr(cx, i));
+    st.w1 = __ldg(fast_word_ptr(cx, i + 1));
+    st.w2 = __ldg(p2);
+    st.off = (uint32_t)(p2 - cx.words);
+    st.wrap_lim = ((((i + 2u) >> cx.lw) + 1u) << (cx.lw + 5u)) - 64u;
+    fast_set_lim(st);
+}
+// The bit position moved from st.p to pn (at most 32 bits on): when that crosses a word boundary the window
+// slides by one word.  Consecutive words of a subsequence are 32 words apart (lane-interleaved layout), so the
+// next word to fetch is simply 32 further — except once per sub_bits, when the window's last word enters the
+// next subsequence.  That slide (the one that takes the position to wrap_lim or past it) fetches from the row
+// below the group instead (allocated, see build of the stream arena) and is put right by fast_fix_wrap(), which
+// the caller runs when it sees st.p >= st.wrap_lim — before the word can reach the decoder, two slides later.
+__device__ __forceinline__ void fast_advance(const FastCtx& cx, FastState& st, uint32_t pn) {
+    const bool cross = ((st.p ^ pn) & ~31u) != 0u;
+    st.p = pn;
+    st.w0 = cross ? st.w1 : st.w0;
+    st.w1 = cross ? st.w2 : st.w1;
+    st.off += cross ? 32u : 0u;
+    asm("{\n .reg .pred q;\n .reg .u64 a;\n setp.ne.u32 q, %3, 0;\n mad.wide.u32 a, %2, 4, %1;\n @q ld.global.nc.u32 %0, [a];\n}"
+        : "+r"(st.w2) : "l"(cx.words), "r"(st.off), "r"((uint32_t)cross));
+}
+__device__ __forceinline__ void fast_fix_wrap(const FastCtx& cx, FastState& st) {   // st.p >= st.wrap_lim
+    const uint32_t* p2 = fast_word_ptr(cx, (st.p >> 5) + 2u);
+    st.w2 = __ldg(p2);
+    st.off = (uint32_t)(p2 - cx.words);
+    st.wrap_lim += 32u << cx.lw;
+    fast_set_lim(st);
 }
 __device__ __forceinline__ uint32_t fast_c(const FastState& st) { return lds32(st.info_ptr + 12u); }
 __device__ __forceinline__ void fast_load_block(const FastCtx& cx, FastState& st) {  // st.info_ptr changed: tables + DC slot
@@ -356,6 +383,7 @@ __device__ __forceinline__ void fast_set_segment(const FastCtx& cx, FastState& s
     st.seg = k;
     st.seg_end = cx.seg[k + 1];
     st.seg_lim = st.seg_end >= 7u ? st.seg_end - 7u : 0u;
+    fast_set_lim(st);
 }
 
 // init_state() of jpgpu_core.h
@@ -364,11 +392,14 @@ __device__ __forceinline__ void fast_init(const FastCtx& cx, FastState& st, uint
     st.flags = 0;
     st.dc_off = 0;
     st.dcur = 0;
+    st.wrap_lim = 0xffffffffu;
     if (p >= cx.stream_bits) {
         st.seg = cx.nseg ? cx.nseg - 1 : 0;
         st.seg_end = cx.stream_bits;
         st.seg_lim = st.seg_end >= 7u ? st.seg_end - 7u : 0u;
-        st.p = p; st.widx = (p >> 5) + 2; st.avail = 64u - (p & 31u); st.hi = st.lo = st.nextw = 0u;
+        st.p = p; st.w0 = st.w1 = st.w2 = 0u;
+        st.off = (uint32_t)(fast_word_ptr(cx, (cx.stream_bits >> 5) + 2) - cx.words);   // inside the zero padding
+        st.lim = st.seg_lim;
         st.g = g;
     } else {
         uint32_t lo = 0, hi = cx.nseg;  // find_segment
@@ -400,7 +431,7 @@ __device__ __forceinline__ uint32_t fast_interval_end(const FastCtx& cx, FastSta
     bool cross = st.p >= st.seg_end;
     if (!cross) {
         const uint32_t rem = st.seg_end - st.p;  // 1..7 pad bits must all be 1 (T.81 F.1.2.3)
-        cross = (st.hi >> (32u - rem)) == ((1u << rem) - 1u);
+        cross = (fast_peek(st) >> (32u - rem)) == ((1u << rem) - 1u);
     }
     if (!cross) return 0u;
     fast_seek(cx, st, st.seg_end);
@@ -415,11 +446,12 @@ __device__ __forceinline__ uint32_t fast_interval_end(const FastCtx& cx, FastSta
 }
 
 // Second-level LUT or canonical walk (huffman.rs:211-227) for codes longer than kLutBits.
-__device__ __forceinline__ uint32_t fast_long_code(const FastCtx& cx, FastState& st, uint32_t lut, uint32_t e) {
-    if (e != 0u) e = lds32(lut + (uint32_t)(kLutSize * 4) + (((e & 511u) + ((st.hi << kLutBits) >> (32u - ((e >> 9) & 7u)))) << 2));
+__device__ __forceinline__ uint32_t fast_long_code(const FastCtx& cx, FastState& st, uint32_t lut, uint32_t e, uint32_t hi) {
+    if (e != 0u) e = lds32(lut + (uint32_t)(kLutSize * 4) + (((e & 511u) + ((hi << kLutBits) >> (32u - ((e >> 9) & 7u)))) << 2));
     if (e == 0u) {
-        e = huff_slow(cx.luts[(lut - cx.lut0_addr) / (uint32_t)sizeof(HuffLut)], st.hi);
+        e = huff_slow(cx.luts[(lut - cx.lut0_addr) / (uint32_t)sizeof(HuffLut)], hi);
         if (e == 0u) { st.flags |= kStBadCode; e = kBadEntry; }
+        st.flags |= (e >> 21) & kStDcSize;        // bit 24 -> kStDcSize (8): such DC symbols are only in the canonical tables
     }
     return e;
 }
@@ -438,6 +470,7 @@ struct WriteLane {
     int32_t seg_limit;         // first coefficient position past the current restart interval (= total without DRI)
     uint32_t store_on;         // 0 while finishing a block that started in the previous subsequence, and past seg_limit
     uint32_t state;            // kRun / kBlocked (out of buffers until the next flush) / kFinished
+    int16_t* coefs;            // coefficient arena of the image
     __device__ __forceinline__ void select(uint32_t c) {
         cur = c;
         row_addr = rows_addr + c * 128u;
@@ -454,47 +487,65 @@ struct WriteLane {
         // finished: block boundary past the subsequence / scan; blocked: no free buffer
         state = (p >= end_bit || g >= total) ? (uint32_t)kFinished : (ndone == (uint32_t)NBUF ? (uint32_t)kBlocked : (uint32_t)kRun);
     }
+    // Rare: the decoder moved to the next restart interval (kEvCross) or reached the end of the data (kEvEnd);
+    // g_before = coefficient position before the move, st.g = first position of the new interval.
+    // A valid stream changes interval exactly where the previous one is complete.  A damaged one may come short
+    // (the missing blocks, a half-written one included, become zeros) or long (the excess was decoded without
+    // being stored); both are reported (kStRestart).
+    template <class CX, class ST>
+    __device__ __forceinline__ void on_interval(uint32_t ev, int32_t g_before, const CX& cx, ST& st) {
+        if (ev & kEvEnd) { state = kFinished; return; }
+        const int32_t old_limit = seg_limit, gap_from = g_before & ~63;
+        seg_limit = min(total, st.g + (int32_t)cx.seg_units);
+        if (g_before != old_limit) st.flags |= kStRestart;
+        if ((g_before & 63) != 0 && store_on) close_block(0xffffffffu, st.p, st.g);
+        for (int32_t g = gap_from; g < old_limit && g < st.g; g += 64) {
+            uint4* dst = reinterpret_cast<uint4*>(coefs + (size_t)g);
+#pragma unroll
+            for (int i = 0; i < 8; i++) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        store_on = 1u;
+        if (st.p >= end_bit || st.g >= total) state = kFinished;
+        else if (state != kBlocked) state = kRun;
+    }
 };
 struct NoLane {};
 
-// CHECK = false: the caller guarantees st.p < st.seg_lim (no look at the interval end needed).
+// CHECK = false: the caller guarantees st.p < st.lim (no look at the interval end, no window wrap pending).
 template <bool WRITE, bool CHECK, typename LANE>
 __device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, LANE& wl) {
-    {   // refill: one word when 32 or fewer bits are left; the word was fetched one refill ago (predicated, no branch)
-        const bool need = st.avail <= 32u;
-        const uint32_t w = need ? st.nextw : 0u;
-        st.hi |= __funnelshift_rc(w, 0u, st.avail);
-        st.lo |= __funnelshift_lc(0u, w, 32u - st.avail);
-        st.avail += need ? 32u : 0u;
-        st.widx += need ? 1u : 0u;
-        const uint32_t* np = fast_word_ptr(cx, st.widx);
-        asm("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q ld.global.nc.u32 %0, [%1];\n}" : "+r"(st.nextw) : "l"(np), "r"((uint32_t)need));
+    if (CHECK && st.p >= st.lim) {
+        if (st.p >= st.wrap_lim) fast_fix_wrap(cx, st);
+        if (st.p >= st.seg_lim) {
+            const int32_t g_before = st.g;
+            const uint32_t ev = fast_interval_end(cx, st);
+            if (ev) {
+                if constexpr (WRITE) wl.on_interval(ev, g_before, cx, st);
+                return ev;
+            }
+        }
     }
-    if (CHECK && st.p >= st.seg_lim) {
-        const uint32_t ev = fast_interval_end(cx, st);
-        if (ev) return ev;
-    }
+    const uint32_t hi = fast_peek(st);            // the next 32 bits
     const uint32_t z = (uint32_t)st.g & 63u;
     const uint32_t lut = z ? st.lut_ac : st.lut_dc;
-    uint32_t e = lds32(lut + ((st.hi >> (32 - kLutBits)) << 2));
-    if ((int32_t)e <= 0) e = fast_long_code(cx, st, lut, e);
+    uint32_t e = lds32(lut + ((hi >> (32 - kLutBits)) << 2));
+    if ((int32_t)e <= 0) e = fast_long_code(cx, st, lut, e, hi);
     const uint32_t tb = e & 255u, len = __byte_perm(e, 0u, 0x4441), adv = __byte_perm(e, 0u, 0x4442);
-    st.flags |= (e >> 21) & kStDcSize;            // bit 24 -> kStDcSize (8)
     const uint32_t size = tb - len;
-    const uint32_t top = st.hi << len;            // len <= 16
-    const uint32_t v = __funnelshift_l(top, 0u, size);
-    const int32_t val = (int32_t)v - (int32_t)((uint32_t)((int32_t)~top >> 31) & ((1u << size) - 1u));
+    const uint32_t top = hi << len;               // len <= 16
+    // EXTEND (huffman.rs:256-268): first value bit 1 -> the bits as they are, 0 -> minus their complement
+    const uint32_t sgn = (uint32_t)((int32_t)top >> 31);
+    const uint32_t mag = __funnelshift_l(top ^ ~sgn, 0u, size);
+    const int32_t val = (int32_t)((mag ^ ~sgn) - ~sgn);
     const bool is_dc = z == 0u;
     st.dcur += is_dc ? val : 0;                   // decoder.rs:208-210
     const uint32_t nz = z + adv;
     if constexpr (WRITE) {
-        const uint32_t off = lds8(cx.sp_addr + min(nz - 1u, 63u));   // huffman.rs:183-189
-        sts16_if(wl.row_addr + (off ^ wl.swz16), (uint32_t)(is_dc ? st.dcur : val), wl.store_on != 0u && (is_dc || val != 0));
+        // huffman.rs:183-189.  Symbols without a value (EOB, ZRL) store a zero at a position the block has not reached.
+        const uint32_t off = lds8(cx.sp_addr + min(nz - 1u, 63u));
+        sts16_if(wl.row_addr | (off ^ wl.swz16), (uint32_t)(is_dc ? st.dcur : val), wl.store_on != 0u);
     }
-    st.hi = __funnelshift_lc(st.lo, st.hi, tb);
-    st.lo = __funnelshift_lc(0u, st.lo, tb);
-    st.avail -= tb;
-    st.p += tb;
+    fast_advance(cx, st, st.p + tb);
     if (nz >= 64u) {  // block complete
         st.g = (st.g | 63) + 1;
         st.info_ptr = lds32(st.info_ptr + 8u);
@@ -511,9 +562,11 @@ __device__ __forceinline__ void fast_run_to(const FastCtx& cx, FastState& st, ui
     NoLane nl;
 #pragma unroll 1
     while (true) {
-        const uint32_t lim = min(end_bit, st.seg_lim);
+        if (st.p >= st.wrap_lim) fast_fix_wrap(cx, st);
+        const uint32_t lim = min(end_bit, st.lim);
 #pragma unroll 1
         while (st.p < lim) fast_step<false, false>(cx, st, nl);
+        if (st.p >= st.wrap_lim) continue;
         if (st.p >= end_bit) return;
         const uint32_t ev = fast_interval_end(cx, st);
         if (ev & kEvEnd) return;
@@ -529,6 +582,7 @@ __device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const SM& sm
     cx.lw = b.lw;
     cx.wmask5 = ((1u << b.lw) - 1u) << 5;
     cx.gmask_inv = ~((32u << b.lw) - 1u);
+    
     cx.seg = b.segtab + im.seg_off;
     cx.nseg = d.nseg;
     cx.stream_bits = d.stream_bits;
@@ -541,7 +595,7 @@ __device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const SM& sm
     cx.lut0_addr = smem_addr(&sm.lut[0]);
     // keep the per-symbol operands in registers instead of re-deriving them from the parameter bank every step
     JPGPU_PIN64(cx.words);
-    JPGPU_PIN32(cx.lw); JPGPU_PIN32(cx.wmask5); JPGPU_PIN32(cx.gmask_inv);
+    JPGPU_PIN32(cx.wmask5);
     JPGPU_PIN32(cx.dc_addr); JPGPU_PIN32(cx.sp_addr);
     return cx;
 }
@@ -785,8 +839,8 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
         store_on = (st.g & 63) == 0;
         if (st.g >= total || (st.p >= end_bit && store_on)) active = false;
     } else {
-        st.p = 0; st.g = 0; st.flags = 0; st.info_ptr = cx.info_addr; st.avail = 64; st.hi = st.lo = st.nextw = 0; st.widx = 0;
-        st.seg = 0; st.seg_end = st.seg_lim = 0; st.dcur = 0; st.dc_off = 0; st.lut_dc = st.lut_ac = cx.lut0_addr;
+        st.p = 0; st.g = 0; st.flags = 0; st.info_ptr = cx.info_addr; st.w0 = st.w1 = st.w2 = 0; st.off = 0;
+        st.seg = 0; st.seg_end = st.seg_lim = st.lim = 0; st.wrap_lim = 0xffffffffu; st.dcur = 0; st.dc_off = 0; st.lut_dc = st.lut_ac = cx.lut0_addr;
     }
     const int32_t g_start = st.g;
     WriteLane<NBUF> wl;
@@ -800,40 +854,16 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
     wl.seg_limit = cx.seg_units ? min(total, (int32_t)((st.seg + 1u) * cx.seg_units)) : total;
     wl.store_on = store_on && st.g < wl.seg_limit ? 1u : 0u;
     wl.state = active ? (uint32_t)WriteLane<NBUF>::kRun : (uint32_t)WriteLane<NBUF>::kFinished;
+    wl.coefs = coefs;
 
 #pragma unroll 1
     while (true) {
         // ---- phase A: every lane decodes up to PHASE symbols into its own buffers.  Whether a lane is finished
         // (block boundary at or past the end of its subsequence, or past the last block of the scan) or out of
-        // buffers can only change when a block completes, so it is only looked at there (WriteLane::close_block).
+        // buffers can only change when a block completes or a restart interval ends, so it is only looked at
+        // there (WriteLane::close_block / on_interval).
 #pragma unroll 1
-        for (int k = 0; k < PHASE; k++) {
-            if (wl.state == WriteLane<NBUF>::kRun) {
-                const int32_t g_before = st.g;
-                const uint32_t ev = fast_step<true, true>(cx, st, wl);
-                if (ev & (kEvCross | kEvEnd)) {  // rare: restart interval / end of data
-                    if (ev & kEvEnd) {
-                        wl.state = WriteLane<NBUF>::kFinished;
-                    } else {
-                        // A valid stream changes interval exactly where the previous one is complete.  A damaged one may
-                        // come short (the missing blocks, a half-written one included, become zeros) or long (the excess
-                        // was decoded without being stored); both are reported (kStRestart).
-                        const int32_t old_limit = wl.seg_limit, gap_from = g_before & ~63;
-                        wl.seg_limit = min(total, st.g + (int32_t)cx.seg_units);
-                        if (g_before != old_limit) st.flags |= kStRestart;
-                        if ((g_before & 63) != 0 && wl.store_on) wl.close_block(0xffffffffu, st.p, st.g);
-                        for (int32_t g = gap_from; g < old_limit && g < st.g; g += 64) {
-                            uint4* dst = reinterpret_cast<uint4*>(coefs + (size_t)g);
-#pragma unroll
-                            for (int i = 0; i < 8; i++) dst[i] = make_uint4(0u, 0u, 0u, 0u);
-                        }
-                        wl.store_on = 1u;
-                        if (st.p >= end_bit || st.g >= total) wl.state = WriteLane<NBUF>::kFinished;
-                        else if (wl.state != WriteLane<NBUF>::kBlocked) wl.state = WriteLane<NBUF>::kRun;
-                    }
-                }
-            }
-        }
+        for (int k = PHASE; k > 0 && wl.state == WriteLane<NBUF>::kRun; k--) fast_step<true, true>(cx, st, wl);
         if (wl.state == WriteLane<NBUF>::kBlocked) wl.state = WriteLane<NBUF>::kRun;
         active = wl.state != WriteLane<NBUF>::kFinished;
         const uint32_t ndone = wl.ndone, cur = wl.cur, row0 = wl.row0;
