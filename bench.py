@@ -283,6 +283,7 @@ def main():
                 "kernels": {
                     "prepass_count+scan+write": {"ms": prof["prepass_count"] + prof["prepass_scan"] + prof["prepass_write"],
                                                  "algorithmic_GBps": 2 * stats["scan_bytes"] / ((prof["prepass_count"] + prof["prepass_scan"] + prof["prepass_write"]) * 1e-3) / 1e9,
+                                                 "split_ms": [prof["prepass_count"], prof["prepass_scan"], prof["prepass_write"]],
                                                  "bound": "L2 partial-sector stores of the lane-interleaved stream + instruction issue"},
                     "sync": {"ms": prof["sync"], "bitstream_GBps": stats["scan_bytes"] / (prof["sync"] * 1e-3) / 1e9,
                              "bound": "instruction issue (serial bit-dependent decode, ~75 instructions per symbol step)"},

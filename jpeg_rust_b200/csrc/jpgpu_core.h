@@ -38,7 +38,10 @@ constexpr int kMinSegBits = 512;           // smallest checkpoint distance insid
 constexpr int kSeqThreads = JPGPU_SEQ_THREADS;  // subsequences per sequence (= CTA size of the sync/write kernels)
 constexpr int kStreamPadWords = 8;         // zero words readable past every image's stream
 constexpr int kWriteBufs = 1;              // coefficient block buffers per lane in the write kernel
-constexpr int kPhaseSymbols = 5;           // symbols a lane decodes between two cooperative flushes
+#ifndef JPGPU_PHASE_SYMBOLS
+#define JPGPU_PHASE_SYMBOLS 5
+#endif
+constexpr int kPhaseSymbols = JPGPU_PHASE_SYMBOLS;  // symbols a lane decodes between two cooperative flushes
 
 // status bits accumulated per image on the device (mapped to JPGPU_* by the host)
 enum : uint32_t {
@@ -183,12 +186,21 @@ JPGPU_HD int zigzag_to_colmajor(int k, const uint8_t* zz_nat) {
 // ------------------------------------------------------------------ bit reader
 // The compacted stream is stored as 32-bit words holding 4 stream bytes each, first byte
 // in the most significant position, so a word IS the next 32 bits.  Words are laid out
-// LANE-INTERLEAVED: with W = S/32 words per subsequence, a group of 32 consecutive
-// subsequences (one warp of decode threads) occupies 32*W words and word k of
-// subsequence l sits at k*32 + l inside it.  When the 32 lanes of a warp refill at similar
-// depths k they touch the same one or two 128-byte lines instead of 32 different ones.
+// LANE-INTERLEAVED in pieces of kPieceWords words (32 bytes = one memory sector): with
+// W = S/32 words per subsequence, a group of 32 consecutive subsequences (one warp of decode
+// threads) occupies 32*W words; word k of subsequence l sits at
+//     (k / kPieceWords) * 32 * kPieceWords + l * kPieceWords + k % kPieceWords
+// inside it.  A lane reads its own sector front to back (eight refills from one 32-byte
+// sector, whatever the other lanes do), the 32 lanes of a warp at similar depths share
+// 1 KiB row blocks, and the pre-pass writes whole sectors.
+#ifndef JPGPU_PIECE_SHIFT
+#define JPGPU_PIECE_SHIFT 3
+#endif
+constexpr uint32_t kPieceShift = JPGPU_PIECE_SHIFT;
+constexpr uint32_t kPieceWords = 1u << kPieceShift;
 JPGPU_HD uint32_t stream_phys(uint32_t i, uint32_t lw) {  // lw = log2(W)
-    return (i & ~((32u << lw) - 1u)) | ((i & ((1u << lw) - 1u)) << 5) | ((i >> lw) & 31u);
+    const uint32_t k = i & ((1u << lw) - 1u);
+    return (i & ~((32u << lw) - 1u)) | ((k & ~(kPieceWords - 1u)) << 5) | (((i >> lw) & 31u) << kPieceShift) | (k & (kPieceWords - 1u));
 }
 
 struct BitReader {

@@ -156,10 +156,12 @@ __global__ void __launch_bounds__(kPreThreads) prepass_scan_kernel(BatchDev b) {
 }
 
 // (3) grid as (1): every chunk writes its kept bytes at its offset. A stream word IS the next 32 bits (first byte
-// in the most significant position); words a chunk only partly covers are written byte by byte, since the
-// neighbouring chunk owns the other bytes.
+// in the most significant position).  The bytes are staged in shared memory aligned to the 32-byte pieces of the
+// stream layout (stream_phys), so a piece the chunk covers entirely leaves as two 16-byte stores (a whole sector);
+// the first and last piece are shared with the neighbouring chunks and are written word by word, the words a
+// chunk only partly covers byte by byte.
 __global__ void __launch_bounds__(kPreThreads) prepass_write_kernel(BatchDev b) {
-    __shared__ uint32_t s_stage[kPreChunk / 4 + 8];
+    __shared__ __align__(16) uint32_t s_stage[kPreChunk / 4 + 2 * kPieceWords];
     __shared__ uint32_t s_wsum[2][kPreThreads / 32];
     const uint32_t img = b.img0 + blockIdx.y;
     const ImgDev& im = b.imgs[img];
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(kPreThreads) prepass_write_kernel(BatchDev b) 
     uint32_t exc, exr, totc, totr;
     pre_scan(__popc(pb.keep), __popc(pb.rstm), s_wsum, exc, exr, totc, totr);
     uint8_t* stage_bytes = reinterpret_cast<uint8_t*>(s_stage);
-    const uint32_t carry = start.x & 3u;
+    const uint32_t carry = start.x & (4u * kPieceWords - 1u);       // the chunk's first byte inside its first piece
     uint32_t pos = carry + exc;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -195,14 +197,28 @@ __global__ void __launch_bounds__(kPreThreads) prepass_write_kernel(BatchDev b) 
     }
     __syncthreads();
     uint32_t* out = b.stream + im.stream_off;
-    const uint32_t staged = carry + totc, w0 = start.x >> 2, nw = (staged + 3u) >> 2;
-    for (uint32_t i = tid; i < nw; i += kPreThreads) {
-        const uint32_t lo = max(4u * i, carry), hi = min(4u * i + 4u, staged);
-        if (hi - lo == 4u) {
-            out[stream_phys(w0 + i, lw)] = s_stage[i];
+    const uint32_t staged = carry + totc;                            // staged bytes, counted from the piece boundary
+    const uint32_t w0 = (start.x >> 2) & ~(kPieceWords - 1u);        // stream word of s_stage[0]
+    const uint32_t npieces = (staged + 4u * kPieceWords - 1u) / (4u * kPieceWords);
+    for (uint32_t t = tid; t < npieces; t += kPreThreads) {
+        const uint32_t b0 = t * 4u * kPieceWords;
+        uint32_t* dst = out + stream_phys(w0 + t * kPieceWords, lw);
+        if (b0 >= carry && b0 + 4u * kPieceWords <= staged) {
+            const uint4* src = reinterpret_cast<const uint4*>(s_stage + t * kPieceWords);
+#pragma unroll
+            for (uint32_t i = 0; i < kPieceWords / 4u; i++) reinterpret_cast<uint4*>(dst)[i] = src[i];
         } else {
-            uint8_t* wb = reinterpret_cast<uint8_t*>(out + stream_phys(w0 + i, lw));
-            for (uint32_t q = lo; q < hi; q++) wb[3u - (q & 3u)] = stage_bytes[q ^ 3u];
+#pragma unroll 1
+            for (uint32_t i = 0; i < kPieceWords; i++) {
+                const uint32_t lo = max(b0 + 4u * i, carry), hi = min(b0 + 4u * i + 4u, staged);
+                if (lo >= hi) continue;
+                if (hi - lo == 4u) {
+                    dst[i] = s_stage[t * kPieceWords + i];
+                } else {
+                    uint8_t* wb = reinterpret_cast<uint8_t*>(dst + i);
+                    for (uint32_t q = lo; q < hi; q++) wb[3u - (q & 3u)] = stage_bytes[q ^ 3u];
+                }
+            }
         }
     }
 }
@@ -266,7 +282,7 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 
 struct FastCtx {
     const uint32_t* words;   // lane-interleaved stream of the image (global)
-    uint32_t lw, wmask5, gmask_inv;   // wmask5 = row bits of a physical word offset: ((words per subsequence) - 1) << 5
+    uint32_t lw, wmask5, gmask_inv;   // wmask5 = piece-row bits of a physical word offset
     const uint32_t* seg;
     uint32_t nseg, stream_bits, seg_units;
     uint32_t info_addr;      // shared: FastTables::info
@@ -319,7 +335,7 @@ __device__ __forceinline__ void fast_tables_init(FT& ft, const SM& sm, bool vali
 }
 
 __device__ __forceinline__ const uint32_t* fast_word_ptr(const FastCtx& cx, uint32_t i) {
-    const uint32_t phys = (i & cx.gmask_inv) | ((i << 5) & cx.wmask5) | ((i >> cx.lw) & 31u);
+    const uint32_t phys = (i & cx.gmask_inv) | ((i << 5) & cx.wmask5) | (((i >> cx.lw) & 31u) << kPieceShift) | (i & (kPieceWords - 1u));
     return cx.words + phys;
 }
 __device__ __forceinline__ uint32_t fast_peek(const FastState& st) { return __funnelshift_l(st.w1, st.w0, st.p); }
@@ -336,19 +352,27 @@ __device__ __forceinline__ void fast_seek(const FastCtx& cx, FastState& st, uint
     fast_set_lim(st);
 }
 // The bit position moved from st.p to pn (at most 32 bits on): when that crosses a word boundary the window
-// slides by one word.  Consecutive words of a subsequence are 32 words apart (lane-interleaved layout), so the
-// next word to fetch is simply 32 further — except once per sub_bits, when the window's last word enters the
-// next subsequence.  That slide (the one that takes the position to wrap_lim or past it) fetches from the row
-// below the group instead (allocated, see build of the stream arena) and is put right by fast_fix_wrap(), which
-// the caller runs when it sees st.p >= st.wrap_lim — before the word can reach the decoder, two slides later.
+// slides by one word.  The next word to fetch is the next one of this lane's 32-byte piece or, after its
+// last, the first of the lane's piece in the next row block (stream_phys) — except once per sub_bits, when the
+// window's last word enters the next subsequence.  That slide (the one that takes the position to wrap_lim or
+// past it) fetches from the row block below the group instead (allocated, see the stream arena) and is put right
+// by fast_fix_wrap(), which the caller runs when it sees st.p >= st.wrap_lim — before the word can reach the
+// decoder, two slides later.
 __device__ __forceinline__ void fast_advance(const FastCtx& cx, FastState& st, uint32_t pn) {
     const bool cross = ((st.p ^ pn) & ~31u) != 0u;
     st.p = pn;
     st.w0 = cross ? st.w1 : st.w0;
     st.w1 = cross ? st.w2 : st.w1;
-    st.off += cross ? 32u : 0u;
-    asm("{\n .reg .pred q;\n .reg .u64 a;\n setp.ne.u32 q, %3, 0;\n mad.wide.u32 a, %2, 4, %1;\n @q ld.global.nc.u32 %0, [a];\n}"
-        : "+r"(st.w2) : "l"(cx.words), "r"(st.off), "r"((uint32_t)cross));
+    const uint32_t step = (~st.off & (kPieceWords - 1u)) != 0u ? 1u : 32u * kPieceWords - (kPieceWords - 1u);
+    st.off += cross ? step : 0u;
+#ifndef JPGPU_PF_BYTES
+#define JPGPU_PF_BYTES (128 << JPGPU_PIECE_SHIFT)   // the lane's piece in the next row block
+#endif
+    asm("{\n .reg .pred q;\n .reg .u64 a;\n setp.ne.u32 q, %3, 0;\n mad.wide.u32 a, %2, 4, %1;\n @q ld.global.nc.u32 %0, [a];\n"
+#if JPGPU_PF_BYTES > 0
+        " @q prefetch.global.L1 [a + %4];\n"
+#endif
+        "}" : "+r"(st.w2) : "l"(cx.words), "r"(st.off), "r"((uint32_t)cross), "n"(JPGPU_PF_BYTES));
 }
 __device__ __forceinline__ void fast_fix_wrap(const FastCtx& cx, FastState& st) {   // st.p >= st.wrap_lim
     const uint32_t* p2 = fast_word_ptr(cx, (st.p >> 5) + 2u);
@@ -580,7 +604,7 @@ __device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const SM& sm
     FastCtx cx;
     cx.words = b.stream + im.stream_off;
     cx.lw = b.lw;
-    cx.wmask5 = ((1u << b.lw) - 1u) << 5;
+    cx.wmask5 = (((1u << b.lw) - 1u) & ~(kPieceWords - 1u)) << 5;
     cx.gmask_inv = ~((32u << b.lw) - 1u);
     
     cx.seg = b.segtab + im.seg_off;
@@ -915,7 +939,15 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
 
 // ============================================ stage 2+3: dequant + IDCT + upsample + colour
 constexpr int kIdctThreads = 128;
-constexpr int kTilesPerCta = 5;      // consecutive tiles one CTA walks (amortises set-up, lets loads run ahead)
+#ifndef JPGPU_TILES_PER_CTA
+#define JPGPU_TILES_PER_CTA 5
+#endif
+#ifdef JPGPU_IDCT_MIN_CTAS
+#define JPGPU_IDCT_BOUNDS __launch_bounds__(kIdctThreads, JPGPU_IDCT_MIN_CTAS)
+#else
+#define JPGPU_IDCT_BOUNDS __launch_bounds__(kIdctThreads)
+#endif
+constexpr int kTilesPerCta = JPGPU_TILES_PER_CTA;  // consecutive tiles one CTA walks (amortises set-up, lets loads run ahead)
 constexpr int kScrRowPitch = 12;     // floats; 4*odd -> conflict-free 128-bit row reads
 constexpr int kScrBlkPitch = 104;    // floats; 8 mod 32 -> conflict-free column writes across the 4 blocks of a warp
 constexpr int kOutPitch = 400;       // bytes per staged output row (128 px * 3 = 384, padded)
@@ -975,7 +1007,7 @@ __device__ __forceinline__ uint32_t pack4(int32_t a, int32_t b, int32_t c, int32
 // tiles; the coefficient loads of the next tile are issued before the current one is
 // computed.
 template <int HY, int VY, bool GRAY>
-__global__ void __launch_bounds__(kIdctThreads) idct_colour_kernel(BatchDev b, const uint32_t* __restrict__ img_list) {
+__global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t* __restrict__ img_list) {
     constexpr int MH = 8 * VY;
     constexpr int NM = 128 / (8 * HY);         // MCUs per tile
     constexpr int NY = HY * VY;                // luma blocks per MCU
