@@ -163,6 +163,32 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of the
+    end-to-end leg (first touch) and the threads feeding the copies are local to the GPU's PCIe root.  Best
+    effort: returns the node, or None when the topology cannot be read (then nothing is changed)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -180,6 +206,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the decode path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)   # before any pinned allocation: first touch places the pages
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -348,7 +375,8 @@ def main():
         e2e = {"value": world * pixels / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(sum(sizes)),
                "d2h_bytes_per_step": int(n * per), "ms_per_step": e2e_ms,
                "note": f"jpgpu_batch_upload + decode + download of {len(chunks)} chunks of {chunk} images alternating "
-                       "between two contexts/streams (copies overlap kernels); pinned host memory; plans reused"}
+                       "between two contexts/streams (copies overlap kernels); pinned host memory; plans reused",
+               "numa_node": numa}
         for cb, _ in chunks:
             cb.close()
         for cx in ctxs:

@@ -73,6 +73,11 @@ enum {
  * For gray, 4:4:4 with W%8==0 and 4:2:2 (H2V1) with W%16==0 both are identical. */
 enum { JPGPU_LAYOUT_REF = 0, JPGPU_LAYOUT_SPEC = 1 };
 
+/* Sample arrangement of the output (the step after the path).  INTERLEAVED is the
+ * reference's Vec<(u8,u8,u8)> (decoder.rs:162, 317-331): W*H triples, row-major.  PLANAR holds the same W*H*3
+ * bytes as three W x H planes R, G, B (a CHW uint8 tensor).  Same values, same size, same per-image offsets. */
+enum { JPGPU_OUT_RGB_INTERLEAVED = 0, JPGPU_OUT_RGB_PLANAR = 1 };
+
 /* Parser extensions beyond the reference's accepted subset (bit flags). */
 enum {
     JPGPU_EXT_NONE = 0,
@@ -172,6 +177,8 @@ int jpgpu_batch_set_device_scans(jpgpu_batch *b, const void *dev_base, const uin
  * and bitstream arenas sized for one wave) then serves wave after wave: set_device_scans / upload, set_device_output,
  * decode.  NULL restores the batch's own arena.  `capacity` is checked against jpgpu_batch_stats()[2] rounded up. */
 int jpgpu_batch_set_device_output(jpgpu_batch *b, void *dev_base, size_t capacity);
+/* Output arrangement (JPGPU_OUT_*) of the following idct / decode calls; kept across replans.  Default: interleaved. */
+int jpgpu_batch_set_output_format(jpgpu_batch *b, uint32_t format);
 int jpgpu_batch_entropy(jpgpu_batch *b); /* stage 1: unstuff/RST pre-pass, self-synchronising Huffman decode */
 int jpgpu_batch_idct(jpgpu_batch *b);    /* stage 2+3: dequant, IDCT, upsample, YCbCr->RGB, interleaved store */
 int jpgpu_batch_decode(jpgpu_batch *b);  /* entropy + idct */

@@ -171,8 +171,10 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     HostPlan& p = b->plan;
     const bool external_rgb = b->dev.rgb && b->dev.rgb != b->own_rgb;
     uint8_t* const ext_rgb = b->dev.rgb;
+    const uint32_t out_planar = b->dev.out_planar;   // the output format outlives a replan
     memset(&b->dev, 0, sizeof b->dev);
     BatchDev& d = b->dev;
+    d.out_planar = out_planar;
     d.n_images = (uint32_t)n;
     d.n_seqs = (uint32_t)p.seqs.size();
     d.sub_bits = p.sub_bits;
@@ -375,6 +377,12 @@ extern "C" int jpgpu_batch_download(jpgpu_batch* b, uint8_t* const* outs) {
         CK(cudaMemcpyAsync(outs[i], b->dev.rgb + im.rgb_off, (size_t)im.width * im.height * 3, cudaMemcpyDeviceToHost,
                            ctx->stream));
     }
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_batch_set_output_format(jpgpu_batch* b, uint32_t format) {
+    if (!b || format > JPGPU_OUT_RGB_PLANAR) return JPGPU_ERR_INVALID_ARG;
+    b->dev.out_planar = format == JPGPU_OUT_RGB_PLANAR ? 1u : 0u;
     return JPGPU_OK;
 }
 

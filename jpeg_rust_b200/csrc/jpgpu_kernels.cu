@@ -621,6 +621,10 @@ __device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const SM& sm
     JPGPU_PIN64(cx.words);
     JPGPU_PIN32(cx.wmask5);
     JPGPU_PIN32(cx.dc_addr); JPGPU_PIN32(cx.sp_addr);
+    // The shared-memory reads of the fast path are plain (non-volatile) asm: nothing but their address operands
+    // orders them.  Making the table addresses opaque here - after the tables were written - keeps the compiler
+    // from moving such a read above the code that fills the table (it did, when a loop was put around this).
+    JPGPU_PIN32(cx.info_addr); JPGPU_PIN32(cx.lut0_addr);
     return cx;
 }
 
@@ -1006,7 +1010,8 @@ __device__ __forceinline__ uint32_t pack4(int32_t a, int32_t b, int32_t c, int32
 // staged tile is stored with 16-byte vectors.  A CTA walks kTilesPerCta consecutive
 // tiles; the coefficient loads of the next tile are issued before the current one is
 // computed.
-template <int HY, int VY, bool GRAY>
+// PLANAR: the output is three W x H byte planes (R, G, B) instead of interleaved triples (jpgpu_batch_set_output_format).
+template <int HY, int VY, bool GRAY, bool PLANAR>
 __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t* __restrict__ img_list) {
     constexpr int MH = 8 * VY;
     constexpr int NM = 128 / (8 * HY);         // MCUs per tile
@@ -1019,7 +1024,9 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
     constexpr int NL = CH_PASSES + Y_PASSES;   // 16-byte loads per thread and tile
     __shared__ __align__(16) float s_scr[16 * kScrBlkPitch];
     __shared__ __align__(16) float s_chroma[GRAY ? 4 : 2 * 8 * CWP];
-    __shared__ __align__(16) uint8_t s_out[MH * kOutPitch];
+    constexpr int kPlanePitch = 144;                      // bytes per staged row of one plane (128 + 16: rows 4 banks apart)
+    constexpr int kPlaneSize = MH * kPlanePitch;
+    __shared__ __align__(16) uint8_t s_out[PLANAR ? 3 * kPlaneSize : MH * kOutPitch];
     __shared__ __align__(16) float s_qt[3 * 64];
 
     const ImgDev& im = b.imgs[img_list[blockIdx.y]];
@@ -1058,14 +1065,23 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
 
     // copy-out plan of this thread: which 16-byte vectors of the staged tile it stores (tile-invariant)
     constexpr int NV = (MH * 24 + kIdctThreads - 1) / kIdctThreads;
-    const bool vec_ok = ((W * 3u) & 15u) == 0u;
+    const bool vec_ok = PLANAR ? (W & 15u) == 0u : ((W * 3u) & 15u) == 0u;
+    const uint32_t plane_bytes = W * H;
     uint32_t co_rk[NV], co_s[NV], co_g[NV];
 #pragma unroll
     for (int n = 0; n < NV; n++) {
-        const uint32_t i = (uint32_t)tid + (uint32_t)n * kIdctThreads, r = i / 24u, k = i - r * 24u;
-        co_rk[n] = i < (uint32_t)MH * 24u ? (r | (k << 8)) : 255u;   // row 255 never passes the bounds test
-        co_s[n] = r * kOutPitch + k * 16u;
-        co_g[n] = r * W * 3u + k * 16u;
+        const uint32_t i = (uint32_t)tid + (uint32_t)n * kIdctThreads;
+        if (PLANAR) {   // vector i: plane i / (MH*8), row (i / 8) % MH, 16-byte piece i % 8
+            const uint32_t pl = i / (MH * 8u), r = (i >> 3) % MH, k = i & 7u;
+            co_rk[n] = i < (uint32_t)MH * 24u ? (r | (k << 8)) : 255u;
+            co_s[n] = pl * kPlaneSize + r * kPlanePitch + k * 16u;
+            co_g[n] = pl * plane_bytes + r * W + k * 16u;
+        } else {
+            const uint32_t r = i / 24u, k = i - r * 24u;
+            co_rk[n] = i < (uint32_t)MH * 24u ? (r | (k << 8)) : 255u;   // row 255 never passes the bounds test
+            co_s[n] = r * kOutPitch + k * 16u;
+            co_g[n] = r * W * 3u + k * 16u;
+        }
     }
 
     uint4 cur[NL], nxt[NL];
@@ -1137,19 +1153,26 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
                     r8[x] = f32_to_u8_sat(rr); g8[x] = f32_to_u8_sat(gg); b8[x] = f32_to_u8_sat(bb);
                 }
             }
-            uint2* dst = reinterpret_cast<uint2*>(s_out + row * kOutPitch + px0 * 3);
-            dst[0] = make_uint2(pack4(r8[0], g8[0], b8[0], r8[1]), pack4(g8[1], b8[1], r8[2], g8[2]));
-            dst[1] = make_uint2(pack4(b8[2], r8[3], g8[3], b8[3]), pack4(r8[4], g8[4], b8[4], r8[5]));
-            dst[2] = make_uint2(pack4(g8[5], b8[5], r8[6], g8[6]), pack4(b8[6], r8[7], g8[7], b8[7]));
+            if (PLANAR) {
+                uint8_t* dst = s_out + row * kPlanePitch + px0;
+                *reinterpret_cast<uint2*>(dst) = make_uint2(pack4(r8[0], r8[1], r8[2], r8[3]), pack4(r8[4], r8[5], r8[6], r8[7]));
+                *reinterpret_cast<uint2*>(dst + kPlaneSize) = make_uint2(pack4(g8[0], g8[1], g8[2], g8[3]), pack4(g8[4], g8[5], g8[6], g8[7]));
+                *reinterpret_cast<uint2*>(dst + 2 * kPlaneSize) = make_uint2(pack4(b8[0], b8[1], b8[2], b8[3]), pack4(b8[4], b8[5], b8[6], b8[7]));
+            } else {
+                uint2* dst = reinterpret_cast<uint2*>(s_out + row * kOutPitch + px0 * 3);
+                dst[0] = make_uint2(pack4(r8[0], g8[0], b8[0], r8[1]), pack4(g8[1], b8[1], r8[2], g8[2]));
+                dst[1] = make_uint2(pack4(b8[2], r8[3], g8[3], b8[3]), pack4(r8[4], g8[4], b8[4], r8[5]));
+                dst[2] = make_uint2(pack4(g8[5], b8[5], r8[6], g8[6]), pack4(b8[6], r8[7], g8[7], b8[7]));
+            }
         }
         __syncthreads();
 
         const uint32_t x0 = tx * 128u, y0 = ty * MH;
         const uint32_t wpx = min(128u, W - x0), rows = min((uint32_t)MH, H - y0);
-        const uint32_t rowbytes = wpx * 3u;
-        uint8_t* const tile_out = rgb + ((size_t)y0 * W + x0) * 3u;
+        const uint32_t rowbytes = PLANAR ? wpx : wpx * 3u;
+        uint8_t* const tile_out = PLANAR ? rgb + (size_t)y0 * W + x0 : rgb + ((size_t)y0 * W + x0) * 3u;
         if (vec_ok && (rowbytes & 15u) == 0u) {
-            const uint32_t vpr = rowbytes >> 4;  // <= 24
+            const uint32_t vpr = rowbytes >> 4;  // <= 24 (planar: <= 8)
 #pragma unroll
             for (int n = 0; n < NV; n++) {
                 const uint32_t r = co_rk[n] & 255u, k = co_rk[n] >> 8;
@@ -1157,6 +1180,11 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
                     const uint4 v = *reinterpret_cast<const uint4*>(s_out + co_s[n]);
                     *reinterpret_cast<uint4*>(tile_out + co_g[n]) = v;
                 }
+            }
+        } else if (PLANAR) {
+            for (uint32_t i = tid; i < 3u * rows * rowbytes; i += kIdctThreads) {
+                const uint32_t pl = i / (rows * rowbytes), q = i - pl * rows * rowbytes, r = q / rowbytes, k = q - r * rowbytes;
+                tile_out[(size_t)pl * plane_bytes + (size_t)r * W + k] = s_out[pl * kPlaneSize + r * kPlanePitch + k];
             }
         } else {
             for (uint32_t i = tid; i < rows * rowbytes; i += kIdctThreads) {
@@ -1236,6 +1264,19 @@ __global__ void __launch_bounds__(kGatherThreads) gather_colour_kernel(BatchDev 
             b8[k] = f32_to_u8_sat(fmaf(cb, 1.772f, y));
         }
     }
+    if (b.out_planar) {
+        uint8_t* out = b.rgb + im.rgb_off + (size_t)q * 4u;
+        if (q * 4u + 4u <= npix && (npix & 3u) == 0u) {
+            *reinterpret_cast<uint32_t*>(out) = pack4(r8[0], r8[1], r8[2], r8[3]);
+            *reinterpret_cast<uint32_t*>(out + npix) = pack4(g8[0], g8[1], g8[2], g8[3]);
+            *reinterpret_cast<uint32_t*>(out + 2 * (size_t)npix) = pack4(b8[0], b8[1], b8[2], b8[3]);
+        } else {
+            for (uint32_t k = 0; k < 4u && q * 4u + k < npix; k++) {
+                out[k] = (uint8_t)min(max(r8[k], 0), 255); out[npix + k] = (uint8_t)min(max(g8[k], 0), 255); out[2 * (size_t)npix + k] = (uint8_t)min(max(b8[k], 0), 255);
+            }
+        }
+        return;
+    }
     uint8_t* out = b.rgb + im.rgb_off + (size_t)q * 12u;
     if (q * 4u + 4u <= npix) {
         uint32_t* o32 = reinterpret_cast<uint32_t*>(out);
@@ -1293,14 +1334,20 @@ int launch_idct_colour(const BatchDev& b, cudaStream_t s) {
     for (int k = 0; k < kNumKinds; k++) {
         if (!b.kind_count[k] || !b.kind_max_tiles[k]) continue;
         dim3 grid((b.kind_max_tiles[k] + kTilesPerCta - 1) / kTilesPerCta, b.kind_count[k]);
+#define JPGPU_LAUNCH_IDCT(HY, VY, GRAY)                                                                          \
+    do {                                                                                                        \
+        if (b.out_planar) idct_colour_kernel<HY, VY, GRAY, true><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]);  \
+        else idct_colour_kernel<HY, VY, GRAY, false><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]);          \
+    } while (0)
         switch (k) {
-            case kKindGray: idct_colour_kernel<1, 1, true><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;
-            case kKind444: idct_colour_kernel<1, 1, false><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;
-            case kKind422: idct_colour_kernel<2, 1, false><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;
-            case kKind420: idct_colour_kernel<2, 2, false><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;
-            case kKind440: idct_colour_kernel<1, 2, false><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]); break;
+            case kKindGray: JPGPU_LAUNCH_IDCT(1, 1, true); break;
+            case kKind444: JPGPU_LAUNCH_IDCT(1, 1, false); break;
+            case kKind422: JPGPU_LAUNCH_IDCT(2, 1, false); break;
+            case kKind420: JPGPU_LAUNCH_IDCT(2, 2, false); break;
+            case kKind440: JPGPU_LAUNCH_IDCT(1, 2, false); break;
             default: continue;
         }
+#undef JPGPU_LAUNCH_IDCT
         launches++;
     }
     if (b.kind_count[kKindGeneric] && b.gather_max_blocks) {

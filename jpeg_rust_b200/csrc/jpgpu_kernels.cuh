@@ -26,6 +26,7 @@ struct BatchDev {        // device pointers of one planned batch
     SubInfo* subs;
     int16_t* coefs;
     uint8_t* rgb;
+    uint32_t out_planar;     // 0: interleaved RGB triples (the reference's Vec<(u8,u8,u8)>), 1: three W x H planes per image
     uint32_t n_images;   // images this launch covers, starting at img0 (a whole batch or one group of it)
     uint32_t n_seqs;     // warp jobs this launch covers, starting at job0
     uint32_t img0, job0;

@@ -343,7 +343,17 @@ class Batch:
     def decode(self):
         return self._call("decode")
 
+    def set_output_format(self, fmt):
+        """OUT_RGB_INTERLEAVED (default; the reference's Vec<(u8,u8,u8)>, arrays of shape (H, W, 3)) or
+        OUT_RGB_PLANAR (three W x H planes R, G, B: arrays / tensors of shape (3, H, W)) for the following
+        idct / decode calls."""
+        self.ctx._ck(_ffi.lib().jpgpu_batch_set_output_format(self._h, int(fmt)), "jpgpu_batch_set_output_format")
+        self.out_format = int(fmt)
+        return self
+
     def shape(self, i):
+        if getattr(self, "out_format", _ffi.OUT_RGB_INTERLEAVED) == _ffi.OUT_RGB_PLANAR:
+            return (3, self.descs[i].height, self.descs[i].width)
         return (self.descs[i].height, self.descs[i].width, 3)
 
     def download(self, outs=None):
@@ -390,13 +400,14 @@ class Batch:
         return p_i - p_0, nb
 
     def device_tensor(self, i):
-        """Zero-copy torch view (H, W, 3) uint8 of image i's RGB output in device memory."""
+        """Zero-copy torch view of image i's RGB output in device memory: uint8, (H, W, 3) or, with
+        OUT_RGB_PLANAR, (3, H, W)."""
         import torch
         ptr, nb = self.device_rgb(i)
-        h, w, _ = self.shape(i)
+        shp = tuple(self.shape(i))
 
         class _Cai:
-            __cuda_array_interface__ = {"shape": (h, w, 3), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+            __cuda_array_interface__ = {"shape": shp, "typestr": "|u1", "data": (int(ptr), False), "version": 2}
         return torch.as_tensor(_Cai(), device=f"cuda:{self.ctx.device}")
 
     def device_rgb(self, i):

@@ -345,3 +345,31 @@ def test_one_bit_huffman_codes_decode_although_the_reference_cannot():
         assert statuses == [0, 0]
         assert all(np.array_equal(a, b) for a, b in zip(coefs[0], g))
         assert np.array_equal(outs[0], outs[1])
+
+
+def test_planar_output_holds_the_same_samples():
+    """OUT_RGB_PLANAR is the interleaved output (decoder.rs:317-331) transposed to three planes —
+    every fused kernel variant, ragged widths (byte path of the copy-out) and the gather path (REF placement)."""
+    from jpeg_rust_b200 import OUT_RGB_INTERLEAVED, OUT_RGB_PLANAR
+    files = [synth.synth_jpeg(500, 640, 480, "420"), synth.synth_jpeg(501, 320, 240, "422"), synth.synth_jpeg(502, 256, 64, "444"),
+             synth.synth_jpeg(503, 128, 200, "440"), synth.synth_jpeg(504, 512, 96, "gray"), synth.synth_jpeg(505, 251, 131, "420"),
+             synth.synth_jpeg(506, 77, 50, "444"), fixture_bytes("lena.jpeg")]
+    for layout in (LAYOUT_SPEC, LAYOUT_REF):
+        b = Batch(files, layout=layout)
+        b.upload().decode()
+        inter = b.download()
+        b.set_output_format(OUT_RGB_PLANAR).idct()
+        planar = b.download()
+        st, _ = b.results()
+        assert all(s == 0 for s in st), st
+        for i in range(len(files)):
+            h, w = inter[i].shape[:2]
+            assert planar[i].shape == (3, h, w)
+            assert np.array_equal(planar[i], inter[i].transpose(2, 0, 1)), f"layout {layout} image {i}"
+        t = b.device_tensor(0)
+        assert tuple(t.shape) == planar[0].shape and np.array_equal(t.cpu().numpy(), planar[0])
+        b.set_output_format(OUT_RGB_INTERLEAVED).idct()
+        again = b.download()
+        b.ctx.sync()
+        assert all(np.array_equal(x, y) for x, y in zip(again, inter))
+        b.close()
