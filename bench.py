@@ -311,14 +311,14 @@ def main():
                     "prepass_count+scan+write": {"ms": prof["prepass_count"] + prof["prepass_scan"] + prof["prepass_write"],
                                                  "algorithmic_GBps": 2 * stats["scan_bytes"] / ((prof["prepass_count"] + prof["prepass_scan"] + prof["prepass_write"]) * 1e-3) / 1e9,
                                                  "split_ms": [prof["prepass_count"], prof["prepass_scan"], prof["prepass_write"]],
-                                                 "bound": "L2 partial-sector stores of the lane-interleaved stream + instruction issue"},
+                                                 "bound": "instruction issue and latency of the classify / scan / byte-scatter chain (two reads of the raw bytes, whole-sector stores)"},
                     "sync": {"ms": prof["sync"], "bitstream_GBps": stats["scan_bytes"] / (prof["sync"] * 1e-3) / 1e9,
-                             "bound": "instruction issue (serial bit-dependent decode, ~75 instructions per symbol step)"},
+                             "bound": "instruction issue + load latency of a serial bit-dependent decode (~45 instructions per symbol step, ~20 of 32 lanes active)"},
                     "verify_scan": {"ms": prof["verify_scan"], "bound": "latency of the longest repair walk"},
                     "decode_write": {"ms": prof["decode_write"],
                                      "algorithmic_GBps": (stats["scan_bytes"] + stats["coef_bytes"]) / (prof["decode_write"] * 1e-3) / 1e9,
                                      "frac_of_hbm_peak": (stats["scan_bytes"] + stats["coef_bytes"]) / (prof["decode_write"] * 1e-3) / 1e9 / peak,
-                                     "bound": "instruction issue (~75 % issue-active in ncu), not HBM"},
+                                     "bound": "instruction issue (~55 instructions per symbol step plus the cooperative block flush, ~19 of 32 lanes active), not HBM"},
                     "idct_colour": {"ms": prof["idct_colour"]}},
                 "entropy_stage": {"ms": ent_ms, "bitstream_GBps": stats["scan_bytes"] / (ent_ms * 1e-3) / 1e9,
                                   "algorithmic_GBps": (stats["scan_bytes"] + stats["coef_bytes"]) / (ent_ms * 1e-3) / 1e9}}
