@@ -177,6 +177,7 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     d.out_planar = out_planar;
     d.n_images = (uint32_t)n;
     d.n_seqs = (uint32_t)p.seqs.size();
+    d.nsync = p.nsync;
     d.sub_bits = p.sub_bits;
     d.lw = p.lw;
     d.lookback_bits = p.lookback_bits;
@@ -311,6 +312,7 @@ BatchDev group_dev(const jpgpu_batch* b, const GroupPlan& g) {
     BatchDev d = b->dev;
     d.img0 = g.img0; d.n_images = g.nimg;
     d.job0 = g.job0; d.n_seqs = g.njobs;
+    d.nsync = g.nsync;
     d.max_chunks = g.max_chunks;
     for (int k = 0; k < kNumKinds; k++) {
         d.kind_imgs[k] = b->dev.kind_imgs[k] + g.kind_lo[k];

@@ -93,7 +93,8 @@ struct ImgDev {
     uint32_t sub_off;         // offset into the subsequence-info array
     uint32_t nsub_cap;        // capacity in subsequences (from raw_len)
     uint32_t chunk_off;       // offset of this image's entries in the pre-pass chunk table
-    uint32_t pad2;
+    uint32_t interval_mode;   // 1: restart intervals are short against a subsequence: decode threads start at interval
+                              // boundaries, which are known states - no synchronisation pass for this image
     uint32_t seq_first;       // index of this image's first sequence in the global sequence list
     uint32_t nseq;
     uint32_t mcux, mcuy;      // MCU grid (SPEC geometry)
@@ -288,6 +289,16 @@ JPGPU_HD uint32_t find_segment(const DecCtx& cx, uint32_t p) {
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
         if (cx.seg[mid] <= p) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Smallest k with seg[k] >= bit (k = nseg when there is none; seg[nseg] = stream_bits).
+JPGPU_HD uint32_t first_interval_from(const uint32_t* seg, uint32_t nseg, uint32_t bit) {
+    uint32_t lo = 0, hi = nseg;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (seg[mid] >= bit) hi = mid; else lo = mid + 1;
     }
     return lo;
 }

@@ -353,6 +353,11 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         plan.stream_words += im.stream_cap_words;
         im.nseg_cap = d.restart_interval ? (g.units + d.restart_interval - 1) / d.restart_interval : 1u;
         if (im.nseg_cap == 0) im.nseg_cap = 1;
+        // Restart intervals of at most 2.5 subsequences (measured crossover on B200: between 2 and 4): a decode thread finds an interval start (a known
+        // state) near the start of its subsequence, so the image skips the synchronisation and verification passes.
+        im.interval_mode = d.restart_interval && (uint64_t)im.raw_len * 8 / im.nseg_cap * 2 <= (uint64_t)sub_bits * 5 ? 1u : 0u;
+        if (const char* e = getenv("JPGPU_INTERVAL_MODE")) im.interval_mode = d.restart_interval && atoi(e) ? 1u : 0u;
+        if (!im.interval_mode) { plan.nsync++; plan.groups.back().nsync++; }
         im.seg_off = (uint32_t)plan.seg_entries;
         plan.seg_entries += im.nseg_cap + 2;
         {

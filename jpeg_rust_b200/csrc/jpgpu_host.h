@@ -38,6 +38,7 @@ struct GroupPlan {
     uint32_t kind_lo[kNumKinds] = {0, 0, 0, 0, 0, 0}, kind_hi[kNumKinds] = {0, 0, 0, 0, 0, 0};
     uint32_t kind_max_tiles[kNumKinds] = {0, 0, 0, 0, 0, 0};
     uint32_t gather_max_blocks = 0, gather_max_quads = 0;
+    uint32_t nsync = 0;          // images of the group that need the synchronisation pass (not interval_mode)
 };
 
 struct HostPlan {
@@ -47,6 +48,7 @@ struct HostPlan {
     uint32_t lookback_bits = kDefaultLookbackBits;
     uint32_t seg_bits = kMinSegBits;  // checkpoint distance inside a subsequence
     uint32_t max_slots = 1;      // most Huffman LUT slots any image references
+    uint32_t nsync = 0;          // images that need the synchronisation pass
     std::vector<ImgDev> imgs;
     std::vector<int32_t> status;  // per image: JPGPU_OK or why it is skipped
     std::vector<SeqDesc> seqs;

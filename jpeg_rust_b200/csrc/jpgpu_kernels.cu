@@ -489,7 +489,7 @@ struct WriteLane {
     uint32_t rows_addr, row0;  // address of this lane's first row, its row number
     uint32_t cur, ndone;       // ring position, completed (unflushed) buffers
     uint32_t dest0, dest1;     // arena block index of each completed buffer, oldest first (0xffffffff = discard)
-    uint32_t end_bit;
+    uint32_t end_bit, end_bit_blk;   // where the lane stops: at a restart-interval / at a block boundary at or past this bit
     int32_t total;
     int32_t seg_limit;         // first coefficient position past the current restart interval (= total without DRI)
     uint32_t store_on;         // 0 while finishing a block that started in the previous subsequence, and past seg_limit
@@ -509,7 +509,7 @@ struct WriteLane {
         }
         store_on = g < seg_limit ? 1u : 0u;   // a damaged interval holding more MCUs than it should is decoded, not stored
         // finished: block boundary past the subsequence / scan; blocked: no free buffer
-        state = (p >= end_bit || g >= total) ? (uint32_t)kFinished : (ndone == (uint32_t)NBUF ? (uint32_t)kBlocked : (uint32_t)kRun);
+        state = (p >= end_bit_blk || g >= total) ? (uint32_t)kFinished : (ndone == (uint32_t)NBUF ? (uint32_t)kBlocked : (uint32_t)kRun);
     }
     // Rare: the decoder moved to the next restart interval (kEvCross) or reached the end of the data (kEvEnd);
     // g_before = coefficient position before the move, st.g = first position of the new interval.
@@ -697,6 +697,7 @@ __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     __syncthreads();
     if (sd.img == kNoImage) return;
     const ImgDev& img = sm.img[warp];
+    if (img.interval_mode) return;   // its decode threads start at restart-interval boundaries: nothing to synchronise
     const ImgDyn dyn = b.dyn[sd.img];
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     const FastCtx cx = make_fast_ctx(b, sm, warp, dyn, ft);
@@ -735,6 +736,7 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
     const uint32_t S = b.sub_bits;
     load_entropy_img(b, threadIdx.x < 32 ? img : kNoImage, sm, 32);
     const ImgDev& im = sm.img[0];
+    if (im.interval_mode) return;
     const ImgDyn dyn = b.dyn[img];
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     SubInfo* subs = b.subs + im.sub_off;
@@ -860,9 +862,19 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
     const uint32_t end_bit = (j + 1) * S;
     FastState st;
     bool store_on = true;
+    const bool by_interval = img.interval_mode != 0u;
+    uint32_t k0 = 0;
+    if (active && by_interval) {   // this lane owns the restart intervals that start inside its subsequence
+        k0 = first_interval_from(cx.seg, cx.nseg, j * S);
+        active = k0 < cx.nseg && cx.seg[k0] < end_bit;
+    }
     if (active) {
-        const SubInfo me = b.subs[img.sub_off + j];
-        fast_init(cx, st, me.pA, me.n, (me.cz >> 6) & 15u, me.dc[0], me.dc[1], me.dc[2]);
+        if (by_interval) {
+            fast_init(cx, st, cx.seg[k0], (int32_t)(k0 * cx.seg_units), 0u, 0, 0, 0);
+        } else {
+            const SubInfo me = b.subs[img.sub_off + j];
+            fast_init(cx, st, me.pA, me.n, (me.cz >> 6) & 15u, me.dc[0], me.dc[1], me.dc[2]);
+        }
         st.flags &= ~kCrossed;
         store_on = (st.g & 63) == 0;
         if (st.g >= total || (st.p >= end_bit && store_on)) active = false;
@@ -878,6 +890,7 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
     wl.ndone = 0;
     wl.dest0 = wl.dest1 = 0u;
     wl.end_bit = end_bit;
+    wl.end_bit_blk = by_interval ? 0xffffffffu : end_bit;   // an interval-mode lane only ends where an interval ends
     wl.total = total;
     wl.seg_limit = cx.seg_units ? min(total, (int32_t)((st.seg + 1u) * cx.seg_units)) : total;
     wl.store_on = store_on && st.g < wl.seg_limit ? 1u : 0u;
@@ -1302,10 +1315,10 @@ void launch_prepass(const BatchDev& b, cudaStream_t s) {
     for (int step = 0; step < 3; step++) launch_prepass_step(b, s, step);
 }
 void launch_sync(const BatchDev& b, cudaStream_t s) {
-    if (b.n_seqs) sync_kernel<<<b.n_seqs / kJobsPerCta, kSeqThreads, 0, s>>>(b);
+    if (b.n_seqs && b.nsync) sync_kernel<<<b.n_seqs / kJobsPerCta, kSeqThreads, 0, s>>>(b);
 }
 void launch_verify_scan(const BatchDev& b, cudaStream_t s) {
-    if (b.n_images) verify_scan_kernel<<<b.n_images, kInterThreads, 0, s>>>(b);
+    if (b.n_images && b.nsync) verify_scan_kernel<<<b.n_images, kInterThreads, 0, s>>>(b);
 }
 template <int NBUF, int PHASE>
 static cudaError_t launch_write_variant(const BatchDev& b, cudaStream_t s) {

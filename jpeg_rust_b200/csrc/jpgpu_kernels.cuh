@@ -30,6 +30,7 @@ struct BatchDev {        // device pointers of one planned batch
     uint32_t n_images;   // images this launch covers, starting at img0 (a whole batch or one group of it)
     uint32_t n_seqs;     // warp jobs this launch covers, starting at job0
     uint32_t img0, job0;
+    uint32_t nsync;      // images of this launch range that need sync_kernel / verify_scan_kernel (not interval_mode)
     uint32_t sub_bits;   // bits per subsequence for this batch
     uint32_t lw;         // log2(sub_bits / 32): words per subsequence
     uint32_t lookback_bits;

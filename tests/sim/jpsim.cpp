@@ -108,6 +108,7 @@ void sim_sync(SimBatch& sb, const SeqDesc& sd) {
     std::vector<HuffLut> slots;
     load_slots(sb, sd.img, slots);
     const ImgDev& im = sb.plan.imgs[sd.img];
+    if (im.interval_mode) return;
     const ImgDyn dyn = sb.dyn[sd.img];
     const uint32_t S = sb.plan.sub_bits, L = sb.plan.lookback_bits;
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
@@ -138,6 +139,7 @@ void sim_verify_scan(SimBatch& sb, size_t img) {
     std::vector<HuffLut> slots;
     load_slots(sb, img, slots);
     const ImgDev& im = sb.plan.imgs[img];
+    if (im.interval_mode) return;
     const ImgDyn dyn = sb.dyn[img];
     const uint32_t S = sb.plan.sub_bits, C = sb.plan.seg_bits;
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
@@ -203,9 +205,18 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
             l.cur = l.ndone = 0;
             l.store_on = true;
             l.st.p = 0; l.st.g = 0; l.st.flags = 0;
+            uint32_t k0 = 0;
+            if (l.active && im.interval_mode) {   // the lane owns the restart intervals that start inside its subsequence
+                k0 = first_interval_from(cx.seg, cx.nseg, l.j * S);
+                l.active = k0 < cx.nseg && cx.seg[k0] < l.end_bit;
+            }
             if (l.active) {
-                const SubInfo me = sb.subs[im.sub_off + l.j];
-                init_state(cx, l.st, me.pA, me.n, (int32_t)((me.cz >> 6) & 15u), me.dc[0], me.dc[1], me.dc[2]);
+                if (im.interval_mode) {
+                    init_state(cx, l.st, cx.seg[k0], (int32_t)(k0 * cx.seg_units), 0, 0, 0, 0);
+                } else {
+                    const SubInfo me = sb.subs[im.sub_off + l.j];
+                    init_state(cx, l.st, me.pA, me.n, (int32_t)((me.cz >> 6) & 15u), me.dc[0], me.dc[1], me.dc[2]);
+                }
                 l.st.flags &= ~kCrossed;
                 l.seg_limit = cx.seg_units ? std::min(total, (int32_t)((l.st.seg + 1u) * cx.seg_units)) : total;
                 l.store_on = (l.st.g & 63) == 0 && l.st.g < l.seg_limit;
@@ -224,7 +235,7 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
                 Lane& l = ln[lane];
                 const uint32_t row0 = (warp * 32 + lane) * kWriteBufs;
                 for (int k = 0; k < kPhaseSymbols && l.active && l.ndone < (uint32_t)kWriteBufs; k++) {
-                    if ((l.st.p >= l.end_bit && (l.st.g & 63) == 0) || l.st.g >= total) { l.active = false; break; }
+                    if ((!im.interval_mode && l.st.p >= l.end_bit && (l.st.g & 63) == 0) || l.st.g >= total) { l.active = false; break; }
                     const uint32_t row = row0 + l.cur;
                     const int32_t g_before = l.st.g;
                     const uint32_t ev = decode_symbol<true>(cx, l.st, bufs.data() + (size_t)row * 64, row & 7u, sb.store_pos, l.store_on);
@@ -239,6 +250,7 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
                         for (int32_t g = gap_from; g < old_limit && g < l.st.g; g += 64)
                             for (int e = 0; e < 64; e++) coefs[(size_t)g + e] = 0;
                         l.store_on = true;
+                        if (im.interval_mode && l.st.p >= l.end_bit) l.active = false;   // the next interval is another lane's
                     } else if (ev & kEvEnd) {
                         l.active = false;
                     }

@@ -373,3 +373,14 @@ def test_planar_output_holds_the_same_samples():
         b.ctx.sync()
         assert all(np.array_equal(x, y) for x, y in zip(again, inter))
         b.close()
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_restart_interval_modes_agree(mode, monkeypatch):
+    """Images with restart intervals decode either like any other image (look-back synchronisation, mode 0) or, when
+    the intervals are short against a subsequence, with every decode thread starting at an interval boundary and no
+    synchronisation pass at all (mode 1; the planner picks per image).  Both must give the oracle's coefficients."""
+    monkeypatch.setenv("JPGPU_INTERVAL_MODE", mode)
+    files = [synth.synth_jpeg(700, 640, 480, "420", restart_interval=2), synth.synth_jpeg(701, 333, 200, "444", restart_interval=40),
+             synth.synth_jpeg(702, 512, 512, "gray", restart_interval=64), synth.synth_jpeg(703, 320, 240, "422", restart_interval=0)]
+    compare_with_oracle(files, LAYOUT_SPEC, ext=EXT_DRI)
