@@ -183,6 +183,7 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     d.lookback_bits = p.lookback_bits;
     d.max_slots = p.max_slots;
     d.seg_bits = p.seg_bits;
+    d.wp_shift = p.wp_shift;
 #define TRY(x) do { st = (x); if (st != JPGPU_OK) return st; } while (0)
     TRY(dev_upload(b, jpgpu_batch::kImgs, &d.imgs, p.imgs));
     TRY(dev_upload(b, jpgpu_batch::kSeqs, &d.seqs, p.seqs));

@@ -34,6 +34,7 @@ constexpr int kMaxLutSlots = 6;            // distinct (DC, AC) tables one image
 constexpr int kMinSubseqBits = 1024;
 constexpr int kMaxSubseqBits = 8192;
 constexpr int kDefaultLookbackBits = 1024;
+constexpr int kDefaultWriteParts = 1;       // write-pass units per subsequence (BatchDev::wp_shift), never shorter than kMinSubseqBits
 constexpr int kMinSegBits = 512;           // smallest checkpoint distance inside a subsequence (BatchDev::seg_bits) // cold-start distance before a subsequence (BatchDev::lookback_bits)
 constexpr int kSeqThreads = JPGPU_SEQ_THREADS;  // subsequences per sequence (= CTA size of the sync/write kernels)
 constexpr int kStreamPadWords = 8;         // zero words readable past every image's stream

@@ -185,6 +185,14 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         const long v = atol(e);
         if (v >= 64 && v <= (long)sub_bits && (v & (v - 1)) == 0) plan.seg_bits = (uint32_t)v;
     }
+    // the write pass cuts every subsequence into units at checkpoint boundaries (decode_write_kernel)
+    {
+        uint32_t parts = kDefaultWriteParts;
+        if (const char* e = getenv("JPGPU_WRITE_PARTS")) { const long v = atol(e); if (v >= 1 && v <= 64 && (v & (v - 1)) == 0) parts = (uint32_t)v; }
+        while (parts > 1 && (parts > sub_bits / plan.seg_bits || sub_bits / parts < (uint32_t)kMinSubseqBits)) parts >>= 1;
+        plan.wp_shift = 0;
+        while ((1u << plan.wp_shift) < parts) plan.wp_shift++;
+    }
     uint32_t lw = 0;
     while ((32u << lw) < sub_bits) lw++;
     plan.lw = lw;

@@ -47,6 +47,7 @@ struct HostPlan {
     uint32_t lw = 5;             // log2(words per subsequence)
     uint32_t lookback_bits = kDefaultLookbackBits;
     uint32_t seg_bits = kMinSegBits;  // checkpoint distance inside a subsequence
+    uint32_t wp_shift = 0;       // log2(write-pass units per subsequence); a unit is a whole number of segments
     uint32_t max_slots = 1;      // most Huffman LUT slots any image references
     uint32_t nsync = 0;          // images that need the synchronisation pass
     std::vector<ImgDev> imgs;

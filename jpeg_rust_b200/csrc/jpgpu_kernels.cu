@@ -838,9 +838,14 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint2* const flist = reinterpret_cast<uint2*>(dyn_smem + lay.list_off) + warp * (32 * NBUF);
 
-    if (b.seqs[b.job0 + blockIdx.x * kWriteJobsPerCta].img == kNoImage) return;   // a CTA of padding jobs only
+    // The write pass works in UNITS of sub_bits >> wp_shift bits (a whole number of checkpoint segments): the
+    // synchronisation pass wants long subsequences (less look-back per decoded bit, fewer links to verify), this pass
+    // short ones (many short jobs fill the machine better and end closer together).  Warp job q covers the 32 units
+    // q*32 .. q*32+31 of sequence q >> wp_shift; unit u of a sequence is part u & (H-1) of its subsequence u >> wp_shift.
+    const uint32_t hs = b.wp_shift, H = 1u << hs;
+    if (b.seqs[b.job0 + ((blockIdx.x * kWriteJobsPerCta) >> hs)].img == kNoImage) return;   // a CTA of padding jobs only
     const uint32_t job = blockIdx.x * kWriteJobsPerCta + warp;
-    const SeqDesc sd = job < b.n_seqs ? b.seqs[b.job0 + job] : SeqDesc{kNoImage, 0u};
+    const SeqDesc sd = (job >> hs) < b.n_seqs ? b.seqs[b.job0 + (job >> hs)] : SeqDesc{kNoImage, 0u};
     const uint32_t S = b.sub_bits;
     load_entropy_img(b, sd.img, sm, 32);
     load_entropy_luts(b, sm, kWriteThreads);
@@ -853,27 +858,42 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
     const ImgDyn dyn = b.dyn[sd.img];
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     const FastCtx cx = make_fast_ctx(b, sm, warp, dyn, ft);
-    const uint32_t j = sd.first_sub + lane;
-    bool active = j < nsub;
+    const uint32_t unit = ((job & (H - 1u)) << 5) + lane;
+    const uint32_t j = sd.first_sub + (unit >> hs), part = unit & (H - 1u);
+    const uint32_t unit_bit = j * S + part * (S >> hs), end_bit = unit_bit + (S >> hs);
+    bool active = j < nsub && unit_bit < dyn.stream_bits;
     if (!__ballot_sync(0xffffffffu, active)) return;
 
     const int32_t total = (int32_t)img.total_coefs;
     int16_t* __restrict__ coefs = b.coefs + img.coef_off;
-    const uint32_t end_bit = (j + 1) * S;
     FastState st;
     bool store_on = true;
     const bool by_interval = img.interval_mode != 0u;
     uint32_t k0 = 0;
-    if (active && by_interval) {   // this lane owns the restart intervals that start inside its subsequence
-        k0 = first_interval_from(cx.seg, cx.nseg, j * S);
+    if (active && by_interval) {   // this lane owns the restart intervals that start inside its unit
+        k0 = first_interval_from(cx.seg, cx.nseg, unit_bit);
         active = k0 < cx.nseg && cx.seg[k0] < end_bit;
     }
     if (active) {
         if (by_interval) {
             fast_init(cx, st, cx.seg[k0], (int32_t)(k0 * cx.seg_units), 0u, 0, 0, 0);
         } else {
+            // state at the start of the unit: that of its subsequence at A (exact after verify_scan_kernel), carried
+            // over the checkpoint segments that precede the unit
             const SubInfo me = b.subs[img.sub_off + j];
-            fast_init(cx, st, me.pA, me.n, (me.cz >> 6) & 15u, me.dc[0], me.dc[1], me.dc[2]);
+            uint32_t p0 = me.pA, cz0 = me.cz & kCzMask, crossed = 0u;
+            int32_t acc[4] = {me.n, me.dc[0], me.dc[1], me.dc[2]};
+            const uint32_t nsegs = S / b.seg_bits, npre = part * (nsegs >> hs);
+            const SegRec* sg = b.segs + (size_t)(img.sub_off + j) * nsegs;
+#pragma unroll 1
+            for (uint32_t k = 0; k < npre; k++) {
+                const uint4 lo = __ldg(reinterpret_cast<const uint4*>(sg + k));
+                const uint2 hi = __ldg(reinterpret_cast<const uint2*>(sg + k) + 2);
+                const int32_t dc[3] = {(int32_t)lo.w, (int32_t)hi.x, (int32_t)hi.y};
+                fold_advance(acc, crossed, lo.y, (int32_t)lo.z, dc);
+                p0 = lo.x; cz0 = lo.y & kCzMask;
+            }
+            fast_init(cx, st, p0, acc[0], (cz0 >> 6) & 15u, acc[1], acc[2], acc[3]);
         }
         st.flags &= ~kCrossed;
         store_on = (st.g & 63) == 0;
@@ -944,7 +964,7 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
         __syncwarp();
         wl.ndone = 0;
     }
-    if (j < nsub) {
+    if (j < nsub && unit_bit < dyn.stream_bits) {
         uint32_t bits = st.flags & (kStBadCode | kStDcSize | kStRestart);
         if (g_start < total && st.g >= total) {  // this thread decoded the last block of the scan
             b.dyn[sd.img].bits_consumed = st.p;
@@ -1332,7 +1352,8 @@ static cudaError_t launch_write_variant(const BatchDev& b, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = lay.total;
     }
-    decode_write_kernel<NBUF, PHASE><<<(b.n_seqs + kWriteJobsPerCta - 1) / kWriteJobsPerCta, kWriteThreads, lay.total, s>>>(b);
+    const uint32_t jobs = b.n_seqs << b.wp_shift;   // n_seqs is a multiple of kWriteJobsPerCta (build_plan)
+    decode_write_kernel<NBUF, PHASE><<<(jobs + kWriteJobsPerCta - 1) / kWriteJobsPerCta, kWriteThreads, lay.total, s>>>(b);
     return cudaSuccess;
 }
 cudaError_t launch_decode_write(const BatchDev& b, cudaStream_t s) {

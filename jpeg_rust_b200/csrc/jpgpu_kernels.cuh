@@ -38,6 +38,7 @@ struct BatchDev {        // device pointers of one planned batch
     uint32_t max_chunks;      // most 4 KiB raw chunks any image has
     uint2* chunk_counts;      // per chunk: kept bytes / RSTn markers, then (after the scan) those before the chunk
     uint32_t seg_bits;        // checkpoint distance inside a subsequence (divides sub_bits)
+    uint32_t wp_shift;        // log2(units of the write pass per subsequence); a unit is a whole number of segments
     SegRec* segs;             // sub_bits / seg_bits records per subsequence
     // images grouped by colour-kernel variant (ImgKind)
     const uint32_t* kind_imgs[kNumKinds];

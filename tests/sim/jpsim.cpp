@@ -179,7 +179,8 @@ void sim_verify_scan(SimBatch& sb, size_t img) {
 }
 
 // mirrors decode_write_kernel: warps in lock-step phases, per-lane swizzled block buffers, cooperative flush
-void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
+// one warp job of the write kernel: units group*32 .. group*32+31 of sequence sd (a unit = sub_bits >> wp_shift bits)
+void sim_decode_write(SimBatch& sb, const SeqDesc& sd, uint32_t group) {
     if (sd.img == kNoImage) return;
     std::vector<HuffLut> slots;
     load_slots(sb, sd.img, slots);
@@ -188,34 +189,43 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
     const uint32_t S = sb.plan.sub_bits;
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
+    const uint32_t hs = sb.plan.wp_shift, H = 1u << hs, C = sb.plan.seg_bits, nsegs = S / C;
     const DecCtx cx = make_ctx(sb, sd.img, slots.data());
     const int32_t total = (int32_t)im.total_coefs;
     int16_t* coefs = sb.coefs.data() + im.coef_off;
     std::vector<int16_t> bufs((size_t)32 * kWriteBufs * 64, 0);
     for (uint32_t warp = 0; warp < 1u; warp++) {  // one warp job
-        struct Lane { DecState st; bool active, store_on; uint32_t j, end_bit, cur, ndone, dest[kWriteBufs]; int32_t g_start, seg_limit; };
+        struct Lane { DecState st; bool active, store_on, valid; uint32_t j, unit_bit, end_bit, cur, ndone, dest[kWriteBufs]; int32_t g_start, seg_limit; };
         Lane ln[32];
         bool any_active = false;
         for (uint32_t lane = 0; lane < 32; lane++) {
             Lane& l = ln[lane];
-            const uint32_t tid = warp * 32 + lane;
-            l.j = sd.first_sub + tid;
-            l.active = l.j < nsub;
-            l.end_bit = (l.j + 1) * S;
+            const uint32_t unit = group * 32 + lane, part = unit & (H - 1u);
+            l.j = sd.first_sub + (unit >> hs);
+            l.unit_bit = l.j * S + part * (S >> hs);
+            l.end_bit = l.unit_bit + (S >> hs);
+            l.valid = l.active = l.j < nsub && l.unit_bit < dyn.stream_bits;
             l.cur = l.ndone = 0;
             l.store_on = true;
             l.st.p = 0; l.st.g = 0; l.st.flags = 0;
             uint32_t k0 = 0;
             if (l.active && im.interval_mode) {   // the lane owns the restart intervals that start inside its subsequence
-                k0 = first_interval_from(cx.seg, cx.nseg, l.j * S);
+                k0 = first_interval_from(cx.seg, cx.nseg, l.unit_bit);
                 l.active = k0 < cx.nseg && cx.seg[k0] < l.end_bit;
             }
             if (l.active) {
                 if (im.interval_mode) {
                     init_state(cx, l.st, cx.seg[k0], (int32_t)(k0 * cx.seg_units), 0, 0, 0, 0);
                 } else {
-                    const SubInfo me = sb.subs[im.sub_off + l.j];
-                    init_state(cx, l.st, me.pA, me.n, (int32_t)((me.cz >> 6) & 15u), me.dc[0], me.dc[1], me.dc[2]);
+                    const SubInfo me = sb.subs[im.sub_off + l.j];   // state at A, carried over the segments before the unit
+                    uint32_t p0 = me.pA, cz0 = me.cz & kCzMask, crossed = 0;
+                    int32_t acc[4] = {me.n, me.dc[0], me.dc[1], me.dc[2]};
+                    const SegRec* sg = sb.segs.data() + (size_t)(im.sub_off + l.j) * nsegs;
+                    for (uint32_t k = 0; k < part * (nsegs >> hs); k++) {
+                        fold_advance(acc, crossed, sg[k].cz, sg[k].n, sg[k].dc);
+                        p0 = sg[k].p; cz0 = sg[k].cz & kCzMask;
+                    }
+                    init_state(cx, l.st, p0, acc[0], (int32_t)((cz0 >> 6) & 15u), acc[1], acc[2], acc[3]);
                 }
                 l.st.flags &= ~kCrossed;
                 l.seg_limit = cx.seg_units ? std::min(total, (int32_t)((l.st.seg + 1u) * cx.seg_units)) : total;
@@ -227,7 +237,7 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
         }
         if (!any_active) {
             bool any_j = false;
-            for (auto& l : ln) any_j = any_j || l.j < nsub;
+            for (auto& l : ln) any_j = any_j || l.valid;
             if (!any_j) continue;
         }
         while (true) {
@@ -281,7 +291,7 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd) {
             sb.flush_phases++;
         }
         for (auto& l : ln) {
-            if (l.j >= nsub) continue;
+            if (!l.valid) continue;
             uint32_t bits = l.st.flags & (kStBadCode | kStDcSize | kStRestart);
             if (l.g_start < total && l.st.g >= total) { sb.dyn[sd.img].bits_consumed = l.st.p; bits |= kStDone; }
             sb.dyn[sd.img].status |= bits;
@@ -415,7 +425,8 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
     for (size_t i = 0; i < n; i++) sim_prepass(sb, i);
     for (const SeqDesc& sd : p.seqs) sim_sync(sb, sd);
     for (size_t i = 0; i < n; i++) sim_verify_scan(sb, i);
-    for (const SeqDesc& sd : p.seqs) sim_decode_write(sb, sd);
+    for (const SeqDesc& sd : p.seqs)
+        for (uint32_t group = 0; group < (1u << p.wp_shift); group++) sim_decode_write(sb, sd, group);
     for (size_t i = 0; i < n; i++)
         if (p.status[i] == JPGPU_OK) { if (p.imgs[i].kind == kKindGeneric) sim_gather(sb, i); else sim_idct_colour(sb, i); }
     for (size_t i = 0; i < n; i++) {

@@ -225,3 +225,22 @@ def test_one_bit_huffman_codes_decode_although_the_reference_cannot():
         assert r.status == 0 and rp.status == 0
         assert all(np.array_equal(a, b) for a, b in zip(r.coefs, g))
         assert np.array_equal(r.rgb, rp.rgb)
+
+
+@pytest.mark.parametrize("parts", [2, 4, 8])
+def test_write_pass_units(parts, monkeypatch):
+    """The write pass cuts every subsequence into units at checkpoint boundaries and starts each unit from the state
+    of its subsequence at A carried over the checkpoint records before it (decode_write_kernel): same coefficients
+    for every cut — repaired links (short look-back), restart intervals on the general path and on the interval path."""
+    monkeypatch.setenv("JPGPU_WRITE_PARTS", str(parts))
+    monkeypatch.setenv("JPGPU_LOOKBACK_BITS", "128")
+    files = [fixture_bytes("lena.jpeg"), synth.synth_jpeg(31, 640, 360, "420", quality=92),
+             synth.synth_jpeg(32, 320, 240, "444", restart_interval=40), synth.synth_jpeg(33, 320, 240, "422", restart_interval=2)]
+    rs, diag = S.decode_batch(files, layout=1, ext=2, sub_bits=8192)
+    assert diag["repairs"] > 0
+    for k, (f, r) in enumerate(zip(files, rs)):
+        o = O.decode(f, layout=1, ext=2)
+        assert o.status == 0 and r.status == 0, (k, r.status, o.msg)
+        for a, b in zip(r.coefs, o.coefs):
+            assert np.array_equal(a, b), f"image {k}: coefficients differ"
+        assert np.abs(r.rgb.astype(int) - o.rgb.astype(int)).max() <= 1
