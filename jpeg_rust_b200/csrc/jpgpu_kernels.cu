@@ -484,7 +484,7 @@ __device__ __forceinline__ uint32_t fast_long_code(const FastCtx& cx, FastState&
 template <int NBUF>
 struct WriteLane {
     static_assert(NBUF >= 1 && NBUF <= 2, "two completion slots");
-    enum : uint32_t { kRun = 0, kBlocked = 1, kFinished = 2 };
+    enum : uint32_t { kRun = 0, kBlocked = 1, kFinished = 2, kBlockEnd = 3 };
     uint32_t row_addr, swz16;  // shared address / piece swizzle of the buffer being filled
     uint32_t rows_addr, row0;  // address of this lane's first row, its row number
     uint32_t cur, ndone;       // ring position, completed (unflushed) buffers
@@ -533,7 +533,7 @@ struct WriteLane {
         else if (state != kBlocked) state = kRun;
     }
 };
-struct NoLane {};
+struct NoLane { enum : uint32_t { kBlockEnd = 3 }; uint32_t state; };
 
 // CHECK = false: the caller guarantees st.p < st.lim (no look at the interval end, no window wrap pending).
 template <bool WRITE, bool CHECK, typename LANE>
@@ -570,15 +570,31 @@ __device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, 
         sts16_if(wl.row_addr | (off ^ wl.swz16), (uint32_t)(is_dc ? st.dcur : val), wl.store_on != 0u);
     }
     fast_advance(cx, st, st.p + tb);
-    if (nz >= 64u) {  // block complete
-        st.g = (st.g | 63) + 1;
-        st.info_ptr = lds32(st.info_ptr + 8u);
-        fast_load_block(cx, st);
-        if constexpr (WRITE) wl.close_block((uint32_t)(st.g >> 6) - 1u, st.p, st.g);
-        return kEvBlock;
+    if constexpr (WRITE) {
+        // Block complete: the lane has no free buffer before the next flush anyway, so everything a block end takes
+        // (next block's tables and predictor, buffer bookkeeping) waits for the phase boundary, where all lanes that
+        // completed a block do it together (fast_block_end) instead of one or two at a time in every step.
+        st.g += (int32_t)adv;                        // z + adv >= 64 carries into the block index
+        wl.state = nz >= 64u ? (uint32_t)LANE::kBlockEnd : wl.state;
+        return 0u;
+    } else {
+        if (nz >= 64u) {  // block complete
+            st.g = (st.g | 63) + 1;
+            st.info_ptr = lds32(st.info_ptr + 8u);
+            fast_load_block(cx, st);
+            return kEvBlock;
+        }
+        st.g += (int32_t)adv;
+        return 0u;
     }
-    st.g += (int32_t)adv;
-    return 0u;
+}
+// Write pass, at a phase boundary: what fast_step() left undone for a lane in state kBlockEnd.
+template <typename LANE>
+__device__ __forceinline__ void fast_block_end(const FastCtx& cx, FastState& st, LANE& wl) {
+    st.g &= ~63;
+    st.info_ptr = lds32(st.info_ptr + 8u);
+    fast_load_block(cx, st);
+    wl.close_block((uint32_t)(st.g >> 6) - 1u, st.p, st.g);
 }
 
 // Decode every symbol that starts before end_bit (sync pass form: the interval-end test is hoisted out of the loop).
@@ -925,6 +941,7 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
         // there (WriteLane::close_block / on_interval).
 #pragma unroll 1
         for (int k = PHASE; k > 0 && wl.state == WriteLane<NBUF>::kRun; k--) fast_step<true, true>(cx, st, wl);
+        if (wl.state == WriteLane<NBUF>::kBlockEnd) fast_block_end(cx, st, wl);
         if (wl.state == WriteLane<NBUF>::kBlocked) wl.state = WriteLane<NBUF>::kRun;
         active = wl.state != WriteLane<NBUF>::kFinished;
         const uint32_t ndone = wl.ndone, cur = wl.cur, row0 = wl.row0;
