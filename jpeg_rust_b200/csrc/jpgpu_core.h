@@ -32,7 +32,8 @@ constexpr int kMaxLutSlots = 6;            // distinct (DC, AC) tables one image
 // (BatchDev::sub_bits), a power of two in [kMinSubseqBits, kMaxSubseqBits]: larger means less
 // look-back overhead per decoded bit, smaller means more threads for small batches.
 constexpr int kMinSubseqBits = 1024;
-constexpr int kMaxSubseqBits = 8192;
+constexpr int kMaxSubseqBits = 32768;
+constexpr int kDefaultMaxSubseqBits = 8192;   // what the planner picks for large batches
 constexpr int kDefaultLookbackBits = 1024;
 constexpr int kDefaultWriteParts = 1;       // write-pass units per subsequence (BatchDev::wp_shift), never shorter than kMinSubseqBits
 constexpr int kMinSegBits = 512;           // smallest checkpoint distance inside a subsequence (BatchDev::seg_bits) // cold-start distance before a subsequence (BatchDev::lookback_bits)

@@ -158,7 +158,7 @@ uint32_t choose_subseq_bits(uint64_t total_scan_bytes) {
     }
     // keep at least ~1.3 subsequences per hardware thread slot (148 SMs x 1536 threads)
     const uint64_t bits = total_scan_bytes * 8, want = 300000;
-    uint32_t s = kMaxSubseqBits;
+    uint32_t s = kDefaultMaxSubseqBits;
     while (s > (uint32_t)kMinSubseqBits && bits / s < want) s >>= 1;
     return s;
 }
