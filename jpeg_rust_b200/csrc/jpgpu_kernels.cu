@@ -1054,6 +1054,84 @@ __device__ __forceinline__ uint32_t pack4(int32_t a, int32_t b, int32_t c, int32
     return r;
 }
 
+// ---- two blocks at a time on the packed FP32 pipe (FADD2 / FMUL2 / FFMA2 of sm_100: one instruction, two lanes of a
+// 64-bit register pair).  A thread that has two blocks of the same component to transform (two luma or two chroma
+// passes of a tile) runs them as the two halves of f32x2 values: the butterflies cost half the issue slots, and the
+// transposition through shared memory moves both blocks with 8-byte stores / 16-byte loads.
+#ifndef JPGPU_IDCT_PAIRS
+#define JPGPU_IDCT_PAIRS 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// idct8() of jpgpu_core.h on both halves
+__device__ __forceinline__ void idct8x2(f32x2 (&x)[8]) {
+    const f32x2 c1414 = pk2(1.414213562f, 1.414213562f), c1847 = pk2(1.847759065f, 1.847759065f);
+    const f32x2 n1082 = pk2(-1.082392200f, -1.082392200f), n2613 = pk2(-2.613125930f, -2.613125930f);
+    const f32x2 t10 = add2(x[0], x[4]), t11 = sub2(x[0], x[4]);
+    const f32x2 t13 = add2(x[2], x[6]);
+    const f32x2 t12 = sub2(mul2(sub2(x[2], x[6]), c1414), t13);
+    const f32x2 e0 = add2(t10, t13), e3 = sub2(t10, t13), e1 = add2(t11, t12), e2 = sub2(t11, t12);
+    const f32x2 z13 = add2(x[5], x[3]), z10 = sub2(x[5], x[3]), z11 = add2(x[1], x[7]), z12 = sub2(x[1], x[7]);
+    const f32x2 o7 = add2(z11, z13);
+    const f32x2 t11o = mul2(sub2(z11, z13), c1414);
+    const f32x2 z5 = mul2(add2(z10, z12), c1847);
+    const f32x2 t10o = fma2(z12, n1082, z5);
+    const f32x2 t12o = fma2(z10, n2613, z5);
+    const f32x2 o6 = sub2(t12o, o7);
+    const f32x2 o5 = sub2(t11o, o6);
+    const f32x2 o4 = sub2(t10o, o5);
+    x[0] = add2(e0, o7); x[7] = sub2(e0, o7);
+    x[1] = add2(e1, o6); x[6] = sub2(e1, o6);
+    x[2] = add2(e2, o5); x[5] = sub2(e2, o5);
+    x[3] = add2(e3, o4); x[4] = sub2(e3, o4);
+}
+
+constexpr int kScr2RowPitch = 10;    // f32x2 units; 2*odd -> conflict-free 16-byte row reads
+constexpr int kScr2BlkPitch = 88;    // f32x2 units; 8 mod 16 -> conflict-free 8-byte column writes across a half warp
+// block_idct() for two blocks (raw_a, raw_b: column t of each, same component): out_a / out_b = row t of each.
+// scr_w = scratch + bp * kScr2BlkPitch + t, scr_r = scratch + bp * kScr2BlkPitch + t * kScr2RowPitch (f32x2 units).
+__device__ __forceinline__ void block_idct2p(const uint4 raw_a, const uint4 raw_b, const float* __restrict__ qt, int t,
+                                             f32x2* scr_w, const f32x2* scr_r, float dc_bias, f32x2 (&x)[8]);
+__device__ __forceinline__ void block_idct2(const uint4 raw_a, const uint4 raw_b, const float* __restrict__ qt, int t,
+                                            f32x2* scr_w, const f32x2* scr_r, float dc_bias, float out_a[8], float out_b[8]) {
+    f32x2 x[8];
+    block_idct2p(raw_a, raw_b, qt, t, scr_w, scr_r, dc_bias, x);
+#pragma unroll
+    for (int i = 0; i < 8; i++) upk2(x[i], out_a[i], out_b[i]);
+}
+// the same, rows left packed: x[i] = (sample i of row t of block a, of block b)
+__device__ __forceinline__ void block_idct2p(const uint4 raw_a, const uint4 raw_b, const float* __restrict__ qt, int t,
+                                             f32x2* scr_w, const f32x2* scr_r, float dc_bias, f32x2 (&x)[8]) {
+    const float4 q0 = *reinterpret_cast<const float4*>(qt), q1 = *reinterpret_cast<const float4*>(qt + 32);
+    const float q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    const uint32_t wa[4] = {raw_a.x, raw_a.y, raw_a.z, raw_a.w}, wb[4] = {raw_b.x, raw_b.y, raw_b.z, raw_b.w};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t ua = wa[i >> 1], ub = wb[i >> 1];
+        float fa = (float)(int16_t)((i & 1) ? (ua >> 16) : (ua & 0xffffu)) * q[i];
+        float fb = (float)(int16_t)((i & 1) ? (ub >> 16) : (ub & 0xffffu)) * q[i];
+        if (i == 0 && t == 0) { fa += dc_bias; fb += dc_bias; }   // level shift folded into the DC term
+        x[i] = pk2(fa, fb);
+    }
+    idct8x2(x);   // vertical
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 8; r++) scr_w[r * kScr2RowPitch] = x[r];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(scr_r + 2 * k);
+        x[2 * k] = v.x; x[2 * k + 1] = v.y;
+    }
+    idct8x2(x);   // horizontal
+}
+
 // Tile = 128 pixels x (8*VY) rows = 16/HY MCUs.  Phase A: chroma blocks -> shared f32
 // planes.  Phase B: luma blocks; each lane ends with 8 horizontally adjacent Y samples,
 // fetches the replicated chroma, converts and stages 24 output bytes.  Phase C: the
@@ -1072,7 +1150,17 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
     constexpr int CH_PASSES = GRAY ? 0 : (2 * NM) / 16;
     constexpr int Y_PASSES = (NM * NY) / 16;
     constexpr int NL = CH_PASSES + Y_PASSES;   // 16-byte loads per thread and tile
-    __shared__ __align__(16) float s_scr[16 * kScrBlkPitch];
+#ifndef JPGPU_IDCT_PACKED_COLOUR
+#define JPGPU_IDCT_PACKED_COLOUR 1
+#endif
+    constexpr bool Y_PAIRS = JPGPU_IDCT_PAIRS && Y_PASSES % 2 == 0, CH_PAIRS = JPGPU_IDCT_PAIRS && CH_PASSES > 0 && CH_PASSES % 2 == 0;
+    // 4:2:0: a thread's two luma blocks are the horizontal neighbours 2*bp, 2*bp+1 of one MCU row; they share their
+    // chroma rows, so the colour conversion runs packed as well (the chroma samples c and c+4 of an MCU are stored
+    // next to each other)
+    constexpr bool PACKED_COLOUR = Y_PAIRS && !GRAY && HY == 2 && VY == 2 && Y_PASSES == 2 && JPGPU_IDCT_PACKED_COLOUR;
+    auto luma_block = [](int p, int bp) { return PACKED_COLOUR ? 2 * bp + p : p * 16 + bp; };   // index in the tile
+    constexpr int kScrFloats = (Y_PAIRS || CH_PAIRS) ? 16 * kScr2BlkPitch * 2 : 16 * kScrBlkPitch;
+    __shared__ __align__(16) float s_scr[kScrFloats];
     __shared__ __align__(16) float s_chroma[GRAY ? 4 : 2 * 8 * CWP];
     constexpr int kPlanePitch = 144;                      // bytes per staged row of one plane (128 + 16: rows 4 banks apart)
     constexpr int kPlaneSize = MH * kPlanePitch;
@@ -1097,6 +1185,8 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
     const uint32_t W = im.width, H = im.height, mcux = im.mcux, units = im.units, tiles_x = im.tiles_x;
     float* const scr_w = s_scr + bp * kScrBlkPitch + t;
     const float* const scr_r = s_scr + bp * kScrBlkPitch + t * kScrRowPitch;
+    f32x2* const scr2_w = reinterpret_cast<f32x2*>(s_scr) + bp * kScr2BlkPitch + t;
+    const f32x2* const scr2_r = reinterpret_cast<const f32x2*>(s_scr) + bp * kScr2BlkPitch + t * kScr2RowPitch;
     const float* const qt_l = s_qt + t * 4;
 
     // per-thread block assignment inside a tile (in units of blocks, relative to the tile's first MCU)
@@ -1109,7 +1199,7 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
     }
 #pragma unroll
     for (int p = 0; p < Y_PASSES; p++) {
-        const int yb = p * 16 + bp, m = yb / NY;
+        const int yb = luma_block(p, bp), m = yb / NY;
         mcu_of[CH_PASSES + p] = m; blk_of[CH_PASSES + p] = m * NB + yb % NY;
     }
 
@@ -1155,30 +1245,62 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
         if (tile + 1 < tile_end) issue_loads(ntx, nty, nxt);
 
         if (!GRAY) {
-#pragma unroll
-            for (int a = 0; a < CH_PASSES; a++) {
+            auto put_chroma = [&](int a, const float (&o)[8]) {
                 const int cb = a * 16 + bp, m = cb >> 1, comp = 1 + (cb & 1);
-                float o[8];
-                block_idct(cur[a], qt_l + comp * 64, t, scr_w, scr_r, 0.0f, o);
                 float* dst = s_chroma + ((comp - 1) * 8 + t) * CWP + m * 8;
-                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                if constexpr (PACKED_COLOUR) {   // (c0,c4) (c1,c5) (c2,c6) (c3,c7): left / right luma block of the MCU
+                    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[4], o[1], o[5]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[2], o[6], o[3], o[7]);
+                } else {
+                    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                }
+            };
+            if constexpr (CH_PAIRS) {
+#pragma unroll
+                for (int a = 0; a < CH_PASSES; a += 2) {   // blocks a*16+bp and (a+1)*16+bp: same component (bp & 1)
+                    float oa[8], ob[8];
+                    block_idct2(cur[a], cur[a + 1], qt_l + (1 + (bp & 1)) * 64, t, scr2_w, scr2_r, 0.0f, oa, ob);
+                    put_chroma(a, oa);
+                    put_chroma(a + 1, ob);
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < CH_PASSES; a++) {
+                    float o[8];
+                    block_idct(cur[a], qt_l + (1 + (bp & 1)) * 64, t, scr_w, scr_r, 0.0f, o);
+                    put_chroma(a, o);
+                }
             }
             __syncthreads();
         }
 
-#pragma unroll
-        for (int p = 0; p < Y_PASSES; p++) {
-            const int yb = p * 16 + bp, m = yb / NY, sub = yb % NY, by = sub / HY, bx = sub % HY;
-            float y[8];
-            block_idct(cur[CH_PASSES + p], qt_l, t, scr_w, scr_r, 128.0f, y);
+        // truncation / clamp (decoder.rs:382-390) and staging of row t of luma block p of this thread
+        auto stage_rgb = [&](int p, const float (&rf)[8], const float (&gf)[8], const float (&bf)[8], bool) {
+            const int yb = luma_block(p, bp), m = yb / NY, sub = yb % NY, by = sub / HY, bx = sub % HY;
             const int px0 = (m * HY + bx) * 8, row = by * 8 + t;
             int32_t r8[8], g8[8], b8[8];
-            if (GRAY) {
 #pragma unroll
-                for (int x = 0; x < 8; x++) { r8[x] = f32_to_u8_sat(y[x]); g8[x] = r8[x]; b8[x] = r8[x]; }  // decoder.rs:317-324
+            for (int x = 0; x < 8; x++) { r8[x] = f32_to_u8_sat(rf[x]); g8[x] = f32_to_u8_sat(gf[x]); b8[x] = f32_to_u8_sat(bf[x]); }
+            if (PLANAR) {
+                uint8_t* dst = s_out + row * kPlanePitch + px0;
+                *reinterpret_cast<uint2*>(dst) = make_uint2(pack4(r8[0], r8[1], r8[2], r8[3]), pack4(r8[4], r8[5], r8[6], r8[7]));
+                *reinterpret_cast<uint2*>(dst + kPlaneSize) = make_uint2(pack4(g8[0], g8[1], g8[2], g8[3]), pack4(g8[4], g8[5], g8[6], g8[7]));
+                *reinterpret_cast<uint2*>(dst + 2 * kPlaneSize) = make_uint2(pack4(b8[0], b8[1], b8[2], b8[3]), pack4(b8[4], b8[5], b8[6], b8[7]));
             } else {
-                const int crow = row / VY, cc0 = px0 / HY;
+                uint2* dst = reinterpret_cast<uint2*>(s_out + row * kOutPitch + px0 * 3);
+                dst[0] = make_uint2(pack4(r8[0], g8[0], b8[0], r8[1]), pack4(g8[1], b8[1], r8[2], g8[2]));
+                dst[1] = make_uint2(pack4(b8[2], r8[3], g8[3], b8[3]), pack4(r8[4], g8[4], b8[4], r8[5]));
+                dst[2] = make_uint2(pack4(g8[5], b8[5], r8[6], g8[6]), pack4(b8[6], r8[7], g8[7], b8[7]));
+            }
+        };
+        // colour conversion of one transformed luma block (pass p of this thread, not paired): y = row t of the block
+        auto finish_luma = [&](int p, const float (&y)[8]) {
+            if constexpr (GRAY) {
+                stage_rgb(p, y, y, y, true);   // decoder.rs:317-324
+            } else {
+                const int yb = luma_block(p, bp), m = yb / NY, sub = yb % NY, by = sub / HY, bx = sub % HY;
+                const int crow = (by * 8 + t) / VY, cc0 = ((m * HY + bx) * 8) / HY;
                 float cbv[8], crv[8];
                 const float* pcb = s_chroma + (0 * 8 + crow) * CWP + cc0;
                 const float* pcr = s_chroma + (1 * 8 + crow) * CWP + cc0;
@@ -1193,26 +1315,62 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
                     cbv[0] = u0.x; cbv[1] = u0.y; cbv[2] = u0.z; cbv[3] = u0.w; cbv[4] = u1.x; cbv[5] = u1.y; cbv[6] = u1.z; cbv[7] = u1.w;
                     crv[0] = v0.x; crv[1] = v0.y; crv[2] = v0.z; crv[3] = v0.w; crv[4] = v1.x; crv[5] = v1.y; crv[6] = v1.z; crv[7] = v1.w;
                 }
+                float rr[8], gg[8], bb[8];
 #pragma unroll
                 for (int x = 0; x < 8; x++) {
                     // decoder.rs:392-401 with the +128 already inside y: r = cr*(2-2*0.299) + y, b = cb*(2-2*0.114) + y,
                     // g = (y - 0.114*b - 0.299*r)/0.587 = y - 0.344136*cb - 0.714136*cr
-                    const float rr = fmaf(crv[x], 1.402f, y[x]);
-                    const float bb = fmaf(cbv[x], 1.772f, y[x]);
-                    const float gg = fmaf(cbv[x], -0.34413629f, fmaf(crv[x], -0.71413629f, y[x]));
-                    r8[x] = f32_to_u8_sat(rr); g8[x] = f32_to_u8_sat(gg); b8[x] = f32_to_u8_sat(bb);
+                    rr[x] = fmaf(crv[x], 1.402f, y[x]);
+                    bb[x] = fmaf(cbv[x], 1.772f, y[x]);
+                    gg[x] = fmaf(cbv[x], -0.34413629f, fmaf(crv[x], -0.71413629f, y[x]));
+                }
+                stage_rgb(p, rr, gg, bb, false);
+            }
+        };
+        if constexpr (Y_PAIRS) {
+#pragma unroll
+            for (int p = 0; p < Y_PASSES; p += 2) {
+                f32x2 y2[8];
+                block_idct2p(cur[CH_PASSES + p], cur[CH_PASSES + p + 1], qt_l, t, scr2_w, scr2_r, 128.0f, y2);
+                if constexpr (!PACKED_COLOUR) {
+                    float ya[8], yb2[8];
+#pragma unroll
+                    for (int x = 0; x < 8; x++) upk2(y2[x], ya[x], yb2[x]);
+                    finish_luma(p, ya);
+                    finish_luma(p + 1, yb2);
+                } else {
+                    // both blocks of the pair at once: the left block's chroma is the first, the right block's the
+                    // second half of the pairs stored by put_chroma
+                    const int yb = luma_block(p, bp), m = yb / NY, by = (yb % NY) / HY;
+                    const int crow = (by * 8 + t) / VY;
+                    const f32x2* pcb = reinterpret_cast<const f32x2*>(s_chroma + (0 * 8 + crow) * CWP) + m * 4;
+                    const f32x2* pcr = reinterpret_cast<const f32x2*>(s_chroma + (1 * 8 + crow) * CWP) + m * 4;
+                    f32x2 cb2[4], cr2[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k += 2) {
+                        const ulonglong2 u = *reinterpret_cast<const ulonglong2*>(pcb + k), v = *reinterpret_cast<const ulonglong2*>(pcr + k);
+                        cb2[k] = u.x; cb2[k + 1] = u.y; cr2[k] = v.x; cr2[k + 1] = v.y;
+                    }
+                    const f32x2 k1402 = pk2(1.402f, 1.402f), k1772 = pk2(1.772f, 1.772f);
+                    const f32x2 kn0344 = pk2(-0.34413629f, -0.34413629f), kn0714 = pk2(-0.71413629f, -0.71413629f);
+                    float ra[8], ga[8], ba[8], rb[8], gb[8], bb[8];
+#pragma unroll
+                    for (int x = 0; x < 8; x++) {   // decoder.rs:392-401, as in finish_luma
+                        const f32x2 c_b = cb2[x / 2], c_r = cr2[x / 2];
+                        upk2(fma2(c_r, k1402, y2[x]), ra[x], rb[x]);
+                        upk2(fma2(c_b, k1772, y2[x]), ba[x], bb[x]);
+                        upk2(fma2(c_b, kn0344, fma2(c_r, kn0714, y2[x])), ga[x], gb[x]);
+                    }
+                    stage_rgb(p, ra, ga, ba, false);
+                    stage_rgb(p + 1, rb, gb, bb, false);
                 }
             }
-            if (PLANAR) {
-                uint8_t* dst = s_out + row * kPlanePitch + px0;
-                *reinterpret_cast<uint2*>(dst) = make_uint2(pack4(r8[0], r8[1], r8[2], r8[3]), pack4(r8[4], r8[5], r8[6], r8[7]));
-                *reinterpret_cast<uint2*>(dst + kPlaneSize) = make_uint2(pack4(g8[0], g8[1], g8[2], g8[3]), pack4(g8[4], g8[5], g8[6], g8[7]));
-                *reinterpret_cast<uint2*>(dst + 2 * kPlaneSize) = make_uint2(pack4(b8[0], b8[1], b8[2], b8[3]), pack4(b8[4], b8[5], b8[6], b8[7]));
-            } else {
-                uint2* dst = reinterpret_cast<uint2*>(s_out + row * kOutPitch + px0 * 3);
-                dst[0] = make_uint2(pack4(r8[0], g8[0], b8[0], r8[1]), pack4(g8[1], b8[1], r8[2], g8[2]));
-                dst[1] = make_uint2(pack4(b8[2], r8[3], g8[3], b8[3]), pack4(r8[4], g8[4], b8[4], r8[5]));
-                dst[2] = make_uint2(pack4(g8[5], b8[5], r8[6], g8[6]), pack4(b8[6], r8[7], g8[7], b8[7]));
+        } else {
+#pragma unroll
+            for (int p = 0; p < Y_PASSES; p++) {
+                float y[8];
+                block_idct(cur[CH_PASSES + p], qt_l, t, scr_w, scr_r, 128.0f, y);
+                finish_luma(p, y);
             }
         }
         __syncthreads();
