@@ -3,7 +3,7 @@
 # command, ncu --set full of the seven full-batch kernels (launches 42..48 of this command line), config-4 line,
 # compute-sanitizer.  Outputs land in gpurun_out/<T>_*; profiles/summarize_ncu.py turns the .ncu-rep into the summary.
 cd $GRAFT_REPO_ROOT
-T=r01z
+T=r01za
 timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/${T}_pytest_gpu.log; cat gpurun_out/${T}_pytest_gpu.log
 timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/${T}_bench_1024img.json 2> gpurun_out/${T}_bench.err; tail -c 600 gpurun_out/${T}_bench_1024img.json; echo
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference.json 2>> gpurun_out/${T}_bench.err; cat gpurun_out/${T}_bench_reference.json
