@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the CPU baseline sample (0 = 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--waves", type=int, default=0, help="also time a job of WAVES x --images images decoded wave after wave "
+                    "through the one batch object, every wave's scans and RGB output resident in HBM (BASELINE configs[4] "
+                    "on one GPU: 16 waves of 1024)")
     ap.add_argument("--e2e-chunk", type=int, default=128, help="images per chunk of the pipelined end-to-end run")
     return ap.parse_args()
 
@@ -323,6 +326,49 @@ def main():
                 "entropy_stage": {"ms": ent_ms, "bitstream_GBps": stats["scan_bytes"] / (ent_ms * 1e-3) / 1e9,
                                   "algorithmic_GBps": (stats["scan_bytes"] + stats["coef_bytes"]) / (ent_ms * 1e-3) / 1e9}}
 
+    # ---- BASELINE configs[4] on this GPU: a job larger than one set of arenas, wave after wave through the same batch
+    # object.  Every wave has its own scan bytes (one resident device buffer per job) and its
+    # own slice of one resident output arena; bitstream and coefficient arenas are the batch's, reused.
+    waves = None
+    if args.waves > 1:
+        import ctypes as C
+        K = args.waves
+        wave_out = batch.output_bytes()
+        out_arena = torch.empty(K * wave_out + 256, dtype=torch.uint8, device="cuda")
+        out_base = (out_arena.data_ptr() + 255) // 256 * 256
+        scan_stride = (int(offs[-1]) + 255) // 256 * 256
+        scans = torch.empty(K * scan_stride, dtype=torch.uint8, device="cuda")
+        for w in range(K):
+            scans[w * scan_stride:w * scan_stride + int(offs[-1])].copy_(host_in, non_blocking=True)
+        scan_offs = [int(descs[i].scan) - hin.ctypes.data for i in range(n)]   # where image i's entropy-coded bytes start
+        torch.cuda.synchronize()
+
+        def run_job():
+            for w in range(K):
+                batch.set_device_scans(scans.data_ptr() + w * scan_stride, scan_offs)
+                batch.set_device_output(out_base + w * wave_out, wave_out)
+                batch.decode()
+        run_job()
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(stream)
+        run_job()
+        w1.record(stream)
+        barrier()
+        job_ms = max_over_ranks(w0.elapsed_time(w1))
+        first = torch.empty(wave_out, dtype=torch.uint8, device="cuda")
+        first.copy_(out_arena[out_base - out_arena.data_ptr():out_base - out_arena.data_ptr() + wave_out])
+        last = out_arena[out_base - out_arena.data_ptr() + (K - 1) * wave_out:out_base - out_arena.data_ptr() + K * wave_out]
+        assert torch.equal(first, last), "waves of identical input differ"
+        batch.set_device_output(None, 0)
+        batch.upload()   # the batch's own scans again
+        batch.decode()
+        waves = {"images": K * n, "waves": K, "value": world * K * pixels / (job_ms * 1e-3) / 1e6, "unit": UNIT, "ms": job_ms,
+                 "resident_GB": {"scans": K * scan_stride / 1e9, "rgb": K * wave_out / 1e9},
+                 "note": "per wave: device-to-device hand-over of the wave's scan bytes, decode into the wave's slice of one "
+                         "resident output arena; arenas of one batch object reused"}
+        del out_arena, scans
+
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region.  The batch is cut into chunks that
     # alternate between two contexts (= two streams) so that the H2D of one chunk, the kernels of another and the D2H
     # of a third overlap; the plans and device arenas of the chunks are created once, outside the timed region.
@@ -432,7 +478,7 @@ def main():
                        f"{stats['scan_bytes'] / 1e6:.0f} MB bitstream, {stats['coef_bytes'] / 1e9:.2f} GB coefficients",
                        "parallelism": f"images sharded over {world} GPU(s), no collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "config0_single_image": config0,
+            "config0_single_image": config0, "config4_waves": waves,
             "stage_ms": {"entropy": ent_ms, "idct_colour": idct_ms, "note": "stages run one after the other on one stream; "
                          "`value` is timed over jpgpu_batch_decode, which overlaps the image groups of a batch"},
         }

@@ -36,7 +36,7 @@ struct jpgpu_batch {
     BatchDev dev;
     struct Arena { void* p = nullptr; size_t cap = 0; };
     enum { kImgs, kSeqs, kLuts, kQt, kKind0, kGmap = kKind0 + kNumKinds, kSamples, kRaw, kDyn, kStream, kSegtab, kSubs, kSegs, kChunks, kCoefs,
-           kRgb, kNumArenas };
+           kRgb, kScanOffs, kNumArenas };
     Arena arena[kNumArenas];   // device allocations, grown on demand by jpgpu_batch_replan()
     uint64_t launches = 0;
     size_t coef_bytes = 0;
@@ -257,12 +257,15 @@ extern "C" int jpgpu_batch_set_device_scans(jpgpu_batch* b, const void* dev_base
     if (!b || !dev_base || !offsets) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
-    uint8_t* raw = const_cast<uint8_t*>(b->dev.raw);
-    for (size_t i = 0; i < b->n; i++) {
-        if (b->plan.status[i] != JPGPU_OK) continue;
-        CK(cudaMemcpyAsync(raw + b->plan.imgs[i].raw_off, (const uint8_t*)dev_base + offsets[i], b->plan.imgs[i].raw_len,
-                           cudaMemcpyDeviceToDevice, ctx->stream));
-    }
+    if (!b->n) return JPGPU_OK;
+    // one launch for the whole batch (a copy per image would serialise ~4 us each on the stream)
+    uint64_t* dev_offs = nullptr;
+    int st = dev_ensure(b, jpgpu_batch::kScanOffs, &dev_offs, b->n);
+    if (st != JPGPU_OK) return st;
+    CK(cudaMemcpyAsync(dev_offs, offsets, b->n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    launch_gather_scans(b->dev, dev_base, dev_offs, ctx->stream);
+    CK(cudaGetLastError());
+    b->launches += 1;
     return JPGPU_OK;
 }
 

@@ -223,6 +223,30 @@ __global__ void __launch_bounds__(kPreThreads) prepass_write_kernel(BatchDev b) 
     }
 }
 
+// jpgpu_batch_set_device_scans(): the raw scan bytes of the images already lie in device memory, image i at
+// base + offs[i] (any alignment).  One launch moves them into the batch's raw arena (16-byte aligned per image):
+// every thread assembles one aligned 16-byte vector from five aligned source words.
+__global__ void __launch_bounds__(kPreThreads) gather_scans_kernel(BatchDev b, const uint8_t* __restrict__ base, const uint64_t* __restrict__ offs) {
+    const uint32_t img = b.img0 + blockIdx.y;
+    const ImgDev& im = b.imgs[img];
+    const uint32_t n = im.raw_len, o = blockIdx.x * kPreChunk + threadIdx.x * 16u;
+    if (o >= n) return;
+    const uint8_t* sp = base + offs[img] + o;
+    uint4 v;
+    if (o + 20u <= n) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(sp);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+        v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    } else {   // the last bytes of the image: nothing is read past them
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (uint32_t k = 0; k < 16u && o + k < n; k++) w[k >> 2] |= (uint32_t)sp[k] << (8u * (k & 3u));
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(const_cast<uint8_t*>(b.raw) + im.raw_off + o) = v;
+}
+
 // ========================================================= stage 1b-1d: entropy decode
 constexpr int kJobsPerCta = kSeqThreads / 32;      // sync kernel
 constexpr int kWriteThreads = 256;                 // write kernel: more warps share one copy of the Huffman tables
@@ -1505,6 +1529,10 @@ void launch_prepass_step(const BatchDev& b, cudaStream_t s, int step) {
     if (step == 0) prepass_count_kernel<<<grid, kPreThreads, 0, s>>>(b);
     else if (step == 1) prepass_scan_kernel<<<b.n_images, kPreThreads, 0, s>>>(b);
     else prepass_write_kernel<<<grid, kPreThreads, 0, s>>>(b);
+}
+void launch_gather_scans(const BatchDev& b, const void* base, const uint64_t* dev_offs, cudaStream_t s) {
+    if (!b.n_images || !b.max_chunks) return;
+    gather_scans_kernel<<<dim3(b.max_chunks, b.n_images), kPreThreads, 0, s>>>(b, static_cast<const uint8_t*>(base), dev_offs);
 }
 void launch_prepass(const BatchDev& b, cudaStream_t s) {
     for (int step = 0; step < 3; step++) launch_prepass_step(b, s, step);

@@ -384,3 +384,33 @@ def test_restart_interval_modes_agree(mode, monkeypatch):
     files = [synth.synth_jpeg(700, 640, 480, "420", restart_interval=2), synth.synth_jpeg(701, 333, 200, "444", restart_interval=40),
              synth.synth_jpeg(702, 512, 512, "gray", restart_interval=64), synth.synth_jpeg(703, 320, 240, "422", restart_interval=0)]
     compare_with_oracle(files, LAYOUT_SPEC, ext=EXT_DRI)
+
+
+def test_scans_handed_over_in_device_memory():
+    """jpgpu_batch_set_device_scans: the entropy-coded bytes already lie in device memory, image i at base + offsets[i]
+    at any alignment (here: whole files packed back to back with odd gaps, the last one ending with the buffer).
+    Same output as the host upload."""
+    import torch
+    files = [synth.synth_jpeg(900 + i, 200 + 24 * i, 96 + 8 * i, ["420", "444", "gray", "422", "440"][i % 5], restart_interval=(3 if i == 2 else 0))
+             for i in range(7)]
+    ref = run_batch(files, LAYOUT_SPEC, EXT_DRI)
+    b = Batch(files, layout=LAYOUT_SPEC, ext=EXT_DRI)
+    blob, offsets, pos = bytearray(), [], 0
+    for i, f in enumerate(files):
+        gap = (i * 5 + 1) % 7          # odd alignments
+        blob += b"\xa5" * gap
+        pos += gap
+        scan_at = len(f) - b.descs[i].scan_len          # the scan runs to the end of the file (mod.rs:371-385)
+        offsets.append(pos + scan_at)
+        blob += f
+        pos += len(f)
+    dev = torch.from_numpy(np.frombuffer(bytes(blob), dtype=np.uint8).copy()).cuda()
+    assert dev.numel() == offsets[-1] + b.descs[len(files) - 1].scan_len
+    b.set_device_scans(dev.data_ptr(), offsets).decode()
+    outs = b.download()
+    st, br = b.results()
+    assert st == ref[1] and br == ref[2]
+    for i in range(len(files)):
+        assert np.array_equal(outs[i], ref[0][i]), i
+        assert all(np.array_equal(x, y) for x, y in zip(b.coefficients(i), ref[3][i]))
+    b.close()
