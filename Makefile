@@ -15,6 +15,7 @@ all: $(LIB)/libjpgpu.so $(LIB)/libjpgenc.so oracle tests/sim/libjpsim.so
 $(LIB)/libjpgpu.so: $(CSRC)/jpgpu_kernels.cu $(CSRC)/jpgpu_api.cu $(CSRC)/jpgpu_host.cpp $(CSRC)/jpgpu_core.h $(CSRC)/jpgpu_kernels.cuh $(CSRC)/jpgpu_host.h include/jpgpu.h
 	@mkdir -p $(LIB)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/jpgpu_kernels.cu $(CSRC)/jpgpu_api.cu $(CSRC)/jpgpu_host.cpp -lcudart 2> $(LIB)/ptxas_report.txt || (cat $(LIB)/ptxas_report.txt; false)
+	@grep -v "Compile time" $(LIB)/ptxas_report.txt > $(LIB)/ptxas_report.tmp; mv $(LIB)/ptxas_report.tmp $(LIB)/ptxas_report.txt
 	@grep -E "error|warning" $(LIB)/ptxas_report.txt | grep -v "ptxas info" || true
 
 $(LIB)/libjpgenc.so: $(CSRC)/jpgenc.cpp
