@@ -246,6 +246,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         if (st == JPGPU_OK && (d.scan == nullptr || d.scan_len < 4)) st = JPGPU_PANIC_INDEX_OOB;  // huffman.rs:127-128
         if (st == JPGPU_OK && d.scan_len > 0x1ff00000ull) st = JPGPU_ERR_UNSUPPORTED;             // bit positions are 32-bit
         if (st == JPGPU_OK && (uint64_t)g.units * g.blocks_per_mcu * 64 > 0x7fffffffull) st = JPGPU_ERR_UNSUPPORTED;
+        if (st == JPGPU_OK && (uint64_t)d.width * d.height * 3 > 0xffffffffull) st = JPGPU_ERR_UNSUPPORTED;   // 32-bit byte offsets inside an image's output
 
         // Huffman tables -> slots
         uint32_t slot_lut[kMaxLutSlots];
