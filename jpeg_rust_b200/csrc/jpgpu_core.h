@@ -424,7 +424,10 @@ JPGPU_HD uint32_t pack_cz(const DecState& st) { return (uint32_t)(st.g & 63) | (
 JPGPU_HD void sync_segment(const DecCtx& cx, DecState& st, uint32_t end_bit, SegRec& r) {
     const int32_t g_base = st.g;
     st.dc0 = st.dc1 = st.dc2 = 0;
-    st.flags &= ~kCrossed;
+    // A decoder standing on the first bit of a restart interval (it was put there, or its last step crossed into
+    // it) is in an absolute state: the record must say so even if no crossing happens inside the segment.  (A
+    // predecessor whose last symbol ended exactly on the interval's last bit stops there without having crossed.)
+    if (st.p == cx.seg[st.seg] && st.p < cx.stream_bits) st.flags |= kCrossed; else st.flags &= ~kCrossed;
     if (end_bit > cx.stream_bits) end_bit = cx.stream_bits;
 #pragma unroll 1
     while (st.p < end_bit) {

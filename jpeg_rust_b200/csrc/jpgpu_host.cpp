@@ -163,12 +163,19 @@ uint32_t choose_subseq_bits(uint64_t total_scan_bytes) {
     return s;
 }
 
-uint32_t choose_lookback_bits() {
+// Cold-start distance of the synchronisation pass.  A batch that fills the machine with 8192-bit subsequences pays
+// for every look-back bit (1024: 12.5 % more decoding, ~15 % of the links left to the repair walks).  A small batch
+// leaves most of the machine idle, and there the rounds of repair walks are what the caller waits for - with 4:2:0,
+// whose six-block MCUs (two table sets in a 4+1+1 pattern) lock in slowly (a single 4096 x 4096 4:2:0 image: 9.5 ms
+// with 1024 bits, 1.3 ms with 8192; MCUs of up to four blocks synchronise within 1024 bits and gain nothing).
+uint32_t choose_lookback_bits(uint64_t total_scan_bytes, uint32_t sub_bits, uint32_t max_blocks_per_mcu) {
     if (const char* e = getenv("JPGPU_LOOKBACK_BITS")) {
         const long v = atol(e);
         if (v >= 0 && v <= (1 << 20)) return (uint32_t)v;
     }
-    return kDefaultLookbackBits;
+    const uint64_t threads = total_scan_bytes * 8 / sub_bits;
+    if (threads >= 300000 || max_blocks_per_mcu < 6) return kDefaultLookbackBits;
+    return threads >= 40000 ? 4096u : 8192u;
 }
 
 int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t sub_bits) {
@@ -179,7 +186,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         sub_bits = choose_subseq_bits(tot);
     }
     plan.sub_bits = sub_bits;
-    plan.lookback_bits = choose_lookback_bits();
+    plan.lookback_bits = kDefaultLookbackBits;   // settled below, once the MCU structure of the images is known
     plan.seg_bits = std::max<uint32_t>(kMinSegBits, sub_bits / 8);
     if (const char* e = getenv("JPGPU_SEG_BITS")) {
         const long v = atol(e);
@@ -211,6 +218,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
     if (want_groups > n) want_groups = n ? (uint32_t)n : 1u;
     const uint64_t group_bytes = tot_bytes / want_groups + 1;
     uint64_t acc_bytes = 0;
+    uint32_t max_bpm = 0;
     constexpr uint32_t kJobsPerCta = 8;   // write kernel CTAs take 8 warp jobs, sync kernel CTAs 4: pad to the larger
     auto close_group = [&](size_t next_img) {
         while (plan.seqs.size() % kJobsPerCta != 0) plan.seqs.push_back(SeqDesc{0xffffffffu, 0u});
@@ -324,6 +332,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         im.raw_len = (uint32_t)d.scan_len;
         im.ncomp = (uint8_t)d.ncomp;
         im.blocks_per_mcu = (uint8_t)g.blocks_per_mcu;
+        max_bpm = std::max<uint32_t>(max_bpm, g.blocks_per_mcu);
         im.hmax = g.hmax; im.vmax = g.vmax;
         im.mcux = g.mcux; im.mcuy = g.mcuy; im.units = g.units;
         im.kind = g.fused_ok ? g.kind : (uint8_t)kKindGeneric; im.layout = (uint8_t)d.layout;
@@ -418,6 +427,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         plan.tot_rgb_bytes += (uint64_t)im.width * im.height * 3;
     }
     close_group(n);
+    plan.lookback_bits = choose_lookback_bits(tot_bytes, sub_bits, max_bpm);
     if (plan.sub_entries > 0xffffffffull || plan.seg_entries > 0xffffffffull) return JPGPU_ERR_UNSUPPORTED;
     return JPGPU_OK;
 }

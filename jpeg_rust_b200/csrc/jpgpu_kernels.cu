@@ -672,7 +672,9 @@ __device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const SM& sm
 __device__ __forceinline__ void fast_sync_segment(const FastCtx& cx, FastState& st, uint32_t end_bit, SegRec& r) {
     const int32_t g_base = st.g;
     fast_set_dc(cx, st, 0, 0, 0);
-    st.flags &= ~kCrossed;
+    // standing on the first bit of a restart interval = absolute state, crossing inside the segment or not (see
+    // sync_segment() in jpgpu_core.h)
+    if (st.p == cx.seg[st.seg] && st.p < cx.stream_bits) st.flags |= kCrossed; else st.flags &= ~kCrossed;
     fast_run_to(cx, st, min(end_bit, cx.stream_bits));
     r.p = st.p;
     r.cz = ((uint32_t)st.g & 63u) | (fast_c(st) << 6) | (st.flags & kCrossed);

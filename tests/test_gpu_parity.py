@@ -414,3 +414,30 @@ def test_scans_handed_over_in_device_memory():
         assert np.array_equal(outs[i], ref[0][i]), i
         assert all(np.array_equal(x, y) for x, y in zip(b.coefficients(i), ref[3][i]))
     b.close()
+
+
+def test_large_image_32bit_offsets():
+    """A 16384 x 8192 4:2:0 image (134 Mpixel, 201 M coefficients, 403 MB of RGB): every per-image offset of the
+    kernels is exercised far beyond 2^24.  Coefficients against the encoder's own (the oracle's O(N^4) IDCT would
+    take minutes here), samples against the same image carrying restart markers (DRI-invariance: two different
+    decode paths — look-back synchronisation vs interval starts — must agree byte for byte), planar against interleaved."""
+    from jpeg_rust_b200 import OUT_RGB_PLANAR
+    w, h = 16384, 8192
+    f, gt = synth.synth_jpeg(77, w, h, "420", want_coefs=True)
+    fr = synth.synth_jpeg(77, w, h, "420", restart_interval=64)
+    b = Batch([f, fr], layout=LAYOUT_SPEC, ext=EXT_DRI)
+    b.upload().decode()
+    st, _ = b.results()
+    assert st == [0, 0], st
+    for i in range(2):
+        got = b.coefficients(i)
+        for a, c in zip(got, gt):
+            assert np.array_equal(a[:len(c)], c[:len(a)])
+    t0, t1 = b.device_tensor(0), b.device_tensor(1)
+    import torch
+    assert torch.equal(t0, t1)
+    inter = t0.clone()
+    b.set_output_format(OUT_RGB_PLANAR).idct()
+    b.ctx.sync()
+    assert torch.equal(b.device_tensor(0), inter.permute(2, 0, 1))
+    b.close()

@@ -244,3 +244,19 @@ def test_write_pass_units(parts, monkeypatch):
         for a, b in zip(r.coefs, o.coefs):
             assert np.array_equal(a, b), f"image {k}: coefficients differ"
         assert np.abs(r.rgb.astype(int) - o.rgb.astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("lookback", ["1024", None])
+def test_interval_start_on_a_subsequence_boundary(lookback, monkeypatch):
+    """Regression: in this image restart interval 678 starts exactly on a subsequence boundary and its predecessor's last
+    symbol ends on the interval's last bit (no pad bits), so the predecessor stops without having crossed.  The
+    subsequence starting there stands on the first bit of an interval — an absolute state — and must record it as such,
+    or every DC predictor up to the next marker is off by the previous interval's sums (coefficients against the
+    encoder's own; the oracle's O(N^4) IDCT would take minutes on 16 Mpixel)."""
+    if lookback:
+        monkeypatch.setenv("JPGPU_LOOKBACK_BITS", lookback)
+    f, gt = synth.synth_jpeg(77, 4096, 4096, "420", restart_interval=64, want_coefs=True)
+    rs, diag = S.decode_batch([f], layout=1, ext=2)
+    assert rs[0].status == 0
+    for a, g in zip(rs[0].coefs, gt):
+        assert np.array_equal(a, g)
