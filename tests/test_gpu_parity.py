@@ -441,3 +441,31 @@ def test_large_image_32bit_offsets():
     b.ctx.sync()
     assert torch.equal(b.device_tensor(0), inter.permute(2, 0, 1))
     b.close()
+
+
+@pytest.mark.parametrize("env", [{}, {"JPGPU_SUBSEQ_BITS": "4096", "JPGPU_LOOKBACK_BITS": "256", "JPGPU_WRITE_PARTS": "2"},
+                                 {"JPGPU_SUBSEQ_BITS": "8192", "JPGPU_LOOKBACK_BITS": "1024", "JPGPU_INTERVAL_MODE": "0"}])
+def test_randomised_batches(env, monkeypatch):
+    """Fixed-seed mixed batches (sampling, size, quality, restart interval all over the place) under different planner
+    settings: coefficients against the encoder's own for every image, statuses clean."""
+    import random
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = random.Random(4242 + len(env))
+    files, gts = [], []
+    for it in range(120):
+        sub = rng.choice(["420", "420", "422", "444", "440", "gray"])
+        w = rng.choice([rng.randint(8, 300), rng.randint(300, 1400), rng.choice([512, 1024, 2048])])
+        h = rng.choice([rng.randint(8, 300), rng.randint(300, 1000), rng.choice([512, 1024])])
+        ri = rng.choice([0, 0, 1, 2, 3, 5, 8, 16, 33, 64, 100, 256, 1000])
+        f, g = synth.synth_jpeg(rng.randint(0, 10 ** 6), w, h, sub, quality=rng.choice([30, 60, 85, 95]), restart_interval=ri, want_coefs=True)
+        files.append(f)
+        gts.append(g)
+    b = Batch(files, layout=LAYOUT_SPEC, ext=EXT_DRI)
+    b.upload().decode()
+    st, _ = b.results()
+    assert all(s == 0 for s in st), [(i, s) for i, s in enumerate(st) if s]
+    for i in range(len(files)):
+        for a, g in zip(b.coefficients(i), gts[i]):
+            assert np.array_equal(a[:len(g)], g[:len(a)]), i
+    b.close()

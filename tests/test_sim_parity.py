@@ -260,3 +260,30 @@ def test_interval_start_on_a_subsequence_boundary(lookback, monkeypatch):
     assert rs[0].status == 0
     for a, g in zip(rs[0].coefs, gt):
         assert np.array_equal(a, g)
+
+
+def test_randomised_configurations(monkeypatch):
+    """A fixed-seed sweep over what the planner can vary (subsequence length, look-back, write-pass units, interval
+    mode) and what the input can (sampling, size, quality, restart interval): coefficients against the encoder's own.
+    (A 10 000-image run of the same generator is how the interval-start fix above was validated.)"""
+    import random
+    rng = random.Random(20261017)
+    for it in range(60):
+        sub = rng.choice(["420", "420", "422", "444", "440", "gray"])
+        w = rng.choice([rng.randint(8, 300), rng.randint(300, 1100)])
+        h = rng.choice([rng.randint(8, 300), rng.randint(300, 900)])
+        ri = rng.choice([0, 0, 1, 2, 3, 5, 8, 16, 33, 64, 100, 256, 1000])
+        q = rng.choice([30, 60, 85, 95])
+        sb = rng.choice([0, 1024, 2048, 4096, 8192])
+        monkeypatch.setenv("JPGPU_LOOKBACK_BITS", str(rng.choice([64, 256, 1024, 1024, 4096])))
+        monkeypatch.setenv("JPGPU_WRITE_PARTS", str(rng.choice([1, 1, 2, 4])))
+        if rng.random() < 0.3:
+            monkeypatch.setenv("JPGPU_INTERVAL_MODE", str(rng.choice([0, 1])))
+        else:
+            monkeypatch.delenv("JPGPU_INTERVAL_MODE", raising=False)
+        seed = rng.randint(0, 10 ** 6)
+        f, gt = synth.synth_jpeg(seed, w, h, sub, quality=q, restart_interval=ri, want_coefs=True)
+        rs, _ = S.decode_batch([f], layout=1, ext=2, sub_bits=sb)
+        assert rs[0].status == 0, (it, seed, w, h, sub, ri, q, sb)
+        for a, g in zip(rs[0].coefs, gt):
+            assert np.array_equal(a, g), (it, seed, w, h, sub, ri, q, sb)
