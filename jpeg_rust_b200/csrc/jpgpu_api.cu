@@ -340,7 +340,7 @@ int ensure_aux(jpgpu_ctx* ctx) {
 }  // namespace
 
 // entropy + idct.  A large batch is cut into groups of images (HostPlan::groups) whose kernel chains alternate
-// between two auxiliary streams: the low-occupancy ends of one group's kernels (repair walks, last waves) overlap
+// between three auxiliary streams: the low-occupancy ends of one group's kernels (repair walks, last waves) overlap
 // the next group's work.  Forked from and joined back into the context stream.
 extern "C" int jpgpu_batch_decode(jpgpu_batch* b) {
     if (!b) return JPGPU_ERR_INVALID_ARG;

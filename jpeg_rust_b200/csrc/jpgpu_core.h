@@ -34,9 +34,9 @@ constexpr int kMaxLutSlots = 6;            // distinct (DC, AC) tables one image
 constexpr int kMinSubseqBits = 1024;
 constexpr int kMaxSubseqBits = 32768;
 constexpr int kDefaultMaxSubseqBits = 8192;   // what the planner picks for large batches
-constexpr int kDefaultLookbackBits = 1024;
+constexpr int kDefaultLookbackBits = 1024;   // cold-start distance before a subsequence for machine-filling batches (choose_lookback_bits)
 constexpr int kDefaultWriteParts = 1;       // write-pass units per subsequence (BatchDev::wp_shift), never shorter than kMinSubseqBits
-constexpr int kMinSegBits = 512;           // smallest checkpoint distance inside a subsequence (BatchDev::seg_bits) // cold-start distance before a subsequence (BatchDev::lookback_bits)
+constexpr int kMinSegBits = 512;           // smallest checkpoint distance inside a subsequence (BatchDev::seg_bits)
 constexpr int kSeqThreads = JPGPU_SEQ_THREADS;  // subsequences per sequence (= CTA size of the sync/write kernels)
 constexpr int kStreamPadWords = 8;         // zero words readable past every image's stream
 constexpr int kWriteBufs = 1;              // coefficient block buffers per lane in the write kernel
