@@ -156,10 +156,14 @@ uint32_t choose_subseq_bits(uint64_t total_scan_bytes) {
         const long v = atol(e);
         if (v >= kMinSubseqBits && v <= kMaxSubseqBits && (v & (v - 1)) == 0) return (uint32_t)v;
     }
-    // keep at least ~1.3 subsequences per hardware thread slot (148 SMs x 1536 threads)
-    const uint64_t bits = total_scan_bytes * 8, want = 300000;
+    // 8192-bit subsequences when that still gives ~1.3 decode threads per hardware thread slot (148 SMs x 1536); a
+    // smaller batch trades threads for less look-back and verification per decoded bit: halve only while fewer than
+    // ~120 k threads would be left (256 x 1080p: 4096 bits / 153 k threads beat 2048 bits / 306 k by 11 %).
+    const uint64_t bits = total_scan_bytes * 8;
     uint32_t s = kDefaultMaxSubseqBits;
-    while (s > (uint32_t)kMinSubseqBits && bits / s < want) s >>= 1;
+    if (bits / s >= 300000) return s;
+    s >>= 1;
+    while (s > (uint32_t)kMinSubseqBits && bits / s < 120000) s >>= 1;
     return s;
 }
 
@@ -174,8 +178,9 @@ uint32_t choose_lookback_bits(uint64_t total_scan_bytes, uint32_t sub_bits, uint
         if (v >= 0 && v <= (1 << 20)) return (uint32_t)v;
     }
     const uint64_t threads = total_scan_bytes * 8 / sub_bits;
-    if (threads >= 300000 || max_blocks_per_mcu < 6) return kDefaultLookbackBits;
-    return threads >= 40000 ? 4096u : 8192u;
+    if (max_blocks_per_mcu < 6 || (sub_bits >= (uint32_t)kDefaultMaxSubseqBits && threads >= 300000)) return kDefaultLookbackBits;
+    if (sub_bits >= 4096) return 2048u;          // measured: 256 / 512 x 1080p
+    return threads >= 40000 ? 4096u : 8192u;     // measured: 64 / 16 / 1 x 1080p, 1 x 4096 x 4096
 }
 
 int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t sub_bits) {
