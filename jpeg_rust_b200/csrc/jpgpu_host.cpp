@@ -123,23 +123,31 @@ int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, bool 
     }
     // second level: one sub-table per kLutBits-prefix that starts longer codes, as wide as its longest code up to
     // kLutBits+7 bits; what does not fit the pool (or is longer) is left to the canonical walk (entry 0).
-    uint32_t pool_used = 0;
-    for (uint32_t prefix = 0; prefix < (uint32_t)kLutSize; prefix++) {
-        int maxlen = 0;
-        for (const Code& c : codes)
-            if (c.len > kLutBits && (c.code >> (c.len - kLutBits)) == prefix) maxlen = std::max(maxlen, c.len);
-        if (!maxlen) continue;
-        const int nb = std::min(maxlen - kLutBits, 7);
-        if (pool_used + (1u << nb) > (uint32_t)kPoolSize) continue;
-        const uint32_t base = pool_used;
-        pool_used += 1u << nb;
-        for (const Code& c : codes) {
-            if (c.len <= kLutBits || (c.code >> (c.len - kLutBits)) != prefix || c.len > kLutBits + nb) continue;
-            const int rest = c.len - kLutBits;  // bits of the code inside the sub-table index
-            const uint32_t first = (c.code & ((1u << rest) - 1u)) << (nb - rest), cnt = 1u << (nb - rest);
-            for (uint32_t e = 0; e < cnt; e++) out.pool[base + first + e] = make_entry(c.val, (uint32_t)c.len, is_dc);
+    uint8_t maxlen_of[kLutSize] = {0};
+    for (const Code& c : codes)
+        if (c.len > kLutBits) {
+            uint8_t& m = maxlen_of[c.code >> (c.len - kLutBits)];
+            m = std::max<uint8_t>(m, (uint8_t)c.len);
         }
-        out.fast[prefix] = kLinkBit | base | ((uint32_t)nb << 9);
+    uint32_t pool_used = 0;
+    int32_t base_of[kLutSize], nb_of[kLutSize];
+    for (uint32_t prefix = 0; prefix < (uint32_t)kLutSize; prefix++) {   // pools are handed out in prefix order
+        base_of[prefix] = -1;
+        if (!maxlen_of[prefix]) continue;
+        const int nb = std::min((int)maxlen_of[prefix] - kLutBits, 7);
+        if (pool_used + (1u << nb) > (uint32_t)kPoolSize) continue;
+        base_of[prefix] = (int32_t)pool_used;
+        nb_of[prefix] = nb;
+        pool_used += 1u << nb;
+        out.fast[prefix] = kLinkBit | (uint32_t)base_of[prefix] | ((uint32_t)nb << 9);
+    }
+    for (const Code& c : codes) {
+        if (c.len <= kLutBits) continue;
+        const uint32_t prefix = c.code >> (c.len - kLutBits);
+        if (base_of[prefix] < 0 || c.len > kLutBits + nb_of[prefix]) continue;
+        const int nb = nb_of[prefix], rest = c.len - kLutBits;  // bits of the code inside the sub-table index
+        const uint32_t first = (c.code & ((1u << rest) - 1u)) << (nb - rest), cnt = 1u << (nb - rest);
+        for (uint32_t e = 0; e < cnt; e++) out.pool[(uint32_t)base_of[prefix] + first + e] = make_entry(c.val, (uint32_t)c.len, is_dc);
     }
     return JPGPU_OK;
 }
