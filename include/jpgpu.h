@@ -134,6 +134,12 @@ int jpgpu_parse(const uint8_t *file, size_t len, uint32_t ext_flags, uint32_t la
  * for REF; true MCU count for SPEC).  Returns a status. */
 int jpgpu_geometry(const jpgpu_image_desc *desc, uint32_t *mcus, uint32_t *blocks_per_mcu, uint32_t nblocks_per_comp[4]);
 
+/* What the planner decides for these images (host only, needs no GPU): info[0] bits per subsequence (one decode thread
+ * each), [1] look-back bits of the synchronisation pass, [2] checkpoint distance in bits, [3] write-pass units per
+ * subsequence, [4] image groups of the pipelined decode, [5] images decoded from their restart-interval starts (no
+ * synchronisation pass), [6] warp jobs (incl. padding), [7] device bytes of the arenas.  See DESIGN.md section 4. */
+int jpgpu_plan_info(const jpgpu_image_desc *descs, size_t n, uint64_t info[8]);
+
 const char *jpgpu_status_string(int status);
 int jpgpu_abi_version(void);
 

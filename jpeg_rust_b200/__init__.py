@@ -9,9 +9,9 @@ from ._ffi import (EXT_DRI, EXT_NONE, EXT_SKIP_APPN, LAYOUT_REF, LAYOUT_SPEC, OU
                    JpgpuError)
 from .jpeg import (Batch, Context, FrameComponentHeader, FrameHeader, HuffmanTable, JPEGDecoder, JPEGImage,
                    JPEGPanic, ScanComponentHeader, ScanHeader, context, decode_batch, decode_waves, parse_descriptor,
-                   shard_range)
+                   plan_info, shard_range)
 
 __all__ = ["_ffi", "EXT_DRI", "EXT_NONE", "EXT_SKIP_APPN", "LAYOUT_REF", "LAYOUT_SPEC", "OUT_RGB_INTERLEAVED",
            "OUT_RGB_PLANAR", "JpgpuError", "Batch",
            "Context", "FrameComponentHeader", "FrameHeader", "HuffmanTable", "JPEGDecoder", "JPEGImage", "JPEGPanic",
-           "ScanComponentHeader", "ScanHeader", "context", "decode_batch", "decode_waves", "parse_descriptor", "shard_range"]
+           "ScanComponentHeader", "ScanHeader", "context", "decode_batch", "decode_waves", "parse_descriptor", "plan_info", "shard_range"]

@@ -68,6 +68,7 @@ def lib():
         L.jpgpu_parse.argtypes = [vp, sz, C.c_uint32, C.c_uint32, C.POINTER(ImageDesc)]
         L.jpgpu_geometry.argtypes = [C.POINTER(ImageDesc), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                      C.POINTER(C.c_uint32)]
+        L.jpgpu_plan_info.argtypes = [C.POINTER(ImageDesc), sz, C.POINTER(C.c_uint64)]
         L.jpgpu_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.jpgpu_destroy.argtypes = [vp]
         L.jpgpu_destroy.restype = None
@@ -111,6 +112,7 @@ def check(status, what=""):
 
 EXPORTED_SYMBOLS = [
     "jpgpu_parse", "jpgpu_geometry", "jpgpu_status_string", "jpgpu_abi_version",
+    "jpgpu_plan_info",
     "jpgpu_create", "jpgpu_destroy", "jpgpu_last_error", "jpgpu_set_stream", "jpgpu_sync",
     "jpgpu_decode", "jpgpu_decode_file",
     "jpgpu_batch_create", "jpgpu_batch_replan", "jpgpu_batch_destroy", "jpgpu_batch_upload", "jpgpu_batch_set_device_scans", "jpgpu_batch_set_device_output",

@@ -735,3 +735,23 @@ extern "C" int jpgpu_geometry(const jpgpu_image_desc* desc, uint32_t* mcus, uint
     if (nblocks) for (int c = 0; c < 4; c++) nblocks[c] = g.nblocks[c];
     return JPGPU_OK;
 }
+
+// What the planner decides for a set of images (host only; the decisions DESIGN.md 4.2 / 4.5 describe, testable
+// without a GPU).
+extern "C" int jpgpu_plan_info(const jpgpu_image_desc* descs, size_t n, uint64_t info[8]) {
+    if ((!descs && n) || !info) return JPGPU_ERR_INVALID_ARG;
+    HostPlan plan;
+    const int st = build_plan(descs, n, plan, 0);
+    if (st != JPGPU_OK) return st;
+    uint64_t by_interval = 0;
+    for (size_t i = 0; i < n; i++) by_interval += plan.status[i] == JPGPU_OK && plan.imgs[i].interval_mode ? 1u : 0u;
+    info[0] = plan.sub_bits;
+    info[1] = plan.lookback_bits;
+    info[2] = plan.seg_bits;
+    info[3] = 1ull << plan.wp_shift;
+    info[4] = plan.groups.size();
+    info[5] = by_interval;
+    info[6] = plan.seqs.size();
+    info[7] = plan.raw_bytes + plan.stream_words * 4 + plan.coef_elems * 2 + plan.rgb_bytes;
+    return JPGPU_OK;
+}

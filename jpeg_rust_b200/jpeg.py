@@ -235,6 +235,27 @@ def parse_descriptor(data, ext=EXT_NONE, layout=LAYOUT_REF):
     return st, d, buf
 
 
+def plan_info(files=None, descs=None, ext=EXT_NONE, layout=LAYOUT_SPEC, copies=1):
+    """What the planner decides for a batch (jpgpu_plan_info; host only, needs no GPU): dict with sub_bits,
+    lookback_bits, seg_bits, write_parts, groups, interval_images, warp_jobs, device_bytes.  `copies` repeats the
+    given images (descriptors pointing at the same bytes) to ask about a large batch without building one."""
+    keep = []
+    if descs is None:
+        ds = []
+        for f in files:
+            st, d, buf = parse_descriptor(f, ext, layout)
+            _check(st, "jpgpu_parse")
+            ds.append(d)
+            keep.append(buf)
+        descs = ds
+    descs = list(descs) * copies
+    arr = (_ffi.ImageDesc * len(descs))(*descs)
+    info = (C.c_uint64 * 8)()
+    _check(_ffi.lib().jpgpu_plan_info(arr, len(descs), info), "jpgpu_plan_info")
+    names = ["sub_bits", "lookback_bits", "seg_bits", "write_parts", "groups", "interval_images", "warp_jobs", "device_bytes"]
+    return {k: int(info[i]) for i, k in enumerate(names)}
+
+
 class JPEGImage:
     """Result of JPEGImage::parse (mod.rs:202): dimensions and decoded pixels."""
 
