@@ -181,7 +181,9 @@ int jpgpu_batch_set_device_scans(jpgpu_batch *b, const void *dev_base, const uin
  * decode to caller-owned device memory instead of the batch's own arena — image i goes to dev_base + the same
  * 256-byte aligned offsets jpgpu_batch_device_rgb() reports relative to image 0.  One planned batch (coefficient
  * and bitstream arenas sized for one wave) then serves wave after wave: set_device_scans / upload, set_device_output,
- * decode.  NULL restores the batch's own arena.  `capacity` is checked against jpgpu_batch_stats()[2] rounded up. */
+ * decode.  NULL restores the batch's own arena (sized for the current plan).  `capacity` must be at least
+ * jpgpu_batch_output_bytes(); it is remembered, and a later jpgpu_batch_replan() whose plan no longer fits it falls
+ * back to the batch's own arena (check jpgpu_batch_device_rgb() or set the output again after a replan). */
 int jpgpu_batch_set_device_output(jpgpu_batch *b, void *dev_base, size_t capacity);
 /* Output arrangement (JPGPU_OUT_*) of the following idct / decode calls; kept across replans.  Default: interleaved. */
 int jpgpu_batch_set_output_format(jpgpu_batch *b, uint32_t format);
@@ -192,6 +194,12 @@ int jpgpu_batch_decode(jpgpu_batch *b);  /* entropy + idct */
 int jpgpu_batch_download(jpgpu_batch *b, uint8_t *const *outs);
 /* Device pointer / size of image i's interleaved RGB output. */
 void *jpgpu_batch_device_rgb(jpgpu_batch *b, size_t i, size_t *nbytes);
+/* Bytes the RGB outputs of the planned images occupy together (every image at a 256-byte aligned offset): the size a
+ * caller-owned arena for jpgpu_batch_set_device_output() / jpgpu_batch_download_contiguous() needs. */
+size_t jpgpu_batch_output_bytes(const jpgpu_batch *b);
+/* Where image i's output lies inside that arena, and its size (0 for an image that failed to parse or plan; such an
+ * image still has an offset - an empty slice - so one bad file never breaks the bookkeeping of a wave). */
+int jpgpu_batch_rgb_offset(const jpgpu_batch *b, size_t i, size_t *offset, size_t *nbytes);
 /* Synchronises the stream; per image: status (JPGPU_*) and the reference's bytes_read. Either may be NULL. */
 int jpgpu_batch_results(jpgpu_batch *b, int32_t *statuses, uint64_t *bytes_read);
 /* Debug export for the bit-exact gate: the decoded coefficients of image i in the

@@ -91,6 +91,9 @@ def lib():
         L.jpgpu_batch_download.argtypes = [vp, C.POINTER(vp)]
         L.jpgpu_batch_device_rgb.restype = vp
         L.jpgpu_batch_device_rgb.argtypes = [vp, sz, C.POINTER(sz)]
+        L.jpgpu_batch_output_bytes.restype = sz
+        L.jpgpu_batch_output_bytes.argtypes = [vp]
+        L.jpgpu_batch_rgb_offset.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz)]
         L.jpgpu_batch_results.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
         L.jpgpu_batch_coefficients.argtypes = [vp, sz, vp, sz, C.POINTER(C.c_uint32)]
         L.jpgpu_batch_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -118,6 +121,6 @@ EXPORTED_SYMBOLS = [
     "jpgpu_batch_create", "jpgpu_batch_replan", "jpgpu_batch_destroy", "jpgpu_batch_upload", "jpgpu_batch_set_device_scans", "jpgpu_batch_set_device_output",
     "jpgpu_batch_set_output_format",
     "jpgpu_batch_entropy", "jpgpu_batch_idct", "jpgpu_batch_decode", "jpgpu_batch_download",
-    "jpgpu_batch_device_rgb", "jpgpu_batch_results", "jpgpu_batch_coefficients", "jpgpu_batch_stats",
+    "jpgpu_batch_device_rgb", "jpgpu_batch_output_bytes", "jpgpu_batch_rgb_offset", "jpgpu_batch_results", "jpgpu_batch_coefficients", "jpgpu_batch_stats",
     "jpgpu_batch_profile", "jpgpu_batch_launch_count",
 ]

@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -13,6 +15,12 @@
 #include "jpgpu_kernels.cuh"
 
 using namespace jpgpu;
+
+// No C++ exception may cross the C ABI (std::bad_alloc from a planner vector under a memory limit would otherwise
+// terminate the caller's process): every int-returning entry point is a function-try-block ending in this.
+#define JPGPU_CATCH_ALL                                              \
+    catch (const std::bad_alloc&) { return JPGPU_ERR_OOM; }          \
+    catch (...) { return JPGPU_ERR_INVALID_ARG; }
 
 struct jpgpu_ctx {
     int device = 0;
@@ -41,6 +49,7 @@ struct jpgpu_batch {
     uint64_t launches = 0;
     size_t coef_bytes = 0;
     uint8_t* own_rgb = nullptr;
+    size_t ext_rgb_cap = 0;    // capacity of the caller's output arena while jpgpu_batch_set_device_output() is in force
     bool decoded = false;
 };
 
@@ -94,7 +103,7 @@ int dev_upload(jpgpu_batch* b, int which, const T** out, const std::vector<T>& v
 
 }  // namespace
 
-extern "C" int jpgpu_create(int device, jpgpu_ctx** out) {
+extern "C" int jpgpu_create(int device, jpgpu_ctx** out) try {
     if (!out) return JPGPU_ERR_INVALID_ARG;
     *out = nullptr;
     int count = 0;
@@ -113,7 +122,7 @@ extern "C" int jpgpu_create(int device, jpgpu_ctx** out) {
     if (init_constants() != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return JPGPU_ERR_CUDA; }
     *out = c;
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
 extern "C" void jpgpu_destroy(jpgpu_ctx* c) {
     if (!c) return;
@@ -130,21 +139,21 @@ extern "C" void jpgpu_destroy(jpgpu_ctx* c) {
 
 extern "C" const char* jpgpu_last_error(const jpgpu_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
-extern "C" int jpgpu_set_stream(jpgpu_ctx* c, void* s) {
+extern "C" int jpgpu_set_stream(jpgpu_ctx* c, void* s) try {
     if (!c) return JPGPU_ERR_INVALID_ARG;
     cudaSetDevice(c->device);
     if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     c->stream = reinterpret_cast<cudaStream_t>(s);
     c->own_stream = false;
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_sync(jpgpu_ctx* ctx) {
+extern "C" int jpgpu_sync(jpgpu_ctx* ctx) try {
     if (!ctx) return JPGPU_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
 extern "C" void jpgpu_batch_destroy(jpgpu_batch* b);
 
@@ -156,7 +165,7 @@ extern "C" void jpgpu_batch_destroy(jpgpu_batch* b) {
     delete b;
 }
 
-extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs, size_t n) {
+extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs, size_t n) try {
     if (!b || (!descs && n)) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
@@ -211,9 +220,11 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     TRY(dev_ensure(b, jpgpu_batch::kChunks, &d.chunk_counts, p.chunk_entries + 1));
     d.max_chunks = p.max_chunks;
     TRY(dev_ensure(b, jpgpu_batch::kCoefs, &d.coefs, p.coef_elems + 64));
-    if (external_rgb) {
-        d.rgb = ext_rgb;   // stays where jpgpu_batch_set_device_output() pointed it; the caller sized it
+    if (external_rgb && b->ext_rgb_cap >= p.rgb_bytes) {
+        d.rgb = ext_rgb;   // stays where jpgpu_batch_set_device_output() pointed it: the new plan fits the caller's arena
     } else {
+        // no external arena, or one too small for the new plan: the batch's own arena (grown to the plan)
+        b->ext_rgb_cap = 0;
         TRY(dev_ensure(b, jpgpu_batch::kRgb, &d.rgb, p.rgb_bytes + 256));
     }
     b->own_rgb = static_cast<uint8_t*>(b->arena[jpgpu_batch::kRgb].p);
@@ -223,12 +234,13 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     CK(cudaMemsetAsync(raw, 0, p.raw_bytes + 64, ctx->stream));
     CK(cudaMemsetAsync(d.stream, 0, stream_alloc_words * 4, ctx->stream));
     CK(cudaMemsetAsync(d.dyn, 0, (n + 1) * sizeof(ImgDyn), ctx->stream));
-    CK(cudaMemsetAsync(d.coefs, 0, (p.coef_elems + 64) * 2, ctx->stream));
+    // (the coefficient arena is not cleared: the write pass stores every block of a complete scan, and the blocks a
+    // damaged scan never reaches are masked by ImgDyn::coef_end in the IDCT stage)
     CK(cudaMemsetAsync(d.segtab, 0, (p.seg_entries + 8) * 4, ctx->stream));
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs, size_t n, jpgpu_batch** out) {
+extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs, size_t n, jpgpu_batch** out) try {
     if (!ctx || !out || (!descs && n)) return JPGPU_ERR_INVALID_ARG;
     *out = nullptr;
     jpgpu_batch* b = new jpgpu_batch();
@@ -238,9 +250,9 @@ extern "C" int jpgpu_batch_create(jpgpu_ctx* ctx, const jpgpu_image_desc* descs,
     if (st != JPGPU_OK) { jpgpu_batch_destroy(b); return st; }
     *out = b;
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_batch_upload(jpgpu_batch* b) {
+extern "C" int jpgpu_batch_upload(jpgpu_batch* b) try {
     if (!b) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
@@ -251,9 +263,9 @@ extern "C" int jpgpu_batch_upload(jpgpu_batch* b) {
                            cudaMemcpyHostToDevice, ctx->stream));
     }
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_batch_set_device_scans(jpgpu_batch* b, const void* dev_base, const uint64_t* offsets) {
+extern "C" int jpgpu_batch_set_device_scans(jpgpu_batch* b, const void* dev_base, const uint64_t* offsets) try {
     if (!b || !dev_base || !offsets) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
@@ -267,26 +279,28 @@ extern "C" int jpgpu_batch_set_device_scans(jpgpu_batch* b, const void* dev_base
     CK(cudaGetLastError());
     b->launches += 1;
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_batch_set_device_output(jpgpu_batch* b, void* dev_base, size_t capacity) {
+extern "C" int jpgpu_batch_set_device_output(jpgpu_batch* b, void* dev_base, size_t capacity) try {
     if (!b) return JPGPU_ERR_INVALID_ARG;
     if (!dev_base) {
         jpgpu_ctx* ctx = b->ctx;
         CK(cudaSetDevice(ctx->device));
-        if (!b->own_rgb) {
-            int st = dev_ensure(b, jpgpu_batch::kRgb, &b->own_rgb, b->plan.rgb_bytes + 256);
-            if (st != JPGPU_OK) return st;
-        }
+        // the own arena may never have been allocated, or only for an earlier, smaller plan (replans under an external
+        // output skip it): size it for the current plan
+        int st = dev_ensure(b, jpgpu_batch::kRgb, &b->own_rgb, b->plan.rgb_bytes + 256);
+        if (st != JPGPU_OK) return st;
         b->dev.rgb = b->own_rgb;
+        b->ext_rgb_cap = 0;
         return JPGPU_OK;
     }
     if (capacity < b->plan.rgb_bytes || (reinterpret_cast<uintptr_t>(dev_base) & 255u)) return JPGPU_ERR_INVALID_ARG;
     b->dev.rgb = static_cast<uint8_t*>(dev_base);
+    b->ext_rgb_cap = capacity;
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_batch_entropy(jpgpu_batch* b) {
+extern "C" int jpgpu_batch_entropy(jpgpu_batch* b) try {
     if (!b) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
@@ -298,9 +312,9 @@ extern "C" int jpgpu_batch_entropy(jpgpu_batch* b) {
     b->launches += 6;
     CK(cudaGetLastError());
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_batch_idct(jpgpu_batch* b) {
+extern "C" int jpgpu_batch_idct(jpgpu_batch* b) try {
     if (!b) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
@@ -308,7 +322,7 @@ extern "C" int jpgpu_batch_idct(jpgpu_batch* b) {
     CK(cudaGetLastError());
     b->decoded = true;
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
 namespace {
 
@@ -342,7 +356,7 @@ int ensure_aux(jpgpu_ctx* ctx) {
 // entropy + idct.  A large batch is cut into groups of images (HostPlan::groups) whose kernel chains alternate
 // between three auxiliary streams: the low-occupancy ends of one group's kernels (repair walks, last waves) overlap
 // the next group's work.  Forked from and joined back into the context stream.
-extern "C" int jpgpu_batch_decode(jpgpu_batch* b) {
+extern "C" int jpgpu_batch_decode(jpgpu_batch* b) try {
     if (!b) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     if (b->plan.groups.size() <= 1) {
@@ -371,9 +385,9 @@ extern "C" int jpgpu_batch_decode(jpgpu_batch* b) {
     CK(cudaGetLastError());
     b->decoded = true;
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_batch_download(jpgpu_batch* b, uint8_t* const* outs) {
+extern "C" int jpgpu_batch_download(jpgpu_batch* b, uint8_t* const* outs) try {
     if (!b || !outs) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
@@ -384,13 +398,13 @@ extern "C" int jpgpu_batch_download(jpgpu_batch* b, uint8_t* const* outs) {
                            ctx->stream));
     }
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_batch_set_output_format(jpgpu_batch* b, uint32_t format) {
+extern "C" int jpgpu_batch_set_output_format(jpgpu_batch* b, uint32_t format) try {
     if (!b || format > JPGPU_OUT_RGB_PLANAR) return JPGPU_ERR_INVALID_ARG;
     b->dev.out_planar = format == JPGPU_OUT_RGB_PLANAR ? 1u : 0u;
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
 extern "C" void* jpgpu_batch_device_rgb(jpgpu_batch* b, size_t i, size_t* nbytes) {
     if (!b || i >= b->n || b->plan.status[i] != JPGPU_OK) return nullptr;
@@ -399,7 +413,17 @@ extern "C" void* jpgpu_batch_device_rgb(jpgpu_batch* b, size_t i, size_t* nbytes
     return b->dev.rgb + im.rgb_off;
 }
 
-extern "C" int jpgpu_batch_results(jpgpu_batch* b, int32_t* statuses, uint64_t* bytes_read) {
+extern "C" size_t jpgpu_batch_output_bytes(const jpgpu_batch* b) { return b ? (size_t)b->plan.rgb_bytes : 0; }
+
+extern "C" int jpgpu_batch_rgb_offset(const jpgpu_batch* b, size_t i, size_t* offset, size_t* nbytes) {
+    if (!b || i >= b->n) return JPGPU_ERR_INVALID_ARG;
+    const ImgDev& im = b->plan.imgs[i];
+    if (offset) *offset = (size_t)im.rgb_off;
+    if (nbytes) *nbytes = b->plan.status[i] == JPGPU_OK ? (size_t)im.width * im.height * 3 : 0;
+    return JPGPU_OK;
+}
+
+extern "C" int jpgpu_batch_results(jpgpu_batch* b, int32_t* statuses, uint64_t* bytes_read) try {
     if (!b) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
@@ -421,9 +445,9 @@ extern "C" int jpgpu_batch_results(jpgpu_batch* b, int32_t* statuses, uint64_t* 
         if (bytes_read) bytes_read[i] = br;
     }
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_batch_coefficients(jpgpu_batch* b, size_t i, int16_t* out, size_t cap, uint32_t nblocks[4]) {
+extern "C" int jpgpu_batch_coefficients(jpgpu_batch* b, size_t i, int16_t* out, size_t cap, uint32_t nblocks[4]) try {
     if (!b || i >= b->n || !out || !nblocks) return JPGPU_ERR_INVALID_ARG;
     if (b->plan.status[i] != JPGPU_OK) return b->plan.status[i];
     jpgpu_ctx* ctx = b->ctx;
@@ -431,14 +455,19 @@ extern "C" int jpgpu_batch_coefficients(jpgpu_batch* b, size_t i, int16_t* out, 
     const ImgDev& im = b->plan.imgs[i];
     if (cap < im.total_coefs) return JPGPU_ERR_INVALID_ARG;
     std::vector<int16_t> arena(im.total_coefs);
+    ImgDyn dyn;
     CK(cudaMemcpyAsync(arena.data(), b->dev.coefs + im.coef_off, (size_t)im.total_coefs * 2, cudaMemcpyDeviceToHost,
                        ctx->stream));
+    CK(cudaMemcpyAsync(&dyn, b->dev.dyn + i, sizeof dyn, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    // what the IDCT stage sees: blocks the decode never reached (data ended early) are zeros, whatever the reused arena holds
+    const uint64_t limit = (uint64_t)coef_block_limit(dyn) * 64;
+    if (limit < im.total_coefs) std::fill(arena.begin() + (size_t)limit, arena.end(), (int16_t)0);
     export_reference_order(im, arena.data(), out, nblocks);
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_batch_stats(jpgpu_batch* b, uint64_t stats[8]) {
+extern "C" int jpgpu_batch_stats(jpgpu_batch* b, uint64_t stats[8]) try {
     if (!b || !stats) return JPGPU_ERR_INVALID_ARG;
     const HostPlan& p = b->plan;
     stats[0] = p.tot_scan_bytes;
@@ -451,9 +480,9 @@ extern "C" int jpgpu_batch_stats(jpgpu_batch* b, uint64_t stats[8]) {
     stats[7] = p.raw_bytes + p.stream_words * 4 + p.coef_elems * 2 + p.rgb_bytes + p.sub_entries * sizeof(SubInfo);
     stats[2] = p.tot_rgb_bytes;
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
-extern "C" int jpgpu_batch_profile(jpgpu_batch* b, float ms[8]) {
+extern "C" int jpgpu_batch_profile(jpgpu_batch* b, float ms[8]) try {
     if (!b || !ms) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
@@ -477,11 +506,11 @@ extern "C" int jpgpu_batch_profile(jpgpu_batch* b, float ms[8]) {
     for (auto& e : ev) cudaEventDestroy(e);
     b->decoded = true;
     return JPGPU_OK;
-}
+} JPGPU_CATCH_ALL
 
 extern "C" uint64_t jpgpu_batch_launch_count(const jpgpu_batch* b) { return b ? b->launches : 0; }
 
-extern "C" int jpgpu_decode(jpgpu_ctx* ctx, const jpgpu_image_desc* desc, uint8_t* rgb_out, size_t* bytes_read) {
+extern "C" int jpgpu_decode(jpgpu_ctx* ctx, const jpgpu_image_desc* desc, uint8_t* rgb_out, size_t* bytes_read) try {
     if (!ctx || !desc || !rgb_out) return JPGPU_ERR_INVALID_ARG;
     int st;
     if (!ctx->single) st = jpgpu_batch_create(ctx, desc, 1, &ctx->single);
@@ -498,10 +527,10 @@ extern "C" int jpgpu_decode(jpgpu_ctx* ctx, const jpgpu_image_desc* desc, uint8_
     if (st != JPGPU_OK) return st;
     if (bytes_read) *bytes_read = (size_t)br;
     return ist;
-}
+} JPGPU_CATCH_ALL
 
 extern "C" int jpgpu_decode_file(jpgpu_ctx* ctx, const uint8_t* file, size_t len, uint32_t ext_flags, uint32_t layout,
-                                 uint8_t* rgb_out, size_t rgb_cap, uint32_t* width, uint32_t* height, size_t* bytes_read) {
+                                 uint8_t* rgb_out, size_t rgb_cap, uint32_t* width, uint32_t* height, size_t* bytes_read) try {
     if (!ctx || !file || !rgb_out) return JPGPU_ERR_INVALID_ARG;
     jpgpu_image_desc d;
     int st = jpgpu_parse(file, len, ext_flags, layout, &d);
@@ -510,4 +539,4 @@ extern "C" int jpgpu_decode_file(jpgpu_ctx* ctx, const uint8_t* file, size_t len
     if (height) *height = d.height;
     if ((size_t)d.width * d.height * 3 > rgb_cap) return JPGPU_ERR_INVALID_ARG;
     return jpgpu_decode(ctx, &d, rgb_out, bytes_read);
-}
+} JPGPU_CATCH_ALL

@@ -130,7 +130,14 @@ struct ImgDyn {
     uint32_t nseg;          // restart intervals found (RST markers + 1)
     uint32_t status;        // kSt* bits
     uint32_t bits_consumed; // bit position after the last decoded MCU -> bytes_read
+    // Without kStDone (data ended early): coefficient positions [0, coef_end) are what this decode produced; the blocks
+    // from there on were never written and read as zeros (the arenas are reused wave after wave and never cleared, so
+    // they hold an earlier image's coefficients).  See coef_block_limit().
+    uint32_t coef_end;
+    uint32_t pad[3];
 };
+// Blocks of an image the IDCT stage may read from the coefficient arena; blocks at or past it are zeros.
+JPGPU_HD uint32_t coef_block_limit(const ImgDyn& d) { return (d.status & kStDone) ? 0xffffffffu : d.coef_end >> 6; }
 
 // Synchronisation record of one subsequence j (bits [j*S, (j+1)*S) of the compacted stream).
 // A = state at the first symbol starting at or after j*S, reached from a cold start
@@ -440,10 +447,25 @@ JPGPU_HD void sync_segment(const DecCtx& cx, DecState& st, uint32_t end_bit, Seg
     r.pad[0] = r.pad[1] = 0;
 }
 
+// Coefficient positions saturate here.  The stream after an image's last MCU is still decoded by the
+// synchronisation pass (nobody knows yet where the scan ends), and a crafted file can hold far more "blocks" than its
+// header declares (1-bit EOB codes: one block per bit), so the running position over a whole stream does not fit
+// 32 bits.  Advances are never negative, so a saturating sum stays associative; the planner keeps total_coefs below
+// kPosSat, and one subsequence advances less than 2^31 - kPosSat (32768 bits x 64 positions), so a saturated position
+// is "past the scan" for every consumer and never wraps.
+constexpr int32_t kPosSat = 0x7f000000;
+JPGPU_HD int32_t sat_pos(int64_t v) { return v > (int64_t)kPosSat ? kPosSat : (int32_t)v; }
+
 // Accumulate segment / subsequence advances: a restart interval makes the values absolute.
+// DC sums wrap modulo 2^32 (they are values, never addresses).
 JPGPU_HD void fold_advance(int32_t acc[4], uint32_t& crossed, uint32_t cz, int32_t n, const int32_t dc[3]) {
-    if (cz & kCrossed) { acc[0] = n; acc[1] = dc[0]; acc[2] = dc[1]; acc[3] = dc[2]; crossed = kCrossed; }
-    else { acc[0] += n; acc[1] += dc[0]; acc[2] += dc[1]; acc[3] += dc[2]; }
+    if (cz & kCrossed) { acc[0] = sat_pos(n); acc[1] = dc[0]; acc[2] = dc[1]; acc[3] = dc[2]; crossed = kCrossed; }
+    else {
+        acc[0] = sat_pos((int64_t)acc[0] + n);
+        acc[1] = (int32_t)((uint32_t)acc[1] + (uint32_t)dc[0]);
+        acc[2] = (int32_t)((uint32_t)acc[2] + (uint32_t)dc[1]);
+        acc[3] = (int32_t)((uint32_t)acc[3] + (uint32_t)dc[2]);
+    }
 }
 
 // Decode subsequence [own, own + S) from the state in `st` (standing at A; rec.pA / rec.cz(A) set by the

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <map>
+#include <new>
 
 namespace jpgpu {
 
@@ -266,8 +267,13 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         int st = compute_geometry(d, g);
         if (st == JPGPU_OK && (d.scan == nullptr || d.scan_len < 4)) st = JPGPU_PANIC_INDEX_OOB;  // huffman.rs:127-128
         if (st == JPGPU_OK && d.scan_len > 0x1ff00000ull) st = JPGPU_ERR_UNSUPPORTED;             // bit positions are 32-bit
-        if (st == JPGPU_OK && (uint64_t)g.units * g.blocks_per_mcu * 64 > 0x7fffffffull) st = JPGPU_ERR_UNSUPPORTED;
+        if (st == JPGPU_OK && (uint64_t)g.units * g.blocks_per_mcu * 64 >= (uint64_t)kPosSat) st = JPGPU_ERR_UNSUPPORTED;   // positions saturate there (fold_advance)
         if (st == JPGPU_OK && (uint64_t)d.width * d.height * 3 > 0xffffffffull) st = JPGPU_ERR_UNSUPPORTED;   // 32-bit byte offsets inside an image's output
+        // The header's claim is tied to the bytes that came with it: no block is shorter than two bits (a 1-bit DC
+        // code and a 1-bit EOB), so a scan of scan_len bytes holds at most 4 * scan_len blocks.  A file claiming more
+        // can only end as JPGPU_ERR_TRUNCATED, and is turned away here before anything is sized by its header (a 90 KB
+        // file declaring 30001 x 30001 would otherwise reserve 10 GB of placement map, coefficients and RGB).
+        if (st == JPGPU_OK && (uint64_t)g.units * g.blocks_per_mcu > (uint64_t)d.scan_len * 4 + 8) st = JPGPU_ERR_TRUNCATED;
 
         // Huffman tables -> slots
         uint32_t slot_lut[kMaxLutSlots];
@@ -304,7 +310,8 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         uint64_t map_off = 0;
         const uint32_t map_plane = (uint32_t)align_up((uint64_t)d.width * d.height, 4);
         if (st == JPGPU_OK && !g.fused_ok) {
-            if ((uint64_t)d.width * d.height > 0x3fffffffull) st = JPGPU_ERR_UNSUPPORTED;
+            // the host-built placement map is 4 bytes per pixel and component, built pixel by pixel: 64 Mpixel at most
+            if ((uint64_t)d.width * d.height > kMaxGatherPixels) st = JPGPU_ERR_UNSUPPORTED;
             char key[64];
             const int kl = snprintf(key, sizeof key, "%u,%u,%u,%u|%u%u,%u%u,%u%u", d.width, d.height, d.ncomp, d.layout,
                                     g.h[0], g.v[0], g.h[1], g.v[1], g.h[2], g.v[2]);
@@ -721,6 +728,10 @@ extern "C" int jpgpu_parse(const uint8_t* file, size_t len, uint32_t ext, uint32
         }
     } catch (const ParseError& e) {
         return e.code;
+    } catch (const std::bad_alloc&) {   // no C++ exception crosses the C ABI
+        return JPGPU_ERR_OOM;
+    } catch (...) {
+        return JPGPU_ERR_INVALID_ARG;
     }
     return JPGPU_NO_SCAN;                                                    // mod.rs:464
 }
@@ -738,7 +749,7 @@ extern "C" int jpgpu_geometry(const jpgpu_image_desc* desc, uint32_t* mcus, uint
 
 // What the planner decides for a set of images (host only; the decisions DESIGN.md 4.2 / 4.5 describe, testable
 // without a GPU).
-extern "C" int jpgpu_plan_info(const jpgpu_image_desc* descs, size_t n, uint64_t info[8]) {
+extern "C" int jpgpu_plan_info(const jpgpu_image_desc* descs, size_t n, uint64_t info[8]) try {
     if ((!descs && n) || !info) return JPGPU_ERR_INVALID_ARG;
     HostPlan plan;
     const int st = build_plan(descs, n, plan, 0);
@@ -754,4 +765,8 @@ extern "C" int jpgpu_plan_info(const jpgpu_image_desc* descs, size_t n, uint64_t
     info[6] = plan.seqs.size();
     info[7] = plan.raw_bytes + plan.stream_words * 4 + plan.coef_elems * 2 + plan.rgb_bytes;
     return JPGPU_OK;
+} catch (const std::bad_alloc&) {
+    return JPGPU_ERR_OOM;
+} catch (...) {
+    return JPGPU_ERR_INVALID_ARG;
 }

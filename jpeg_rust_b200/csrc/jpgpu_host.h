@@ -76,6 +76,8 @@ struct HostPlan {
 uint32_t choose_subseq_bits(uint64_t total_scan_bytes);
 int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t sub_bits = 0);
 
+constexpr uint64_t kMaxGatherPixels = 1ull << 26;   // largest image the gather path (REF placement / generic sampling) takes
+
 // Placement map of the gather path: for every component plane and pixel the (arena block index << 6 | sample index)
 // whose value the layout puts there, kMapNone where nothing is written.  REF replays decoder.rs:290-312 + 347-379 on
 // indices (last writer wins, spill past the right edge included); SPEC is T.81 A.2.3 with box replication.  Returns

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "jpgpu_kernels.cuh"
 
 namespace jpgpu {
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(kPreThreads) prepass_scan_kernel(BatchDev b) {
         seg[nseg] = totc * 8u;
         ImgDyn d;
         d.stream_bits = totc * 8u; d.nseg = nseg; d.status = st; d.bits_consumed = 0u;
+        d.coef_end = 0u; d.pad[0] = d.pad[1] = d.pad[2] = 0u;
         b.dyn[img] = d;
     }
 }
@@ -939,7 +942,7 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
         }
         st.flags &= ~kCrossed;
         store_on = (st.g & 63) == 0;
-        if (st.g >= total || (st.p >= end_bit && store_on)) active = false;
+        if ((uint32_t)st.g >= (uint32_t)total || (st.p >= end_bit && store_on)) active = false;   // past the scan (or a saturated position)
     } else {
         st.p = 0; st.g = 0; st.flags = 0; st.info_ptr = cx.info_addr; st.w0 = st.w1 = st.w2 = 0; st.off = 0;
         st.seg = 0; st.seg_end = st.seg_lim = st.lim = 0; st.wrap_lim = 0xffffffffu; st.dcur = 0; st.dc_off = 0; st.lut_dc = st.lut_ac = cx.lut0_addr;
@@ -1014,6 +1017,8 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
             bits |= kStDone;
         }
         if (bits) atomicOr(&b.dyn[sd.img].status, bits);
+        // the data ended before the scan was complete: everything from the block this lane stood in is unwritten
+        if (g_start < total && st.g < total && st.p >= dyn.stream_bits) atomicMax(&b.dyn[sd.img].coef_end, (uint32_t)st.g & ~63u);
     }
 }
 
@@ -1193,10 +1198,12 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
     __shared__ __align__(16) uint8_t s_out[PLANAR ? 3 * kPlaneSize : MH * kOutPitch];
     __shared__ __align__(16) float s_qt[3 * 64];
 
-    const ImgDev& im = b.imgs[img_list[blockIdx.y]];
+    const uint32_t img_index = img_list[blockIdx.y];
+    const ImgDev& im = b.imgs[img_index];
     const uint32_t ntiles = im.tiles_x * im.tiles_y;
     uint32_t tile = blockIdx.x * kTilesPerCta;
     if (tile >= ntiles) return;
+    const uint32_t blk_limit = coef_block_limit(b.dyn[img_index]);   // an image whose data ended early: zeros from there on
     const uint32_t tile_end = min(ntiles, tile + kTilesPerCta);
     const int tid = threadIdx.x, t = tid & 7, bp = tid >> 3;
 
@@ -1256,7 +1263,7 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
         const uint32_t here = min((uint32_t)NM, mcux - tx * NM);
 #pragma unroll
         for (int l = 0; l < NL; l++) {
-            const bool valid = (uint32_t)mcu_of[l] < here && mcu0 + mcu_of[l] < units;
+            const bool valid = (uint32_t)mcu_of[l] < here && mcu0 + mcu_of[l] < units && mcu0 * NB + blk_of[l] < blk_limit;
             dst[l] = make_uint4(0u, 0u, 0u, 0u);
             if (valid) dst[l] = __ldg(coefs + ((size_t)mcu0 * NB + blk_of[l]) * 8 + t);
         }
@@ -1446,10 +1453,11 @@ __global__ void __launch_bounds__(kIdctThreads) block_idct_kernel(BatchDev b, co
     const uint32_t blk = blockIdx.x * 16u + bp;
     if (blockIdx.x * 16u >= nblk) return;
     const bool valid = blk < nblk;
+    const bool written = blk < coef_block_limit(b.dyn[img_list[blockIdx.y]]);
     const uint32_t comp = valid ? im.blk_comp[blk % im.blocks_per_mcu] : 0u;
     const float* __restrict__ qt = b.qt + im.qt_off[comp] + t * 8;
     uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-    if (valid) raw = __ldg(reinterpret_cast<const uint4*>(b.coefs + im.coef_off) + (size_t)blk * 8 + t);
+    if (valid && written) raw = __ldg(reinterpret_cast<const uint4*>(b.coefs + im.coef_off) + (size_t)blk * 8 + t);
     float o[8];
     block_idct(raw, __ldg(reinterpret_cast<const float4*>(qt)), __ldg(reinterpret_cast<const float4*>(qt + 4)), t,
                s_scr + bp * kScrBlkPitch + t, s_scr + bp * kScrBlkPitch + t * kScrRowPitch, comp == 0u ? 128.0f : 0.0f, o);
@@ -1525,16 +1533,31 @@ __global__ void __launch_bounds__(kGatherThreads) gather_colour_kernel(BatchDev 
 }
 
 // ===================================================================== launchers
+// Kernels that take the image from blockIdx.y are launched in slices of at most kMaxGridY images (grid.y <= 65535).
+constexpr uint32_t kMaxGridY = 65535;
+template <class F>
+static void for_image_slices(const BatchDev& b, F&& launch) {
+    for (uint32_t i0 = 0; i0 < b.n_images; i0 += kMaxGridY) {
+        BatchDev d = b;
+        d.img0 = b.img0 + i0;
+        d.n_images = min(kMaxGridY, b.n_images - i0);
+        launch(d);
+    }
+}
 void launch_prepass_step(const BatchDev& b, cudaStream_t s, int step) {
     if (!b.n_images || !b.max_chunks) return;
-    const dim3 grid(b.max_chunks, b.n_images);
-    if (step == 0) prepass_count_kernel<<<grid, kPreThreads, 0, s>>>(b);
-    else if (step == 1) prepass_scan_kernel<<<b.n_images, kPreThreads, 0, s>>>(b);
-    else prepass_write_kernel<<<grid, kPreThreads, 0, s>>>(b);
+    if (step == 1) { prepass_scan_kernel<<<b.n_images, kPreThreads, 0, s>>>(b); return; }
+    for_image_slices(b, [&](const BatchDev& d) {
+        const dim3 grid(d.max_chunks, d.n_images);
+        if (step == 0) prepass_count_kernel<<<grid, kPreThreads, 0, s>>>(d);
+        else prepass_write_kernel<<<grid, kPreThreads, 0, s>>>(d);
+    });
 }
 void launch_gather_scans(const BatchDev& b, const void* base, const uint64_t* dev_offs, cudaStream_t s) {
     if (!b.n_images || !b.max_chunks) return;
-    gather_scans_kernel<<<dim3(b.max_chunks, b.n_images), kPreThreads, 0, s>>>(b, static_cast<const uint8_t*>(base), dev_offs);
+    for_image_slices(b, [&](const BatchDev& d) {
+        gather_scans_kernel<<<dim3(d.max_chunks, d.n_images), kPreThreads, 0, s>>>(d, static_cast<const uint8_t*>(base), dev_offs);
+    });
 }
 void launch_prepass(const BatchDev& b, cudaStream_t s) {
     for (int step = 0; step < 3; step++) launch_prepass_step(b, s, step);
@@ -1548,14 +1571,21 @@ void launch_verify_scan(const BatchDev& b, cudaStream_t s) {
 template <int NBUF, int PHASE>
 static cudaError_t launch_write_variant(const BatchDev& b, cudaStream_t s) {
     const WriteLayout lay = write_layout(b.max_slots, NBUF);
-    static uint32_t configured[64] = {0};   // the opt-in shared-memory size is a per-device attribute of the kernel
+    // The opt-in shared-memory size is a per-device attribute of the kernel: set once per device to what the largest
+    // layout needs.  Contexts of several devices decode from several host threads (jpgpu_multi_*), hence the lock.
+    static std::mutex mu;
+    static uint64_t configured = 0;   // bit d: device d is set up
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64 || lay.total > configured[dev]) {
-        e = cudaFuncSetAttribute(decode_write_kernel<NBUF, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) configured[dev] = lay.total;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 0 || dev >= 64 || !(configured >> dev & 1u)) {
+            e = cudaFuncSetAttribute(decode_write_kernel<NBUF, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)write_layout(kMaxLutSlots, NBUF).total);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) configured |= 1ull << dev;
+        }
     }
     const uint32_t jobs = b.n_seqs << b.wp_shift;   // n_seqs is a multiple of kWriteJobsPerCta (build_plan)
     decode_write_kernel<NBUF, PHASE><<<(jobs + kWriteJobsPerCta - 1) / kWriteJobsPerCta, kWriteThreads, lay.total, s>>>(b);
@@ -1572,29 +1602,34 @@ int launch_idct_colour(const BatchDev& b, cudaStream_t s) {
     int launches = 0;
     for (int k = 0; k < kNumKinds; k++) {
         if (!b.kind_count[k] || !b.kind_max_tiles[k]) continue;
-        dim3 grid((b.kind_max_tiles[k] + kTilesPerCta - 1) / kTilesPerCta, b.kind_count[k]);
-#define JPGPU_LAUNCH_IDCT(HY, VY, GRAY)                                                                          \
-    do {                                                                                                        \
-        if (b.out_planar) idct_colour_kernel<HY, VY, GRAY, true><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]);  \
-        else idct_colour_kernel<HY, VY, GRAY, false><<<grid, kIdctThreads, 0, s>>>(b, b.kind_imgs[k]);          \
+        for (uint32_t i0 = 0; i0 < b.kind_count[k]; i0 += kMaxGridY) {
+            const dim3 grid((b.kind_max_tiles[k] + kTilesPerCta - 1) / kTilesPerCta, min(kMaxGridY, b.kind_count[k] - i0));
+            const uint32_t* list = b.kind_imgs[k] + i0;
+#define JPGPU_LAUNCH_IDCT(HY, VY, GRAY)                                                                 \
+    do {                                                                                               \
+        if (b.out_planar) idct_colour_kernel<HY, VY, GRAY, true><<<grid, kIdctThreads, 0, s>>>(b, list);  \
+        else idct_colour_kernel<HY, VY, GRAY, false><<<grid, kIdctThreads, 0, s>>>(b, list);          \
     } while (0)
-        switch (k) {
-            case kKindGray: JPGPU_LAUNCH_IDCT(1, 1, true); break;
-            case kKind444: JPGPU_LAUNCH_IDCT(1, 1, false); break;
-            case kKind422: JPGPU_LAUNCH_IDCT(2, 1, false); break;
-            case kKind420: JPGPU_LAUNCH_IDCT(2, 2, false); break;
-            case kKind440: JPGPU_LAUNCH_IDCT(1, 2, false); break;
-            default: continue;
-        }
+            switch (k) {
+                case kKindGray: JPGPU_LAUNCH_IDCT(1, 1, true); break;
+                case kKind444: JPGPU_LAUNCH_IDCT(1, 1, false); break;
+                case kKind422: JPGPU_LAUNCH_IDCT(2, 1, false); break;
+                case kKind420: JPGPU_LAUNCH_IDCT(2, 2, false); break;
+                case kKind440: JPGPU_LAUNCH_IDCT(1, 2, false); break;
+                default: continue;
+            }
 #undef JPGPU_LAUNCH_IDCT
-        launches++;
+            launches++;
+        }
     }
-    if (b.kind_count[kKindGeneric] && b.gather_max_blocks) {
-        dim3 ga((b.gather_max_blocks + 15) / 16, b.kind_count[kKindGeneric]);
-        block_idct_kernel<<<ga, kIdctThreads, 0, s>>>(b, b.kind_imgs[kKindGeneric]);
-        dim3 gb((b.gather_max_quads + kGatherThreads - 1) / kGatherThreads, b.kind_count[kKindGeneric]);
-        gather_colour_kernel<<<gb, kGatherThreads, 0, s>>>(b, b.kind_imgs[kKindGeneric]);
-        launches += 2;
+    if (b.gather_max_blocks) {
+        for (uint32_t i0 = 0; i0 < b.kind_count[kKindGeneric]; i0 += kMaxGridY) {
+            const uint32_t cnt = min(kMaxGridY, b.kind_count[kKindGeneric] - i0);
+            const uint32_t* list = b.kind_imgs[kKindGeneric] + i0;
+            block_idct_kernel<<<dim3((b.gather_max_blocks + 15) / 16, cnt), kIdctThreads, 0, s>>>(b, list);
+            gather_colour_kernel<<<dim3((b.gather_max_quads + kGatherThreads - 1) / kGatherThreads, cnt), kGatherThreads, 0, s>>>(b, list);
+            launches += 2;
+        }
     }
     return launches;
 }

@@ -410,15 +410,14 @@ class Batch:
         return self
 
     def output_bytes(self):
-        """Bytes one wave of RGB output occupies (images at 256-byte aligned offsets)."""
-        p_last, nb = self.device_rgb(self.n - 1)
-        p_first, _ = self.device_rgb(0)
-        return (p_last - p_first) + (nb + 255) // 256 * 256
+        """Bytes one wave of RGB output occupies (images at 256-byte aligned offsets; failed images take none)."""
+        return int(_ffi.lib().jpgpu_batch_output_bytes(self._h))
 
     def rgb_offset(self, i):
-        p_i, nb = self.device_rgb(i)
-        p_0, _ = self.device_rgb(0)
-        return p_i - p_0, nb
+        """(offset of image i inside the wave's output arena, its size in bytes; size 0 for a failed image)."""
+        off, nb = C.c_size_t(0), C.c_size_t(0)
+        _check(_ffi.lib().jpgpu_batch_rgb_offset(self._h, i, C.byref(off), C.byref(nb)), "jpgpu_batch_rgb_offset")
+        return off.value, nb.value
 
     def device_tensor(self, i):
         """Zero-copy torch view of image i's RGB output in device memory: uint8, (H, W, 3) or, with
@@ -511,7 +510,7 @@ def decode_waves(files, wave, ext=EXT_NONE, layout=LAYOUT_SPEC, device=0):
         else:
             batch.replan(descs=arr, keepalive=bufs)
         batch.parse_status = pstat[i0:i0 + wave]
-        nbytes = batch.output_bytes() if any(s == 0 for s in batch.parse_status) else 0
+        nbytes = batch.output_bytes()
         batch.set_device_output(base + off, max(nbytes, 256))
         batch.upload().decode()
         st, br = batch.results()

@@ -112,3 +112,18 @@ def synth_corpus(count, width, height, subsampling="420", quality=85, restart_in
     with ThreadPoolExecutor(threads) as ex:
         return list(ex.map(lambda i: synth_jpeg(first_index + i, width, height, subsampling, quality,
                                                 restart_interval, noise_sigma), range(count)))
+
+
+def crafted_flood_jpeg(scan_bytes, width=8, height=8):
+    """A hand-made gray baseline JPEG whose header declares `width` x `height` but whose scan goes on for `scan_bytes`
+    zero bytes: with a 1-bit DC code (size 0) and a 1-bit EOB every two bits are one more "block", so the running
+    coefficient position of anything that decodes the whole stream exceeds 2^31 beyond 8.39 MB (the
+    position must saturate).  The declared blocks decode to 128-gray; the rest is trailing garbage a decoder ignores."""
+    def seg(marker, payload):
+        return bytes([0xFF, marker]) + (len(payload) + 2).to_bytes(2, "big") + payload
+    dqt = seg(0xDB, bytes([0]) + bytes([1] * 64))
+    sof = seg(0xC0, bytes([8]) + height.to_bytes(2, "big") + width.to_bytes(2, "big") + bytes([1, 1, 0x11, 0]))
+    dht_dc = seg(0xC4, bytes([0x00]) + bytes([1] + [0] * 15) + bytes([0]))        # one code "0": size category 0
+    dht_ac = seg(0xC4, bytes([0x10]) + bytes([1] + [0] * 15) + bytes([0x00]))     # one code "0": EOB
+    sos = seg(0xDA, bytes([1, 1, 0x00, 0, 63, 0]))
+    return b"\xff\xd8" + dqt + sof + dht_dc + dht_ac + sos + bytes(scan_bytes) + b"\xff\xd9"

@@ -295,6 +295,8 @@ void sim_decode_write(SimBatch& sb, const SeqDesc& sd, uint32_t group) {
             uint32_t bits = l.st.flags & (kStBadCode | kStDcSize | kStRestart);
             if (l.g_start < total && l.st.g >= total) { sb.dyn[sd.img].bits_consumed = l.st.p; bits |= kStDone; }
             sb.dyn[sd.img].status |= bits;
+            if (l.g_start < total && l.st.g < total && l.st.p >= dyn.stream_bits)
+                sb.dyn[sd.img].coef_end = std::max(sb.dyn[sd.img].coef_end, (uint32_t)l.st.g & ~63u);
         }
     }
 }
@@ -332,19 +334,21 @@ void sim_idct_colour(SimBatch& sb, size_t img) {
     uint8_t* rgb = sb.rgb.data() + im.rgb_off;
     const float* qt = sb.plan.qt.data();
     const uint32_t W = im.width, H = im.height;
+    const uint32_t blk_limit = coef_block_limit(sb.dyn[img]);
     for (uint32_t my = 0; my < im.mcuy; my++)
         for (uint32_t mx = 0; mx < im.mcux; mx++) {
             const uint32_t mcu = my * im.mcux + mx;
             const bool valid = mcu < im.units;
+            auto ok = [&](uint32_t blk) { return valid && blk < blk_limit; };
             float cb[64], cr[64];
             if (!gray) {
-                sim_block_idct(coefs + ((size_t)mcu * NB + NY) * 64, valid, qt + im.qt_off[1], 0.0f, cb);
-                sim_block_idct(coefs + ((size_t)mcu * NB + NY + 1) * 64, valid, qt + im.qt_off[2], 0.0f, cr);
+                sim_block_idct(coefs + ((size_t)mcu * NB + NY) * 64, ok(mcu * NB + NY), qt + im.qt_off[1], 0.0f, cb);
+                sim_block_idct(coefs + ((size_t)mcu * NB + NY + 1) * 64, ok(mcu * NB + NY + 1), qt + im.qt_off[2], 0.0f, cr);
             }
             for (int sub = 0; sub < NY; sub++) {
                 const int by = sub / HY, bx = sub % HY;
                 float y[64];
-                sim_block_idct(coefs + ((size_t)mcu * NB + sub) * 64, valid, qt + im.qt_off[0], 128.0f, y);
+                sim_block_idct(coefs + ((size_t)mcu * NB + sub) * 64, ok(mcu * NB + sub), qt + im.qt_off[0], 128.0f, y);
                 for (int t = 0; t < 8; t++)
                     for (int x = 0; x < 8; x++) {
                         const uint32_t px = (mx * HY + bx) * 8 + x, py = (my * VY + by) * 8 + t;
@@ -373,7 +377,7 @@ void sim_gather(SimBatch& sb, size_t img) {
     std::vector<float> smp((size_t)nblk * 64);
     for (uint32_t blk = 0; blk < nblk; blk++) {
         const int comp = im.blk_comp[blk % im.blocks_per_mcu];
-        sim_block_idct(coefs + (size_t)blk * 64, true, qt + im.qt_off[comp], comp == 0 ? 128.0f : 0.0f, smp.data() + (size_t)blk * 64);
+        sim_block_idct(coefs + (size_t)blk * 64, blk < coef_block_limit(sb.dyn[img]), qt + im.qt_off[comp], comp == 0 ? 128.0f : 0.0f, smp.data() + (size_t)blk * 64);
     }
     const uint32_t* map = sb.plan.gmap.data() + im.map_off;
     uint8_t* rgb = sb.rgb.data() + im.rgb_off;

@@ -469,3 +469,171 @@ def test_randomised_batches(env, monkeypatch):
         for a, g in zip(b.coefficients(i), gts[i]):
             assert np.array_equal(a[:len(g)], g[:len(a)]), i
     b.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The path bench.py times: jpgpu_batch_decode of >= 192 images = three image groups on three auxiliary streams with the
+# planner's own subsequence / look-back choice (the largest batch under -m gpu used to be 120
+# images = one group on one stream).
+
+def _grouped_batch_check(files, gts, expect_groups, oracle_every):
+    from jpeg_rust_b200 import plan_info
+    info = plan_info(files, layout=LAYOUT_SPEC)
+    assert info["groups"] == expect_groups, info
+    b = Batch(files, layout=LAYOUT_SPEC)
+    b.upload().decode()
+    outs = b.download()
+    statuses, br = b.results()
+    assert all(s == 0 for s in statuses)
+    for i, f in enumerate(files):
+        got = b.coefficients(i)
+        for a, w in zip(got, gts[i]):
+            assert np.array_equal(a[:len(w)], w[:len(a)]), f"image {i}: coefficients differ from the encoder's"
+    worst = (0, 0.0)
+    for i in range(0, len(files), oracle_every):
+        o = O.decode(files[i], layout=LAYOUT_SPEC)
+        assert br[i] == o.bytes_read
+        m = assert_samples(outs[i], o.rgb, f"image {i}")
+        worst = (max(worst[0], m[0]), max(worst[1], m[1]))
+    b.close()
+    return info, worst
+
+
+def test_three_group_decode_of_a_mixed_corpus():
+    """208 images of mixed size and sampling (>= 192: three groups, default planner): every image's coefficients against
+    the encoder's, every 13th image's samples against the oracle."""
+    subs = ["420", "444", "422", "gray", "440"]
+    made = [synth.synth_jpeg(3000 + i, 96 + 16 * (i % 11), 64 + 8 * (i % 7), subs[i % 5], want_coefs=True) for i in range(208)]
+    info, worst = _grouped_batch_check([m[0] for m in made], [m[1] for m in made], 3, 13)
+    print("208 mixed images, 3 groups:", info, "max/mean |delta|:", worst)
+
+
+def test_three_group_decode_of_1024_small_images():
+    """1024 small 4:2:0 images through the three-group path (the benchmark's image count)."""
+    made = [synth.synth_jpeg(4000 + i, 64 + 16 * (i % 4), 48 + 16 * (i % 3), "420", want_coefs=True) for i in range(64)]
+    files = [made[i % 64][0] for i in range(1024)]
+    gts = [made[i % 64][1] for i in range(1024)]
+    info, worst = _grouped_batch_check(files, gts, 3, 97)
+    print("1024 small images, 3 groups:", info, "max/mean |delta|:", worst)
+
+
+def test_benchmark_planner_settings_on_full_size_images():
+    """256 x 1080p 4:2:0 (16 distinct): three groups, 4096-bit subsequences - and the same images with the planner
+    forced to what it picks for the 1024-image benchmark batch (8192-bit subsequences, 1024 bits of look-back, three
+    groups).  All coefficients against the encoder's; four images against the oracle."""
+    import os
+    made = [synth.synth_jpeg(5000 + i, 1920, 1080, "420", want_coefs=True) for i in range(16)]
+    files = [made[i % 16][0] for i in range(256)]
+    gts = [made[i % 16][1] for i in range(256)]
+    info, worst = _grouped_batch_check(files, gts, 3, 64)
+    print("256 x 1080p default plan:", info, worst)
+    keep = {k: os.environ.get(k) for k in ("JPGPU_SUBSEQ_BITS", "JPGPU_LOOKBACK_BITS", "JPGPU_GROUPS")}
+    os.environ.update(JPGPU_SUBSEQ_BITS="8192", JPGPU_LOOKBACK_BITS="1024", JPGPU_GROUPS="3")
+    try:
+        info, worst = _grouped_batch_check(files, gts, 3, 64)
+        assert info["sub_bits"] == 8192 and info["lookback_bits"] == 1024
+        print("256 x 1080p benchmark plan:", info, worst)
+    finally:
+        for k, v in keep.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_jpegdecoder_builder_decodes_on_the_gpu():
+    """the reference's builder sequence (mod.rs:388-415 / decoder.rs:55-162) on the Python mirror -
+    JPEGDecoder.new(raw).frame_header(..).scan_header(..).dimensions(..), the three table setters, .decode() - must give
+    what JPEGImage.parse gives for the same file, and what the oracle gives."""
+    from jpeg_rust_b200.jpeg import (FrameComponentHeader, FrameHeader, HuffmanTable, JPEGDecoder, ScanComponentHeader,
+                                     ScanHeader, parse_descriptor)
+    for name, ext in (("lena.jpeg", EXT_NONE), ("lena-bw.jpeg", EXT_NONE), ("2x2-chroma.jpeg", EXT_NONE)):
+        data = fixture_bytes(name)
+        st, d, buf = parse_descriptor(data, ext, LAYOUT_REF)
+        assert st == 0
+        raw = np.ctypeslib.as_array((_ffi.C.c_uint8 * d.scan_len).from_address(d.scan)).copy()
+        fh = FrameHeader(8, d.height, d.width, d.ncomp,
+                         [FrameComponentHeader(d.comp[c].id, d.comp[c].h, d.comp[c].v, d.comp[c].tq) for c in range(d.ncomp)])
+        sh = ScanHeader(d.ncomp, [ScanComponentHeader(d.comp[c].id, d.comp[c].td, d.comp[c].ta) for c in range(d.ncomp)])
+        dec = JPEGDecoder.new(raw, layout=LAYOUT_REF).frame_header(fh).scan_header(sh).dimensions((d.width, d.height))
+        for t in range(4):
+            if d.ac_present[t]:
+                dec.huffman_ac_tables(t, HuffmanTable.from_size_data_tables(bytes(d.ac_bits[t]), bytes(d.ac_vals[t][:d.ac_nvals[t]])))
+            if d.dc_present[t]:
+                dec.huffman_dc_tables(t, HuffmanTable.from_size_data_tables(bytes(d.dc_bits[t]), bytes(d.dc_vals[t][:d.dc_nvals[t]])))
+            if d.qt_present[t]:
+                dec.quantization_table(t, list(d.qt[t]))
+        pixels, bytes_read = dec.decode()
+        img = JPEGImage.parse(data, ext=ext, layout=LAYOUT_REF)
+        o = O.decode(data, layout=LAYOUT_REF, ext=ext)
+        assert pixels.shape == (d.width * d.height, 3)
+        assert np.array_equal(pixels, img.image_data()) and bytes_read == img.bytes_read == o.bytes_read
+        assert_samples(pixels.reshape(d.height, d.width, 3), o.rgb, name)
+
+
+def test_position_saturates_on_a_flooded_scan():
+    """see tests/test_sim_parity.py; 8.5 MB and 17 MB of zeros behind an 8x8 image, next to good
+    images in the same batch.  No wild store, the declared block decodes, the neighbours are untouched."""
+    good = synth.synth_jpeg(601, 64, 64, "420")
+    files = [good, synth.crafted_flood_jpeg(8_500_000), good, synth.crafted_flood_jpeg(17_000_000), good]
+    outs, statuses, br, coefs, _ = run_batch(files)
+    assert statuses == [0, 0, 0, 0, 0]
+    assert br[1] == 1 and br[3] == 1 and (outs[1] == 128).all() and (outs[3] == 128).all()
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[0], outs[4])
+    assert_samples(outs[0], O.decode(good, layout=LAYOUT_SPEC).rgb)
+
+
+def test_truncated_image_reads_as_zeros_past_its_data():
+    """Arenas are reused wave after wave and never cleared: an image whose data ends early must not show the previous
+    wave's coefficients in the blocks it never reached.  Decode a full image, then - same batch
+    object, same shape - its truncated twin: the tail is mid-gray (all-zero blocks), twice the same bytes."""
+    full = synth.synth_jpeg(7001, 256, 256, "420")
+    other = synth.synth_jpeg(7002, 256, 256, "420")
+    cut = other[:len(other) * 2 // 3]
+    b = Batch([full], layout=LAYOUT_SPEC)
+    b.upload().decode()
+    ref_full = b.download()[0].copy()
+    b.ctx.sync()
+    runs = []
+    for _ in range(2):
+        b.replan([cut])
+        b.upload().decode()
+        out = b.download()[0].copy()
+        st, _ = b.results()
+        assert st[0] == _ffi.ERR_TRUNCATED
+        runs.append(out)
+        b.replan([full])
+        b.upload().decode()
+        b.results()
+    assert np.array_equal(runs[0], runs[1])
+    assert (runs[0][-16:] == 128).all(), "rows past the end of the data must come from zero blocks"
+    assert not np.array_equal(runs[0][-16:], ref_full[-16:])
+    b.close()
+
+
+def test_replan_under_an_external_output_arena():
+    """a replan to a larger plan while a caller-owned output arena is set falls back to the
+    batch's own arena, sized for the new plan; restoring the own arena after that never leaves it too small."""
+    import torch
+    small = [synth.synth_jpeg(7100, 64, 64, "420")]
+    big = [synth.synth_jpeg(7101 + i, 640, 480, "420") for i in range(3)]
+    b = Batch(small, layout=LAYOUT_SPEC)
+    arena = torch.empty(b.output_bytes() + 256, dtype=torch.uint8, device="cuda")
+    base = (arena.data_ptr() + 255) // 256 * 256
+    b.set_device_output(base, b.output_bytes())
+    b.upload().decode()
+    assert b.device_rgb(0)[0] == base
+    b.replan(big)                      # does not fit the caller's arena any more
+    assert b.device_rgb(0)[0] != base
+    b.upload().decode()
+    outs = b.download()
+    statuses, _ = b.results()
+    assert all(s == 0 for s in statuses)
+    b.set_device_output(None, 0)
+    b.upload().decode()
+    outs2 = b.download()
+    b.results()
+    for a, c, f in zip(outs, outs2, big):
+        assert np.array_equal(a, c)
+        assert_samples(a, O.decode(f, layout=LAYOUT_SPEC).rgb)
+    b.close()

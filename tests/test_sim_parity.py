@@ -287,3 +287,28 @@ def test_randomised_configurations(monkeypatch):
         assert rs[0].status == 0, (it, seed, w, h, sub, ri, q, sb)
         for a, g in zip(rs[0].coefs, gt):
             assert np.array_equal(a, g), (it, seed, w, h, sub, ri, q, sb)
+
+
+def test_position_saturates_on_a_flooded_scan():
+    """an 8x8 image with 1-bit DC/EOB codes followed by > 8.39 MB of zero scan bytes takes the
+    running coefficient position of the synchronisation pass past 2^31.  The position saturates (fold_advance), the
+    declared block decodes, the flood behind it is ignored."""
+    flood = synth.crafted_flood_jpeg(8_500_000)
+    good = synth.synth_jpeg(601, 64, 64, "420")
+    rs, _ = S.decode_batch([good, flood, good])
+    assert [r.status for r in rs] == [0, 0, 0]
+    assert rs[1].bytes_read == 1 and (rs[1].rgb == 128).all()
+    assert np.array_equal(rs[0].rgb, rs[2].rgb)
+
+
+def test_header_claim_is_tied_to_the_scan_bytes():
+    """a small file whose SOF0 declares 30001 x 30001 must not make the planner size anything
+    by its header (10 GB of placement map on the REF gather path): it cannot hold that many blocks and is turned away
+    as truncated at plan time."""
+    import time
+    f = bytearray(synth.synth_jpeg(602, 64, 64, "420"))
+    sof = bytes(f).index(b"\xff\xc0")
+    f[sof + 5:sof + 9] = (30001).to_bytes(2, "big") + (30001).to_bytes(2, "big")
+    t0 = time.time()
+    rs, _ = S.decode_batch([bytes(f)], layout=0)
+    assert rs[0].status == 37 and time.time() - t0 < 2.0     # JPGPU_ERR_TRUNCATED, without the 10 GB detour
