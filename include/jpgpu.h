@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define JPGPU_ABI_VERSION 1
+#define JPGPU_ABI_VERSION 2
 
 /* ------------------------------------------------------------------ statuses
  * 0 = success.  1..15 mirror the panics of the reference so that a host shim
@@ -141,6 +141,9 @@ int jpgpu_geometry(const jpgpu_image_desc *desc, uint32_t *mcus, uint32_t *block
 int jpgpu_plan_info(const jpgpu_image_desc *descs, size_t n, uint64_t info[8]);
 
 const char *jpgpu_status_string(int status);
+/* The literal part of the reference's own panic message for statuses 1..15 (e.g. "got to restart interval def",
+ * mod.rs:427), NULL otherwise: what a strict drop-in shim hands to panic!() (rust/src/jpeg/ffi.rs). */
+const char *jpgpu_panic_message(int status);
 int jpgpu_abi_version(void);
 
 /* ------------------------------------------------------------- device part */
@@ -217,6 +220,74 @@ int jpgpu_batch_stats(jpgpu_batch *b, uint64_t stats[8]);
 int jpgpu_batch_profile(jpgpu_batch *b, float ms[8]);
 /* Number of kernel launches enqueued by this batch object so far. */
 uint64_t jpgpu_batch_launch_count(const jpgpu_batch *b);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Transfers as single copies, and the host-to-host pipeline (the step before and after the path). */
+
+/* The cudaStream_t the context enqueues on. */
+void *jpgpu_stream(const jpgpu_ctx *ctx);
+/* Like jpgpu_batch_upload, for scans that all lie in ONE readable host buffer [host_base, host_base + host_bytes) -
+ * the files of the batch back to back, ideally pinned: one host->device copy of the used span, then one kernel that
+ * spreads it into the batch's raw arena. */
+int jpgpu_batch_upload_from(jpgpu_batch *b, const void *host_base, size_t host_bytes);
+/* Like jpgpu_batch_download, as ONE device->host copy of the whole output arena: image i lands at
+ * host_base + jpgpu_batch_rgb_offset(i).  capacity >= jpgpu_batch_output_bytes(). */
+int jpgpu_batch_download_contiguous(jpgpu_batch *b, void *host_base, size_t capacity);
+
+/* Host buffers in, host buffers out, for many files at once: the images are cut into chunks of `chunk_images`
+ * (0 = default) that alternate between two stream sets of `device`, so that the upload of one chunk, the kernels of
+ * another and the download of a third overlap; every transfer is a single copy.  Plans and arenas are made at creation;
+ * jpgpu_pipeline_run only enqueues.  The descriptors (tables, sizes, scan pointers) are fixed at creation, so a second
+ * run decodes whatever those scan pointers hold then. */
+typedef struct jpgpu_pipeline jpgpu_pipeline;
+int jpgpu_pipeline_create(int device, const jpgpu_image_desc *descs, size_t n, size_t chunk_images, jpgpu_pipeline **out);
+void jpgpu_pipeline_destroy(jpgpu_pipeline *p);
+/* Size of the host output buffer, and where image i lies in it (nbytes = W*H*3, 0 for an image that failed to plan). */
+size_t jpgpu_pipeline_output_bytes(const jpgpu_pipeline *p);
+int jpgpu_pipeline_image_offset(const jpgpu_pipeline *p, size_t i, size_t *offset, size_t *nbytes);
+/* Enqueue the whole job (asynchronous).  Every descs[i].scan must lie inside [host_in, host_in + host_in_bytes). */
+int jpgpu_pipeline_run(jpgpu_pipeline *p, const void *host_in, size_t host_in_bytes, void *host_out, size_t host_out_bytes);
+int jpgpu_pipeline_sync(jpgpu_pipeline *p);
+/* Device time of the last run, first upload to last download (CUDA events).  Synchronises. */
+int jpgpu_pipeline_elapsed_ms(jpgpu_pipeline *p, float *ms);
+int jpgpu_pipeline_results(jpgpu_pipeline *p, int32_t *statuses, uint64_t *bytes_read);
+uint64_t jpgpu_pipeline_launch_count(const jpgpu_pipeline *p);
+const char *jpgpu_pipeline_last_error(const jpgpu_pipeline *p);
+/* One synchronous call: create, run, results, destroy.  out_offsets[i] (may be NULL) receives image i's offset in host_out;
+ * host_out_bytes must cover the sum of all W*H*3 rounded up to 256 per image and per chunk (n * 256 + sum is enough). */
+int jpgpu_decode_batch_host(int device, const jpgpu_image_desc *descs, size_t n, const void *host_in, size_t host_in_bytes,
+                            void *host_out, size_t host_out_bytes, size_t *out_offsets, int32_t *statuses, uint64_t *bytes_read);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * One process, several devices (SURVEY.md 8(b) "jpgpu_create(device_ids*, n_devices)", 8(e)).  The batch is cut into
+ * contiguous image ranges of about equal scan bytes, one per device; every device has its own context, stream set,
+ * batch object and host worker thread.  No collective, no peer traffic: the decode has no cross-image step. */
+enum { JPGPU_MEMORY_HOST = 0, JPGPU_MEMORY_DEVICE = 1 };
+typedef struct jpgpu_multi jpgpu_multi;
+int jpgpu_multi_create(const int *devices, int n_devices, jpgpu_multi **out);
+void jpgpu_multi_destroy(jpgpu_multi *m);
+int jpgpu_multi_device_count(const jpgpu_multi *m);
+/* Host only (needs no GPU): the partition jpgpu_multi_plan uses - n images into `parts` contiguous ranges of about equal
+ * scan bytes; range k is first[k] .. first[k+1], `first` has parts + 1 entries. */
+int jpgpu_partition(const jpgpu_image_desc *descs, size_t n, size_t parts, size_t *first);
+int jpgpu_multi_plan(jpgpu_multi *m, const jpgpu_image_desc *descs, size_t n);
+/* Range k: the CUDA device it runs on and its images [first, first + count). */
+int jpgpu_multi_range(const jpgpu_multi *m, int k, int *device, size_t *first, size_t *count);
+int jpgpu_multi_upload(jpgpu_multi *m);
+int jpgpu_multi_decode(jpgpu_multi *m);       /* enqueues on every device; jpgpu_multi_sync waits */
+int jpgpu_multi_sync(jpgpu_multi *m);
+int jpgpu_multi_set_output_format(jpgpu_multi *m, uint32_t format);
+int jpgpu_multi_download(jpgpu_multi *m, uint8_t *const *outs);
+int jpgpu_multi_results(jpgpu_multi *m, int32_t *statuses, uint64_t *bytes_read);
+/* Device pointer of image i's output and the CUDA device it lives on. */
+void *jpgpu_multi_device_rgb(jpgpu_multi *m, size_t i, int *device, size_t *nbytes);
+int jpgpu_multi_coefficients(jpgpu_multi *m, size_t i, int16_t *out, size_t cap, uint32_t nblocks[4]);
+uint64_t jpgpu_multi_launch_count(const jpgpu_multi *m);
+/* `steps` decodes on every device, all released together; ms[k] = device time of range k's steps (CUDA events). */
+int jpgpu_multi_time_decode(jpgpu_multi *m, int steps, float *ms);
+/* Plan + upload + decode (+ download to outs[i] for JPGPU_MEMORY_HOST) + results in one synchronous call. */
+int jpgpu_multi_decode_batch(jpgpu_multi *m, const jpgpu_image_desc *descs, size_t n, uint8_t *const *outs,
+                             int32_t *statuses, uint64_t *bytes_read, uint32_t memory_kind);
 
 #ifdef __cplusplus
 }

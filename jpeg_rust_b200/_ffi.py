@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libjpgpu.so")
 LAYOUT_REF, LAYOUT_SPEC = 0, 1
 EXT_NONE, EXT_SKIP_APPN, EXT_DRI = 0, 1, 2
 OUT_RGB_INTERLEAVED, OUT_RGB_PLANAR = 0, 1
+MEMORY_HOST, MEMORY_DEVICE = 0, 1
 
 OK = 0
 PANIC_UNHANDLED_MARKER, PANIC_DRI, PANIC_APP12_14, PANIC_DQT_PRECISION = 1, 2, 3, 4
@@ -65,6 +66,8 @@ def lib():
         L.jpgpu_abi_version.restype = C.c_int
         L.jpgpu_status_string.restype = C.c_char_p
         L.jpgpu_status_string.argtypes = [C.c_int]
+        L.jpgpu_panic_message.restype = C.c_char_p
+        L.jpgpu_panic_message.argtypes = [C.c_int]
         L.jpgpu_parse.argtypes = [vp, sz, C.c_uint32, C.c_uint32, C.POINTER(ImageDesc)]
         L.jpgpu_geometry.argtypes = [C.POINTER(ImageDesc), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                      C.POINTER(C.c_uint32)]
@@ -100,6 +103,46 @@ def lib():
         L.jpgpu_batch_profile.argtypes = [vp, C.POINTER(C.c_float)]
         L.jpgpu_batch_launch_count.restype = C.c_uint64
         L.jpgpu_batch_launch_count.argtypes = [vp]
+        L.jpgpu_stream.restype = vp
+        L.jpgpu_stream.argtypes = [vp]
+        L.jpgpu_batch_upload_from.argtypes = [vp, vp, sz]
+        L.jpgpu_batch_download_contiguous.argtypes = [vp, vp, sz]
+        L.jpgpu_pipeline_create.argtypes = [C.c_int, C.POINTER(ImageDesc), sz, sz, C.POINTER(vp)]
+        L.jpgpu_pipeline_destroy.argtypes = [vp]
+        L.jpgpu_pipeline_destroy.restype = None
+        L.jpgpu_pipeline_output_bytes.restype = sz
+        L.jpgpu_pipeline_output_bytes.argtypes = [vp]
+        L.jpgpu_pipeline_image_offset.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz)]
+        L.jpgpu_pipeline_run.argtypes = [vp, vp, sz, vp, sz]
+        L.jpgpu_pipeline_sync.argtypes = [vp]
+        L.jpgpu_pipeline_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.jpgpu_pipeline_results.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+        L.jpgpu_pipeline_launch_count.restype = C.c_uint64
+        L.jpgpu_pipeline_launch_count.argtypes = [vp]
+        L.jpgpu_pipeline_last_error.restype = C.c_char_p
+        L.jpgpu_pipeline_last_error.argtypes = [vp]
+        L.jpgpu_decode_batch_host.argtypes = [C.c_int, C.POINTER(ImageDesc), sz, vp, sz, vp, sz, C.POINTER(sz),
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+        L.jpgpu_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+        L.jpgpu_multi_destroy.argtypes = [vp]
+        L.jpgpu_multi_destroy.restype = None
+        L.jpgpu_multi_device_count.argtypes = [vp]
+        L.jpgpu_partition.argtypes = [C.POINTER(ImageDesc), sz, sz, C.POINTER(sz)]
+        L.jpgpu_multi_plan.argtypes = [vp, C.POINTER(ImageDesc), sz]
+        L.jpgpu_multi_range.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(sz), C.POINTER(sz)]
+        for name in ("upload", "decode", "sync"):
+            getattr(L, "jpgpu_multi_" + name).argtypes = [vp]
+        L.jpgpu_multi_set_output_format.argtypes = [vp, C.c_uint32]
+        L.jpgpu_multi_download.argtypes = [vp, C.POINTER(vp)]
+        L.jpgpu_multi_results.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+        L.jpgpu_multi_device_rgb.restype = vp
+        L.jpgpu_multi_device_rgb.argtypes = [vp, sz, C.POINTER(C.c_int), C.POINTER(sz)]
+        L.jpgpu_multi_coefficients.argtypes = [vp, sz, vp, sz, C.POINTER(C.c_uint32)]
+        L.jpgpu_multi_launch_count.restype = C.c_uint64
+        L.jpgpu_multi_launch_count.argtypes = [vp]
+        L.jpgpu_multi_time_decode.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+        L.jpgpu_multi_decode_batch.argtypes = [vp, C.POINTER(ImageDesc), sz, C.POINTER(vp), C.POINTER(C.c_int32),
+                                               C.POINTER(C.c_uint64), C.c_uint32]
         _lib = L
     return _lib
 
@@ -114,7 +157,7 @@ def check(status, what=""):
 
 
 EXPORTED_SYMBOLS = [
-    "jpgpu_parse", "jpgpu_geometry", "jpgpu_status_string", "jpgpu_abi_version",
+    "jpgpu_parse", "jpgpu_geometry", "jpgpu_status_string", "jpgpu_panic_message", "jpgpu_abi_version",
     "jpgpu_plan_info",
     "jpgpu_create", "jpgpu_destroy", "jpgpu_last_error", "jpgpu_set_stream", "jpgpu_sync",
     "jpgpu_decode", "jpgpu_decode_file",
@@ -123,4 +166,12 @@ EXPORTED_SYMBOLS = [
     "jpgpu_batch_entropy", "jpgpu_batch_idct", "jpgpu_batch_decode", "jpgpu_batch_download",
     "jpgpu_batch_device_rgb", "jpgpu_batch_output_bytes", "jpgpu_batch_rgb_offset", "jpgpu_batch_results", "jpgpu_batch_coefficients", "jpgpu_batch_stats",
     "jpgpu_batch_profile", "jpgpu_batch_launch_count",
+    "jpgpu_stream", "jpgpu_batch_upload_from", "jpgpu_batch_download_contiguous",
+    "jpgpu_pipeline_create", "jpgpu_pipeline_destroy", "jpgpu_pipeline_output_bytes", "jpgpu_pipeline_image_offset",
+    "jpgpu_pipeline_run", "jpgpu_pipeline_sync", "jpgpu_pipeline_elapsed_ms", "jpgpu_pipeline_results",
+    "jpgpu_pipeline_launch_count", "jpgpu_pipeline_last_error", "jpgpu_decode_batch_host",
+    "jpgpu_multi_create", "jpgpu_multi_destroy", "jpgpu_multi_device_count", "jpgpu_partition", "jpgpu_multi_plan", "jpgpu_multi_range",
+    "jpgpu_multi_upload", "jpgpu_multi_decode", "jpgpu_multi_sync", "jpgpu_multi_set_output_format", "jpgpu_multi_download",
+    "jpgpu_multi_results", "jpgpu_multi_device_rgb", "jpgpu_multi_coefficients", "jpgpu_multi_launch_count",
+    "jpgpu_multi_time_decode", "jpgpu_multi_decode_batch",
 ]

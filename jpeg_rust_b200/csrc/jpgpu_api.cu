@@ -2,6 +2,7 @@
 // planning on the device, stage launches, transfers.  There is no CPU fallback:
 // without a usable sm_100 device every entry point returns JPGPU_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -41,10 +42,11 @@ struct jpgpu_batch {
     HostPlan plan;
     std::vector<const uint8_t*> host_scan;
     std::vector<size_t> host_scan_len;
+    std::vector<uint64_t> scan_offs;   // jpgpu_batch_upload_from(): where each scan lies in the staging arena
     BatchDev dev;
     struct Arena { void* p = nullptr; size_t cap = 0; };
     enum { kImgs, kSeqs, kLuts, kQt, kKind0, kGmap = kKind0 + kNumKinds, kSamples, kRaw, kDyn, kStream, kSegtab, kSubs, kSegs, kChunks, kCoefs,
-           kRgb, kScanOffs, kNumArenas };
+           kRgb, kScanOffs, kStage, kNumArenas };
     Arena arena[kNumArenas];   // device allocations, grown on demand by jpgpu_batch_replan()
     uint64_t launches = 0;
     size_t coef_bytes = 0;
@@ -147,6 +149,8 @@ extern "C" int jpgpu_set_stream(jpgpu_ctx* c, void* s) try {
     c->own_stream = false;
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
+
+extern "C" void* jpgpu_stream(const jpgpu_ctx* c) { return c ? reinterpret_cast<void*>(c->stream) : nullptr; }
 
 extern "C" int jpgpu_sync(jpgpu_ctx* ctx) try {
     if (!ctx) return JPGPU_ERR_INVALID_ARG;
@@ -278,6 +282,54 @@ extern "C" int jpgpu_batch_set_device_scans(jpgpu_batch* b, const void* dev_base
     launch_gather_scans(b->dev, dev_base, dev_offs, ctx->stream);
     CK(cudaGetLastError());
     b->launches += 1;
+    return JPGPU_OK;
+} JPGPU_CATCH_ALL
+
+// One host->device copy for the whole batch: all scans lie in one readable host range, so the used
+// span goes over PCIe as ONE transfer into a staging arena and one kernel spreads it into the raw arena (per-image
+// copies cost ~2 us of launch each and 1024 of them keep the copy engine far from its rate).
+extern "C" int jpgpu_batch_upload_from(jpgpu_batch* b, const void* host_base, size_t host_bytes) try {
+    if (!b || !host_base) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (!b->n) return JPGPU_OK;
+    const uint8_t* base = static_cast<const uint8_t*>(host_base);
+    size_t lo = SIZE_MAX, hi = 0;
+    for (size_t i = 0; i < b->n; i++) {
+        if (b->plan.status[i] != JPGPU_OK) continue;
+        if (b->host_scan[i] < base) return JPGPU_ERR_INVALID_ARG;
+        const size_t o = (size_t)(b->host_scan[i] - base);
+        if (o > host_bytes || b->host_scan_len[i] > host_bytes - o) return JPGPU_ERR_INVALID_ARG;
+        lo = std::min(lo, o);
+        hi = std::max(hi, o + b->host_scan_len[i]);
+    }
+    if (lo >= hi) return JPGPU_OK;   // no decodable image
+    lo &= ~(size_t)15;                // keeps every scan's alignment relative to the staging arena
+    uint8_t* stage = nullptr;
+    int st = dev_ensure(b, jpgpu_batch::kStage, &stage, hi - lo + 64);
+    if (st != JPGPU_OK) return st;
+    uint64_t* dev_offs = nullptr;
+    st = dev_ensure(b, jpgpu_batch::kScanOffs, &dev_offs, b->n);
+    if (st != JPGPU_OK) return st;
+    b->scan_offs.resize(b->n);
+    for (size_t i = 0; i < b->n; i++)
+        b->scan_offs[i] = b->plan.status[i] == JPGPU_OK ? (uint64_t)(b->host_scan[i] - base) - lo : 0;
+    CK(cudaMemcpyAsync(stage, base + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dev_offs, b->scan_offs.data(), b->n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    launch_gather_scans(b->dev, stage, dev_offs, ctx->stream);
+    CK(cudaGetLastError());
+    b->launches += 1;
+    return JPGPU_OK;
+} JPGPU_CATCH_ALL
+
+// One device->host copy of the whole output arena: image i lands at host_base + jpgpu_batch_rgb_offset(i), the
+// layout the device arena has (256-byte aligned slices).
+extern "C" int jpgpu_batch_download_contiguous(jpgpu_batch* b, void* host_base, size_t capacity) try {
+    if (!b || !host_base) return JPGPU_ERR_INVALID_ARG;
+    if (capacity < b->plan.rgb_bytes) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (b->plan.rgb_bytes) CK(cudaMemcpyAsync(host_base, b->dev.rgb, b->plan.rgb_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
 
@@ -539,4 +591,146 @@ extern "C" int jpgpu_decode_file(jpgpu_ctx* ctx, const uint8_t* file, size_t len
     if (height) *height = d.height;
     if ((size_t)d.width * d.height * 3 > rgb_cap) return JPGPU_ERR_INVALID_ARG;
     return jpgpu_decode(ctx, &d, rgb_out, bytes_read);
+} JPGPU_CATCH_ALL
+
+
+// ====================================================================================================================
+// Host buffers in, host buffers out (the reference-facing call for many files: what mod.rs:415 would
+// call per image, for a whole directory at once).  The images are cut into chunks that alternate between two stream
+// sets: the upload of one chunk, the kernels of another and the download of a third overlap, every transfer is one
+// cudaMemcpyAsync.  Plans and device arenas are made once at creation; a run only enqueues work.
+struct jpgpu_pipeline {
+    int device = 0;
+    jpgpu_ctx* ctx[2] = {nullptr, nullptr};
+    std::vector<jpgpu_batch*> chunks;
+    std::vector<size_t> first;        // first image of every chunk (+ n at the end)
+    std::vector<size_t> out_off;      // where every chunk's output arena lies in the caller's host buffer (+ total)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
+    bool ran = false;
+};
+
+extern "C" void jpgpu_pipeline_destroy(jpgpu_pipeline* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (jpgpu_batch* b : p->chunks) jpgpu_batch_destroy(b);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->ev_mid) cudaEventDestroy(p->ev_mid);
+    for (jpgpu_ctx* c : p->ctx) jpgpu_destroy(c);
+    delete p;
+}
+
+extern "C" int jpgpu_pipeline_create(int device, const jpgpu_image_desc* descs, size_t n, size_t chunk_images, jpgpu_pipeline** out) try {
+    if (!out || (!descs && n)) return JPGPU_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (chunk_images == 0) chunk_images = 64;
+    jpgpu_pipeline* p = new jpgpu_pipeline();
+    p->device = device;
+    int st = JPGPU_OK;
+    for (int k = 0; k < 2 && st == JPGPU_OK; k++) st = jpgpu_create(device, &p->ctx[k]);
+    size_t off = 0;
+    for (size_t i0 = 0; i0 < n && st == JPGPU_OK; i0 += chunk_images) {
+        const size_t m = std::min(chunk_images, n - i0);
+        jpgpu_batch* b = nullptr;
+        st = jpgpu_batch_create(p->ctx[p->chunks.size() & 1], descs + i0, m, &b);
+        if (st != JPGPU_OK) break;
+        p->first.push_back(i0);
+        p->out_off.push_back(off);
+        off += (jpgpu_batch_output_bytes(b) + 255) & ~(size_t)255;
+        p->chunks.push_back(b);
+    }
+    p->first.push_back(n);
+    p->out_off.push_back(off);
+    if (st == JPGPU_OK && (cudaEventCreate(&p->ev0) != cudaSuccess || cudaEventCreate(&p->ev1) != cudaSuccess ||
+                           cudaEventCreateWithFlags(&p->ev_mid, cudaEventDisableTiming) != cudaSuccess))
+        st = JPGPU_ERR_CUDA;
+    if (st != JPGPU_OK) { jpgpu_pipeline_destroy(p); return st; }
+    *out = p;
+    return JPGPU_OK;
+} JPGPU_CATCH_ALL
+
+extern "C" size_t jpgpu_pipeline_output_bytes(const jpgpu_pipeline* p) { return p ? p->out_off.back() : 0; }
+
+extern "C" int jpgpu_pipeline_image_offset(const jpgpu_pipeline* p, size_t i, size_t* offset, size_t* nbytes) {
+    if (!p || i >= p->first.back()) return JPGPU_ERR_INVALID_ARG;
+    const size_t c = (size_t)(std::upper_bound(p->first.begin(), p->first.end(), i) - p->first.begin()) - 1;
+    size_t o = 0, nb = 0;
+    const int st = jpgpu_batch_rgb_offset(p->chunks[c], i - p->first[c], &o, &nb);
+    if (offset) *offset = p->out_off[c] + o;
+    if (nbytes) *nbytes = nb;
+    return st;
+}
+
+// Enqueues the whole job: per chunk one upload (all its scans lie in [host_in, host_in + host_in_bytes)), the decode,
+// one download to host_out + its chunk offset.  Asynchronous; jpgpu_pipeline_sync() waits.
+extern "C" int jpgpu_pipeline_run(jpgpu_pipeline* p, const void* host_in, size_t host_in_bytes, void* host_out, size_t host_out_bytes) try {
+    if (!p || !host_in || !host_out || host_out_bytes < p->out_off.back()) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = p->ctx[0];
+    CK(cudaSetDevice(p->device));
+    // both stream sets start together and end together, so that ev0..ev1 brackets the job on the device
+    CK(cudaEventRecord(p->ev0, p->ctx[0]->stream));
+    CK(cudaStreamWaitEvent(p->ctx[1]->stream, p->ev0, 0));
+    for (size_t c = 0; c < p->chunks.size(); c++) {
+        jpgpu_batch* b = p->chunks[c];
+        int st = jpgpu_batch_upload_from(b, host_in, host_in_bytes);
+        if (st == JPGPU_OK) st = jpgpu_batch_decode(b);
+        if (st == JPGPU_OK) st = jpgpu_batch_download_contiguous(b, static_cast<uint8_t*>(host_out) + p->out_off[c], p->out_off[c + 1] - p->out_off[c]);
+        if (st != JPGPU_OK) { ctx->err = p->ctx[c & 1]->err; return st; }
+    }
+    CK(cudaEventRecord(p->ev_mid, p->ctx[1]->stream));
+    CK(cudaStreamWaitEvent(p->ctx[0]->stream, p->ev_mid, 0));
+    CK(cudaEventRecord(p->ev1, p->ctx[0]->stream));
+    p->ran = true;
+    return JPGPU_OK;
+} JPGPU_CATCH_ALL
+
+extern "C" int jpgpu_pipeline_sync(jpgpu_pipeline* p) try {
+    if (!p) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = p->ctx[0];
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->ctx[1]->stream));
+    CK(cudaStreamSynchronize(p->ctx[0]->stream));
+    return JPGPU_OK;
+} JPGPU_CATCH_ALL
+
+// Device time of the last run in milliseconds (first upload enqueued .. last download finished). Synchronises.
+extern "C" int jpgpu_pipeline_elapsed_ms(jpgpu_pipeline* p, float* ms) try {
+    if (!p || !ms || !p->ran) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = p->ctx[0];
+    int st = jpgpu_pipeline_sync(p);
+    if (st != JPGPU_OK) return st;
+    CK(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return JPGPU_OK;
+} JPGPU_CATCH_ALL
+
+extern "C" int jpgpu_pipeline_results(jpgpu_pipeline* p, int32_t* statuses, uint64_t* bytes_read) try {
+    if (!p) return JPGPU_ERR_INVALID_ARG;
+    for (size_t c = 0; c < p->chunks.size(); c++) {
+        const int st = jpgpu_batch_results(p->chunks[c], statuses ? statuses + p->first[c] : nullptr, bytes_read ? bytes_read + p->first[c] : nullptr);
+        if (st != JPGPU_OK) return st;
+    }
+    return JPGPU_OK;
+} JPGPU_CATCH_ALL
+
+extern "C" uint64_t jpgpu_pipeline_launch_count(const jpgpu_pipeline* p) {
+    uint64_t n = 0;
+    if (p) for (const jpgpu_batch* b : p->chunks) n += b->launches;
+    return n;
+}
+
+extern "C" const char* jpgpu_pipeline_last_error(const jpgpu_pipeline* p) { return p && p->ctx[0] ? p->ctx[0]->err.c_str() : "null pipeline"; }
+
+// One call: host files in, host pixels out (the SURVEY 8(b) proposal's jpgpu_decode_batch with memory_kind HOST on one device).
+extern "C" int jpgpu_decode_batch_host(int device, const jpgpu_image_desc* descs, size_t n, const void* host_in, size_t host_in_bytes,
+                                       void* host_out, size_t host_out_bytes, size_t* out_offsets, int32_t* statuses, uint64_t* bytes_read) try {
+    jpgpu_pipeline* p = nullptr;
+    int st = jpgpu_pipeline_create(device, descs, n, 0, &p);
+    if (st != JPGPU_OK) return st;
+    st = jpgpu_pipeline_run(p, host_in, host_in_bytes, host_out, host_out_bytes);
+    if (st == JPGPU_OK) st = jpgpu_pipeline_results(p, statuses, bytes_read);   // synchronises the chunk streams
+    if (st == JPGPU_OK) st = jpgpu_pipeline_sync(p);
+    if (st == JPGPU_OK && out_offsets)
+        for (size_t i = 0; i < n; i++) jpgpu_pipeline_image_offset(p, i, &out_offsets[i], nullptr);
+    jpgpu_pipeline_destroy(p);
+    return st;
 } JPGPU_CATCH_ALL

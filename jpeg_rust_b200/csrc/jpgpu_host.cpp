@@ -581,6 +581,29 @@ extern "C" const char* jpgpu_status_string(int s) {
     }
 }
 
+// The reference's own panic text for statuses 1..15 (the literal part of its message, without formatted arguments):
+// what a strict drop-in shim passes to panic!() so that callers and tests matching on the message see what they saw
+// before.  NULL for statuses that are not reference panics.
+extern "C" const char* jpgpu_panic_message(int s) {
+    switch (s) {
+        case JPGPU_PANIC_UNHANDLED_MARKER: return "Unhandled byte marker";                                   // mod.rs:457
+        case JPGPU_PANIC_DRI: return "got to restart interval def";                                          // mod.rs:427
+        case JPGPU_PANIC_APP12_14: return "got ApplicationSegment";                                          // mod.rs:446,449 ("got {:?}")
+        case JPGPU_PANIC_DQT_PRECISION: return "Unknown precision of quantization table";                    // mod.rs:258
+        case JPGPU_PANIC_SAMPLING_ASSERT: return "assertion failed: horizontal_sampling_factor > 0";         // mod.rs:275-277
+        case JPGPU_PANIC_INDEX_OOB: return "index out of bounds";
+        case JPGPU_PANIC_NO_FRAME_HEADER: return "called `Option::unwrap()` on a `None` value";             // mod.rs:388
+        case JPGPU_PANIC_MISSING_TABLE: return "Did not find quantization table for";                        // decoder.rs:224 (155,159: unwrap on None)
+        case JPGPU_PANIC_DC_LOOKUP: return "called `Option::unwrap()` on a `None` value";                   // huffman.rs:156
+        case JPGPU_PANIC_AC_LOOKUP: return "ILLEGAL STATE!";                                                 // huffman.rs:162
+        case JPGPU_PANIC_COMPONENT_COUNT: return "asd";                                                      // decoder.rs:330
+        case JPGPU_PANIC_READ_BITS_ASSERT: return "Should not read more than 16 bits at a time!";            // huffman.rs:202
+        case JPGPU_PANIC_SCAN_COMPONENT: return "called `Option::unwrap()` on a `None` value";              // decoder.rs:148
+        case JPGPU_PANIC_ARITH: return "attempt to subtract with overflow";                                  // mod.rs:218 (debug build)
+        default: return nullptr;
+    }
+}
+
 // JPEGImage::parse, mod.rs:202-414 — marker walk up to (not including) decode().
 extern "C" int jpgpu_parse(const uint8_t* file, size_t len, uint32_t ext, uint32_t layout, jpgpu_image_desc* out) {
     if (!file || !out) return JPGPU_ERR_INVALID_ARG;

@@ -836,7 +836,7 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
     int32_t run[4] = {0, 0, 0, 0};
     for (uint32_t k = 0; k < tid; k++) {  // exclusive prefix over the preceding chunks
         if (s_agg[k][4]) { run[0] = s_agg[k][0]; run[1] = s_agg[k][1]; run[2] = s_agg[k][2]; run[3] = s_agg[k][3]; }
-        else { run[0] += s_agg[k][0]; run[1] += s_agg[k][1]; run[2] += s_agg[k][2]; run[3] += s_agg[k][3]; }
+        else { run[0] = sat_pos((int64_t)run[0] + s_agg[k][0]); run[1] += s_agg[k][1]; run[2] += s_agg[k][2]; run[3] += s_agg[k][3]; }
     }
     for (uint32_t jj = lo; jj < hi; jj++) {
         SubInfo s = subs[jj];

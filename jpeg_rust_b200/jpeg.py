@@ -385,6 +385,16 @@ class Batch:
         self.ctx._ck(_ffi.lib().jpgpu_batch_download(self._h, ptrs), "jpgpu_batch_download")
         return outs
 
+    def upload_from(self, buf):
+        """All scans lie in the one host buffer `buf` (numpy uint8, ideally pinned): a single host->device copy."""
+        self.ctx._ck(_ffi.lib().jpgpu_batch_upload_from(self._h, buf.ctypes.data, buf.size), "jpgpu_batch_upload_from")
+        return self
+
+    def download_contiguous(self, out):
+        """One device->host copy of the whole output arena into `out` (numpy uint8 of output_bytes()); image i at rgb_offset(i)."""
+        self.ctx._ck(_ffi.lib().jpgpu_batch_download_contiguous(self._h, out.ctypes.data, out.size), "jpgpu_batch_download_contiguous")
+        return self
+
     def download_ptrs(self, ptrs):
         arr = (C.c_void_p * self.n)(*[int(p) for p in ptrs])
         self.ctx._ck(_ffi.lib().jpgpu_batch_download(self._h, arr), "jpgpu_batch_download")
@@ -467,6 +477,224 @@ class Batch:
     def close(self):
         if self._h:
             _ffi.lib().jpgpu_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pack_files(files, pinned=True):
+    """The files of a batch back to back (64-byte aligned) in ONE host buffer - pinned if torch with CUDA is there -
+    so that the library moves them with one copy (jpgpu_batch_upload_from / jpgpu_pipeline_run).
+    Returns (uint8 numpy view of the buffer, offsets, object that owns the memory)."""
+    sizes = [len(f) for f in files]
+    offs = np.zeros(len(files) + 1, np.int64)
+    offs[1:] = np.cumsum([(s + 63) // 64 * 64 for s in sizes])
+    owner = None
+    if pinned:
+        try:
+            import torch
+            owner = torch.empty(max(int(offs[-1]), 64), dtype=torch.uint8).pin_memory()
+            buf = owner.numpy()
+        except Exception:
+            owner = None
+    if owner is None:
+        owner = buf = np.empty(max(int(offs[-1]), 64), np.uint8)
+    for i, f in enumerate(files):
+        buf[offs[i]:offs[i] + sizes[i]] = np.frombuffer(f, np.uint8)
+    return buf, offs, owner
+
+
+def parse_packed(buf, offs, sizes, ext=EXT_NONE, layout=LAYOUT_SPEC):
+    """jpgpu_parse on every file of a packed buffer: (ImageDesc array pointing into buf, parse statuses)."""
+    n = len(sizes)
+    descs = (_ffi.ImageDesc * n)()
+    statuses = []
+    for i in range(n):
+        st, d, _ = parse_descriptor(buf[offs[i]:offs[i] + sizes[i]], ext, layout)
+        descs[i] = d
+        statuses.append(st)
+    return descs, statuses
+
+
+class Pipeline:
+    """Host files in, host pixels out through jpgpu_pipeline_* (chunks alternating between two stream sets; every
+    transfer one copy).  `files` are packed into one pinned buffer; the output is one pinned buffer, image i at
+    `offset(i)`."""
+
+    def __init__(self, files=None, ext=EXT_NONE, layout=LAYOUT_SPEC, device=0, chunk=0, packed=None, descs=None):
+        import torch
+        L = _ffi.lib()
+        if packed is None:
+            self.buf, self.offs, self._owner = pack_files(files)
+            self.descs, self.parse_status = parse_packed(self.buf, self.offs, [len(f) for f in files], ext, layout)
+        else:   # (buf, owner, descs): already packed and parsed by the caller
+            self.buf, self._owner = packed
+            self.descs = descs
+            self.parse_status = [0] * len(descs)
+        self.n = len(self.descs)
+        self.device = device
+        self._h = C.c_void_p()
+        _check(L.jpgpu_pipeline_create(device, self.descs, self.n, chunk, C.byref(self._h)), "jpgpu_pipeline_create")
+        self.out_bytes = int(L.jpgpu_pipeline_output_bytes(self._h))
+        self._out_owner = torch.empty(max(self.out_bytes, 256), dtype=torch.uint8).pin_memory()
+        self.out = self._out_owner.numpy()
+
+    def _ck(self, st, what):
+        if st in (_ffi.ERR_CUDA, _ffi.ERR_OOM):
+            what += " " + _ffi.lib().jpgpu_pipeline_last_error(self._h).decode()
+        _check(st, what)
+
+    def run(self):
+        self._ck(_ffi.lib().jpgpu_pipeline_run(self._h, self.buf.ctypes.data, self.buf.size, self.out.ctypes.data, self.out.size),
+                 "jpgpu_pipeline_run")
+        return self
+
+    def sync(self):
+        self._ck(_ffi.lib().jpgpu_pipeline_sync(self._h), "jpgpu_pipeline_sync")
+        return self
+
+    def elapsed_ms(self):
+        ms = C.c_float(0)
+        self._ck(_ffi.lib().jpgpu_pipeline_elapsed_ms(self._h, C.byref(ms)), "jpgpu_pipeline_elapsed_ms")
+        return float(ms.value)
+
+    def offset(self, i):
+        off, nb = C.c_size_t(0), C.c_size_t(0)
+        _check(_ffi.lib().jpgpu_pipeline_image_offset(self._h, i, C.byref(off), C.byref(nb)))
+        return off.value, nb.value
+
+    def image(self, i):
+        off, nb = self.offset(i)
+        d = self.descs[i]
+        return self.out[off:off + nb].reshape(d.height, d.width, 3)
+
+    def results(self):
+        st = (C.c_int32 * self.n)()
+        br = (C.c_uint64 * self.n)()
+        self._ck(_ffi.lib().jpgpu_pipeline_results(self._h, st, br), "jpgpu_pipeline_results")
+        return [self.parse_status[i] if self.parse_status[i] else st[i] for i in range(self.n)], list(br)
+
+    def launch_count(self):
+        return int(_ffi.lib().jpgpu_pipeline_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            _ffi.lib().jpgpu_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiDevice:
+    """One process, several GPUs (jpgpu_multi_*): contiguous image ranges of about equal scan bytes, one per device,
+    each with its own context, streams and worker thread; no communication between devices."""
+
+    def __init__(self, devices):
+        devs = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p()
+        _check(_ffi.lib().jpgpu_multi_create(devs, len(devices), C.byref(self._h)), "jpgpu_multi_create")
+        self.devices = list(devices)
+        self.n = 0
+        self._keep = None
+
+    def plan(self, files=None, descs=None, ext=EXT_NONE, layout=LAYOUT_SPEC, keepalive=None):
+        if descs is None:
+            self._keep = []
+            descs = (_ffi.ImageDesc * len(files))()
+            self.parse_status = []
+            for i, f in enumerate(files):
+                st, d, buf = parse_descriptor(f, ext, layout)
+                descs[i] = d
+                self.parse_status.append(st)
+                self._keep.append(buf)
+        else:
+            self._keep = keepalive
+            self.parse_status = [0] * len(descs)
+        self.descs = descs
+        self.n = len(descs)
+        _check(_ffi.lib().jpgpu_multi_plan(self._h, descs, self.n), "jpgpu_multi_plan")
+        return self
+
+    def ranges(self):
+        out = []
+        for k in range(len(self.devices)):
+            dev, first, count = C.c_int(0), C.c_size_t(0), C.c_size_t(0)
+            _check(_ffi.lib().jpgpu_multi_range(self._h, k, C.byref(dev), C.byref(first), C.byref(count)))
+            out.append((dev.value, first.value, count.value))
+        return out
+
+    def upload(self):
+        _check(_ffi.lib().jpgpu_multi_upload(self._h), "jpgpu_multi_upload")
+        return self
+
+    def decode(self):
+        _check(_ffi.lib().jpgpu_multi_decode(self._h), "jpgpu_multi_decode")
+        return self
+
+    def sync(self):
+        _check(_ffi.lib().jpgpu_multi_sync(self._h), "jpgpu_multi_sync")
+        return self
+
+    def download(self):
+        outs = [np.empty((self.descs[i].height, self.descs[i].width, 3), np.uint8) for i in range(self.n)]
+        ptrs = (C.c_void_p * self.n)(*[o.ctypes.data for o in outs])
+        _check(_ffi.lib().jpgpu_multi_download(self._h, ptrs), "jpgpu_multi_download")
+        return outs
+
+    def results(self):
+        st = (C.c_int32 * self.n)()
+        br = (C.c_uint64 * self.n)()
+        _check(_ffi.lib().jpgpu_multi_results(self._h, st, br), "jpgpu_multi_results")
+        return [self.parse_status[i] if self.parse_status[i] else st[i] for i in range(self.n)], list(br)
+
+    def coefficients(self, i):
+        d = self.descs[i]
+        cap = ((d.width + 15) // 16 + 1) * ((d.height + 15) // 16 + 1) * 12 * 64
+        out = np.zeros(cap, np.int16)
+        nb = (C.c_uint32 * 4)()
+        _check(_ffi.lib().jpgpu_multi_coefficients(self._h, i, out.ctypes.data, cap, nb), "jpgpu_multi_coefficients")
+        comps, off = [], 0
+        for c in range(d.ncomp):
+            comps.append(out[off:off + nb[c] * 64].reshape(-1, 64).copy())
+            off += nb[c] * 64
+        return comps
+
+    def time_decode(self, steps):
+        ms = (C.c_float * len(self.devices))()
+        _check(_ffi.lib().jpgpu_multi_time_decode(self._h, steps, ms), "jpgpu_multi_time_decode")
+        return [float(x) for x in ms]
+
+    def launch_count(self):
+        return int(_ffi.lib().jpgpu_multi_launch_count(self._h))
+
+    def decode_batch(self, files, ext=EXT_NONE, layout=LAYOUT_SPEC):
+        """jpgpu_multi_decode_batch with host output: (list of HxWx3 arrays, statuses, bytes_read)."""
+        bufs, pst = [], []
+        descs = (_ffi.ImageDesc * len(files))()
+        for i, f in enumerate(files):
+            st, d, buf = parse_descriptor(f, ext, layout)
+            descs[i] = d
+            pst.append(st)
+            bufs.append(buf)
+        n = len(files)
+        outs = [np.zeros((max(1, descs[i].height), max(1, descs[i].width), 3), np.uint8) for i in range(n)]
+        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        st = (C.c_int32 * n)()
+        br = (C.c_uint64 * n)()
+        _check(_ffi.lib().jpgpu_multi_decode_batch(self._h, descs, n, ptrs, st, br, _ffi.MEMORY_HOST), "jpgpu_multi_decode_batch")
+        return outs, [pst[i] if pst[i] else st[i] for i in range(n)], list(br)
+
+    def close(self):
+        if self._h:
+            _ffi.lib().jpgpu_multi_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported():
 
 def test_abi_version_and_status_strings():
     L = _ffi.lib()
-    assert L.jpgpu_abi_version() == 1
+    assert L.jpgpu_abi_version() == 2
     assert "restart interval" in _ffi.status_string(_ffi.PANIC_DRI)
     assert "no CPU fallback" in _ffi.status_string(_ffi.ERR_NO_DEVICE)
 
@@ -67,3 +67,33 @@ def test_decode_fails_loudly_without_a_gpu():
     with pytest.raises(JpgpuError) as e:
         JPEGImage.parse(fixture_bytes("lena.jpeg"))
     assert e.value.status == _ffi.ERR_NO_DEVICE
+
+
+def test_c_consumer_builds_and_fails_cleanly_without_a_gpu():
+    """tests/c/abi_smoke.c: plain C against include/jpgpu.h + libjpgpu.so (what a cgo / JNI / Rust binding does).
+    It must build with gcc alone; without a GPU it stops at jpgpu_create with JPGPU_ERR_NO_DEVICE - no CPU fallback."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "c", "abi_smoke")
+    subprocess.check_call(["make", "-s", "-C", ROOT, "tests/c/abi_smoke"])
+    assert os.path.exists(exe)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "fixtures", "lena.jpeg")], capture_output=True, text=True)
+        assert r.returncode == 33 and "no usable CUDA device" in r.stderr
+
+
+def test_panic_messages_are_the_references_own():
+    L = _ffi.lib()
+    assert L.jpgpu_panic_message(_ffi.PANIC_DRI) == b"got to restart interval def"            # mod.rs:427
+    assert L.jpgpu_panic_message(_ffi.PANIC_AC_LOOKUP) == b"ILLEGAL STATE!"                   # huffman.rs:162
+    assert L.jpgpu_panic_message(_ffi.PANIC_READ_BITS_ASSERT) == b"Should not read more than 16 bits at a time!"
+    assert L.jpgpu_panic_message(_ffi.PANIC_COMPONENT_COUNT) == b"asd"                        # decoder.rs:330
+    assert L.jpgpu_panic_message(_ffi.PANIC_DQT_PRECISION) == b"Unknown precision of quantization table"
+    assert L.jpgpu_panic_message(_ffi.OK) is None and L.jpgpu_panic_message(_ffi.ERR_TRUNCATED) is None
+    for s in range(1, 16):
+        if s != _ffi.NO_SCAN:
+            assert L.jpgpu_panic_message(s), s

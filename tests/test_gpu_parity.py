@@ -637,3 +637,104 @@ def test_replan_under_an_external_output_arena():
         assert np.array_equal(a, c)
         assert_samples(a, O.decode(f, layout=LAYOUT_SPEC).rgb)
     b.close()
+
+
+def test_pipeline_host_to_host_matches_the_batch_path():
+    """jpgpu_pipeline_* (SURVEY 8(f) row 3): files in one pinned buffer in, pixels in one pinned buffer out, chunks
+    alternating between two stream sets, every transfer a single copy - byte-identical to upload/decode/download."""
+    from jpeg_rust_b200 import Pipeline
+    subs = ["420", "444", "422", "gray"]
+    files = [synth.synth_jpeg(7200 + i, 80 + 16 * (i % 5), 56 + 8 * (i % 3), subs[i % 4]) for i in range(23)]
+    files[7] = files[7][:len(files[7]) // 2]
+    ref, ref_st, ref_br = run_batch(files)[:3]
+    p = Pipeline(files, chunk=5)
+    for _ in range(2):            # a second run on the same plans gives the same bytes
+        p.run().sync()
+        st, br = p.results()
+        assert st == ref_st and st[7] != 0
+        for i in range(len(files)):
+            if st[i] == 0:
+                assert br[i] == ref_br[i]
+                assert np.array_equal(p.image(i), ref[i]), i
+    assert p.elapsed_ms() > 0 and p.launch_count() > 0
+    p.close()
+
+
+def test_single_copy_transfers():
+    """jpgpu_batch_upload_from / jpgpu_batch_download_contiguous: one copy each way instead of one per image."""
+    from jpeg_rust_b200 import pack_files, parse_packed
+    files = [synth.synth_jpeg(7300 + i, 64 + 16 * (i % 4), 64, "420") for i in range(9)]
+    ref = run_batch(files)[0]
+    buf, offs, owner = pack_files(files)
+    descs, pst = parse_packed(buf, offs, [len(f) for f in files])
+    assert not any(pst)
+    b = Batch(descs=descs, keepalive=owner)
+    out = np.zeros(b.output_bytes(), np.uint8)
+    b.upload_from(buf).decode().download_contiguous(out)
+    st, _ = b.results()
+    assert all(s == 0 for s in st)
+    for i in range(len(files)):
+        off, nb = b.rgb_offset(i)
+        assert np.array_equal(out[off:off + nb].reshape(ref[i].shape), ref[i])
+    b.close()
+
+
+def test_multi_device_handle_matches_one_device():
+    """jpgpu_multi_*: one process, one context + stream set + worker thread per device, contiguous ranges balanced by
+    scan bytes, no collective.  On every device count available (1, and 2+ when the box has them) the result is
+    byte-identical to the single-device batch."""
+    import torch
+    from jpeg_rust_b200 import MultiDevice
+    subs = ["420", "444", "422", "gray"]
+    made = [synth.synth_jpeg(7400 + i, 96 + 16 * (i % 6), 64 + 8 * (i % 4), subs[i % 4], want_coefs=True) for i in range(37)]
+    files = [m[0] for m in made]
+    ref, ref_st, ref_br = run_batch(files)[:3]
+    ndev = torch.cuda.device_count()
+    for devices in ([0], list(range(min(ndev, 2))), list(range(ndev))):
+        m = MultiDevice(devices)
+        m.plan(files).upload().decode()
+        outs = m.download()
+        st, br = m.results()
+        rngs = m.ranges()
+        assert rngs[0][1] == 0 and sum(r[2] for r in rngs) == len(files) and [r[0] for r in rngs] == devices
+        assert st == ref_st and br == ref_br
+        for i in range(len(files)):
+            assert np.array_equal(outs[i], ref[i]), (devices, i)
+        for i in (0, 18, 36):
+            for a, w in zip(m.coefficients(i), made[i][1]):
+                assert np.array_equal(a[:len(w)], w[:len(a)])
+        ms = m.time_decode(2)
+        assert len(ms) == len(devices) and all(x > 0 for x in ms)
+        outs2, st2, br2 = m.decode_batch(files[:11])          # the one-call form, replanning the same handle
+        assert st2 == ref_st[:11] and br2 == ref_br[:11]
+        for i in range(11):
+            assert np.array_equal(outs2[i], ref[i])
+        m.close()
+
+
+def test_c_program_decodes_through_the_abi():
+    """tests/c/abi_smoke: a C program that knows nothing but include/jpgpu.h decodes the fixtures through
+    jpgpu_decode_file, the batch calls and the host pipeline; its output hash equals the Python binding's, its
+    dimensions and bytes_read the oracle's."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "c", "abi_smoke")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", root, "tests/c/abi_smoke"])
+
+    def fnv1a(buf):
+        h = 1469598103934665603
+        for chunk in np.frombuffer(buf, np.uint8).tolist():
+            h = ((h ^ chunk) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+    for name, ext in (("lena.jpeg", 0), ("lena-bw.jpeg", 0), ("huff_simple0.jpg", 1)):
+        path = os.path.join(root, "tests", "golden", "fixtures", name)
+        r = subprocess.run([exe, path, str(ext), "0"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        w, h, br, digest, batch_same, pipe_same = r.stdout.split()
+        o = O.decode(fixture_bytes(name), layout=LAYOUT_REF, ext=ext)
+        img = JPEGImage.parse(fixture_bytes(name), ext=ext, layout=LAYOUT_REF)
+        assert (int(w), int(h), int(br)) == (o.width, o.height, o.bytes_read)
+        assert int(digest, 16) == fnv1a(img.image_data().tobytes())
+        assert batch_same == "1" and pipe_same == "1"

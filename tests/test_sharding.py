@@ -63,3 +63,36 @@ def test_two_ranks_reproduce_the_single_process_result():
         got[lo:hi] = dig
     assert got == want
     assert pixels == sum(r.width * r.height for r in single)
+
+
+def test_partition_by_scan_bytes():
+    """jpgpu_partition (host only): contiguous ranges that cover all images, balanced by scan bytes - the partition
+    jpgpu_multi_plan gives every device."""
+    import ctypes as C
+    from jpeg_rust_b200 import _ffi
+    L = _ffi.lib()
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 5, 64, 1000):
+        descs = (_ffi.ImageDesc * max(n, 1))()
+        sizes = rng.integers(100, 100000, n)
+        for i in range(n):
+            descs[i].scan_len = int(sizes[i])
+        for parts in (1, 2, 3, 8):
+            first = (C.c_size_t * (parts + 1))()
+            assert L.jpgpu_partition(descs, n, parts, first) == 0
+            f = list(first)
+            assert f[0] == 0 and f[-1] == n and all(a <= b for a, b in zip(f, f[1:]))
+            if n >= 64:
+                loads = [int(sizes[a:b].sum()) for a, b in zip(f, f[1:])]
+                assert max(loads) - min(loads) <= 2 * int(sizes.max())
+
+
+def test_multi_create_without_a_device_fails_cleanly():
+    """No CPU fallback, no crash: without a usable sm_100 device the multi-device handle reports JPGPU_ERR_NO_DEVICE."""
+    import ctypes as C
+    from jpeg_rust_b200 import _ffi
+    if torch.cuda.is_available():
+        return
+    h = C.c_void_p()
+    devs = (C.c_int * 2)(0, 1)
+    assert _ffi.lib().jpgpu_multi_create(devs, 2, C.byref(h)) == _ffi.ERR_NO_DEVICE and not h

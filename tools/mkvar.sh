@@ -5,5 +5,5 @@
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p build/variants
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $2 -shared -o build/variants/$1.so jpeg_rust_b200/csrc/jpgpu_kernels.cu jpeg_rust_b200/csrc/jpgpu_api.cu jpeg_rust_b200/csrc/jpgpu_host.cpp -lcudart 2>&1 | grep -E "error" || true
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $2 -shared -o build/variants/$1.so jpeg_rust_b200/csrc/jpgpu_kernels.cu jpeg_rust_b200/csrc/jpgpu_api.cu jpeg_rust_b200/csrc/jpgpu_host.cpp jpeg_rust_b200/csrc/jpgpu_multi.cpp -lcudart -lpthread 2>&1 | grep -E "error" || true
 ls -la build/variants/$1.so | awk '{print $5, $9}'
