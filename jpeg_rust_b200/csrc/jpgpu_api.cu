@@ -45,7 +45,7 @@ struct jpgpu_batch {
     std::vector<uint64_t> scan_offs;   // jpgpu_batch_upload_from(): where each scan lies in the staging arena
     BatchDev dev;
     struct Arena { void* p = nullptr; size_t cap = 0; };
-    enum { kImgs, kSeqs, kLuts, kQt, kKind0, kGmap = kKind0 + kNumKinds, kSamples, kRaw, kDyn, kStream, kSegtab, kSubs, kSegs, kChunks, kCoefs,
+    enum { kImgs, kSeqs, kLuts, kMluts, kMlutOff, kQt, kKind0, kGmap = kKind0 + kNumKinds, kSamples, kRaw, kDyn, kStream, kSegtab, kSubs, kSegs, kChunks, kCoefs,
            kRgb, kScanOffs, kStage, kNumArenas };
     Arena arena[kNumArenas];   // device allocations, grown on demand by jpgpu_batch_replan()
     uint64_t launches = 0;
@@ -201,6 +201,13 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     TRY(dev_upload(b, jpgpu_batch::kImgs, &d.imgs, p.imgs));
     TRY(dev_upload(b, jpgpu_batch::kSeqs, &d.seqs, p.seqs));
     TRY(dev_upload(b, jpgpu_batch::kLuts, &d.luts, p.luts));
+    TRY(dev_upload(b, jpgpu_batch::kMluts, &d.mlut, p.mluts));
+    TRY(dev_upload(b, jpgpu_batch::kMlutOff, &d.mlut_off, p.mlut_off));
+    d.max_mlut_words = p.max_mlut_words;
+    {
+        const char* e = getenv("JPGPU_SYNC_MULTI");   // experiments: 0 = single-symbol synchronisation pass
+        d.sync_multi = e ? (atoi(e) ? 1u : 0u) : 1u;
+    }
     TRY(dev_upload(b, jpgpu_batch::kQt, &d.qt, p.qt));
     for (int k = 0; k < kNumKinds; k++) {
         d.kind_count[k] = (uint32_t)p.kind_imgs[k].size();
@@ -239,7 +246,7 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     CK(cudaMemsetAsync(d.stream, 0, stream_alloc_words * 4, ctx->stream));
     CK(cudaMemsetAsync(d.dyn, 0, (n + 1) * sizeof(ImgDyn), ctx->stream));
     // (the coefficient arena is not cleared: the write pass stores every block of a complete scan, and the blocks a
-    // damaged scan never reaches are masked by ImgDyn::coef_end in the IDCT stage)
+    // damaged scan never reaches are zero-filled from ImgDyn::coef_end on by zero_tail_kernel)
     CK(cudaMemsetAsync(d.segtab, 0, (p.seg_entries + 8) * 4, ctx->stream));
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
@@ -352,16 +359,29 @@ extern "C" int jpgpu_batch_set_device_output(jpgpu_batch* b, void* dev_base, siz
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
 
+namespace {
+// kernels one entropy chain (pre-pass .. write pass) launches for the images / jobs `d` covers
+uint64_t entropy_launches(const BatchDev& d) {
+    const uint64_t slices = (d.n_images + 65534u) / 65535u;   // kernels indexed by image in grid.y go in slices
+    uint64_t n = 0;
+    if (d.n_images && d.max_chunks) n += 2 * slices + 1;      // prepass count / scan / write
+    if (d.n_seqs && d.nsync) n += 1;                          // sync
+    if (d.n_images && d.nsync) n += 1;                        // verify + scan
+    if (d.n_seqs) n += 1 + (d.n_images ? 1 : 0);              // write pass, zero tail
+    return n;
+}
+}  // namespace
+
 extern "C" int jpgpu_batch_entropy(jpgpu_batch* b) try {
     if (!b) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     launch_prepass(b->dev, s);
-    launch_sync(b->dev, s);
+    CK(launch_sync(b->dev, s));
     launch_verify_scan(b->dev, s);
     CK(launch_decode_write(b->dev, s));
-    b->launches += 6;
+    b->launches += entropy_launches(b->dev);
     CK(cudaGetLastError());
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
@@ -425,10 +445,10 @@ extern "C" int jpgpu_batch_decode(jpgpu_batch* b) try {
         cudaStream_t s = ctx->aux[g % jpgpu_ctx::kAux];
         const BatchDev d = group_dev(b, b->plan.groups[g]);
         launch_prepass(d, s);
-        launch_sync(d, s);
+        CK(launch_sync(d, s));
         launch_verify_scan(d, s);
         CK(launch_decode_write(d, s));
-        b->launches += 6 + (uint64_t)launch_idct_colour(d, s);
+        b->launches += entropy_launches(d) + (uint64_t)launch_idct_colour(d, s);
     }
     for (int i = 0; i < jpgpu_ctx::kAux; i++) {
         CK(cudaEventRecord(ctx->join[i], ctx->aux[i]));
@@ -507,14 +527,9 @@ extern "C" int jpgpu_batch_coefficients(jpgpu_batch* b, size_t i, int16_t* out, 
     const ImgDev& im = b->plan.imgs[i];
     if (cap < im.total_coefs) return JPGPU_ERR_INVALID_ARG;
     std::vector<int16_t> arena(im.total_coefs);
-    ImgDyn dyn;
     CK(cudaMemcpyAsync(arena.data(), b->dev.coefs + im.coef_off, (size_t)im.total_coefs * 2, cudaMemcpyDeviceToHost,
                        ctx->stream));
-    CK(cudaMemcpyAsync(&dyn, b->dev.dyn + i, sizeof dyn, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    // what the IDCT stage sees: blocks the decode never reached (data ended early) are zeros, whatever the reused arena holds
-    const uint64_t limit = (uint64_t)coef_block_limit(dyn) * 64;
-    if (limit < im.total_coefs) std::fill(arena.begin() + (size_t)limit, arena.end(), (int16_t)0);
     export_reference_order(im, arena.data(), out, nblocks);
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
@@ -543,13 +558,13 @@ extern "C" int jpgpu_batch_profile(jpgpu_batch* b, float ms[8]) try {
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(ev[0], s));
     for (int step = 0; step < 3; step++) { launch_prepass_step(b->dev, s, step); CK(cudaEventRecord(ev[1 + step], s)); }
-    launch_sync(b->dev, s);
+    CK(launch_sync(b->dev, s));
     CK(cudaEventRecord(ev[4], s));
     launch_verify_scan(b->dev, s);
     CK(cudaEventRecord(ev[5], s));
     CK(launch_decode_write(b->dev, s));
     CK(cudaEventRecord(ev[6], s));
-    b->launches += 6 + (uint64_t)launch_idct_colour(b->dev, s);
+    b->launches += entropy_launches(b->dev) + (uint64_t)launch_idct_colour(b->dev, s);
     CK(cudaEventRecord(ev[7], s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());

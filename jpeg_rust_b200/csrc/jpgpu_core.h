@@ -81,6 +81,28 @@ JPGPU_HD uint32_t make_entry(uint32_t sym, uint32_t len, bool is_dc) {
 }
 constexpr uint32_t kBadEntry = 16u | (16u << 8) | (64u << 16);  // unknown code: 16 bits, ends the block
 
+// ---- multi-symbol tables of the synchronisation pass
+// The synchronisation pass only tracks state (bit position, zigzag index, block in the MCU, DC sums): for AC symbols
+// it needs no values, only how many bits and zigzag positions they take.  Its AC lookups therefore go through a wider
+// table whose entry covers EVERY symbol whose code lies inside the next kMultiBitsAc bits (the benchmark corpus averages
+// 4.65 bits per symbol: 1.7 symbols per lookup).  Entry, for the bits of the window decoded greedily from the left:
+//   bits  0-4   tb_all   bits consumed by all symbols of the entry (codes + value bits; the last one's value bits may
+//                        reach past the window: <= kMultiBitsAc + 15)
+//   bits  5-11  adv_all  zigzag positions they advance (an EOB, always last, counts 64)
+//   bits 12-17  adv_pre  the same without the entry's last symbol; the entry holds for a decoder at zigzag index z iff
+//                        z + adv_pre <= 63 (no symbol before the last one completes the block - what follows a
+//                        completed block is a DC symbol of another table)
+//   bits 18-22  tb1      |
+//   bits 23-29  adv1     | the first symbol alone: what to take when the entry does not hold
+// DC tables have the same format with one symbol per entry, index width kMultiBitsDc, and the code LENGTH in the
+// adv_pre field (the DC difference must be extracted; z = 0 there, so the entry always holds).  0 = no symbol can be
+// determined from the window (code longer than the window, no such code, DC size > 16): single-symbol path.
+constexpr int kMultiBitsAc = 11;
+constexpr int kMultiBitsDc = 9;
+JPGPU_HD uint32_t multi_entry(uint32_t tb_all, uint32_t adv_all, uint32_t adv_pre, uint32_t tb1, uint32_t adv1) {
+    return tb_all | (adv_all << 5) | (adv_pre << 12) | (tb1 << 18) | (adv1 << 23);
+}
+
 // Per-image plan, written by the host, read by every kernel.
 struct ImgDev {
     uint32_t width, height;
@@ -132,7 +154,7 @@ struct ImgDyn {
     uint32_t bits_consumed; // bit position after the last decoded MCU -> bytes_read
     // Without kStDone (data ended early): coefficient positions [0, coef_end) are what this decode produced; the blocks
     // from there on were never written and read as zeros (the arenas are reused wave after wave and never cleared, so
-    // they hold an earlier image's coefficients).  See coef_block_limit().
+    // they hold an earlier image's coefficients): zero_tail_kernel fills them in after the write pass.
     uint32_t coef_end;
     uint32_t pad[3];
 };
@@ -269,6 +291,7 @@ struct DecCtx {               // per-image constants of the entropy decoder
     int32_t nblk;             // blocks per MCU
     const HuffLut* luts;      // slot array
     const uint32_t* blk_info; // per block of an MCU: DC slot | AC slot << 8 | component << 16
+    const uint32_t* const* mluts;  // per slot: its multi-symbol table (synchronisation pass), or nullptr: symbol by symbol
 };
 
 struct DecState {
@@ -425,6 +448,40 @@ JPGPU_HD uint32_t decode_symbol(const DecCtx& cx, DecState& st, int16_t* blk, ui
     return 0u;
 }
 
+// Synchronisation pass, one lookup in the multi-symbol table of the current block's DC / AC slot (format above):
+// every symbol whose code lies inside the window, as far as they stay inside the block.  The caller guarantees
+// st.p + 32 <= the bit it decodes to and <= seg_end - 7 (an entry consumes at most kMultiBitsAc + 15 bits), so no
+// symbol of the entry starts past either.  The kernels' form is fast_mstep() (jpgpu_kernels.cu).
+JPGPU_HD void multi_symbol(const DecCtx& cx, DecState& st) {
+    st.br.refill();
+    const uint32_t peek = st.br.peek();
+    const uint32_t z = (uint32_t)st.g & 63u;
+    const bool is_dc = z == 0u;
+    const uint32_t* tab = cx.mluts[(is_dc ? st.tdc : st.tac) - cx.luts];
+    const uint32_t e = tab[peek >> (32 - (is_dc ? kMultiBitsDc : kMultiBitsAc))];
+    if (e == 0u) { decode_symbol<false>(cx, st, nullptr, 0u, nullptr, false); return; }
+    const uint32_t pre = (e >> 12) & 63u;
+    const bool ok = z + pre <= 63u;
+    const uint32_t tb = (ok ? e : e >> 18) & 31u;
+    const uint32_t adv = (ok ? e >> 5 : e >> 23) & 127u;
+    if (is_dc) {  // DC difference -> running sum (decoder.rs:208-210)
+        const uint32_t len = pre, size = tb - len, top = peek << len;
+        const uint32_t v = size ? top >> (32 - size) : 0u;
+        const int32_t val = extend(v, top, size);
+        if (st.comp == 0) st.dc0 += val; else if (st.comp == 1) st.dc1 += val; else st.dc2 += val;
+    }
+    st.br.skip(tb);
+    st.p += tb;
+    if (z + adv >= 64u) {  // block complete
+        st.g = (st.g | 63) + 1;
+        st.c += 1;
+        if (st.c == cx.nblk) st.c = 0;
+        load_block_tables(cx, st);
+    } else {
+        st.g += (int32_t)adv;
+    }
+}
+
 JPGPU_HD uint32_t pack_cz(const DecState& st) { return (uint32_t)(st.g & 63) | ((uint32_t)st.c << 6); }
 
 // Synchronisation decode of one segment: from the state in `st` to the first symbol at or after end_bit.
@@ -438,6 +495,9 @@ JPGPU_HD void sync_segment(const DecCtx& cx, DecState& st, uint32_t end_bit, Seg
     if (end_bit > cx.stream_bits) end_bit = cx.stream_bits;
 #pragma unroll 1
     while (st.p < end_bit) {
+        // through the multi-symbol tables while no symbol of an entry can start at or past end_bit (or inside the last
+        // bits of a restart interval): the state at end_bit stays that of the FIRST symbol at or after it
+        if (cx.mluts && st.p + 32u <= end_bit && st.p + 39u <= st.seg_end) { multi_symbol(cx, st); continue; }
         if (decode_symbol<false>(cx, st, nullptr, 0u, nullptr, false) & kEvEnd) break;
     }
     r.p = st.p;

@@ -153,6 +153,62 @@ int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, bool 
     return JPGPU_OK;
 }
 
+void build_multi_lut(const uint8_t bits[16], const uint8_t* vals, bool is_dc, std::vector<uint32_t>& out) {
+    // canonical code ranges (T.81 Fig. C.2 / F.2.2.3), as build_huff_lut
+    int32_t maxcode[17], valoff[17];
+    uint32_t code = 0;
+    int k = 0;
+    for (int l = 1; l <= 16; l++) {
+        maxcode[l] = -1;
+        valoff[l] = k - (int32_t)code;
+        k += bits[l - 1];
+        code += bits[l - 1];
+        if (bits[l - 1]) maxcode[l] = (int32_t)code - 1;
+        code <<= 1;
+    }
+    const int K = is_dc ? kMultiBitsDc : kMultiBitsAc;
+    const size_t base = out.size();
+    out.resize(base + ((size_t)1 << K), 0u);
+    for (uint32_t w = 0; w < (1u << K); w++) {
+        int pos = 0, nsym = 0;
+        uint32_t tb_all = 0, adv_all = 0, adv_pre = 0, tb1 = 0, adv1 = 0;
+        while (pos < K) {
+            // the code starting at window bit `pos`, if the window holds all of it
+            int len = 0, sym = -1;
+            for (int l = 1; l <= 16 && pos + l <= K; l++) {
+                const int32_t c = (int32_t)((w >> (K - pos - l)) & ((1u << l) - 1u));
+                if (c <= maxcode[l]) { len = l; sym = vals[(valoff[l] + c) & 255]; break; }
+            }
+            if (sym < 0) break;
+            uint32_t size, adv;
+            bool eob = false;
+            if (is_dc) { if (sym > 16) break; size = (uint32_t)sym; adv = 1; }     // size > 16: huffman.rs:202, single-symbol path reports it
+            else if (sym == 0x00) { size = 0; adv = 64; eob = true; }
+            else if (sym == 0xf0) { size = 0; adv = 16; }
+            else { size = (uint32_t)sym & 15u; adv = ((uint32_t)sym >> 4) + 1u; }
+            if (nsym > 0 && adv_all + (eob ? 0u : adv) > 63u) break;   // would not fit one block whatever z is
+            adv_pre = adv_all;
+            adv_all += adv;
+            tb_all += (uint32_t)len + size;
+            if (nsym == 0) { tb1 = tb_all; adv1 = adv; }
+            nsym++;
+            pos += len + (int)size;
+            if (eob || is_dc) break;
+        }
+        if (nsym == 0) continue;   // 0: single-symbol path
+        out[base + w] = multi_entry(tb_all, adv_all, adv_pre, tb1, adv1);
+        if (is_dc) {
+            // one symbol: the code length goes where AC entries keep adv_pre
+            int len = 0;
+            for (int l = 1; l <= 16 && l <= K; l++) {
+                const int32_t c = (int32_t)((w >> (K - l)) & ((1u << l) - 1u));
+                if (c <= maxcode[l]) { len = l; break; }
+            }
+            out[base + w] = multi_entry(tb_all, 1u, (uint32_t)len, tb1, 1u);
+        }
+    }
+}
+
 void build_qt_multipliers(const uint16_t qt_zigzag[64], float out[64]) {
     for (int k = 0; k < 64; k++) {
         const int nat = kZigzagNaturalHost[k], u = nat & 7, v = nat >> 3;
@@ -296,6 +352,8 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
                     if (st != JPGPU_OK) break;
                     id = (uint32_t)plan.luts.size();
                     plan.luts.push_back(lut);
+                    plan.mlut_off.push_back((uint32_t)plan.mluts.size());
+                    build_multi_lut(bits, vals, cls == 0, plan.mluts);
                     lut_ids.emplace(key, id);
                 } else {
                     id = it->second;
@@ -362,6 +420,11 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         im.nslots = (uint8_t)nslots;
         plan.max_slots = std::max<uint32_t>(plan.max_slots, (uint32_t)nslots);
         for (int s = 0; s < nslots; s++) im.slot_lut[s] = slot_lut[s];
+        {
+            uint32_t words = 0;
+            for (int s = 0; s < nslots; s++) words += 1u << (plan.luts[slot_lut[s]].is_dc ? kMultiBitsDc : kMultiBitsAc);
+            plan.max_mlut_words = std::max(plan.max_mlut_words, words);
+        }
         int blk = 0;
         for (uint32_t c = 0; c < d.ncomp; c++) {
             im.h[c] = g.h[c]; im.v[c] = g.v[c];

@@ -28,6 +28,10 @@ int compute_geometry(const jpgpu_image_desc& d, Geometry& g);
 // Builds the device Huffman table from DHT BITS/HUFFVAL (huffman.rs:37-58, 80-98).
 int build_huff_lut(const uint8_t bits[16], const uint8_t* vals, int nvals, bool is_dc, HuffLut& out);
 
+// Multi-symbol table of the synchronisation pass for one DHT table (format: jpgpu_core.h, multi_entry): appends
+// 2^kMultiBitsDc / 2^kMultiBitsAc entries to `out`.
+void build_multi_lut(const uint8_t bits[16], const uint8_t* vals, bool is_dc, std::vector<uint32_t>& out);
+
 // 64 multipliers (column-major) = q * aan[u] * aan[v] / 8 from a zigzag-order DQT table.
 void build_qt_multipliers(const uint16_t qt_zigzag[64], float out[64]);
 
@@ -54,6 +58,9 @@ struct HostPlan {
     std::vector<int32_t> status;  // per image: JPGPU_OK or why it is skipped
     std::vector<SeqDesc> seqs;
     std::vector<HuffLut> luts;
+    std::vector<uint32_t> mluts;      // multi-symbol tables of the synchronisation pass, one per entry of `luts`
+    std::vector<uint32_t> mlut_off;   // where each begins in `mluts` (words)
+    uint32_t max_mlut_words = 0;      // most words the tables of one image's slots take together
     std::vector<float> qt;
     std::vector<uint32_t> kind_imgs[kNumKinds];
     uint32_t kind_max_tiles[kNumKinds] = {0, 0, 0, 0, 0, 0};

@@ -318,6 +318,7 @@ struct FastCtx {
     uint32_t sp_addr;        // shared: byte offset of zigzag position k inside an unswizzled block buffer
     const HuffLut* luts;     // generic pointer to the shared LUT slots (rare paths)
     uint32_t lut0_addr;
+    uint32_t minfo_addr;     // shared: per job and block of an MCU {DC, AC} multi-symbol table addresses; 0 = kernel without them
 };
 
 struct FastState {
@@ -327,6 +328,7 @@ struct FastState {
     int32_t g;
     uint32_t info_ptr;       // shared address of the FastTables::info entry of the current block-in-MCU
     uint32_t lut_dc, lut_ac, dc_off;
+    uint32_t m_dc, m_ac;     // multi-symbol tables of the current block (synchronisation pass, fast_mstep)
     int32_t dcur;
     uint32_t seg, seg_end, seg_lim, flags;   // seg_lim = seg_end - 7 (0 if shorter): at or past it a step must look at the interval end
     uint32_t wrap_lim, lim;                  // wrap_lim: see fast_advance(); lim = min(seg_lim, wrap_lim)
@@ -409,7 +411,14 @@ __device__ __forceinline__ void fast_fix_wrap(const FastCtx& cx, FastState& st) 
     fast_set_lim(st);
 }
 __device__ __forceinline__ uint32_t fast_c(const FastState& st) { return lds32(st.info_ptr + 12u); }
+__device__ __forceinline__ void fast_load_multi(const FastCtx& cx, FastState& st) {
+    if (cx.minfo_addr) {   // uniform: only the multi-symbol synchronisation kernel has these tables
+        const uint2 m = lds64(cx.minfo_addr + ((st.info_ptr - cx.info_addr) >> 1));
+        st.m_dc = m.x; st.m_ac = m.y;
+    }
+}
 __device__ __forceinline__ void fast_load_block(const FastCtx& cx, FastState& st) {  // st.info_ptr changed: tables + DC slot
+    fast_load_multi(cx, st);
     uint4 info;
     asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(info.x), "=r"(info.y), "=r"(info.z), "=r"(info.w) : "r"(st.info_ptr));
     sts32v(cx.dc_addr + st.dc_off, (uint32_t)st.dcur);
@@ -474,6 +483,8 @@ __device__ __forceinline__ void fast_init(const FastCtx& cx, FastState& st, uint
     st.dc_off = info.y;
     st.lut_dc = info.x & 0xffffu;
     st.lut_ac = info.x >> 16;
+    st.m_dc = st.m_ac = 0u;
+    fast_load_multi(cx, st);
     fast_set_dc(cx, st, d0, d1, d2);
 }
 
@@ -624,13 +635,57 @@ __device__ __forceinline__ void fast_block_end(const FastCtx& cx, FastState& st,
     wl.close_block((uint32_t)(st.g >> 6) - 1u, st.p, st.g);
 }
 
+// Synchronisation pass: one lookup in the multi-symbol tables (jpgpu_core.h) = every symbol whose code lies in the next
+// kMultiBitsAc bits, as far as they stay inside the current block.  The caller guarantees that all of them start before
+// st.lim and before the bit it decodes to (st.p + 32 <= both: an entry consumes at most 26 bits).
+__device__ __forceinline__ void fast_mstep(const FastCtx& cx, FastState& st) {
+    const uint32_t hi = fast_peek(st);
+    const uint32_t z = (uint32_t)st.g & 63u;
+    const bool is_dc = z == 0u;
+    const uint32_t e = lds32((is_dc ? st.m_dc : st.m_ac) + ((hi >> (is_dc ? 32 - kMultiBitsDc : 32 - kMultiBitsAc)) << 2));
+    if (e == 0u) {   // code longer than the window, no such code, oversized DC symbol: the single-symbol step knows
+        NoLane nl;
+        fast_step<false, false>(cx, st, nl);
+        return;
+    }
+    const uint32_t pre = (e >> 12) & 63u;                  // AC: advance before the entry's last symbol; DC: code length
+    const bool ok = z + pre <= 63u;                        // no symbol before the last completes the block
+    const uint32_t tb = (ok ? e : e >> 18) & 31u;
+    const uint32_t adv = (ok ? e >> 5 : e >> 23) & 127u;
+    // DC difference (decoder.rs:208-210): EXTEND of the tb - len bits after the code, as in fast_step
+    const uint32_t len = is_dc ? pre : 0u;
+    const uint32_t top = hi << len;
+    const uint32_t sgn = (uint32_t)((int32_t)top >> 31);
+    const uint32_t mag = __funnelshift_l(top ^ ~sgn, 0u, tb - len);
+    const int32_t val = (int32_t)((mag ^ ~sgn) - ~sgn);
+    st.dcur += is_dc ? val : 0;
+    fast_advance(cx, st, st.p + tb);
+    if (z + adv >= 64u) {  // block complete
+        st.g = (st.g | 63) + 1;
+        st.info_ptr = lds32(st.info_ptr + 8u);
+        fast_load_block(cx, st);
+    } else {
+        st.g += (int32_t)adv;
+    }
+}
+
 // Decode every symbol that starts before end_bit (sync pass form: the interval-end test is hoisted out of the loop).
+// MULTI: through the multi-symbol tables while that cannot carry past end_bit or st.lim; the last 32 bits before either
+// go symbol by symbol, so the state at end_bit is that of the FIRST symbol at or after it however the entries fell -
+// what the chain verification and the repair walks (single-symbol) compare.
+template <bool MULTI>
 __device__ __forceinline__ void fast_run_to(const FastCtx& cx, FastState& st, uint32_t end_bit) {
     NoLane nl;
 #pragma unroll 1
     while (true) {
         if (st.p >= st.wrap_lim) fast_fix_wrap(cx, st);
         const uint32_t lim = min(end_bit, st.lim);
+        if constexpr (MULTI) {
+            const uint32_t mlim = lim >= 32u ? lim - 32u : 0u;
+#pragma unroll 1
+            while (st.p <= mlim && mlim != 0u) fast_mstep(cx, st);
+            if (st.p >= st.wrap_lim) continue;
+        }
 #pragma unroll 1
         while (st.p < lim) fast_step<false, false>(cx, st, nl);
         if (st.p >= st.wrap_lim) continue;
@@ -660,6 +715,7 @@ __device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const SM& sm
     cx.sp_addr = smem_addr(ft.sp);
     cx.luts = sm.lut;
     cx.lut0_addr = smem_addr(&sm.lut[0]);
+    cx.minfo_addr = 0u;
     // keep the per-symbol operands in registers instead of re-deriving them from the parameter bank every step
     JPGPU_PIN64(cx.words);
     JPGPU_PIN32(cx.wmask5);
@@ -672,13 +728,14 @@ __device__ __forceinline__ FastCtx make_fast_ctx(const BatchDev& b, const SM& sm
 }
 
 // sync_segment() / sync_subsequence() of jpgpu_core.h on the fast step.
+template <bool MULTI>
 __device__ __forceinline__ void fast_sync_segment(const FastCtx& cx, FastState& st, uint32_t end_bit, SegRec& r) {
     const int32_t g_base = st.g;
     fast_set_dc(cx, st, 0, 0, 0);
     // standing on the first bit of a restart interval = absolute state, crossing inside the segment or not (see
     // sync_segment() in jpgpu_core.h)
     if (st.p == cx.seg[st.seg] && st.p < cx.stream_bits) st.flags |= kCrossed; else st.flags &= ~kCrossed;
-    fast_run_to(cx, st, min(end_bit, cx.stream_bits));
+    fast_run_to<MULTI>(cx, st, min(end_bit, cx.stream_bits));
     r.p = st.p;
     r.cz = ((uint32_t)st.g & 63u) | (fast_c(st) << 6) | (st.flags & kCrossed);
     r.n = (st.flags & kCrossed) ? st.g : st.g - g_base;
@@ -690,6 +747,7 @@ __device__ __forceinline__ void store_segrec(SegRec* dst, const SegRec& r) {
     d[0] = make_uint4(r.p, r.cz, (uint32_t)r.n, (uint32_t)r.dc[0]);
     d[1] = make_uint4((uint32_t)r.dc[1], (uint32_t)r.dc[2], 0u, 0u);
 }
+template <bool MULTI>
 __device__ __forceinline__ void fast_sync_subsequence(const FastCtx& cx, FastState& st, uint32_t own, uint32_t S, uint32_t C,
                                                       SegRec* segs, bool compare, SubInfo& rec) {
     const uint32_t nsegs = S / C;
@@ -698,7 +756,7 @@ __device__ __forceinline__ void fast_sync_subsequence(const FastCtx& cx, FastSta
 #pragma unroll 1
     for (; k < nsegs; k++) {
         SegRec r;
-        fast_sync_segment(cx, st, own + (k + 1) * C, r);
+        fast_sync_segment<MULTI>(cx, st, own + (k + 1) * C, r);
         bool met = false;
         if (compare) {
             const uint2 old = *reinterpret_cast<const uint2*>(segs + k);
@@ -752,11 +810,95 @@ __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     const uint32_t own = j * S, p0 = own > b.lookback_bits ? own - b.lookback_bits : 0u;
     FastState st;
     fast_init(cx, st, p0, 0, 0u, 0, 0, 0);
-    fast_run_to(cx, st, own);
+    fast_run_to<false>(cx, st, own);
     SubInfo rec;
     rec.pA = st.p;
     rec.cz = ((uint32_t)st.g & 63u) | (fast_c(st) << 6);
-    fast_sync_subsequence(cx, st, own, S, b.seg_bits, b.segs + (size_t)(img.sub_off + j) * (S / b.seg_bits), false, rec);
+    fast_sync_subsequence<false>(cx, st, own, S, b.seg_bits, b.segs + (size_t)(img.sub_off + j) * (S / b.seg_bits), false, rec);
+    b.subs[img.sub_off + j] = rec;
+}
+
+// The same pass through the multi-symbol tables (jpgpu_core.h): 256-thread CTAs (eight warp jobs share one copy of the
+// tables), dynamic shared memory = Huffman tables of the slots in use + fast-path tables + multi-symbol tables.
+constexpr int kSyncThreads = 256;
+constexpr int kSyncJobs = kSyncThreads / 32;
+struct SyncLayout {
+    uint32_t ft_off, minfo_off, mlut_off, total;
+};
+__host__ __device__ inline SyncLayout sync_layout(uint32_t max_slots, uint32_t max_mlut_words) {
+    SyncLayout l;
+    const uint32_t lut_bytes = (uint32_t)(sizeof(EntropySmemT<kSyncJobs>) - (kMaxLutSlots - max_slots) * sizeof(HuffLut));
+    l.ft_off = (lut_bytes + 15u) & ~15u;
+    l.minfo_off = (l.ft_off + (uint32_t)sizeof(FastTablesT<kSyncThreads>) + 15u) & ~15u;
+    l.mlut_off = l.minfo_off + kSyncJobs * kMaxBlocksPerMcu * 8u;
+    l.total = l.mlut_off + max_mlut_words * 4u;
+    return l;
+}
+__global__ void __launch_bounds__(kSyncThreads) sync_multi_kernel(BatchDev b) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
+    using Smem = EntropySmemT<kSyncJobs>;
+    using Tables = FastTablesT<kSyncThreads>;
+    Smem& sm = *reinterpret_cast<Smem*>(dyn_smem);
+    const SyncLayout lay = sync_layout(b.max_slots, b.max_mlut_words);
+    Tables& ft = *reinterpret_cast<Tables*>(dyn_smem + lay.ft_off);
+    uint2* const minfo = reinterpret_cast<uint2*>(dyn_smem + lay.minfo_off);
+    uint32_t* const mlut = reinterpret_cast<uint32_t*>(dyn_smem + lay.mlut_off);
+    const int warp = threadIdx.x >> 5;
+    if (b.seqs[b.job0 + blockIdx.x * kSyncJobs].img == kNoImage) return;   // a CTA of padding jobs only
+    const uint32_t job = blockIdx.x * kSyncJobs + warp;
+    const SeqDesc sd = job < b.n_seqs ? b.seqs[b.job0 + job] : SeqDesc{kNoImage, 0u};
+    const uint32_t S = b.sub_bits;
+    load_entropy_img(b, sd.img, sm, 32);
+    load_entropy_luts(b, sm, kSyncThreads);
+    fast_tables_init(ft, sm, sd.img != kNoImage, 32, kSyncThreads);
+    {   // multi-symbol tables of the CTA's slots (those of job 0, as the Huffman tables), and who uses which
+        const int nslots = sm.img[0].nslots;
+        uint32_t moff[kMaxLutSlots], acc = 0;
+#pragma unroll
+        for (int s2 = 0; s2 < kMaxLutSlots; s2++) {
+            moff[s2] = acc;
+            if (s2 < nslots) acc += 1u << (sm.lut[s2].is_dc ? kMultiBitsDc : kMultiBitsAc);
+        }
+        for (int s2 = 0; s2 < nslots; s2++) {
+            const uint4* src = reinterpret_cast<const uint4*>(b.mlut + b.mlut_off[sm.img[0].slot_lut[s2]]);
+            uint4* dst = reinterpret_cast<uint4*>(mlut + moff[s2]);
+            const int nvec = (1 << (sm.lut[s2].is_dc ? kMultiBitsDc : kMultiBitsAc)) / 4;
+            for (int i = threadIdx.x; i < nvec; i += kSyncThreads) dst[i] = __ldg(src + i);
+        }
+        const int t = threadIdx.x & 31;
+        if (sd.img != kNoImage && t < kMaxBlocksPerMcu) {
+            const int nblk = sm.img[warp].blocks_per_mcu;
+            const uint32_t info = sm.img[warp].blk_info[t < nblk ? t : 0];
+            const uint32_t base = smem_addr(mlut);
+            uint32_t a_dc = base, a_ac = base;
+#pragma unroll
+            for (int s2 = 0; s2 < kMaxLutSlots; s2++) {
+                if ((info & 255u) == (uint32_t)s2) a_dc = base + moff[s2] * 4u;
+                if (((info >> 8) & 255u) == (uint32_t)s2) a_ac = base + moff[s2] * 4u;
+            }
+            minfo[warp * kMaxBlocksPerMcu + t] = make_uint2(a_dc, a_ac);
+        }
+    }
+    __syncthreads();
+    if (sd.img == kNoImage) return;
+    const ImgDev& img = sm.img[warp];
+    if (img.interval_mode) return;   // its decode threads start at restart-interval boundaries: nothing to synchronise
+    const ImgDyn dyn = b.dyn[sd.img];
+    const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
+    FastCtx cx = make_fast_ctx(b, sm, warp, dyn, ft);
+    cx.minfo_addr = smem_addr(minfo + warp * kMaxBlocksPerMcu);
+    JPGPU_PIN32(cx.minfo_addr);
+    const uint32_t j = sd.first_sub + (threadIdx.x & 31u);
+    if (j >= nsub) return;
+
+    const uint32_t own = j * S, p0 = own > b.lookback_bits ? own - b.lookback_bits : 0u;
+    FastState st;
+    fast_init(cx, st, p0, 0, 0u, 0, 0, 0);
+    fast_run_to<true>(cx, st, own);
+    SubInfo rec;
+    rec.pA = st.p;
+    rec.cz = ((uint32_t)st.g & 63u) | (fast_c(st) << 6);
+    fast_sync_subsequence<true>(cx, st, own, S, b.seg_bits, b.segs + (size_t)(img.sub_off + j) * (S / b.seg_bits), false, rec);
     b.subs[img.sub_off + j] = rec;
 }
 
@@ -816,7 +958,7 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
             SubInfo rec;
             rec.pA = st.p;
             rec.cz = job.cz;
-            fast_sync_subsequence(cx, st, job.sub * S, S, b.seg_bits, b.segs + (size_t)(im.sub_off + job.sub) * (S / b.seg_bits), true, rec);
+            fast_sync_subsequence<false>(cx, st, job.sub * S, S, b.seg_bits, b.segs + (size_t)(im.sub_off + job.sub) * (S / b.seg_bits), true, rec);
             subs[job.sub] = rec;
         }
         __syncthreads();
@@ -1022,6 +1164,22 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
     }
 }
 
+// The coefficient arena is reused wave after wave and never cleared (that memset was 6.4 GB per plan).  A complete
+// scan stores every one of its blocks; a scan whose data ended early leaves the blocks from ImgDyn::coef_end on
+// unwritten - holding an earlier image's coefficients - and this kernel, one CTA per image, zero-fills them.  For an
+// image that decoded completely (all but damaged files) it reads one word and returns.
+__global__ void __launch_bounds__(256) zero_tail_kernel(BatchDev b) {
+    const uint32_t img = b.img0 + blockIdx.x;
+    const ImgDyn d = b.dyn[img];
+    const ImgDev& im = b.imgs[img];
+    const uint32_t limit = coef_block_limit(d);
+    const uint32_t nblk = im.total_coefs >> 6;
+    if (limit >= nblk) return;
+    uint4* dst = reinterpret_cast<uint4*>(b.coefs + im.coef_off) + (size_t)limit * 8;
+    const size_t nvec = (size_t)(nblk - limit) * 8;
+    for (size_t i = threadIdx.x; i < nvec; i += 256) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // ============================================ stage 2+3: dequant + IDCT + upsample + colour
 constexpr int kIdctThreads = 128;
 #ifndef JPGPU_TILES_PER_CTA
@@ -1198,12 +1356,10 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
     __shared__ __align__(16) uint8_t s_out[PLANAR ? 3 * kPlaneSize : MH * kOutPitch];
     __shared__ __align__(16) float s_qt[3 * 64];
 
-    const uint32_t img_index = img_list[blockIdx.y];
-    const ImgDev& im = b.imgs[img_index];
+    const ImgDev& im = b.imgs[img_list[blockIdx.y]];
     const uint32_t ntiles = im.tiles_x * im.tiles_y;
     uint32_t tile = blockIdx.x * kTilesPerCta;
     if (tile >= ntiles) return;
-    const uint32_t blk_limit = coef_block_limit(b.dyn[img_index]);   // an image whose data ended early: zeros from there on
     const uint32_t tile_end = min(ntiles, tile + kTilesPerCta);
     const int tid = threadIdx.x, t = tid & 7, bp = tid >> 3;
 
@@ -1263,7 +1419,7 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
         const uint32_t here = min((uint32_t)NM, mcux - tx * NM);
 #pragma unroll
         for (int l = 0; l < NL; l++) {
-            const bool valid = (uint32_t)mcu_of[l] < here && mcu0 + mcu_of[l] < units && mcu0 * NB + blk_of[l] < blk_limit;
+            const bool valid = (uint32_t)mcu_of[l] < here && mcu0 + mcu_of[l] < units;
             dst[l] = make_uint4(0u, 0u, 0u, 0u);
             if (valid) dst[l] = __ldg(coefs + ((size_t)mcu0 * NB + blk_of[l]) * 8 + t);
         }
@@ -1453,11 +1609,10 @@ __global__ void __launch_bounds__(kIdctThreads) block_idct_kernel(BatchDev b, co
     const uint32_t blk = blockIdx.x * 16u + bp;
     if (blockIdx.x * 16u >= nblk) return;
     const bool valid = blk < nblk;
-    const bool written = blk < coef_block_limit(b.dyn[img_list[blockIdx.y]]);
     const uint32_t comp = valid ? im.blk_comp[blk % im.blocks_per_mcu] : 0u;
     const float* __restrict__ qt = b.qt + im.qt_off[comp] + t * 8;
     uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-    if (valid && written) raw = __ldg(reinterpret_cast<const uint4*>(b.coefs + im.coef_off) + (size_t)blk * 8 + t);
+    if (valid) raw = __ldg(reinterpret_cast<const uint4*>(b.coefs + im.coef_off) + (size_t)blk * 8 + t);
     float o[8];
     block_idct(raw, __ldg(reinterpret_cast<const float4*>(qt)), __ldg(reinterpret_cast<const float4*>(qt + 4)), t,
                s_scr + bp * kScrBlkPitch + t, s_scr + bp * kScrBlkPitch + t * kScrRowPitch, comp == 0u ? 128.0f : 0.0f, o);
@@ -1562,8 +1717,34 @@ void launch_gather_scans(const BatchDev& b, const void* base, const uint64_t* de
 void launch_prepass(const BatchDev& b, cudaStream_t s) {
     for (int step = 0; step < 3; step++) launch_prepass_step(b, s, step);
 }
-void launch_sync(const BatchDev& b, cudaStream_t s) {
-    if (b.n_seqs && b.nsync) sync_kernel<<<b.n_seqs / kJobsPerCta, kSeqThreads, 0, s>>>(b);
+// Opt-in dynamic shared memory is a per-device attribute of a kernel: set once per device (contexts of several devices
+// launch from several host threads, hence the lock).
+template <class K>
+static cudaError_t ensure_smem_attr(K kernel, uint32_t bytes, uint64_t& configured, std::mutex& mu) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 0 || dev >= 64 || !(configured >> dev & 1u)) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured |= 1ull << dev;
+    }
+    return cudaSuccess;
+}
+cudaError_t launch_sync(const BatchDev& b, cudaStream_t s) {
+    if (!b.n_seqs || !b.nsync) return cudaSuccess;
+    if (!b.sync_multi) {
+        sync_kernel<<<b.n_seqs / kJobsPerCta, kSeqThreads, 0, s>>>(b);
+        return cudaSuccess;
+    }
+    static std::mutex mu;
+    static uint64_t configured = 0;
+    // the largest layout: every slot an AC table
+    const cudaError_t e = ensure_smem_attr(sync_multi_kernel, sync_layout(kMaxLutSlots, kMaxLutSlots << kMultiBitsAc).total, configured, mu);
+    if (e != cudaSuccess) return e;
+    sync_multi_kernel<<<(b.n_seqs + kSyncJobs - 1) / kSyncJobs, kSyncThreads, sync_layout(b.max_slots, b.max_mlut_words).total, s>>>(b);
+    return cudaSuccess;
 }
 void launch_verify_scan(const BatchDev& b, cudaStream_t s) {
     if (b.n_images && b.nsync) verify_scan_kernel<<<b.n_images, kInterThreads, 0, s>>>(b);
@@ -1571,22 +1752,10 @@ void launch_verify_scan(const BatchDev& b, cudaStream_t s) {
 template <int NBUF, int PHASE>
 static cudaError_t launch_write_variant(const BatchDev& b, cudaStream_t s) {
     const WriteLayout lay = write_layout(b.max_slots, NBUF);
-    // The opt-in shared-memory size is a per-device attribute of the kernel: set once per device to what the largest
-    // layout needs.  Contexts of several devices decode from several host threads (jpgpu_multi_*), hence the lock.
     static std::mutex mu;
-    static uint64_t configured = 0;   // bit d: device d is set up
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    static uint64_t configured = 0;   // bit d: device d is set up (for the largest layout)
+    const cudaError_t e = ensure_smem_attr(decode_write_kernel<NBUF, PHASE>, write_layout(kMaxLutSlots, NBUF).total, configured, mu);
     if (e != cudaSuccess) return e;
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (dev < 0 || dev >= 64 || !(configured >> dev & 1u)) {
-            e = cudaFuncSetAttribute(decode_write_kernel<NBUF, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)write_layout(kMaxLutSlots, NBUF).total);
-            if (e != cudaSuccess) return e;
-            if (dev >= 0 && dev < 64) configured |= 1ull << dev;
-        }
-    }
     const uint32_t jobs = b.n_seqs << b.wp_shift;   // n_seqs is a multiple of kWriteJobsPerCta (build_plan)
     decode_write_kernel<NBUF, PHASE><<<(jobs + kWriteJobsPerCta - 1) / kWriteJobsPerCta, kWriteThreads, lay.total, s>>>(b);
     return cudaSuccess;
@@ -1595,7 +1764,10 @@ cudaError_t launch_decode_write(const BatchDev& b, cudaStream_t s) {
     if (!b.n_seqs) return cudaSuccess;
     // one block buffer per lane and 5-symbol phases measured best on B200 (2 buffers / 8-12 symbols: fewer flushes, but
     // half the resident warps); see DESIGN.md 4.2
-    return launch_write_variant<kWriteBufs, kPhaseSymbols>(b, s);
+    const cudaError_t e = launch_write_variant<kWriteBufs, kPhaseSymbols>(b, s);
+    if (e != cudaSuccess) return e;
+    if (b.n_images) zero_tail_kernel<<<b.n_images, 256, 0, s>>>(b);   // blocks a damaged scan never reached
+    return cudaSuccess;
 }
 
 int launch_idct_colour(const BatchDev& b, cudaStream_t s) {

@@ -19,6 +19,10 @@ struct BatchDev {        // device pointers of one planned batch
     ImgDyn* dyn;
     const SeqDesc* seqs;
     const HuffLut* luts;
+    const uint32_t* mlut;     // multi-symbol tables of the synchronisation pass (jpgpu_core.h), one per entry of luts
+    const uint32_t* mlut_off; // where each begins in mlut (words)
+    uint32_t max_mlut_words;  // most words the tables of one image's slots take together (shared memory of sync_kernel)
+    uint32_t sync_multi;      // 1: the synchronisation pass decodes through the multi-symbol tables
     const float* qt;     // pre-scaled dequantisation multipliers, 64 per table, column-major
     const uint8_t* raw;
     uint32_t* stream;
@@ -59,7 +63,7 @@ void launch_gather_scans(const BatchDev& b, const void* base, const uint64_t* de
 void launch_prepass(const BatchDev& b, cudaStream_t s);
 void launch_prepass_step(const BatchDev& b, cudaStream_t s, int step);  // 0 count, 1 scan, 2 write (profiling)
 // Stage 1b: look-back synchronisation, one thread per subsequence.
-void launch_sync(const BatchDev& b, cudaStream_t s);
+cudaError_t launch_sync(const BatchDev& b, cudaStream_t s);
 // Stage 1c: chain verification, repair of the links the look-back did not synchronise, prefix scan; one CTA per image.
 void launch_verify_scan(const BatchDev& b, cudaStream_t s);
 // Stage 1d: final decode, whole coefficient blocks written to HBM.

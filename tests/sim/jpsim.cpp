@@ -34,6 +34,7 @@ struct SimBatch {
     uint64_t repairs = 0;          // subsequences decoded again because the look-back had not synchronised
     uint64_t sync_decodes = 0;     // subsequences decoded by the sync pass
     uint64_t flush_phases = 0, flushed_blocks = 0;
+    uint64_t sync_digest = 0;      // hash of the records the synchronisation pass wrote (SubInfo + SegRec)
 };
 
 // mirrors prepass_kernel's per-byte rule (the warp/CTA scan itself is GPU plumbing)
@@ -81,6 +82,8 @@ void sim_prepass(SimBatch& sb, size_t img) {
     sb.dyn[img] = ImgDyn{emitted * 8, nseg, status, 0};
 }
 
+bool g_sync_multi = true;   // jpsim_set_sync_multi(): the synchronisation pass goes through the multi-symbol tables
+
 DecCtx make_ctx(const SimBatch& sb, size_t img, const HuffLut* slots) {
     const ImgDev& im = sb.plan.imgs[img];
     DecCtx cx;
@@ -93,6 +96,7 @@ DecCtx make_ctx(const SimBatch& sb, size_t img, const HuffLut* slots) {
     cx.nblk = im.blocks_per_mcu;
     cx.luts = slots;
     cx.blk_info = im.blk_info;
+    cx.mluts = nullptr;
     return cx;
 }
 
@@ -113,7 +117,10 @@ void sim_sync(SimBatch& sb, const SeqDesc& sd) {
     const uint32_t S = sb.plan.sub_bits, L = sb.plan.lookback_bits;
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
     if (sd.first_sub >= nsub) return;
-    const DecCtx cx = make_ctx(sb, sd.img, slots.data());
+    DecCtx cx = make_ctx(sb, sd.img, slots.data());
+    const uint32_t* mslots[kMaxLutSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int s = 0; s < im.nslots; s++) mslots[s] = sb.plan.mluts.data() + sb.plan.mlut_off[im.slot_lut[s]];
+    if (g_sync_multi) cx.mluts = mslots;   // sync_multi_kernel; the repair walks of verify_scan_kernel go symbol by symbol
     for (uint32_t tid = 0; tid < 32u; tid++) {  // one warp job
         const uint32_t j = sd.first_sub + tid;
         if (j >= nsub) continue;
@@ -121,6 +128,7 @@ void sim_sync(SimBatch& sb, const SeqDesc& sd) {
         DecState st;
         init_state(cx, st, p0, 0, 0, 0, 0, 0);
         while (st.p < own) {
+            if (cx.mluts && st.p + 32u <= own && st.p + 39u <= st.seg_end) { multi_symbol(cx, st); continue; }
             if (decode_symbol<false>(cx, st, nullptr, 0u, nullptr, false) & kEvEnd) break;
         }
         SubInfo rec;
@@ -404,6 +412,17 @@ void sim_gather(SimBatch& sb, size_t img) {
 
 extern "C" {
 
+void jpsim_set_sync_multi(int on) { g_sync_multi = on != 0; }
+
+// build_multi_lut for unit tests: writes the 2^kMultiBits entries of one table to out (cap entries); returns their number
+int jpsim_build_multi_lut(const uint8_t bits[16], const uint8_t* vals, int is_dc, uint32_t* out, size_t cap) {
+    std::vector<uint32_t> v;
+    build_multi_lut(bits, vals, is_dc != 0, v);
+    if (v.size() > cap) return -1;
+    memcpy(out, v.data(), v.size() * sizeof(uint32_t));
+    return (int)v.size();
+}
+
 // Runs the whole simulated pipeline on a batch of descriptors.
 //   rgb_out[i]   : W*H*3 bytes (may be NULL)
 //   coef_out[i]  : reference-order coefficients (may be NULL), coef_cap[i] int16 each
@@ -428,6 +447,18 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
         if (p.status[i] == JPGPU_OK) memcpy(sb.raw.data() + p.imgs[i].raw_off, descs[i].scan, p.imgs[i].raw_len);
     for (size_t i = 0; i < n; i++) sim_prepass(sb, i);
     for (const SeqDesc& sd : p.seqs) sim_sync(sb, sd);
+    {   // FNV-1a over what the synchronisation pass recorded (before repairs): the multi-symbol and the symbol-by-symbol
+        // pass must agree on every state they write down, not just on the final result
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&h](const void* ptr, size_t len) { const uint8_t* q = (const uint8_t*)ptr; for (size_t k = 0; k < len; k++) { h ^= q[k]; h *= 1099511628211ull; } };
+        for (size_t i = 0; i < n; i++) {
+            if (p.status[i] != JPGPU_OK || p.imgs[i].interval_mode) continue;
+            const uint32_t nsub = (sb.dyn[i].stream_bits + p.sub_bits - 1) / p.sub_bits;
+            mix(sb.subs.data() + p.imgs[i].sub_off, (size_t)nsub * sizeof(SubInfo));
+            mix(sb.segs.data() + (size_t)p.imgs[i].sub_off * (p.sub_bits / p.seg_bits), (size_t)nsub * (p.sub_bits / p.seg_bits) * sizeof(SegRec));
+        }
+        sb.sync_digest = h;
+    }
     for (size_t i = 0; i < n; i++) sim_verify_scan(sb, i);
     for (const SeqDesc& sd : p.seqs)
         for (uint32_t group = 0; group < (1u << p.wp_shift); group++) sim_decode_write(sb, sd, group);
@@ -451,7 +482,7 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
         if (statuses) statuses[i] = s;
         if (bytes_read) bytes_read[i] = br;
     }
-    if (diag) { diag[0] = sb.repair_iters; diag[1] = sb.repairs; diag[2] = sb.sync_decodes; diag[3] = sb.flush_phases; }
+    if (diag) { diag[0] = sb.repair_iters; diag[1] = sb.repairs; diag[2] = sb.sync_decodes; diag[3] = sb.flush_phases; diag[4] = sb.sync_digest; }
     return JPGPU_OK;
 }
 

@@ -54,7 +54,7 @@ def decode_batch(files, layout=_ffi.LAYOUT_SPEC, ext=_ffi.EXT_NONE, sub_bits=0):
     nblocks = (C.c_uint32 * (4 * n))()
     statuses = (C.c_int32 * n)()
     bytes_read = (C.c_uint64 * n)()
-    diag = (C.c_uint64 * 4)()
+    diag = (C.c_uint64 * 8)()
     st = L.jpsim_decode_batch(descs, n, rgb_p, coef_p, caps, nblocks, statuses, bytes_read, diag, sub_bits)
     assert st == 0, st
     out = []
@@ -72,7 +72,13 @@ def decode_batch(files, layout=_ffi.LAYOUT_SPEC, ext=_ffi.EXT_NONE, sub_bits=0):
             r.coefs.append(coefs[i][off:off + nb[c] * 64].reshape(-1, 64))
             off += nb[c] * 64
         out.append(r)
-    return out, {"repair_iters": diag[0], "repairs": diag[1], "sync_decodes": diag[2], "flush_phases": diag[3]}
+    return out, {"repair_iters": diag[0], "repairs": diag[1], "sync_decodes": diag[2], "flush_phases": diag[3],
+                 "sync_digest": diag[4]}
+
+
+def set_sync_multi(on):
+    """The simulated synchronisation pass through the multi-symbol tables (default, as the product) or symbol by symbol."""
+    lib().jpsim_set_sync_multi(1 if on else 0)
 
 
 def idct_8x8(block_natural):

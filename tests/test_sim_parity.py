@@ -312,3 +312,81 @@ def test_header_claim_is_tied_to_the_scan_bytes():
     t0 = time.time()
     rs, _ = S.decode_batch([bytes(f)], layout=0)
     assert rs[0].status == 37 and time.time() - t0 < 2.0     # JPGPU_ERR_TRUNCATED, without the 10 GB detour
+
+
+def test_multi_symbol_sync_records_equal_the_single_symbol_ones():
+    """The synchronisation pass through the multi-symbol tables (sync_multi_kernel / multi_symbol()) must write down
+    exactly the states the symbol-by-symbol pass writes - every SubInfo and SegRec, not just the final pixels - because
+    the chain verification and the repair walks (symbol by symbol) compare against them."""
+    rng = np.random.default_rng(11)
+    cases = []
+    for name, layout, ext in (("lena.jpeg", 0, 0), ("lena-bw.jpeg", 0, 0), ("huff_simple0.jpg", 0, 1), ("2x2-chroma.jpeg", 1, 0)):
+        cases.append(([fixture_bytes(name)], layout, ext))
+    cases.append(([synth.synth_jpeg(9000 + i, 320 + 16 * i, 200 + 8 * i, s) for i, s in enumerate(["420", "444", "422", "gray", "440"])], 1, 0))
+    cases.append(([synth.synth_jpeg(9010 + i, 256, 192, "420", restart_interval=ri) for i, ri in enumerate([1, 5, 64])], 1, 2))
+    cases.append(([synth.synth_jpeg(9020, 384, 256, "420", optimize=True), synth.synth_jpeg(9021, 384, 256, "444", optimize=True, dqt16=True),
+                   synth.synth_jpeg(9022, 640, 480, "420", quality=98, noise_sigma=25.0), synth.synth_jpeg(9023, 640, 480, "420", quality=20)], 1, 0))
+    cases.append(([synth.encode(rng.integers(0, 256, (96, 128, 3), dtype=np.uint8), "444", quality=100)], 1, 0))
+    cases.append(([synth.crafted_flood_jpeg(300_000)], 1, 0))
+    try:
+        for files, layout, ext in cases:
+            for sub_bits in (0, 1024):
+                S.set_sync_multi(True)
+                a, da = S.decode_batch(files, layout=layout, ext=ext, sub_bits=sub_bits)
+                S.set_sync_multi(False)
+                b, db = S.decode_batch(files, layout=layout, ext=ext, sub_bits=sub_bits)
+                assert da["sync_digest"] == db["sync_digest"] and da["repairs"] == db["repairs"]
+                for x, y in zip(a, b):
+                    assert x.status == y.status and x.bytes_read == y.bytes_read and np.array_equal(x.rgb, y.rgb)
+    finally:
+        S.set_sync_multi(True)
+
+
+def test_multi_symbol_table_entries():
+    """build_multi_lut against a brute-force decode of every window with the Annex-K luminance AC table."""
+    import ctypes as C
+    from jpeg_rust_b200 import parse_descriptor
+    st, d, _ = parse_descriptor(synth.synth_jpeg(1, 16, 16, "gray"))
+    assert st == 0
+    bits, vals = list(d.ac_bits[0]), list(d.ac_vals[0])
+    codes, code, k = {}, 0, 0
+    for length in range(1, 17):
+        for _ in range(bits[length - 1]):
+            codes[(length, code)] = vals[k]
+            code += 1
+            k += 1
+        code <<= 1
+    K = 11
+    n = 1 << K
+    out = (C.c_uint32 * n)()
+    S.lib().jpsim_build_multi_lut((C.c_uint8 * 16)(*bits), (C.c_uint8 * 256)(*(vals + [0] * (256 - len(vals)))), 0, out, n)
+    for w in (0, 1, 0b01010101010, 0b10101010101, 0b11111111111, 0b00000000001, 0b10010011001, 1234, 777, 2047, 2046):
+        pos, syms = 0, []
+        while pos < K:
+            hit = None
+            for length in range(1, 17):
+                if pos + length > K:
+                    break
+                c = (w >> (K - pos - length)) & ((1 << length) - 1)
+                if (length, c) in codes:
+                    hit = (length, codes[(length, c)])
+                    break
+            if hit is None:
+                break
+            length, sym = hit
+            size = 0 if sym in (0x00, 0xF0) else sym & 15
+            adv = 64 if sym == 0 else (16 if sym == 0xF0 else (sym >> 4) + 1)
+            if syms and sum(a for _, a in syms) + (0 if sym == 0 else adv) > 63:
+                break
+            syms.append((length + size, adv))
+            pos += length + size
+            if sym == 0:
+                break
+        e = out[w]
+        if not syms:
+            assert e == 0
+            continue
+        assert e & 31 == sum(t for t, _ in syms)
+        assert (e >> 5) & 127 == sum(a for _, a in syms)
+        assert (e >> 12) & 63 == sum(a for _, a in syms[:-1])
+        assert (e >> 18) & 31 == syms[0][0] and (e >> 23) & 127 == syms[0][1]
