@@ -76,7 +76,12 @@ enum { JPGPU_LAYOUT_REF = 0, JPGPU_LAYOUT_SPEC = 1 };
 /* Sample arrangement of the output (the step after the path).  INTERLEAVED is the
  * reference's Vec<(u8,u8,u8)> (decoder.rs:162, 317-331): W*H triples, row-major.  PLANAR holds the same W*H*3
  * bytes as three W x H planes R, G, B (a CHW uint8 tensor).  Same values, same size, same per-image offsets. */
-enum { JPGPU_OUT_RGB_INTERLEAVED = 0, JPGPU_OUT_RGB_PLANAR = 1 };
+enum { JPGPU_OUT_RGB_INTERLEAVED = 0, JPGPU_OUT_RGB_PLANAR = 1,
+       /* three W x H planes of float: the same 8-bit samples as sample * scale[c] + bias[c] (jpgpu_batch_set_normalisation;
+        * default scale 1/255, bias 0: a CHW float32 tensor in [0, 1]).  Four bytes per sample: every output size and offset
+        * (jpgpu_batch_output_bytes, jpgpu_batch_rgb_offset, jpgpu_batch_device_rgb, the download calls) is four times the
+        * u8 one.  Converted inside the IDCT/colour kernel while a tile is copied out - no second pass over the pixels. */
+       JPGPU_OUT_F32_PLANAR = 2 };
 
 /* Parser extensions beyond the reference's accepted subset (bit flags). */
 enum {
@@ -190,6 +195,8 @@ int jpgpu_batch_set_device_scans(jpgpu_batch *b, const void *dev_base, const uin
 int jpgpu_batch_set_device_output(jpgpu_batch *b, void *dev_base, size_t capacity);
 /* Output arrangement (JPGPU_OUT_*) of the following idct / decode calls; kept across replans.  Default: interleaved. */
 int jpgpu_batch_set_output_format(jpgpu_batch *b, uint32_t format);
+/* JPGPU_OUT_F32_PLANAR: out = sample * scale[c] + bias[c] per channel c = R, G, B (e.g. 1/(255*std), -mean/std). */
+int jpgpu_batch_set_normalisation(jpgpu_batch *b, const float scale[3], const float bias[3]);
 int jpgpu_batch_entropy(jpgpu_batch *b); /* stage 1: unstuff/RST pre-pass, self-synchronising Huffman decode */
 int jpgpu_batch_idct(jpgpu_batch *b);    /* stage 2+3: dequant, IDCT, upsample, YCbCr->RGB, interleaved store */
 int jpgpu_batch_decode(jpgpu_batch *b);  /* entropy + idct */

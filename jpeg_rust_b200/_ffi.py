@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libjpgpu.so")
 
 LAYOUT_REF, LAYOUT_SPEC = 0, 1
 EXT_NONE, EXT_SKIP_APPN, EXT_DRI = 0, 1, 2
-OUT_RGB_INTERLEAVED, OUT_RGB_PLANAR = 0, 1
+OUT_RGB_INTERLEAVED, OUT_RGB_PLANAR, OUT_F32_PLANAR = 0, 1, 2
 MEMORY_HOST, MEMORY_DEVICE = 0, 1
 
 OK = 0
@@ -91,6 +91,7 @@ def lib():
         L.jpgpu_batch_set_device_scans.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
         L.jpgpu_batch_set_device_output.argtypes = [vp, vp, sz]
         L.jpgpu_batch_set_output_format.argtypes = [vp, C.c_uint32]
+        L.jpgpu_batch_set_normalisation.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.jpgpu_batch_download.argtypes = [vp, C.POINTER(vp)]
         L.jpgpu_batch_device_rgb.restype = vp
         L.jpgpu_batch_device_rgb.argtypes = [vp, sz, C.POINTER(sz)]
@@ -162,7 +163,7 @@ EXPORTED_SYMBOLS = [
     "jpgpu_create", "jpgpu_destroy", "jpgpu_last_error", "jpgpu_set_stream", "jpgpu_sync",
     "jpgpu_decode", "jpgpu_decode_file",
     "jpgpu_batch_create", "jpgpu_batch_replan", "jpgpu_batch_destroy", "jpgpu_batch_upload", "jpgpu_batch_set_device_scans", "jpgpu_batch_set_device_output",
-    "jpgpu_batch_set_output_format",
+    "jpgpu_batch_set_output_format", "jpgpu_batch_set_normalisation",
     "jpgpu_batch_entropy", "jpgpu_batch_idct", "jpgpu_batch_decode", "jpgpu_batch_download",
     "jpgpu_batch_device_rgb", "jpgpu_batch_output_bytes", "jpgpu_batch_rgb_offset", "jpgpu_batch_results", "jpgpu_batch_coefficients", "jpgpu_batch_stats",
     "jpgpu_batch_profile", "jpgpu_batch_launch_count",

@@ -92,6 +92,9 @@ int dev_ensure(jpgpu_batch* b, int which, T** out, size_t count) {
     return JPGPU_OK;
 }
 
+// bytes per output sample: 1 (u8 formats) or 4 (JPGPU_OUT_F32_PLANAR); every size and offset of the output scales with it
+size_t sample_bytes(const jpgpu_batch* b) { return b->dev.out_planar == 2u ? 4u : 1u; }
+
 template <typename T>
 int dev_upload(jpgpu_batch* b, int which, const T** out, const std::vector<T>& v) {
     jpgpu_ctx* ctx = b->ctx;
@@ -184,10 +187,11 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     HostPlan& p = b->plan;
     const bool external_rgb = b->dev.rgb && b->dev.rgb != b->own_rgb;
     uint8_t* const ext_rgb = b->dev.rgb;
-    const uint32_t out_planar = b->dev.out_planar;   // the output format outlives a replan
+    const BatchDev prev = b->dev;   // the output format outlives a replan
     memset(&b->dev, 0, sizeof b->dev);
     BatchDev& d = b->dev;
-    d.out_planar = out_planar;
+    d.out_planar = prev.out_planar;
+    for (int k = 0; k < 3; k++) { d.out_scale[k] = prev.out_scale[k]; d.out_bias[k] = prev.out_bias[k]; }
     d.n_images = (uint32_t)n;
     d.n_seqs = (uint32_t)p.seqs.size();
     d.nsync = p.nsync;
@@ -231,12 +235,12 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     TRY(dev_ensure(b, jpgpu_batch::kChunks, &d.chunk_counts, p.chunk_entries + 1));
     d.max_chunks = p.max_chunks;
     TRY(dev_ensure(b, jpgpu_batch::kCoefs, &d.coefs, p.coef_elems + 64));
-    if (external_rgb && b->ext_rgb_cap >= p.rgb_bytes) {
+    if (external_rgb && b->ext_rgb_cap >= p.rgb_bytes * sample_bytes(b)) {
         d.rgb = ext_rgb;   // stays where jpgpu_batch_set_device_output() pointed it: the new plan fits the caller's arena
     } else {
         // no external arena, or one too small for the new plan: the batch's own arena (grown to the plan)
         b->ext_rgb_cap = 0;
-        TRY(dev_ensure(b, jpgpu_batch::kRgb, &d.rgb, p.rgb_bytes + 256));
+        TRY(dev_ensure(b, jpgpu_batch::kRgb, &d.rgb, p.rgb_bytes * sample_bytes(b) + 256));
     }
     b->own_rgb = static_cast<uint8_t*>(b->arena[jpgpu_batch::kRgb].p);
 #undef TRY
@@ -333,10 +337,11 @@ extern "C" int jpgpu_batch_upload_from(jpgpu_batch* b, const void* host_base, si
 // layout the device arena has (256-byte aligned slices).
 extern "C" int jpgpu_batch_download_contiguous(jpgpu_batch* b, void* host_base, size_t capacity) try {
     if (!b || !host_base) return JPGPU_ERR_INVALID_ARG;
-    if (capacity < b->plan.rgb_bytes) return JPGPU_ERR_INVALID_ARG;
+    const size_t total = b->plan.rgb_bytes * sample_bytes(b);
+    if (capacity < total) return JPGPU_ERR_INVALID_ARG;
     jpgpu_ctx* ctx = b->ctx;
     CK(cudaSetDevice(ctx->device));
-    if (b->plan.rgb_bytes) CK(cudaMemcpyAsync(host_base, b->dev.rgb, b->plan.rgb_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (total) CK(cudaMemcpyAsync(host_base, b->dev.rgb, total, cudaMemcpyDeviceToHost, ctx->stream));
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
 
@@ -347,13 +352,13 @@ extern "C" int jpgpu_batch_set_device_output(jpgpu_batch* b, void* dev_base, siz
         CK(cudaSetDevice(ctx->device));
         // the own arena may never have been allocated, or only for an earlier, smaller plan (replans under an external
         // output skip it): size it for the current plan
-        int st = dev_ensure(b, jpgpu_batch::kRgb, &b->own_rgb, b->plan.rgb_bytes + 256);
+        int st = dev_ensure(b, jpgpu_batch::kRgb, &b->own_rgb, b->plan.rgb_bytes * sample_bytes(b) + 256);
         if (st != JPGPU_OK) return st;
         b->dev.rgb = b->own_rgb;
         b->ext_rgb_cap = 0;
         return JPGPU_OK;
     }
-    if (capacity < b->plan.rgb_bytes || (reinterpret_cast<uintptr_t>(dev_base) & 255u)) return JPGPU_ERR_INVALID_ARG;
+    if (capacity < b->plan.rgb_bytes * sample_bytes(b) || (reinterpret_cast<uintptr_t>(dev_base) & 255u)) return JPGPU_ERR_INVALID_ARG;
     b->dev.rgb = static_cast<uint8_t*>(dev_base);
     b->ext_rgb_cap = capacity;
     return JPGPU_OK;
@@ -466,32 +471,51 @@ extern "C" int jpgpu_batch_download(jpgpu_batch* b, uint8_t* const* outs) try {
     for (size_t i = 0; i < b->n; i++) {
         if (b->plan.status[i] != JPGPU_OK || !outs[i]) continue;
         const ImgDev& im = b->plan.imgs[i];
-        CK(cudaMemcpyAsync(outs[i], b->dev.rgb + im.rgb_off, (size_t)im.width * im.height * 3, cudaMemcpyDeviceToHost,
+        const size_t sb = sample_bytes(b);
+        CK(cudaMemcpyAsync(outs[i], b->dev.rgb + im.rgb_off * sb, (size_t)im.width * im.height * 3 * sb, cudaMemcpyDeviceToHost,
                            ctx->stream));
     }
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
 
 extern "C" int jpgpu_batch_set_output_format(jpgpu_batch* b, uint32_t format) try {
-    if (!b || format > JPGPU_OUT_RGB_PLANAR) return JPGPU_ERR_INVALID_ARG;
-    b->dev.out_planar = format == JPGPU_OUT_RGB_PLANAR ? 1u : 0u;
+    if (!b || format > JPGPU_OUT_F32_PLANAR) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    const size_t before = sample_bytes(b);
+    b->dev.out_planar = format;
+    if (format == JPGPU_OUT_F32_PLANAR && b->dev.out_scale[0] == 0.0f && b->dev.out_scale[1] == 0.0f && b->dev.out_scale[2] == 0.0f)
+        for (int k = 0; k < 3; k++) { b->dev.out_scale[k] = 1.0f / 255.0f; b->dev.out_bias[k] = 0.0f; }   // default: [0, 1]
+    if (sample_bytes(b) != before) {
+        // the output grows or shrinks four-fold: a caller-owned arena set for the other format no longer applies
+        CK(cudaSetDevice(ctx->device));
+        const int st = dev_ensure(b, jpgpu_batch::kRgb, &b->own_rgb, b->plan.rgb_bytes * sample_bytes(b) + 256);
+        if (st != JPGPU_OK) return st;
+        b->dev.rgb = b->own_rgb;
+        b->ext_rgb_cap = 0;
+    }
+    return JPGPU_OK;
+} JPGPU_CATCH_ALL
+
+extern "C" int jpgpu_batch_set_normalisation(jpgpu_batch* b, const float scale[3], const float bias[3]) try {
+    if (!b || !scale || !bias) return JPGPU_ERR_INVALID_ARG;
+    for (int k = 0; k < 3; k++) { b->dev.out_scale[k] = scale[k]; b->dev.out_bias[k] = bias[k]; }
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
 
 extern "C" void* jpgpu_batch_device_rgb(jpgpu_batch* b, size_t i, size_t* nbytes) {
     if (!b || i >= b->n || b->plan.status[i] != JPGPU_OK) return nullptr;
     const ImgDev& im = b->plan.imgs[i];
-    if (nbytes) *nbytes = (size_t)im.width * im.height * 3;
-    return b->dev.rgb + im.rgb_off;
+    if (nbytes) *nbytes = (size_t)im.width * im.height * 3 * sample_bytes(b);
+    return b->dev.rgb + im.rgb_off * sample_bytes(b);
 }
 
-extern "C" size_t jpgpu_batch_output_bytes(const jpgpu_batch* b) { return b ? (size_t)b->plan.rgb_bytes : 0; }
+extern "C" size_t jpgpu_batch_output_bytes(const jpgpu_batch* b) { return b ? (size_t)b->plan.rgb_bytes * sample_bytes(b) : 0; }
 
 extern "C" int jpgpu_batch_rgb_offset(const jpgpu_batch* b, size_t i, size_t* offset, size_t* nbytes) {
     if (!b || i >= b->n) return JPGPU_ERR_INVALID_ARG;
     const ImgDev& im = b->plan.imgs[i];
-    if (offset) *offset = (size_t)im.rgb_off;
-    if (nbytes) *nbytes = b->plan.status[i] == JPGPU_OK ? (size_t)im.width * im.height * 3 : 0;
+    if (offset) *offset = (size_t)im.rgb_off * sample_bytes(b);
+    if (nbytes) *nbytes = b->plan.status[i] == JPGPU_OK ? (size_t)im.width * im.height * 3 * sample_bytes(b) : 0;
     return JPGPU_OK;
 }
 

@@ -97,7 +97,10 @@ constexpr uint32_t kBadEntry = 16u | (16u << 8) | (64u << 16);  // unknown code:
 // DC tables have the same format with one symbol per entry, index width kMultiBitsDc, and the code LENGTH in the
 // adv_pre field (the DC difference must be extracted; z = 0 there, so the entry always holds).  0 = no symbol can be
 // determined from the window (code longer than the window, no such code, DC size > 16): single-symbol path.
-constexpr int kMultiBitsAc = 11;
+#ifndef JPGPU_MULTI_BITS
+#define JPGPU_MULTI_BITS 12
+#endif
+constexpr int kMultiBitsAc = JPGPU_MULTI_BITS;
 constexpr int kMultiBitsDc = 9;
 JPGPU_HD uint32_t multi_entry(uint32_t tb_all, uint32_t adv_all, uint32_t adv_pre, uint32_t tb1, uint32_t adv1) {
     return tb_all | (adv_all << 5) | (adv_pre << 12) | (tb1 << 18) | (adv1 << 23);

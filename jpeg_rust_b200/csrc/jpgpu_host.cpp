@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <new>
 
 namespace jpgpu {
@@ -216,6 +218,36 @@ void build_qt_multipliers(const uint16_t qt_zigzag[64], float out[64]) {
     }
 }
 
+namespace {
+struct LutCacheEntry {
+    HuffLut lut;
+    std::vector<uint32_t> mlut;
+};
+// Process-wide, never shrinking below its entries (pointers handed out stay valid); bounded: a stream of files with
+// ever new optimised tables stops being cached after kLutCacheMax entries and builds its tables per plan.
+constexpr size_t kLutCacheMax = 1024;
+int cached_luts(const std::string& key, const uint8_t bits[16], const uint8_t* vals, int nvals, bool is_dc, const LutCacheEntry** out) {
+    static std::mutex mu;
+    static std::map<std::string, std::unique_ptr<LutCacheEntry>> cache;
+    static thread_local LutCacheEntry overflow;   // uncached build
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second.get(); return JPGPU_OK; }
+    }
+    std::unique_ptr<LutCacheEntry> e(new LutCacheEntry());
+    const int st = build_huff_lut(bits, vals, nvals, is_dc, e->lut);
+    if (st != JPGPU_OK) return st;
+    build_multi_lut(bits, vals, is_dc, e->mlut);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second.get(); return JPGPU_OK; }
+    if (cache.size() >= kLutCacheMax) { overflow = std::move(*e); *out = &overflow; return JPGPU_OK; }
+    *out = cache.emplace(key, std::move(e)).first->second.get();
+    return JPGPU_OK;
+}
+}  // namespace
+
 uint32_t choose_subseq_bits(uint64_t total_scan_bytes) {
     if (const char* e = getenv("JPGPU_SUBSEQ_BITS")) {
         const long v = atol(e);
@@ -347,13 +379,15 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
                 auto it = lut_ids.find(key);
                 uint32_t id;
                 if (it == lut_ids.end()) {
-                    HuffLut lut;
-                    st = build_huff_lut(bits, vals, nvals, cls == 0, lut);
+                    // device tables of this DHT table: built once per process (most files carry the Annex-K tables, and a
+                    // multi-symbol table costs ~50 us to build - more than the rest of a single-image plan)
+                    const LutCacheEntry* ce = nullptr;
+                    st = cached_luts(key, bits, vals, nvals, cls == 0, &ce);
                     if (st != JPGPU_OK) break;
                     id = (uint32_t)plan.luts.size();
-                    plan.luts.push_back(lut);
+                    plan.luts.push_back(ce->lut);
                     plan.mlut_off.push_back((uint32_t)plan.mluts.size());
-                    build_multi_lut(bits, vals, cls == 0, plan.mluts);
+                    plan.mluts.insert(plan.mluts.end(), ce->mlut.begin(), ce->mlut.end());
                     lut_ids.emplace(key, id);
                 } else {
                     id = it->second;

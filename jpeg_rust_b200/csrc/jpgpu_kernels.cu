@@ -681,9 +681,11 @@ __device__ __forceinline__ void fast_run_to(const FastCtx& cx, FastState& st, ui
         if (st.p >= st.wrap_lim) fast_fix_wrap(cx, st);
         const uint32_t lim = min(end_bit, st.lim);
         if constexpr (MULTI) {
-            const uint32_t mlim = lim >= 32u ? lim - 32u : 0u;
+            if (lim >= 32u) {
+                const uint32_t mlim = lim - 32u;
 #pragma unroll 1
-            while (st.p <= mlim && mlim != 0u) fast_mstep(cx, st);
+                while (st.p <= mlim) fast_mstep(cx, st);
+            }
             if (st.p >= st.wrap_lim) continue;
         }
 #pragma unroll 1
@@ -820,7 +822,10 @@ __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
 
 // The same pass through the multi-symbol tables (jpgpu_core.h): 256-thread CTAs (eight warp jobs share one copy of the
 // tables), dynamic shared memory = Huffman tables of the slots in use + fast-path tables + multi-symbol tables.
-constexpr int kSyncThreads = 256;
+#ifndef JPGPU_SYNC_THREADS
+#define JPGPU_SYNC_THREADS 256
+#endif
+constexpr int kSyncThreads = JPGPU_SYNC_THREADS;
 constexpr int kSyncJobs = kSyncThreads / 32;
 struct SyncLayout {
     uint32_t ft_off, minfo_off, mlut_off, total;
@@ -1328,8 +1333,11 @@ __device__ __forceinline__ void block_idct2p(const uint4 raw_a, const uint4 raw_
 // tiles; the coefficient loads of the next tile are issued before the current one is
 // computed.
 // PLANAR: the output is three W x H byte planes (R, G, B) instead of interleaved triples (jpgpu_batch_set_output_format).
-template <int HY, int VY, bool GRAY, bool PLANAR>
+template <int HY, int VY, bool GRAY, int FORMAT>
 __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t* __restrict__ img_list) {
+    // FORMAT (jpgpu_batch_set_output_format): 0 interleaved u8 triples, 1 three u8 planes, 2 three f32 planes holding
+    // u8 * scale[c] + bias[c] - staged like 1, converted while the tile is copied out
+    constexpr bool PLANAR = FORMAT != 0, F32 = FORMAT == 2;
     constexpr int MH = 8 * VY;
     constexpr int NM = 128 / (8 * HY);         // MCUs per tile
     constexpr int NY = HY * VY;                // luma blocks per MCU
@@ -1370,7 +1378,7 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
     }
 
     const uint4* __restrict__ coefs = reinterpret_cast<const uint4*>(b.coefs + im.coef_off);
-    uint8_t* __restrict__ rgb = b.rgb + im.rgb_off;
+    uint8_t* __restrict__ rgb = b.rgb + im.rgb_off * (F32 ? 4u : 1u);
     const uint32_t W = im.width, H = im.height, mcux = im.mcux, units = im.units, tiles_x = im.tiles_x;
     float* const scr_w = s_scr + bp * kScrBlkPitch + t;
     const float* const scr_r = s_scr + bp * kScrBlkPitch + t * kScrRowPitch;
@@ -1567,8 +1575,26 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
         const uint32_t x0 = tx * 128u, y0 = ty * MH;
         const uint32_t wpx = min(128u, W - x0), rows = min((uint32_t)MH, H - y0);
         const uint32_t rowbytes = PLANAR ? wpx : wpx * 3u;
-        uint8_t* const tile_out = PLANAR ? rgb + (size_t)y0 * W + x0 : rgb + ((size_t)y0 * W + x0) * 3u;
-        if (vec_ok && (rowbytes & 15u) == 0u) {
+        uint8_t* const tile_out = PLANAR ? rgb + ((size_t)y0 * W + x0) * (F32 ? 4u : 1u) : rgb + ((size_t)y0 * W + x0) * 3u;
+        if constexpr (F32) {
+            // one float per staged byte: thread i converts 4 bytes of one row of one plane into one 16-byte store
+            const uint32_t per_plane = rows * (wpx >> 2);
+            const bool vec4 = (W & 3u) == 0u && (wpx & 3u) == 0u;
+            for (uint32_t i = tid; vec4 && i < 3u * per_plane; i += kIdctThreads) {
+                const uint32_t pl = i / per_plane, q = i - pl * per_plane, r = q / (wpx >> 2), k = q - r * (wpx >> 2);
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(s_out + pl * kPlaneSize + r * kPlanePitch + k * 4u);
+                const float sc = b.out_scale[pl], bi = b.out_bias[pl];
+                float4 f;
+                f.x = fmaf((float)(v & 255u), sc, bi); f.y = fmaf((float)((v >> 8) & 255u), sc, bi);
+                f.z = fmaf((float)((v >> 16) & 255u), sc, bi); f.w = fmaf((float)(v >> 24), sc, bi);
+                *reinterpret_cast<float4*>(tile_out + ((size_t)pl * plane_bytes + (size_t)r * W + k * 4u) * 4u) = f;
+            }
+            for (uint32_t i = tid; !vec4 && i < 3u * rows * wpx; i += kIdctThreads) {
+                const uint32_t pl = i / (rows * wpx), q = i - pl * rows * wpx, r = q / wpx, k = q - r * wpx;
+                reinterpret_cast<float*>(tile_out)[(size_t)pl * plane_bytes + (size_t)r * W + k] =
+                    fmaf((float)s_out[pl * kPlaneSize + r * kPlanePitch + k], b.out_scale[pl], b.out_bias[pl]);
+            }
+        } else if (vec_ok && (rowbytes & 15u) == 0u) {
             const uint32_t vpr = rowbytes >> 4;  // <= 24 (planar: <= 8)
 #pragma unroll
             for (int n = 0; n < NV; n++) {
@@ -1660,6 +1686,15 @@ __global__ void __launch_bounds__(kGatherThreads) gather_colour_kernel(BatchDev 
             g8[k] = f32_to_u8_sat(fmaf(cb, -0.34413629f, fmaf(cr, -0.71413629f, y)));
             b8[k] = f32_to_u8_sat(fmaf(cb, 1.772f, y));
         }
+    }
+    if (b.out_planar == 2u) {   // f32 planes: u8 * scale + bias
+        float* out = reinterpret_cast<float*>(b.rgb + im.rgb_off * 4u) + (size_t)q * 4u;
+        for (uint32_t k = 0; k < 4u && q * 4u + k < npix; k++) {
+            out[k] = fmaf((float)min(max(r8[k], 0), 255), b.out_scale[0], b.out_bias[0]);
+            out[npix + k] = fmaf((float)min(max(g8[k], 0), 255), b.out_scale[1], b.out_bias[1]);
+            out[2 * (size_t)npix + k] = fmaf((float)min(max(b8[k], 0), 255), b.out_scale[2], b.out_bias[2]);
+        }
+        return;
     }
     if (b.out_planar) {
         uint8_t* out = b.rgb + im.rgb_off + (size_t)q * 4u;
@@ -1779,8 +1814,9 @@ int launch_idct_colour(const BatchDev& b, cudaStream_t s) {
             const uint32_t* list = b.kind_imgs[k] + i0;
 #define JPGPU_LAUNCH_IDCT(HY, VY, GRAY)                                                                 \
     do {                                                                                               \
-        if (b.out_planar) idct_colour_kernel<HY, VY, GRAY, true><<<grid, kIdctThreads, 0, s>>>(b, list);  \
-        else idct_colour_kernel<HY, VY, GRAY, false><<<grid, kIdctThreads, 0, s>>>(b, list);          \
+        if (b.out_planar == 2u) idct_colour_kernel<HY, VY, GRAY, 2><<<grid, kIdctThreads, 0, s>>>(b, list);   \
+        else if (b.out_planar) idct_colour_kernel<HY, VY, GRAY, 1><<<grid, kIdctThreads, 0, s>>>(b, list);    \
+        else idct_colour_kernel<HY, VY, GRAY, 0><<<grid, kIdctThreads, 0, s>>>(b, list);                      \
     } while (0)
             switch (k) {
                 case kKindGray: JPGPU_LAUNCH_IDCT(1, 1, true); break;

@@ -30,7 +30,9 @@ struct BatchDev {        // device pointers of one planned batch
     SubInfo* subs;
     int16_t* coefs;
     uint8_t* rgb;
-    uint32_t out_planar;     // 0: interleaved RGB triples (the reference's Vec<(u8,u8,u8)>), 1: three W x H planes per image
+    uint32_t out_planar;     // 0: interleaved RGB triples (the reference's Vec<(u8,u8,u8)>), 1: three W x H u8 planes per image,
+                             // 2: three W x H f32 planes holding u8 * out_scale[c] + out_bias[c] (4 bytes per sample: image i at rgb + 4 * rgb_off)
+    float out_scale[3], out_bias[3];
     uint32_t n_images;   // images this launch covers, starting at img0 (a whole batch or one group of it)
     uint32_t n_seqs;     // warp jobs this launch covers, starting at job0
     uint32_t img0, job0;

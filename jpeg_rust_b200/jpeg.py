@@ -366,21 +366,32 @@ class Batch:
 
     def set_output_format(self, fmt):
         """OUT_RGB_INTERLEAVED (default; the reference's Vec<(u8,u8,u8)>, arrays of shape (H, W, 3)) or
-        OUT_RGB_PLANAR (three W x H planes R, G, B: arrays / tensors of shape (3, H, W)) for the following
-        idct / decode calls."""
+        OUT_RGB_PLANAR (three W x H planes R, G, B: arrays / tensors of shape (3, H, W)) or OUT_F32_PLANAR (the same
+        planes as float32, sample * scale + bias, see set_normalisation) for the following idct / decode calls
+        (SURVEY.md §8(f) row 2)."""
         self.ctx._ck(_ffi.lib().jpgpu_batch_set_output_format(self._h, int(fmt)), "jpgpu_batch_set_output_format")
         self.out_format = int(fmt)
         return self
 
+    def set_normalisation(self, scale, bias):
+        """OUT_F32_PLANAR: out = sample * scale[c] + bias[c] per channel (default 1/255, 0)."""
+        sc = (C.c_float * 3)(*[float(x) for x in scale])
+        bi = (C.c_float * 3)(*[float(x) for x in bias])
+        self.ctx._ck(_ffi.lib().jpgpu_batch_set_normalisation(self._h, sc, bi), "jpgpu_batch_set_normalisation")
+        return self
+
+    def dtype(self):
+        return np.float32 if getattr(self, "out_format", 0) == _ffi.OUT_F32_PLANAR else np.uint8
+
     def shape(self, i):
-        if getattr(self, "out_format", _ffi.OUT_RGB_INTERLEAVED) == _ffi.OUT_RGB_PLANAR:
+        if getattr(self, "out_format", _ffi.OUT_RGB_INTERLEAVED) != _ffi.OUT_RGB_INTERLEAVED:
             return (3, self.descs[i].height, self.descs[i].width)
         return (self.descs[i].height, self.descs[i].width, 3)
 
     def download(self, outs=None):
         """Device->host copy of every image (async on the context stream). Returns the list of arrays."""
         if outs is None:
-            outs = [np.empty(self.shape(i), np.uint8) for i in range(self.n)]
+            outs = [np.empty(self.shape(i), self.dtype()) for i in range(self.n)]
         ptrs = (C.c_void_p * self.n)(*[o.ctypes.data if hasattr(o, "ctypes") else int(o) for o in outs])
         self.ctx._ck(_ffi.lib().jpgpu_batch_download(self._h, ptrs), "jpgpu_batch_download")
         return outs
@@ -436,8 +447,10 @@ class Batch:
         ptr, nb = self.device_rgb(i)
         shp = tuple(self.shape(i))
 
+        ts = "<f4" if self.dtype() == np.float32 else "|u1"
+
         class _Cai:
-            __cuda_array_interface__ = {"shape": shp, "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+            __cuda_array_interface__ = {"shape": shp, "typestr": ts, "data": (int(ptr), False), "version": 2}
         return torch.as_tensor(_Cai(), device=f"cuda:{self.ctx.device}")
 
     def device_rgb(self, i):

@@ -738,3 +738,76 @@ def test_c_program_decodes_through_the_abi():
         assert (int(w), int(h), int(br)) == (o.width, o.height, o.bytes_read)
         assert int(digest, 16) == fnv1a(img.image_data().tobytes())
         assert batch_same == "1" and pipe_same == "1"
+
+
+def test_f32_normalised_planar_output():
+    """JPGPU_OUT_F32_PLANAR - the same 8-bit samples as three float32 planes, sample * scale + bias,
+    converted inside the IDCT/colour kernel.  Default scale 1/255; an ImageNet-style normalisation; every sampling mode,
+    ragged sizes (scalar copy-out) and the gather path (REF layout)."""
+    import torch
+    subs = ["420", "444", "422", "gray", "440"]
+    files = [synth.synth_jpeg(7500 + i, 128 + 16 * i, 96 + 8 * i, subs[i % 5]) for i in range(5)]
+    files += [synth.synth_jpeg(7510, 131, 77, "420"), synth.synth_jpeg(7511, 1920, 1080, "420")]
+    for layout in (LAYOUT_SPEC, LAYOUT_REF):
+        ref = run_batch(files, layout)[0]
+        b = Batch(files, layout=layout)
+        b.set_output_format(_ffi.OUT_F32_PLANAR)
+        b.upload().decode()
+        outs = b.download()
+        st, _ = b.results()
+        assert all(s == 0 for s in st)
+        for i in range(len(files)):
+            assert outs[i].dtype == np.float32 and outs[i].shape == (3,) + ref[i].shape[:2]
+            want = ref[i].transpose(2, 0, 1).astype(np.float32) * np.float32(1.0 / 255.0)
+            assert np.allclose(outs[i], want, rtol=0, atol=1e-6), i
+            t = b.device_tensor(i)
+            assert t.dtype == torch.float32 and np.array_equal(t.cpu().numpy(), outs[i])
+        mean, std = np.array([0.485, 0.456, 0.406], np.float32), np.array([0.229, 0.224, 0.225], np.float32)
+        b.set_normalisation(1.0 / (255.0 * std), -mean / std)
+        b.decode()
+        outs = b.download()
+        b.results()
+        for i in range(len(files)):
+            want = (ref[i].transpose(2, 0, 1).astype(np.float32) / 255.0 - mean[:, None, None]) / std[:, None, None]
+            assert np.allclose(outs[i], want, rtol=0, atol=2e-5), i
+        b.set_output_format(_ffi.OUT_RGB_INTERLEAVED)      # and back: the u8 path is untouched
+        b.decode()
+        outs = b.download()
+        b.results()
+        for i in range(len(files)):
+            assert np.array_equal(outs[i], ref[i])
+        b.close()
+
+
+def test_ppm_writer_matches_main_rs(tmp_path):
+    """main.rs:34-39: "P3\\n{w} {h}\\n255\\n" then one "r g b\\n" line per pixel, row-major.  JPEGImage.write_ppm against
+    a restatement of those lines fed with the oracle's pixels (exact where the GPU and the oracle agree exactly)."""
+    for name in ("lena-bw.jpeg", "lena.jpeg"):
+        data = fixture_bytes(name)
+        img = JPEGImage.parse(data, layout=LAYOUT_REF)
+        path = tmp_path / (name + ".ppm")
+        img.write_ppm(str(path))
+        text = path.read_text()
+        lines = text.split("\n")
+        assert lines[0] == "P3" and lines[1] == f"{img.width()} {img.height()}" and lines[2] == "255" and lines[-1] == ""
+        assert len(lines) == 3 + img.width() * img.height() + 1
+        o = O.decode(data, layout=LAYOUT_REF)
+        want = "".join(f"{r} {g} {b}\n" for r, g, b in o.rgb.reshape(-1, 3).tolist())     # main.rs:36-38
+        got_px = np.array([ln.split() for ln in lines[3:-1]], dtype=np.int16)
+        assert np.abs(got_px - o.rgb.reshape(-1, 3).astype(np.int16)).max() <= 1
+        if np.array_equal(img.image_data().reshape(-1, 3), o.rgb.reshape(-1, 3)):
+            assert text == f"P3\n{o.width} {o.height}\n255\n" + want
+
+
+@pytest.mark.parametrize("multi", ["0", "1"])
+def test_sync_pass_single_and_multi_symbol(multi, monkeypatch):
+    """Both forms of the synchronisation pass (JPGPU_SYNC_MULTI=0: sync_kernel, symbol by symbol; 1: sync_multi_kernel,
+    multi-symbol tables) on mixed images incl. restart intervals, optimised tables and a dense image: coefficients
+    against the oracle's, identical bytes_read."""
+    monkeypatch.setenv("JPGPU_SYNC_MULTI", multi)
+    files = [synth.synth_jpeg(7600 + i, 640 + 32 * i, 400, s) for i, s in enumerate(["420", "444", "422", "gray", "440"])]
+    files += [synth.synth_jpeg(7610, 512, 384, "420", optimize=True), synth.synth_jpeg(7611, 800, 600, "420", quality=97, noise_sigma=25.0),
+              fixture_bytes("lena.jpeg"), fixture_bytes("2x2-chroma.jpeg")]
+    compare_with_oracle(files, LAYOUT_SPEC)
+    dri = [synth.synth_jpeg(7620 + i, 640, 480, "420", restart_interval=ri) for i, ri in enumerate([40, 400])]
+    compare_with_oracle(dri, LAYOUT_SPEC, EXT_DRI)

@@ -356,11 +356,12 @@ def test_multi_symbol_table_entries():
             code += 1
             k += 1
         code <<= 1
-    K = 11
-    n = 1 << K
-    out = (C.c_uint32 * n)()
-    S.lib().jpsim_build_multi_lut((C.c_uint8 * 16)(*bits), (C.c_uint8 * 256)(*(vals + [0] * (256 - len(vals)))), 0, out, n)
-    for w in (0, 1, 0b01010101010, 0b10101010101, 0b11111111111, 0b00000000001, 0b10010011001, 1234, 777, 2047, 2046):
+    out = (C.c_uint32 * (1 << 16))()
+    n = S.lib().jpsim_build_multi_lut((C.c_uint8 * 16)(*bits), (C.c_uint8 * 256)(*(vals + [0] * (256 - len(vals)))), 0, out, 1 << 16)
+    K = n.bit_length() - 1          # kMultiBitsAc
+    assert n == 1 << K and 9 <= K <= 14
+    rng = np.random.default_rng(5)
+    for w in [0, 1, n - 1, n - 2, 0x555 & (n - 1), 0xAAA & (n - 1)] + [int(x) for x in rng.integers(0, n, 300)]:
         pos, syms = 0, []
         while pos < K:
             hit = None

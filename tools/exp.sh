@@ -7,7 +7,7 @@ cd $GRAFT_REPO_ROOT
 cp jpeg_rust_b200/lib/libjpgpu.so /tmp/orig.so
 run() {  # label, extra env...
   label=$1; shift
-  env "$@" timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e $BENCH_ARGS > /tmp/b.json 2>/tmp/b.err
+  env "$@" timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-extra --no-parity $BENCH_ARGS > /tmp/b.json 2>/tmp/b.err
   python - "$label" <<PY
 import json,sys
 try:
