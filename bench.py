@@ -368,8 +368,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the decode path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")   # a barrier that does not park a spinning kernel on the waiting GPUs
 
     def barrier():
         if world > 1:
@@ -606,6 +608,7 @@ def main():
         # no NCCL anywhere near it - rank 0 drives all N GPUs while the other ranks wait at the barrier
         if world > 1:
             barrier()
+            dist.barrier(group=host_group)
             if rank == 0:
                 md = MultiDevice(list(range(world)))
                 allf = [files[i % args.distinct] for i in range(n * world)]
@@ -626,6 +629,7 @@ def main():
                     "note": "jpgpu_multi_*: one process, one context + stream set + worker thread per device, contiguous image "
                             "ranges balanced by scan bytes, CUDA events per device, job time = slowest device"}
                 md.close()
+            dist.barrier(group=host_group)   # the other ranks wait on the host: their GPUs are rank 0's for this arm
             barrier()
 
     if rank == 0:

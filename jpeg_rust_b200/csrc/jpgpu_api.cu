@@ -43,9 +43,10 @@ struct jpgpu_batch {
     std::vector<const uint8_t*> host_scan;
     std::vector<size_t> host_scan_len;
     std::vector<uint64_t> scan_offs;   // jpgpu_batch_upload_from(): where each scan lies in the staging arena
+    std::vector<uint8_t> plan_blob;    // host image of the plan's device tables (one copy per plan)
     BatchDev dev;
     struct Arena { void* p = nullptr; size_t cap = 0; };
-    enum { kImgs, kSeqs, kLuts, kMluts, kMlutOff, kQt, kKind0, kGmap = kKind0 + kNumKinds, kSamples, kRaw, kDyn, kStream, kSegtab, kSubs, kSegs, kChunks, kCoefs,
+    enum { kPlanBlob, kSamples, kRaw, kDyn, kStream, kSegtab, kSubs, kSegs, kChunks, kCoefs,
            kRgb, kScanOffs, kStage, kNumArenas };
     Arena arena[kNumArenas];   // device allocations, grown on demand by jpgpu_batch_replan()
     uint64_t launches = 0;
@@ -53,6 +54,12 @@ struct jpgpu_batch {
     uint8_t* own_rgb = nullptr;
     size_t ext_rgb_cap = 0;    // capacity of the caller's output arena while jpgpu_batch_set_device_output() is in force
     bool decoded = false;
+    // jpgpu_batch_decode() as one CUDA graph launch: the launch parameters of a decode only change with the plan, the
+    // output arena and the output format (dev_gen counts those changes), so the second decode of an unchanged batch
+    // captures the whole chain - all groups, their forks and joins over the auxiliary streams - and later ones replay it.
+    uint64_t dev_gen = 1, graph_gen = 0, seen_gen = 0, graph_launches = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_ok = true;
 };
 
 namespace {
@@ -94,17 +101,6 @@ int dev_ensure(jpgpu_batch* b, int which, T** out, size_t count) {
 
 // bytes per output sample: 1 (u8 formats) or 4 (JPGPU_OUT_F32_PLANAR); every size and offset of the output scales with it
 size_t sample_bytes(const jpgpu_batch* b) { return b->dev.out_planar == 2u ? 4u : 1u; }
-
-template <typename T>
-int dev_upload(jpgpu_batch* b, int which, const T** out, const std::vector<T>& v) {
-    jpgpu_ctx* ctx = b->ctx;
-    T* p = nullptr;
-    int st = dev_ensure(b, which, &p, v.size());
-    if (st != JPGPU_OK) return st;
-    if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    *out = p;
-    return JPGPU_OK;
-}
 
 }  // namespace
 
@@ -168,6 +164,7 @@ extern "C" void jpgpu_batch_destroy(jpgpu_batch* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
+    if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);
     for (auto& a : b->arena) if (a.p) cudaFree(a.p);
     delete b;
 }
@@ -202,23 +199,48 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     d.seg_bits = p.seg_bits;
     d.wp_shift = p.wp_shift;
 #define TRY(x) do { st = (x); if (st != JPGPU_OK) return st; } while (0)
-    TRY(dev_upload(b, jpgpu_batch::kImgs, &d.imgs, p.imgs));
-    TRY(dev_upload(b, jpgpu_batch::kSeqs, &d.seqs, p.seqs));
-    TRY(dev_upload(b, jpgpu_batch::kLuts, &d.luts, p.luts));
-    TRY(dev_upload(b, jpgpu_batch::kMluts, &d.mlut, p.mluts));
-    TRY(dev_upload(b, jpgpu_batch::kMlutOff, &d.mlut_off, p.mlut_off));
+    {
+        // every table of the plan goes to the device as ONE copy: the sections are laid out in a host blob (256-byte
+        // aligned), copied once, and the device pointers are the blob's base plus the section offsets.  (Eleven separate
+        // copies from pageable memory were ~60 us of a single-image call.)
+        std::vector<uint8_t>& blob = b->plan_blob;
+        blob.clear();
+        auto add = [&blob](const void* src, size_t bytes) {
+            const size_t off = (blob.size() + 255) & ~(size_t)255;
+            blob.resize(off + bytes);
+            if (bytes) memcpy(blob.data() + off, src, bytes);
+            return off;
+        };
+        const size_t o_imgs = add(p.imgs.data(), p.imgs.size() * sizeof(ImgDev));
+        const size_t o_seqs = add(p.seqs.data(), p.seqs.size() * sizeof(SeqDesc));
+        const size_t o_luts = add(p.luts.data(), p.luts.size() * sizeof(HuffLut));
+        const size_t o_mlut = add(p.mluts.data(), p.mluts.size() * sizeof(uint32_t));
+        const size_t o_moff = add(p.mlut_off.data(), p.mlut_off.size() * sizeof(uint32_t));
+        const size_t o_qt = add(p.qt.data(), p.qt.size() * sizeof(float));
+        size_t o_kind[kNumKinds];
+        for (int k = 0; k < kNumKinds; k++) o_kind[k] = add(p.kind_imgs[k].data(), p.kind_imgs[k].size() * sizeof(uint32_t));
+        const size_t o_gmap = add(p.gmap.data(), p.gmap.size() * sizeof(uint32_t));
+        uint8_t* base = nullptr;
+        TRY(dev_ensure(b, jpgpu_batch::kPlanBlob, &base, blob.size() + 256));
+        if (!blob.empty()) CK(cudaMemcpyAsync(base, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+        d.imgs = reinterpret_cast<const ImgDev*>(base + o_imgs);
+        d.seqs = reinterpret_cast<const SeqDesc*>(base + o_seqs);
+        d.luts = reinterpret_cast<const HuffLut*>(base + o_luts);
+        d.mlut = reinterpret_cast<const uint32_t*>(base + o_mlut);
+        d.mlut_off = reinterpret_cast<const uint32_t*>(base + o_moff);
+        d.qt = reinterpret_cast<const float*>(base + o_qt);
+        for (int k = 0; k < kNumKinds; k++) d.kind_imgs[k] = reinterpret_cast<const uint32_t*>(base + o_kind[k]);
+        d.gmap = reinterpret_cast<const uint32_t*>(base + o_gmap);
+    }
     d.max_mlut_words = p.max_mlut_words;
     {
         const char* e = getenv("JPGPU_SYNC_MULTI");   // experiments: 0 = single-symbol synchronisation pass
         d.sync_multi = e ? (atoi(e) ? 1u : 0u) : 1u;
     }
-    TRY(dev_upload(b, jpgpu_batch::kQt, &d.qt, p.qt));
     for (int k = 0; k < kNumKinds; k++) {
         d.kind_count[k] = (uint32_t)p.kind_imgs[k].size();
         d.kind_max_tiles[k] = p.kind_max_tiles[k];
-        TRY(dev_upload(b, jpgpu_batch::kKind0 + k, &d.kind_imgs[k], p.kind_imgs[k]));
     }
-    TRY(dev_upload(b, jpgpu_batch::kGmap, &d.gmap, p.gmap));
     d.gather_max_blocks = p.gather_max_blocks;
     d.gather_max_quads = p.gather_max_quads;
     if (p.sample_floats) TRY(dev_ensure(b, jpgpu_batch::kSamples, &d.samples, p.sample_floats));
@@ -245,6 +267,7 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     b->own_rgb = static_cast<uint8_t*>(b->arena[jpgpu_batch::kRgb].p);
 #undef TRY
     b->coef_bytes = p.coef_elems * sizeof(int16_t);
+    b->dev_gen++;
     // defined contents for everything a speculative decoder may read
     CK(cudaMemsetAsync(raw, 0, p.raw_bytes + 64, ctx->stream));
     CK(cudaMemsetAsync(d.stream, 0, stream_alloc_words * 4, ctx->stream));
@@ -356,11 +379,13 @@ extern "C" int jpgpu_batch_set_device_output(jpgpu_batch* b, void* dev_base, siz
         if (st != JPGPU_OK) return st;
         b->dev.rgb = b->own_rgb;
         b->ext_rgb_cap = 0;
+        b->dev_gen++;
         return JPGPU_OK;
     }
     if (capacity < b->plan.rgb_bytes * sample_bytes(b) || (reinterpret_cast<uintptr_t>(dev_base) & 255u)) return JPGPU_ERR_INVALID_ARG;
     b->dev.rgb = static_cast<uint8_t*>(dev_base);
     b->ext_rgb_cap = capacity;
+    b->dev_gen++;
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
 
@@ -433,8 +458,50 @@ int ensure_aux(jpgpu_ctx* ctx) {
 // entropy + idct.  A large batch is cut into groups of images (HostPlan::groups) whose kernel chains alternate
 // between three auxiliary streams: the low-occupancy ends of one group's kernels (repair walks, last waves) overlap
 // the next group's work.  Forked from and joined back into the context stream.
+static int enqueue_decode(jpgpu_batch* b);
+
 extern "C" int jpgpu_batch_decode(jpgpu_batch* b) try {
     if (!b) return JPGPU_ERR_INVALID_ARG;
+    jpgpu_ctx* ctx = b->ctx;
+    const char* genv = getenv("JPGPU_GRAPH");   // experiments / tests: 0 = always kernel by kernel
+    const bool graphs_on = !genv || atoi(genv) != 0;
+    if (!graphs_on || !b->graph_ok || !ctx->stream || b->seen_gen != b->dev_gen) {
+        // first decode with these launch parameters (or graphs unavailable): enqueue kernel by kernel.  A batch decoded
+        // once - jpgpu_decode, a wave of a long job - never pays for a capture.
+        b->seen_gen = b->dev_gen;
+        return enqueue_decode(b);
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (!b->graph_exec || b->graph_gen != b->dev_gen) {
+        if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        const uint64_t before = b->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            b->graph_ok = false;
+            return enqueue_decode(b);
+        }
+        const int st = enqueue_decode(b);
+        const cudaError_t ec = cudaStreamEndCapture(ctx->stream, &graph);
+        b->graph_launches = b->launches - before;
+        b->launches = before;
+        if (st != JPGPU_OK || ec != cudaSuccess || !graph || cudaGraphInstantiate(&b->graph_exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            b->graph_exec = nullptr;
+            b->graph_ok = false;          // this batch goes on kernel by kernel
+            return st != JPGPU_OK ? st : enqueue_decode(b);
+        }
+        cudaGraphDestroy(graph);
+        b->graph_gen = b->dev_gen;
+    }
+    CK(cudaGraphLaunch(b->graph_exec, ctx->stream));
+    b->launches += b->graph_launches;
+    b->decoded = true;
+    return JPGPU_OK;
+} JPGPU_CATCH_ALL
+
+static int enqueue_decode(jpgpu_batch* b) {
     jpgpu_ctx* ctx = b->ctx;
     if (b->plan.groups.size() <= 1) {
         int st = jpgpu_batch_entropy(b);
@@ -462,7 +529,7 @@ extern "C" int jpgpu_batch_decode(jpgpu_batch* b) try {
     CK(cudaGetLastError());
     b->decoded = true;
     return JPGPU_OK;
-} JPGPU_CATCH_ALL
+}
 
 extern "C" int jpgpu_batch_download(jpgpu_batch* b, uint8_t* const* outs) try {
     if (!b || !outs) return JPGPU_ERR_INVALID_ARG;
@@ -483,6 +550,7 @@ extern "C" int jpgpu_batch_set_output_format(jpgpu_batch* b, uint32_t format) tr
     jpgpu_ctx* ctx = b->ctx;
     const size_t before = sample_bytes(b);
     b->dev.out_planar = format;
+    b->dev_gen++;
     if (format == JPGPU_OUT_F32_PLANAR && b->dev.out_scale[0] == 0.0f && b->dev.out_scale[1] == 0.0f && b->dev.out_scale[2] == 0.0f)
         for (int k = 0; k < 3; k++) { b->dev.out_scale[k] = 1.0f / 255.0f; b->dev.out_bias[k] = 0.0f; }   // default: [0, 1]
     if (sample_bytes(b) != before) {
@@ -499,6 +567,7 @@ extern "C" int jpgpu_batch_set_output_format(jpgpu_batch* b, uint32_t format) tr
 extern "C" int jpgpu_batch_set_normalisation(jpgpu_batch* b, const float scale[3], const float bias[3]) try {
     if (!b || !scale || !bias) return JPGPU_ERR_INVALID_ARG;
     for (int k = 0; k < 3; k++) { b->dev.out_scale[k] = scale[k]; b->dev.out_bias[k] = bias[k]; }
+    b->dev_gen++;
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
 

@@ -1187,6 +1187,9 @@ __global__ void __launch_bounds__(256) zero_tail_kernel(BatchDev b) {
 
 // ============================================ stage 2+3: dequant + IDCT + upsample + colour
 constexpr int kIdctThreads = 128;
+#ifndef JPGPU_IDCT_TMA
+#define JPGPU_IDCT_TMA 0     // 1: coefficient tiles through cp.async.bulk + mbarrier (experiment)
+#endif
 #ifndef JPGPU_TILES_PER_CTA
 #define JPGPU_TILES_PER_CTA 5
 #endif
@@ -1421,7 +1424,43 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
         }
     }
 
+#if JPGPU_IDCT_TMA
+    // Experiment: the coefficients of a tile are one contiguous run in HBM (consecutive MCUs of an MCU
+    // row), so one elected thread fetches them with a bulk asynchronous copy (cp.async.bulk shared <- global, completion
+    // on an mbarrier) into a double-buffered shared tile, and the IDCT passes read their 16-byte columns from there.  No
+    // coefficient vector lives in registers across the tile loop.
+    constexpr int kTileVecs = NM * NB * 8;
+    __shared__ __align__(128) uint4 s_coef[2][kTileVecs];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const uint32_t bar0 = smem_addr(&s_bar[0]);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0 + 8u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    auto tma_issue = [&](uint32_t tx, uint32_t ty, uint32_t buf) {   // thread 0 only
+        const uint32_t mcu0 = ty * mcux + tx * NM;
+        const uint32_t here = min(min((uint32_t)NM, mcux - tx * NM), units > mcu0 ? units - mcu0 : 0u);
+        const uint32_t bytes = here * NB * 128u;
+        const uint32_t bar = bar0 + buf * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        if (bytes)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_addr(&s_coef[buf][0])), "l"(coefs + (size_t)mcu0 * NB * 8), "r"(bytes), "r"(bar) : "memory");
+    };
+    auto tma_wait = [&](uint32_t buf, uint32_t parity) {
+        uint32_t ok = 0;
+        const uint32_t bar = bar0 + buf * 8u;
+        while (!ok)
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    };
+    uint32_t tma_k = 0, here_cur = 0;
+    // column t of block l of this thread's assignment in the current tile (zeros past the image's last MCU)
+#define JPGPU_COEF(l) ((uint32_t)mcu_of[l] < here_cur ? s_coef[tma_k & 1u][blk_of[l] * 8 + t] : make_uint4(0u, 0u, 0u, 0u))
+#else
     uint4 cur[NL], nxt[NL];
+#define JPGPU_COEF(l) cur[l]
     auto issue_loads = [&](uint32_t tx, uint32_t ty, uint4 (&dst)[NL]) {
         const uint32_t mcu0 = ty * mcux + tx * NM;
         const uint32_t here = min((uint32_t)NM, mcux - tx * NM);
@@ -1432,14 +1471,30 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
             if (valid) dst[l] = __ldg(coefs + ((size_t)mcu0 * NB + blk_of[l]) * 8 + t);
         }
     };
+#endif
     uint32_t tx = tile % tiles_x, ty = tile / tiles_x;   // tile coordinates, advanced incrementally
+#if JPGPU_IDCT_TMA
+    __syncthreads();  // s_qt ready, barriers initialised
+    if (tid == 0) tma_issue(tx, ty, 0u);
+#else
     issue_loads(tx, ty, cur);
     __syncthreads();  // s_qt ready
+#endif
 
 #pragma unroll 1
     for (; tile < tile_end; tile++) {
         const uint32_t ntx = tx + 1u == tiles_x ? 0u : tx + 1u, nty = ty + (tx + 1u == tiles_x ? 1u : 0u);
+#if JPGPU_IDCT_TMA
+        // the other buffer was last read in the previous tile, before that tile's closing barrier: free to refill
+        if (tid == 0 && tile + 1 < tile_end) tma_issue(ntx, nty, (tma_k + 1u) & 1u);
+        {
+            const uint32_t mcu0 = ty * mcux + tx * NM;
+            here_cur = min(min((uint32_t)NM, mcux - tx * NM), units > mcu0 ? units - mcu0 : 0u);
+        }
+        tma_wait(tma_k & 1u, (tma_k >> 1) & 1u);
+#else
         if (tile + 1 < tile_end) issue_loads(ntx, nty, nxt);
+#endif
 
         if (!GRAY) {
             auto put_chroma = [&](int a, const float (&o)[8]) {
@@ -1457,7 +1512,7 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
 #pragma unroll
                 for (int a = 0; a < CH_PASSES; a += 2) {   // blocks a*16+bp and (a+1)*16+bp: same component (bp & 1)
                     float oa[8], ob[8];
-                    block_idct2(cur[a], cur[a + 1], qt_l + (1 + (bp & 1)) * 64, t, scr2_w, scr2_r, 0.0f, oa, ob);
+                    block_idct2(JPGPU_COEF(a), JPGPU_COEF(a + 1), qt_l + (1 + (bp & 1)) * 64, t, scr2_w, scr2_r, 0.0f, oa, ob);
                     put_chroma(a, oa);
                     put_chroma(a + 1, ob);
                 }
@@ -1465,7 +1520,7 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
 #pragma unroll
                 for (int a = 0; a < CH_PASSES; a++) {
                     float o[8];
-                    block_idct(cur[a], qt_l + (1 + (bp & 1)) * 64, t, scr_w, scr_r, 0.0f, o);
+                    block_idct(JPGPU_COEF(a), qt_l + (1 + (bp & 1)) * 64, t, scr_w, scr_r, 0.0f, o);
                     put_chroma(a, o);
                 }
             }
@@ -1528,7 +1583,7 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
 #pragma unroll
             for (int p = 0; p < Y_PASSES; p += 2) {
                 f32x2 y2[8];
-                block_idct2p(cur[CH_PASSES + p], cur[CH_PASSES + p + 1], qt_l, t, scr2_w, scr2_r, 128.0f, y2);
+                block_idct2p(JPGPU_COEF(CH_PASSES + p), JPGPU_COEF(CH_PASSES + p + 1), qt_l, t, scr2_w, scr2_r, 128.0f, y2);
                 if constexpr (!PACKED_COLOUR) {
                     float ya[8], yb2[8];
 #pragma unroll
@@ -1566,7 +1621,7 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
 #pragma unroll
             for (int p = 0; p < Y_PASSES; p++) {
                 float y[8];
-                block_idct(cur[CH_PASSES + p], qt_l, t, scr_w, scr_r, 128.0f, y);
+                block_idct(JPGPU_COEF(CH_PASSES + p), qt_l, t, scr_w, scr_r, 128.0f, y);
                 finish_luma(p, y);
             }
         }
@@ -1619,9 +1674,14 @@ __global__ void JPGPU_IDCT_BOUNDS idct_colour_kernel(BatchDev b, const uint32_t*
         // after the barrier below) — every thread has left phase C by then.
         if (GRAY) __syncthreads();
         tx = ntx; ty = nty;
+#if JPGPU_IDCT_TMA
+        tma_k++;   // (all reads of this tile's buffer lie before the barrier that precedes the copy-out)
+#else
 #pragma unroll
         for (int l = 0; l < NL; l++) cur[l] = nxt[l];
+#endif
     }
+#undef JPGPU_COEF
 }
 
 // ============================================ gather path: REF placement / generic sampling
