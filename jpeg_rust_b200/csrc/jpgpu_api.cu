@@ -236,6 +236,11 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     {
         const char* e = getenv("JPGPU_SYNC_MULTI");   // experiments: 0 = single-symbol synchronisation pass
         d.sync_multi = e ? (atoi(e) ? 1u : 0u) : 1u;
+        // The repair walks are latency-bound, one CTA per image: with the multi-symbol tables in shared memory three CTAs
+        // fit an SM instead of seven, which pays while every image's CTA is resident at once (256 x 1080p: 0.40 -> 0.26 ms)
+        // and costs beyond (1024 images: 0.59 -> 0.64 ms).
+        const char* v = getenv("JPGPU_VERIFY_MULTI");
+        d.verify_multi = d.sync_multi && (v ? atoi(v) != 0 : n <= 3 * 148) ? 1u : 0u;
     }
     for (int k = 0; k < kNumKinds; k++) {
         d.kind_count[k] = (uint32_t)p.kind_imgs[k].size();
@@ -409,7 +414,7 @@ extern "C" int jpgpu_batch_entropy(jpgpu_batch* b) try {
     cudaStream_t s = ctx->stream;
     launch_prepass(b->dev, s);
     CK(launch_sync(b->dev, s));
-    launch_verify_scan(b->dev, s);
+    CK(launch_verify_scan(b->dev, s));
     CK(launch_decode_write(b->dev, s));
     b->launches += entropy_launches(b->dev);
     CK(cudaGetLastError());
@@ -518,7 +523,7 @@ static int enqueue_decode(jpgpu_batch* b) {
         const BatchDev d = group_dev(b, b->plan.groups[g]);
         launch_prepass(d, s);
         CK(launch_sync(d, s));
-        launch_verify_scan(d, s);
+        CK(launch_verify_scan(d, s));
         CK(launch_decode_write(d, s));
         b->launches += entropy_launches(d) + (uint64_t)launch_idct_colour(d, s);
     }
@@ -653,7 +658,7 @@ extern "C" int jpgpu_batch_profile(jpgpu_batch* b, float ms[8]) try {
     for (int step = 0; step < 3; step++) { launch_prepass_step(b->dev, s, step); CK(cudaEventRecord(ev[1 + step], s)); }
     CK(launch_sync(b->dev, s));
     CK(cudaEventRecord(ev[4], s));
-    launch_verify_scan(b->dev, s);
+    CK(launch_verify_scan(b->dev, s));
     CK(cudaEventRecord(ev[5], s));
     CK(launch_decode_write(b->dev, s));
     CK(cudaEventRecord(ev[6], s));

@@ -820,6 +820,39 @@ __global__ void __launch_bounds__(kSeqThreads) sync_kernel(BatchDev b) {
     b.subs[img.sub_off + j] = rec;
 }
 
+// Multi-symbol tables of the CTA's slots (those of sm.img[0], as the Huffman tables) into shared memory, and, for the
+// warp job in `slot` (its image in sm.img[slot]), which of them each block of an MCU uses: minfo[slot * 12 + block] =
+// {DC table address, AC table address}.  The Huffman tables must be loaded (is_dc is read from them).
+template <class SM>
+__device__ __forceinline__ void load_multi_tables(const BatchDev& b, const SM& sm, uint32_t* mlut, uint2* minfo, int slot, bool valid, int nthreads) {
+    const int nslots = sm.img[0].nslots;
+    uint32_t moff[kMaxLutSlots], acc = 0;
+#pragma unroll
+    for (int s2 = 0; s2 < kMaxLutSlots; s2++) {
+        moff[s2] = acc;
+        if (s2 < nslots) acc += 1u << (sm.lut[s2].is_dc ? kMultiBitsDc : kMultiBitsAc);
+    }
+    for (int s2 = 0; s2 < nslots; s2++) {
+        const uint4* src = reinterpret_cast<const uint4*>(b.mlut + b.mlut_off[sm.img[0].slot_lut[s2]]);
+        uint4* dst = reinterpret_cast<uint4*>(mlut + moff[s2]);
+        const int nvec = (1 << (sm.lut[s2].is_dc ? kMultiBitsDc : kMultiBitsAc)) / 4;
+        for (int i = threadIdx.x; i < nvec; i += nthreads) dst[i] = __ldg(src + i);
+    }
+    const int t = threadIdx.x & 31;
+    if (valid && (int)(threadIdx.x >> 5) == slot && t < kMaxBlocksPerMcu) {
+        const int nblk = sm.img[slot].blocks_per_mcu;
+        const uint32_t info = sm.img[slot].blk_info[t < nblk ? t : 0];
+        const uint32_t base = smem_addr(mlut);
+        uint32_t a_dc = base, a_ac = base;
+#pragma unroll
+        for (int s2 = 0; s2 < kMaxLutSlots; s2++) {
+            if ((info & 255u) == (uint32_t)s2) a_dc = base + moff[s2] * 4u;
+            if (((info >> 8) & 255u) == (uint32_t)s2) a_ac = base + moff[s2] * 4u;
+        }
+        minfo[slot * kMaxBlocksPerMcu + t] = make_uint2(a_dc, a_ac);
+    }
+}
+
 // The same pass through the multi-symbol tables (jpgpu_core.h): 256-thread CTAs (eight warp jobs share one copy of the
 // tables), dynamic shared memory = Huffman tables of the slots in use + fast-path tables + multi-symbol tables.
 #ifndef JPGPU_SYNC_THREADS
@@ -856,34 +889,7 @@ __global__ void __launch_bounds__(kSyncThreads) sync_multi_kernel(BatchDev b) {
     load_entropy_img(b, sd.img, sm, 32);
     load_entropy_luts(b, sm, kSyncThreads);
     fast_tables_init(ft, sm, sd.img != kNoImage, 32, kSyncThreads);
-    {   // multi-symbol tables of the CTA's slots (those of job 0, as the Huffman tables), and who uses which
-        const int nslots = sm.img[0].nslots;
-        uint32_t moff[kMaxLutSlots], acc = 0;
-#pragma unroll
-        for (int s2 = 0; s2 < kMaxLutSlots; s2++) {
-            moff[s2] = acc;
-            if (s2 < nslots) acc += 1u << (sm.lut[s2].is_dc ? kMultiBitsDc : kMultiBitsAc);
-        }
-        for (int s2 = 0; s2 < nslots; s2++) {
-            const uint4* src = reinterpret_cast<const uint4*>(b.mlut + b.mlut_off[sm.img[0].slot_lut[s2]]);
-            uint4* dst = reinterpret_cast<uint4*>(mlut + moff[s2]);
-            const int nvec = (1 << (sm.lut[s2].is_dc ? kMultiBitsDc : kMultiBitsAc)) / 4;
-            for (int i = threadIdx.x; i < nvec; i += kSyncThreads) dst[i] = __ldg(src + i);
-        }
-        const int t = threadIdx.x & 31;
-        if (sd.img != kNoImage && t < kMaxBlocksPerMcu) {
-            const int nblk = sm.img[warp].blocks_per_mcu;
-            const uint32_t info = sm.img[warp].blk_info[t < nblk ? t : 0];
-            const uint32_t base = smem_addr(mlut);
-            uint32_t a_dc = base, a_ac = base;
-#pragma unroll
-            for (int s2 = 0; s2 < kMaxLutSlots; s2++) {
-                if ((info & 255u) == (uint32_t)s2) a_dc = base + moff[s2] * 4u;
-                if (((info >> 8) & 255u) == (uint32_t)s2) a_ac = base + moff[s2] * 4u;
-            }
-            minfo[warp * kMaxBlocksPerMcu + t] = make_uint2(a_dc, a_ac);
-        }
-    }
+    load_multi_tables(b, sm, mlut, minfo, warp, sd.img != kNoImage, kSyncThreads);
     __syncthreads();
     if (sd.img == kNoImage) return;
     const ImgDev& img = sm.img[warp];
@@ -917,7 +923,11 @@ constexpr int kRepairJobs = 2 * kInterThreads;
 // broken link always starts from a correct state, so every iteration extends the correct prefix.
 // (2) Exclusive prefix scan turning per-subsequence advances into the absolute state at every A
 // (segmented where a restart interval began).
+// MULTI: the repair walks go through the multi-symbol tables like the synchronisation pass (dynamic shared memory:
+// 12 x 8 bytes of per-block table addresses, then the tables); the states they record at segment ends are the same.
+template <bool MULTI>
 __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
     __shared__ EntropySmem sm;
     __shared__ FastTables ft;
     __shared__ int32_t s_agg[kInterThreads][5];
@@ -952,10 +962,16 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
         if (!loaded) {
             load_entropy_luts(b, sm, kInterThreads);
             fast_tables_init(ft, sm, threadIdx.x < 32, 32, kInterThreads);
+            if constexpr (MULTI)
+                load_multi_tables(b, sm, reinterpret_cast<uint32_t*>(dyn_smem + 128), reinterpret_cast<uint2*>(dyn_smem), 0, true, kInterThreads);
             __syncthreads();
             loaded = true;
         }
-        const FastCtx cx = make_fast_ctx(b, sm, 0, dyn, ft);
+        FastCtx cx = make_fast_ctx(b, sm, 0, dyn, ft);
+        if constexpr (MULTI) {
+            cx.minfo_addr = smem_addr(dyn_smem);
+            JPGPU_PIN32(cx.minfo_addr);
+        }
         for (uint32_t i = tid; i < njobs; i += kInterThreads) {
             const RepairJob job = s_jobs[i];
             FastState st;
@@ -963,7 +979,7 @@ __global__ void __launch_bounds__(kInterThreads) verify_scan_kernel(BatchDev b) 
             SubInfo rec;
             rec.pA = st.p;
             rec.cz = job.cz;
-            fast_sync_subsequence<false>(cx, st, job.sub * S, S, b.seg_bits, b.segs + (size_t)(im.sub_off + job.sub) * (S / b.seg_bits), true, rec);
+            fast_sync_subsequence<MULTI>(cx, st, job.sub * S, S, b.seg_bits, b.segs + (size_t)(im.sub_off + job.sub) * (S / b.seg_bits), true, rec);
             subs[job.sub] = rec;
         }
         __syncthreads();
@@ -1841,8 +1857,18 @@ cudaError_t launch_sync(const BatchDev& b, cudaStream_t s) {
     sync_multi_kernel<<<(b.n_seqs + kSyncJobs - 1) / kSyncJobs, kSyncThreads, sync_layout(b.max_slots, b.max_mlut_words).total, s>>>(b);
     return cudaSuccess;
 }
-void launch_verify_scan(const BatchDev& b, cudaStream_t s) {
-    if (b.n_images && b.nsync) verify_scan_kernel<<<b.n_images, kInterThreads, 0, s>>>(b);
+cudaError_t launch_verify_scan(const BatchDev& b, cudaStream_t s) {
+    if (!b.n_images || !b.nsync) return cudaSuccess;
+    if (!b.verify_multi) {
+        verify_scan_kernel<false><<<b.n_images, kInterThreads, 0, s>>>(b);
+        return cudaSuccess;
+    }
+    static std::mutex mu;
+    static uint64_t configured = 0;
+    const cudaError_t e = ensure_smem_attr(verify_scan_kernel<true>, 128u + ((uint32_t)kMaxLutSlots << kMultiBitsAc) * 4u, configured, mu);
+    if (e != cudaSuccess) return e;
+    verify_scan_kernel<true><<<b.n_images, kInterThreads, 128u + b.max_mlut_words * 4u, s>>>(b);
+    return cudaSuccess;
 }
 template <int NBUF, int PHASE>
 static cudaError_t launch_write_variant(const BatchDev& b, cudaStream_t s) {

@@ -23,6 +23,7 @@ struct BatchDev {        // device pointers of one planned batch
     const uint32_t* mlut_off; // where each begins in mlut (words)
     uint32_t max_mlut_words;  // most words the tables of one image's slots take together (shared memory of sync_kernel)
     uint32_t sync_multi;      // 1: the synchronisation pass decodes through the multi-symbol tables
+    uint32_t verify_multi;    // 1: so do the repair walks (their tables cost shared memory: only while all images' CTAs stay co-resident)
     const float* qt;     // pre-scaled dequantisation multipliers, 64 per table, column-major
     const uint8_t* raw;
     uint32_t* stream;
@@ -67,7 +68,7 @@ void launch_prepass_step(const BatchDev& b, cudaStream_t s, int step);  // 0 cou
 // Stage 1b: look-back synchronisation, one thread per subsequence.
 cudaError_t launch_sync(const BatchDev& b, cudaStream_t s);
 // Stage 1c: chain verification, repair of the links the look-back did not synchronise, prefix scan; one CTA per image.
-void launch_verify_scan(const BatchDev& b, cudaStream_t s);
+cudaError_t launch_verify_scan(const BatchDev& b, cudaStream_t s);
 // Stage 1d: final decode, whole coefficient blocks written to HBM.
 cudaError_t launch_decode_write(const BatchDev& b, cudaStream_t s);
 // Stage 2+3: dequantise, IDCT, upsample, YCbCr->RGB, interleaved store (SPEC geometry).

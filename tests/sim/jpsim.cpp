@@ -120,7 +120,7 @@ void sim_sync(SimBatch& sb, const SeqDesc& sd) {
     DecCtx cx = make_ctx(sb, sd.img, slots.data());
     const uint32_t* mslots[kMaxLutSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int s = 0; s < im.nslots; s++) mslots[s] = sb.plan.mluts.data() + sb.plan.mlut_off[im.slot_lut[s]];
-    if (g_sync_multi) cx.mluts = mslots;   // sync_multi_kernel; the repair walks of verify_scan_kernel go symbol by symbol
+    if (g_sync_multi) cx.mluts = mslots;   // sync_multi_kernel
     for (uint32_t tid = 0; tid < 32u; tid++) {  // one warp job
         const uint32_t j = sd.first_sub + tid;
         if (j >= nsub) continue;
@@ -151,7 +151,10 @@ void sim_verify_scan(SimBatch& sb, size_t img) {
     const ImgDyn dyn = sb.dyn[img];
     const uint32_t S = sb.plan.sub_bits, C = sb.plan.seg_bits;
     const uint32_t nsub = (dyn.stream_bits + S - 1) / S;
-    const DecCtx cx = make_ctx(sb, img, slots.data());
+    DecCtx cx = make_ctx(sb, img, slots.data());
+    const uint32_t* mslots[kMaxLutSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int s = 0; s < im.nslots; s++) mslots[s] = sb.plan.mluts.data() + sb.plan.mlut_off[im.slot_lut[s]];
+    if (g_sync_multi) cx.mluts = mslots;   // verify_scan_kernel<true>: the repair walks use the multi-symbol tables too
     SubInfo* subs = sb.subs.data() + im.sub_off;
     uint32_t iters = 0;
     for (uint32_t iter = 0; iter <= nsub; iter++) {
