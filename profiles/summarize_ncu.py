@@ -48,6 +48,22 @@ def main():
                 w.writerow([m, units[col[m]]] + [r[col[m]] for r in data])
     print(f"{out}: {len(data)} launches: {names}")
     if "--traffic" in sys.argv:
+        # profiles/idct_traffic.json: per workload key ("<W>x<H>_<subsampling>", given after --traffic) the DRAM bytes per
+        # image of the IDCT/colour launch, stamped with the hash of the kernel sources it was measured on - bench.py only
+        # reports the figure while that hash still matches (roofline.traffic is null for any other build).
+        import hashlib
+        key = sys.argv[sys.argv.index("--traffic") + 1]
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        h = hashlib.sha256()
+        for f in ("jpgpu_kernels.cu", "jpgpu_core.h"):
+            h.update(open(os.path.join(root, "jpeg_rust_b200", "csrc", f), "rb").read())
+        path = os.path.join(root, "profiles", "idct_traffic.json")
+        try:
+            table = json.load(open(path))
+            if not isinstance(table, dict) or "width" in table:
+                table = {}
+        except Exception:
+            table = {}
         for r, name in zip(data, names):
             if "idct_colour_kernel" not in name:
                 continue
@@ -55,12 +71,11 @@ def main():
             wr = float(r[col["dram__bytes_write.sum"]]) * UNIT_SCALE[units[col["dram__bytes_write.sum"]]]
             grid = r[col["Grid Size"]].strip("()").split(",")
             images = int(grid[1])
-            meta = {"kernel": name, "source": f"{os.path.basename(out)} (ncu --set full, one launch)",
-                    "width": 1920, "height": 1080, "subsampling": "420", "images": images,
-                    "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_image": (rd + wr) / images}
-            json.dump(meta, open(os.path.join(os.path.dirname(out) or ".", "idct_traffic.json"), "w"), indent=1)
-            print("idct_traffic.json:", meta)
-            break
+            table[key] = {"kernel": name, "profile": os.path.basename(out), "images": images, "dram_bytes_read": rd,
+                          "dram_bytes_write": wr, "dram_bytes_per_image": (rd + wr) / images,
+                          "kernel_source_sha": h.hexdigest()[:16]}
+            print(key, table[key])
+        json.dump(table, open(path, "w"), indent=1)
 
 
 if __name__ == "__main__":

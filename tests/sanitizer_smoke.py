@@ -1,7 +1,8 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck are too slow for the whole GPU suite):
   compute-sanitizer --tool memcheck python tests/sanitizer_smoke.py
 Covers every kernel: fused kernels of all sampling modes, restart intervals, the gather path (REF layout), repairs
-(short look-back), damaged streams, replan and the pipelined group decode."""
+(short look-back, multi-symbol tables), damaged streams (zero-filled tails), replan, the pipelined group decode, graph
+capture and replay, float output and the host-to-host pipeline."""
 import os
 import sys
 
@@ -29,7 +30,7 @@ def main():
     files.append(bytes(damaged))
     files.append(files[1][:len(files[1]) // 2])
     b = Batch(files, ext=EXT_DRI, layout=LAYOUT_SPEC)
-    for _ in range(2):
+    for _ in range(3):           # kernel by kernel, captured into a CUDA graph, replayed
         b.upload().decode()
     outs = b.download()
     statuses, _ = b.results()
@@ -46,7 +47,23 @@ def main():
         o = O.decode(f, layout=O.LAYOUT_REF)
         assert statuses[i] == o.status == 0
         assert np.abs(outs[i].astype(int) - o.rgb.astype(int)).max() <= 1
+    # float planes (converted inside the IDCT/colour kernel), then the host-to-host pipeline with single-copy transfers
+    from jpeg_rust_b200 import Pipeline, _ffi
+    b.replan(files[:6], ext=EXT_DRI, layout=LAYOUT_SPEC)
+    b.set_output_format(_ffi.OUT_F32_PLANAR)
+    b.upload().decode()
+    f32 = b.download()
+    statuses, _ = b.results()
+    assert all(s == 0 for s in statuses) and f32[0].dtype == np.float32 and 0.0 <= float(f32[0].min()) and float(f32[0].max()) <= 1.0
     b.close()
+    p = Pipeline(files, ext=EXT_DRI, layout=LAYOUT_SPEC, chunk=3)
+    p.run().sync()
+    st, _ = p.results()
+    assert st[:6] == [0] * 6 and st[6] != 0 or st[7] != 0
+    for i in range(6):
+        ref = O.decode(files[i], layout=O.LAYOUT_SPEC, ext=EXT_DRI).rgb
+        assert np.abs(p.image(i).astype(int) - ref.astype(int)).max() <= 1
+    p.close()
     print("sanitizer smoke ok")
 
 
