@@ -277,7 +277,9 @@ uint32_t choose_lookback_bits(uint64_t total_scan_bytes, uint32_t sub_bits, uint
     const uint64_t threads = total_scan_bytes * 8 / sub_bits;
     if (max_blocks_per_mcu < 6 || (sub_bits >= (uint32_t)kDefaultMaxSubseqBits && threads >= 300000)) return kDefaultLookbackBits;
     if (sub_bits >= 4096) return 2048u;          // measured: 256 / 512 x 1080p
-    return threads >= 40000 ? 4096u : 8192u;     // measured: 64 / 16 / 1 x 1080p, 1 x 4096 x 4096
+    // measured: 64 x 1080p (2048-bit subsequences) 2048: 1.01 ms, 4096: 1.17 ms with the multi-symbol repair walks of
+    // round 2 (round 1, symbol by symbol: 4096); 16 / 1 x 1080p, 1 x 4096 x 4096: 8192
+    return threads >= 40000 ? 2048u : 8192u;
 }
 
 int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t sub_bits) {
