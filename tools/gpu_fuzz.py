@@ -6,7 +6,8 @@ from jpeg_rust_b200 import Batch, LAYOUT_SPEC, EXT_DRI, synth
 rng = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 7)
 t_end = time.time() + float(sys.argv[2]) if len(sys.argv) > 2 else time.time() + 60
 nimg = bad = nb = 0
-KEYS = ["JPGPU_SUBSEQ_BITS", "JPGPU_LOOKBACK_BITS", "JPGPU_WRITE_PARTS", "JPGPU_INTERVAL_MODE", "JPGPU_GROUPS", "JPGPU_SEG_BITS"]
+KEYS = ["JPGPU_SUBSEQ_BITS", "JPGPU_LOOKBACK_BITS", "JPGPU_WRITE_PARTS", "JPGPU_INTERVAL_MODE", "JPGPU_GROUPS", "JPGPU_SEG_BITS",
+        "JPGPU_SYNC_MULTI", "JPGPU_VERIFY_MULTI"]
 while time.time() < t_end:
     files, gts, meta = [], [], []
     big = rng.random() < 0.15
@@ -19,7 +20,8 @@ while time.time() < t_end:
             h = rng.choice([rng.randint(8, 300), rng.randint(300, 1000), rng.choice([512, 1024])])
         ri = rng.choice([0, 0, 1, 2, 3, 5, 8, 16, 33, 64, 100, 256, 1000])
         seed, q = rng.randint(0, 10 ** 6), rng.choice([30, 60, 85, 95])
-        f, g = synth.synth_jpeg(seed, w, h, sub, quality=q, restart_interval=ri, want_coefs=True)
+        f, g = synth.synth_jpeg(seed, w, h, sub, quality=q, restart_interval=ri, want_coefs=True, optimize=rng.random() < 0.3,
+                                noise_sigma=rng.choice([6.0, 6.0, 20.0]))
         files.append(f); gts.append(g); meta.append((seed, w, h, sub, ri, q))
     outs = []
     for variant in range(2):
@@ -30,9 +32,13 @@ while time.time() < t_end:
             os.environ["JPGPU_WRITE_PARTS"] = str(rng.choice([1, 2, 4]))
             os.environ["JPGPU_GROUPS"] = str(rng.choice([1, 2, 3]))
             if rng.random() < 0.5: os.environ["JPGPU_INTERVAL_MODE"] = str(rng.choice([0, 1]))
+            os.environ["JPGPU_SYNC_MULTI"] = str(rng.choice([0, 1, 1]))
+            os.environ["JPGPU_VERIFY_MULTI"] = str(rng.choice([0, 1]))
         env = {k: os.environ.get(k) for k in KEYS if os.environ.get(k)}
         b = Batch(files, layout=LAYOUT_SPEC, ext=EXT_DRI)
         b.upload().decode()
+        if rng.random() < 0.3:
+            b.decode(); b.decode()      # captured into a CUDA graph, replayed
         o = b.download()
         st, _ = b.results()
         for i in range(len(files)):

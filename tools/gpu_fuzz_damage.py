@@ -12,7 +12,8 @@ while time.time() < t_end:
         sub = rng.choice(["420", "422", "444", "440", "gray"])
         w, h = rng.randint(16, 900), rng.randint(16, 600)
         ri = rng.choice([0, 0, 1, 3, 8, 40, 300])
-        f, g = synth.synth_jpeg(rng.randint(0, 10**6), w, h, sub, quality=rng.choice([50, 85, 95]), restart_interval=ri, want_coefs=True)
+        f, g = synth.synth_jpeg(rng.randint(0, 10**6), w, h, sub, quality=rng.choice([50, 85, 95]), restart_interval=ri, want_coefs=True,
+                                optimize=rng.random() < 0.3)
         f = bytearray(f)
         sos = bytes(f).index(b"\xff\xda") + 14
         mode = rng.choice(["none", "flip", "flip", "trunc", "ff", "zero", "delmarker", "dup"])
@@ -31,7 +32,9 @@ while time.time() < t_end:
             a = rng.randint(sos, len(f) - 1); f[a:a] = f[a:a + rng.randint(1, 64)]
         elif mode == "delmarker": mode = "none"
         files.append(bytes(f)); gts.append(g if mode == "none" else None)
-    for k in ["JPGPU_LOOKBACK_BITS", "JPGPU_SUBSEQ_BITS", "JPGPU_INTERVAL_MODE"]: os.environ.pop(k, None)
+    for k in ["JPGPU_LOOKBACK_BITS", "JPGPU_SUBSEQ_BITS", "JPGPU_INTERVAL_MODE", "JPGPU_SYNC_MULTI", "JPGPU_VERIFY_MULTI"]: os.environ.pop(k, None)
+    if rng.random() < 0.3: os.environ["JPGPU_SYNC_MULTI"] = "0"
+    if rng.random() < 0.3: os.environ["JPGPU_VERIFY_MULTI"] = str(rng.choice([0, 1]))
     if rng.random() < 0.5:
         os.environ["JPGPU_LOOKBACK_BITS"] = str(rng.choice([64, 1024, 4096])); os.environ["JPGPU_SUBSEQ_BITS"] = str(rng.choice([1024, 4096]))
     b = Batch(files, layout=LAYOUT_SPEC, ext=EXT_DRI)
