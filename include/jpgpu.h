@@ -71,7 +71,11 @@ enum {
  * SPEC = what that code intends: T.81 A.2.3 MCU order, true MCU count, box
  *        replication of sub-sampled components, crop at right/bottom edge.
  * For gray, 4:4:4 with W%8==0 and 4:2:2 (H2V1) with W%16==0 both are identical. */
-enum { JPGPU_LAYOUT_REF = 0, JPGPU_LAYOUT_SPEC = 1 };
+enum { JPGPU_LAYOUT_REF = 0, JPGPU_LAYOUT_SPEC = 1,
+       /* SPEC geometry with libjpeg's "fancy" up-sampling of sub-sampled chroma (triangle filter: 3/4 of the nearer,
+        * 1/4 of the farther sample, both directions for 4:2:0) instead of the reference's box replication.  A feature
+        * the reference lacks: results differ from the reference by design; not the tuned path. */
+       JPGPU_LAYOUT_SPEC_FANCY = 2 };
 
 /* Sample arrangement of the output (the step after the path).  INTERLEAVED is the
  * reference's Vec<(u8,u8,u8)> (decoder.rs:162, 317-331): W*H triples, row-major.  PLANAR holds the same W*H*3

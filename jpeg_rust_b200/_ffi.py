@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libjpgpu.so")
 
-LAYOUT_REF, LAYOUT_SPEC = 0, 1
+LAYOUT_REF, LAYOUT_SPEC, LAYOUT_SPEC_FANCY = 0, 1, 2
 EXT_NONE, EXT_SKIP_APPN, EXT_DRI = 0, 1, 2
 OUT_RGB_INTERLEAVED, OUT_RGB_PLANAR, OUT_F32_PLANAR = 0, 1, 2
 MEMORY_HOST, MEMORY_DEVICE = 0, 1

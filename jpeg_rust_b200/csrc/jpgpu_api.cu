@@ -220,6 +220,7 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
         size_t o_kind[kNumKinds];
         for (int k = 0; k < kNumKinds; k++) o_kind[k] = add(p.kind_imgs[k].data(), p.kind_imgs[k].size() * sizeof(uint32_t));
         const size_t o_gmap = add(p.gmap.data(), p.gmap.size() * sizeof(uint32_t));
+        const size_t o_frames = add(p.frames.data(), p.frames.size() * sizeof(FrameDev));
         uint8_t* base = nullptr;
         TRY(dev_ensure(b, jpgpu_batch::kPlanBlob, &base, blob.size() + 256));
         if (!blob.empty()) CK(cudaMemcpyAsync(base, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -231,6 +232,9 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
         d.qt = reinterpret_cast<const float*>(base + o_qt);
         for (int k = 0; k < kNumKinds; k++) d.kind_imgs[k] = reinterpret_cast<const uint32_t*>(base + o_kind[k]);
         d.gmap = reinterpret_cast<const uint32_t*>(base + o_gmap);
+        d.frames = reinterpret_cast<const FrameDev*>(base + o_frames);
+        d.n_frames = (uint32_t)p.frames.size();
+        d.frame_max_quads = p.frame_max_quads;
     }
     d.max_mlut_words = p.max_mlut_words;
     {
@@ -446,6 +450,9 @@ BatchDev group_dev(const jpgpu_batch* b, const GroupPlan& g) {
     }
     d.gather_max_blocks = g.gather_max_blocks;
     d.gather_max_quads = g.gather_max_quads;
+    d.frames = b->dev.frames + g.frame_lo;
+    d.n_frames = g.frame_hi - g.frame_lo;
+    d.frame_max_quads = g.frame_max_quads;
     return d;
 }
 

@@ -143,7 +143,27 @@ struct ImgDev {
     uint64_t map_off;                     // u32 offset of this shape's placement map (ncomp planes of map_plane entries)
     uint64_t smp_off;                     // float offset of this image's per-block IDCT samples
     uint32_t map_plane;                   // entries per component plane (W*H rounded up to 4)
-    uint32_t pad1;
+    uint32_t frame;                       // compose path: index + 1 of the FrameDev this image's samples feed (0: none)
+};
+
+// ---- compose path: per-block IDCT samples (block_idct_kernel) -> pixels, plane by plane.  Serves what the fused
+// kernels do not: libjpeg-style "fancy" (triangle filter) chroma up-sampling, and frames whose components arrive in
+// separate non-interleaved scans (each scan is entropy-decoded as a one-component image of its own).
+struct PlaneRef {          // where the samples of one component of a frame are
+    uint64_t smp_off;      // float offset of the owning image's per-block samples ([block][row * 8 + col])
+    uint32_t mcux, bpm;    // the owning image's MCUs per row and blocks per MCU
+    uint32_t first;        // first block of this component inside an MCU
+    uint32_t h, v;         // its blocks per MCU, horizontally / vertically
+    uint32_t wc, hc;       // samples per line / lines of the component (T.81 A.1.1: ceil(X * H / Hmax), ceil(Y * V / Vmax))
+    uint32_t fx, fy;       // up-sampling factors to the frame (Hmax / H, Vmax / V): 1 or 2
+    float bias;            // added to every sample (chroma decoded as a one-component image carries a +128 it must lose)
+    uint32_t pad;
+};
+struct FrameDev {
+    uint32_t width, height, ncomp;
+    uint32_t fancy;        // 0: box replication (the reference's fill_block_in_array, decoder.rs:347-379), 1: triangle filter
+    uint64_t rgb_off;      // byte offset of the frame's output in the RGB arena (before the format's sample size)
+    PlaneRef pl[3];
 };
 constexpr uint32_t kMapNone = 0xffffffffu;  // placement-map entry of a pixel no block was ever written to
 

@@ -51,7 +51,7 @@ int compute_geometry(const jpgpu_image_desc& d, Geometry& g) {
         g.h[c] = k.h;
         g.v[c] = k.v;
     }
-    if (d.layout == JPGPU_LAYOUT_SPEC && d.ncomp == 1) { g.h[0] = 1; g.v[0] = 1; }  // T.81 A.2.2
+    if (d.layout != JPGPU_LAYOUT_REF && d.ncomp == 1) { g.h[0] = 1; g.v[0] = 1; }  // T.81 A.2.2
     g.hmax = g.vmax = 1;
     g.blocks_per_mcu = 0;
     for (uint32_t c = 0; c < d.ncomp; c++) {
@@ -81,6 +81,11 @@ int compute_geometry(const jpgpu_image_desc& d, Geometry& g) {
     }
     if (d.layout == JPGPU_LAYOUT_SPEC) {
         g.fused_ok = g.kind != kKindGeneric;
+    } else if (d.layout == JPGPU_LAYOUT_SPEC_FANCY) {
+        // without sub-sampled chroma there is nothing to interpolate: the fused kernels serve gray and 4:4:4
+        g.fused_ok = g.kind == kKindGray || g.kind == kKind444;
+        g.compose = !g.fused_ok && g.kind != kKindGeneric;
+        if (!g.fused_ok && !g.compose) return JPGPU_ERR_UNSUPPORTED;
     } else {
         // REF == SPEC exactly for these shape classes (SURVEY.md §8 parity policy)
         g.fused_ok = (g.kind == kKindGray && d.width % 8 == 0) || (g.kind == kKind444 && d.width % 8 == 0) ||
@@ -331,6 +336,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
             g.nimg = (uint32_t)next_img - g.img0;
             g.njobs = (uint32_t)plan.seqs.size() - g.job0;
             for (int k = 0; k < kNumKinds; k++) g.kind_hi[k] = (uint32_t)plan.kind_imgs[k].size();
+            g.frame_hi = (uint32_t)plan.frames.size();
         }
     };
     auto open_group = [&](size_t img) {
@@ -338,6 +344,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         g.img0 = (uint32_t)img;
         g.job0 = (uint32_t)plan.seqs.size();
         for (int k = 0; k < kNumKinds; k++) g.kind_lo[k] = (uint32_t)plan.kind_imgs[k].size();
+        g.frame_lo = (uint32_t)plan.frames.size();
         plan.groups.push_back(g);
         cur_lutset.clear();
     };
@@ -403,7 +410,8 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         // gather path: placement map per distinct shape
         uint64_t map_off = 0;
         const uint32_t map_plane = (uint32_t)align_up((uint64_t)d.width * d.height, 4);
-        if (st == JPGPU_OK && !g.fused_ok) {
+        if (st == JPGPU_OK && d.layout > JPGPU_LAYOUT_SPEC_FANCY) st = JPGPU_ERR_INVALID_ARG;
+        if (st == JPGPU_OK && !g.fused_ok && !g.compose) {
             // the host-built placement map is 4 bytes per pixel and component, built pixel by pixel: 64 Mpixel at most
             if ((uint64_t)d.width * d.height > kMaxGatherPixels) st = JPGPU_ERR_UNSUPPORTED;
             char key[64];
@@ -528,16 +536,40 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         plan.kind_imgs[im.kind].push_back((uint32_t)i);
         plan.kind_max_tiles[im.kind] = std::max(plan.kind_max_tiles[im.kind], im.tiles_x * im.tiles_y);
         plan.groups.back().kind_max_tiles[im.kind] = std::max(plan.groups.back().kind_max_tiles[im.kind], im.tiles_x * im.tiles_y);
+        if (g.compose) {
+            // compose path: one frame of this image's own three components, chroma interpolated (jpgpu_core.h)
+            FrameDev f;
+            memset(&f, 0, sizeof f);
+            f.width = d.width; f.height = d.height; f.ncomp = d.ncomp; f.fancy = 1u;
+            f.rgb_off = im.rgb_off;
+            uint32_t first = 0;
+            for (uint32_t c = 0; c < d.ncomp; c++) {
+                PlaneRef& r = f.pl[c];
+                r.smp_off = plan.sample_floats;
+                r.mcux = g.mcux; r.bpm = g.blocks_per_mcu; r.first = first;
+                r.h = g.h[c]; r.v = g.v[c];
+                r.fx = g.hmax / g.h[c]; r.fy = g.vmax / g.v[c];
+                r.wc = (d.width * g.h[c] + g.hmax - 1) / g.hmax;
+                r.hc = (d.height * g.v[c] + g.vmax - 1) / g.vmax;
+                r.bias = 0.0f;     // block_idct_kernel level-shifts component 0 only
+                first += g.h[c] * g.v[c];
+            }
+            plan.frames.push_back(f);
+            im.frame = (uint32_t)plan.frames.size();
+            const uint32_t quads = (uint32_t)(((uint64_t)d.width * d.height + 3) / 4);
+            plan.frame_max_quads = std::max(plan.frame_max_quads, quads);
+            plan.groups.back().frame_max_quads = std::max(plan.groups.back().frame_max_quads, quads);
+        }
         if (im.kind == kKindGeneric) {
             const uint32_t nblk = g.units * g.blocks_per_mcu;
             im.map_off = map_off;
-            im.map_plane = map_plane;
+            im.map_plane = g.compose ? 0u : map_plane;
             im.smp_off = plan.sample_floats;
             plan.sample_floats += (uint64_t)nblk * 64;
             plan.gather_max_blocks = std::max(plan.gather_max_blocks, nblk);
-            plan.gather_max_quads = std::max(plan.gather_max_quads, map_plane / 4);
+            plan.gather_max_quads = std::max(plan.gather_max_quads, im.map_plane / 4);
             plan.groups.back().gather_max_blocks = std::max(plan.groups.back().gather_max_blocks, nblk);
-            plan.groups.back().gather_max_quads = std::max(plan.groups.back().gather_max_quads, map_plane / 4);
+            plan.groups.back().gather_max_quads = std::max(plan.groups.back().gather_max_quads, im.map_plane / 4);
         }
 
         plan.tot_scan_bytes += im.raw_len;

@@ -19,6 +19,7 @@ struct Geometry {
     uint8_t hmax = 1, vmax = 1;
     uint8_t kind = kKindGeneric;
     bool fused_ok = false;        // the fused SPEC-geometry kernel reproduces the requested layout
+    bool compose = false;         // compose path (block IDCT + plane-wise up-sampling / colour): fancy up-sampling
     uint32_t nblocks[4] = {0, 0, 0, 0};
 };
 
@@ -43,6 +44,7 @@ struct GroupPlan {
     uint32_t kind_max_tiles[kNumKinds] = {0, 0, 0, 0, 0, 0};
     uint32_t gather_max_blocks = 0, gather_max_quads = 0;
     uint32_t nsync = 0;          // images of the group that need the synchronisation pass (not interval_mode)
+    uint32_t frame_lo = 0, frame_hi = 0, frame_max_quads = 0;   // compose path: the group's frames
 };
 
 struct HostPlan {
@@ -72,6 +74,8 @@ struct HostPlan {
     uint32_t max_chunks = 0;
     uint64_t coef_elems = 0;
     uint64_t rgb_bytes = 0;
+    std::vector<FrameDev> frames;   // compose path: output frames (fancy up-sampling)
+    uint32_t frame_max_quads = 0;
     std::vector<uint32_t> gmap;  // placement maps of the gather path, one per distinct shape
     uint64_t sample_floats = 0;  // per-block IDCT samples of the gather-path images
     uint32_t gather_max_blocks = 0, gather_max_quads = 0;

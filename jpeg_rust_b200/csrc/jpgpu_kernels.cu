@@ -1731,6 +1731,7 @@ __global__ void __launch_bounds__(kIdctThreads) block_idct_kernel(BatchDev b, co
 constexpr int kGatherThreads = 256;
 __global__ void __launch_bounds__(kGatherThreads) gather_colour_kernel(BatchDev b, const uint32_t* __restrict__ img_list) {
     const ImgDev& im = b.imgs[img_list[blockIdx.y]];
+    if (im.frame) return;   // its samples go through compose_colour_kernel
     const uint32_t npix = im.width * im.height;
     const uint32_t q = blockIdx.x * kGatherThreads + threadIdx.x;
     if (q * 4u >= npix) return;
@@ -1794,6 +1795,66 @@ __global__ void __launch_bounds__(kGatherThreads) gather_colour_kernel(BatchDev 
     } else {
         for (uint32_t k = 0; q * 4u + k < npix; k++) {
             out[3 * k] = (uint8_t)min(max(r8[k], 0), 255); out[3 * k + 1] = (uint8_t)min(max(g8[k], 0), 255); out[3 * k + 2] = (uint8_t)min(max(b8[k], 0), 255);
+        }
+    }
+}
+
+// Compose path, stage B: four horizontally adjacent pixels of one frame per thread, put together plane by plane from
+// the per-block samples of block_idct_kernel.  Sub-sampled components are either replicated (the reference's
+// fill_block_in_array, decoder.rs:347-379) or interpolated with libjpeg's "fancy" triangle filter: 3/4 of the nearer and
+// 1/4 of the farther sample per direction (jdsample.c h2v1 / h2v2 fancy up-sampling without its integer rounding), the
+// neighbour clamped at the component's edges.  Colour conversion, truncation and clamp as everywhere else
+// (decoder.rs:382-402).  Not the tuned path: one scalar load per sample.
+__device__ __forceinline__ float plane_sample(const float* __restrict__ smp, const PlaneRef& p, int xs, int ys) {
+    xs = min(max(xs, 0), (int)p.wc - 1);
+    ys = min(max(ys, 0), (int)p.hc - 1);
+    const uint32_t bx = (uint32_t)xs >> 3, by = (uint32_t)ys >> 3;
+    const uint32_t blk = ((by / p.v) * p.mcux + bx / p.h) * p.bpm + p.first + (by % p.v) * p.h + bx % p.h;
+    return __ldg(smp + p.smp_off + (size_t)blk * 64 + ((uint32_t)ys & 7u) * 8u + ((uint32_t)xs & 7u)) + p.bias;
+}
+__device__ __forceinline__ float frame_sample(const float* __restrict__ smp, const PlaneRef& p, bool fancy, int x, int y) {
+    if (p.fx == 1u && p.fy == 1u) return plane_sample(smp, p, x, y);
+    const int xs = p.fx == 2u ? x >> 1 : x, ys = p.fy == 2u ? y >> 1 : y;
+    if (!fancy) return plane_sample(smp, p, xs, ys);
+    const int xn = p.fx == 2u ? xs + ((x & 1) ? 1 : -1) : xs, yn = p.fy == 2u ? ys + ((y & 1) ? 1 : -1) : ys;
+    float a = plane_sample(smp, p, xs, ys), c = plane_sample(smp, p, xn, ys);
+    if (p.fy == 2u) {   // vertical first, as libjpeg's h2v2 ("thiscolsum")
+        a = 0.75f * a + 0.25f * plane_sample(smp, p, xs, yn);
+        c = 0.75f * c + 0.25f * plane_sample(smp, p, xn, yn);
+    }
+    return p.fx == 2u ? 0.75f * a + 0.25f * c : a;
+}
+__global__ void __launch_bounds__(kGatherThreads) compose_colour_kernel(BatchDev b, uint32_t frame0) {
+    const FrameDev& f = b.frames[frame0 + blockIdx.y];
+    const uint32_t W = f.width, npix = W * f.height;
+    const uint32_t q = blockIdx.x * kGatherThreads + threadIdx.x;
+    if (q * 4u >= npix) return;
+    const float* __restrict__ smp = b.samples;
+    const size_t sb = b.out_planar == 2u ? 4u : 1u;
+    uint8_t* const base = b.rgb + f.rgb_off * sb;
+    for (uint32_t k = 0; k < 4u && q * 4u + k < npix; k++) {
+        const uint32_t i = q * 4u + k;
+        const int x = (int)(i % W), y = (int)(i / W);
+        int32_t r8, g8, b8;
+        const float yy = frame_sample(smp, f.pl[0], f.fancy != 0u, x, y);
+        if (f.ncomp == 1u) {
+            r8 = g8 = b8 = f32_to_u8_sat(yy);
+        } else {
+            const float cb = frame_sample(smp, f.pl[1], f.fancy != 0u, x, y), cr = frame_sample(smp, f.pl[2], f.fancy != 0u, x, y);
+            r8 = f32_to_u8_sat(fmaf(cr, 1.402f, yy));
+            g8 = f32_to_u8_sat(fmaf(cb, -0.34413629f, fmaf(cr, -0.71413629f, yy)));
+            b8 = f32_to_u8_sat(fmaf(cb, 1.772f, yy));
+        }
+        r8 = min(max(r8, 0), 255); g8 = min(max(g8, 0), 255); b8 = min(max(b8, 0), 255);
+        if (b.out_planar == 2u) {
+            float* o = reinterpret_cast<float*>(base);
+            o[i] = fmaf((float)r8, b.out_scale[0], b.out_bias[0]);
+            o[npix + i] = fmaf((float)g8, b.out_scale[1], b.out_bias[1]);
+            o[2 * (size_t)npix + i] = fmaf((float)b8, b.out_scale[2], b.out_bias[2]);
+        } else if (b.out_planar) {
+            base[i] = (uint8_t)r8; base[npix + i] = (uint8_t)g8; base[2 * (size_t)npix + i] = (uint8_t)b8;
+        } else {
+            base[3 * (size_t)i] = (uint8_t)r8; base[3 * (size_t)i + 1] = (uint8_t)g8; base[3 * (size_t)i + 2] = (uint8_t)b8;
         }
     }
 }
@@ -1921,8 +1982,16 @@ int launch_idct_colour(const BatchDev& b, cudaStream_t s) {
             const uint32_t cnt = min(kMaxGridY, b.kind_count[kKindGeneric] - i0);
             const uint32_t* list = b.kind_imgs[kKindGeneric] + i0;
             block_idct_kernel<<<dim3((b.gather_max_blocks + 15) / 16, cnt), kIdctThreads, 0, s>>>(b, list);
+            launches++;
+            if (!b.gather_max_quads) continue;   // compose-path images only: their pixels come from compose_colour_kernel
             gather_colour_kernel<<<dim3((b.gather_max_quads + kGatherThreads - 1) / kGatherThreads, cnt), kGatherThreads, 0, s>>>(b, list);
-            launches += 2;
+            launches++;
+        }
+    }
+    if (b.n_frames && b.frame_max_quads) {   // compose path (after block_idct_kernel above produced the samples)
+        for (uint32_t i0 = 0; i0 < b.n_frames; i0 += kMaxGridY) {
+            compose_colour_kernel<<<dim3((b.frame_max_quads + kGatherThreads - 1) / kGatherThreads, min(kMaxGridY, b.n_frames - i0)), kGatherThreads, 0, s>>>(b, i0);
+            launches++;
         }
     }
     return launches;

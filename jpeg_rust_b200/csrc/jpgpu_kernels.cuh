@@ -56,6 +56,9 @@ struct BatchDev {        // device pointers of one planned batch
     float* samples;          // per-block IDCT output, [block][row*8+col]
     uint32_t gather_max_blocks;
     uint32_t gather_max_quads;  // most ceil(W*H/4) of any gather image
+    // compose path (jpgpu_core.h): frames whose pixels are put together plane by plane from per-block samples
+    const FrameDev* frames;
+    uint32_t n_frames, frame_max_quads;
 };
 
 cudaError_t init_constants();

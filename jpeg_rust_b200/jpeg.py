@@ -24,7 +24,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import _ffi
-from ._ffi import EXT_DRI, EXT_NONE, EXT_SKIP_APPN, LAYOUT_REF, LAYOUT_SPEC  # noqa: F401
+from ._ffi import EXT_DRI, EXT_NONE, EXT_SKIP_APPN, LAYOUT_REF, LAYOUT_SPEC, LAYOUT_SPEC_FANCY  # noqa: F401
 
 
 class JPEGPanic(_ffi.JpgpuError):

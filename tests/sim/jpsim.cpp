@@ -466,7 +466,11 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
     for (const SeqDesc& sd : p.seqs)
         for (uint32_t group = 0; group < (1u << p.wp_shift); group++) sim_decode_write(sb, sd, group);
     for (size_t i = 0; i < n; i++)
-        if (p.status[i] == JPGPU_OK) { if (p.imgs[i].kind == kKindGeneric) sim_gather(sb, i); else sim_idct_colour(sb, i); }
+        if (p.status[i] == JPGPU_OK) {
+            if (p.imgs[i].frame) p.status[i] = JPGPU_ERR_UNSUPPORTED;   // the compose path (fancy up-sampling) is not mirrored here
+            else if (p.imgs[i].kind == kKindGeneric) sim_gather(sb, i);
+            else sim_idct_colour(sb, i);
+        }
     for (size_t i = 0; i < n; i++) {
         int32_t s = p.status[i];
         uint64_t br = 0;

@@ -853,3 +853,84 @@ def test_repeated_decodes_replay_a_cuda_graph():
         for a, c in zip(runs[0][:50], outs):
             assert np.array_equal(a.transpose(2, 0, 1), c)
     b.close()
+
+
+def _fancy_reference(data, ext=0):
+    """libjpeg's fancy (triangle-filter) chroma up-sampling restated in numpy float32 on the ORACLE's planes: the oracle
+    (SPEC layout) replicates sub-sampled chroma, so every fx-th / fy-th sample of its full-size plane is the decoded
+    chroma sample itself.  Same weights and operation order as compose_colour_kernel; colour conversion and truncation
+    as decoder.rs:382-402."""
+    o = O.decode(data, layout=O.LAYOUT_SPEC, ext=ext)
+    H, W = o.height, o.width
+    st, d, _buf = __import__("jpeg_rust_b200").parse_descriptor(data, ext, LAYOUT_SPEC)
+    hmax = max(d.comp[c].h for c in range(d.ncomp))
+    vmax = max(d.comp[c].v for c in range(d.ncomp))
+    planes = []
+    for c in range(d.ncomp):
+        full = o.planes[c].reshape(H, W).astype(np.float32) + np.float32(128.0 if c == 0 else 0.0)
+        fx, fy = hmax // d.comp[c].h, vmax // d.comp[c].v
+        if fx == 1 and fy == 1:
+            planes.append(full)
+            continue
+        s = full[::fy, ::fx]                       # the component's own samples: (ceil(H/fy), ceil(W/fx))
+        hc, wc = s.shape
+        ys, xs = np.arange(H), np.arange(W)
+        y0 = ys // fy if fy == 2 else ys
+        x0 = xs // fx if fx == 2 else xs
+        yn = np.clip(y0 + np.where(ys & 1, 1, -1), 0, hc - 1) if fy == 2 else y0
+        xn = np.clip(x0 + np.where(xs & 1, 1, -1), 0, wc - 1) if fx == 2 else x0
+        a, cc = s[np.ix_(y0, x0)], s[np.ix_(y0, xn)]
+        if fy == 2:
+            a = np.float32(0.75) * a + np.float32(0.25) * s[np.ix_(yn, x0)]
+            cc = np.float32(0.75) * cc + np.float32(0.25) * s[np.ix_(yn, xn)]
+        planes.append(np.float32(0.75) * a + np.float32(0.25) * cc if fx == 2 else a)
+    if len(planes) == 1:
+        u = np.clip(np.trunc(planes[0]), 0, 255).astype(np.uint8)
+        return np.stack([u, u, u], axis=-1)
+    y, cb, cr = planes
+    f32 = np.float32
+    r = cr * f32(1.402) + y
+    g = cb * f32(-0.34413629) + (cr * f32(-0.71413629) + y)
+    b = cb * f32(1.772) + y
+    return np.stack([np.clip(np.trunc(v), 0, 255).astype(np.uint8) for v in (r, g, b)], axis=-1)
+
+
+def test_fancy_upsampling_layout():
+    """SURVEY 8(f) row 4 (a feature the reference lacks, behind JPGPU_LAYOUT_SPEC_FANCY): sub-sampled chroma interpolated
+    with libjpeg's triangle filter instead of replicated.  Against the numpy restatement above (+-1: fma contraction), and
+    as a sanity check against libjpeg itself (PIL), which this layout must approach much closer than box replication does."""
+    import io
+    from PIL import Image
+    from jpeg_rust_b200 import LAYOUT_SPEC_FANCY
+    cases = [("420", 640, 480, 0), ("422", 333, 217, 0), ("440", 320, 200, 0), ("420", 131, 77, 5), ("420", 1920, 1080, 0),
+             ("444", 200, 100, 0), ("gray", 200, 100, 0)]
+    files = [synth.synth_jpeg(7800 + i, w, h, s, restart_interval=ri) for i, (s, w, h, ri) in enumerate(cases)]
+    files += [fixture_bytes("lena.jpeg"), fixture_bytes("2x2-chroma.jpeg")]
+    fancy, st, br = run_batch(files, LAYOUT_SPEC_FANCY, EXT_DRI)[:3]
+    box, st_box, br_box = run_batch(files, LAYOUT_SPEC, EXT_DRI)[:3]
+    assert st == st_box == [0] * len(files) and br == br_box
+    for i, f in enumerate(files):
+        want = _fancy_reference(f, EXT_DRI)
+        d = np.abs(fancy[i].astype(np.int16) - want.astype(np.int16))
+        assert d.max() <= 1 and d.mean() < 0.01, (i, d.max(), d.mean())
+        pil = np.asarray(Image.open(io.BytesIO(f)).convert("RGB")).astype(np.int16)
+        e_fancy = np.abs(fancy[i].astype(np.int16) - pil).mean()
+        e_box = np.abs(box[i].astype(np.int16) - pil).mean()
+        if i < 5 or i >= 7:      # sub-sampled files: interpolation is what libjpeg does
+            assert e_fancy < 0.8 and e_fancy < e_box, (i, e_fancy, e_box)
+        else:                    # nothing to interpolate: identical to the SPEC layout
+            assert np.array_equal(fancy[i], box[i])
+    # every output format goes through the same kernel
+    b = Batch(files[:2], layout=LAYOUT_SPEC_FANCY)
+    b.set_output_format(_ffi.OUT_RGB_PLANAR)
+    b.upload().decode()
+    planar = b.download()
+    b.results()
+    b.set_output_format(_ffi.OUT_F32_PLANAR)
+    b.decode()
+    f32 = b.download()
+    b.results()
+    for i in range(2):
+        assert np.array_equal(planar[i], fancy[i].transpose(2, 0, 1))
+        assert np.allclose(f32[i], fancy[i].transpose(2, 0, 1).astype(np.float32) / 255.0, atol=1e-6)
+    b.close()
