@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define JPGPU_ABI_VERSION 2
+#define JPGPU_ABI_VERSION 3
 
 /* ------------------------------------------------------------------ statuses
  * 0 = success.  1..15 mirror the panics of the reference so that a host shim
@@ -91,7 +91,8 @@ enum { JPGPU_OUT_RGB_INTERLEAVED = 0, JPGPU_OUT_RGB_PLANAR = 1,
 enum {
     JPGPU_EXT_NONE = 0,
     JPGPU_EXT_SKIP_APPN = 1, /* skip APPn/JPGn segments (incl. APP12/APP14) by their length */
-    JPGPU_EXT_DRI = 2        /* accept DRI; the scan is decoded per restart interval */
+    JPGPU_EXT_DRI = 2,       /* accept DRI; the scan is decoded per restart interval */
+    JPGPU_EXT_MULTISCAN = 4  /* jpgpu_parse_scans only: go on after the first scan (non-interleaved component scans) */
 };
 
 /* One component, in SCAN order (decoder.rs:39-52, after scan_header() reordering). */
@@ -126,6 +127,18 @@ typedef struct jpgpu_image_desc {
      * GPU removes the stuffing and finds RSTn markers itself. */
     const uint8_t *scan;
     size_t scan_len;
+    /* Multi-scan files (jpgpu_parse_scans, a feature the reference lacks: it returns after the first scan,
+     * mod.rs:416-417).  Every non-interleaved scan is one descriptor - a one-component image of the component's own size
+     * (width/height above = ceil(X*H/Hmax) x ceil(Y*V/Vmax), T.81 A.1.1) with the tables in force at its SOS - and the
+     * descriptors of one frame are consecutive.  frame_part: 0 = an image of its own (everything jpgpu_parse fills in),
+     * 1 = first scan of a frame (owns the frame's output), 2 = a further scan of the same frame. */
+    uint32_t frame_part;
+    uint32_t frame_width, frame_height; /* SOF0 X, Y */
+    uint8_t frame_ncomp;                /* components of the frame (3) */
+    uint8_t frame_comp;                 /* which one this scan carries, in SOF0 order (0 = Y, 1 = Cb, 2 = Cr) */
+    uint8_t frame_h, frame_v;           /* its sampling factors */
+    uint8_t frame_hmax, frame_vmax;     /* the largest of the frame */
+    uint8_t frame_pad[2];
 } jpgpu_image_desc;
 
 typedef struct jpgpu_ctx jpgpu_ctx;     /* one per process and device */
@@ -138,6 +151,15 @@ typedef struct jpgpu_batch jpgpu_batch; /* a planned set of images with its devi
  * the status naming the panic the reference would raise.  `layout` is copied
  * into the descriptor.  Needs no GPU. */
 int jpgpu_parse(const uint8_t *file, size_t len, uint32_t ext_flags, uint32_t layout, jpgpu_image_desc *out);
+
+/* jpgpu_parse for files with several scans (ext_flags must hold JPGPU_EXT_MULTISCAN): walks the whole file and writes
+ * one descriptor per scan into out[0 .. *n).  A single interleaved scan gives exactly what jpgpu_parse gives (*n = 1,
+ * frame_part = 0).  Non-interleaved scans (one component each, all components of the frame present) give a frame of
+ * consecutive part descriptors to hand to jpgpu_batch_create / jpgpu_multi_plan together; the frame's pixels are the
+ * output of its first part.  Anything else - scans mixing interleaved and non-interleaved components, components coded
+ * twice - is JPGPU_ERR_UNSUPPORTED.  Returns a status; *n is set in every case. */
+int jpgpu_parse_scans(const uint8_t *file, size_t len, uint32_t ext_flags, uint32_t layout, jpgpu_image_desc *out,
+                      size_t max_out, size_t *n);
 
 /* Number of MCUs decode() reads and blocks per MCU for a descriptor (decoder.rs:164-192
  * for REF; true MCU count for SPEC).  Returns a status. */

@@ -11,7 +11,7 @@ LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libjpgpu.so")
 
 LAYOUT_REF, LAYOUT_SPEC, LAYOUT_SPEC_FANCY = 0, 1, 2
-EXT_NONE, EXT_SKIP_APPN, EXT_DRI = 0, 1, 2
+EXT_NONE, EXT_SKIP_APPN, EXT_DRI, EXT_MULTISCAN = 0, 1, 2, 4
 OUT_RGB_INTERLEAVED, OUT_RGB_PLANAR, OUT_F32_PLANAR = 0, 1, 2
 MEMORY_HOST, MEMORY_DEVICE = 0, 1
 
@@ -41,6 +41,9 @@ class ImageDesc(C.Structure):
         ("ac_nvals", C.c_uint16 * 4), ("ac_present", C.c_uint8 * 4),
         ("restart_interval", C.c_uint32), ("layout", C.c_uint32),
         ("scan", C.c_void_p), ("scan_len", C.c_size_t),
+        ("frame_part", C.c_uint32), ("frame_width", C.c_uint32), ("frame_height", C.c_uint32),
+        ("frame_ncomp", C.c_uint8), ("frame_comp", C.c_uint8), ("frame_h", C.c_uint8), ("frame_v", C.c_uint8),
+        ("frame_hmax", C.c_uint8), ("frame_vmax", C.c_uint8), ("frame_pad", C.c_uint8 * 2),
     ]
 
 
@@ -69,6 +72,7 @@ def lib():
         L.jpgpu_panic_message.restype = C.c_char_p
         L.jpgpu_panic_message.argtypes = [C.c_int]
         L.jpgpu_parse.argtypes = [vp, sz, C.c_uint32, C.c_uint32, C.POINTER(ImageDesc)]
+        L.jpgpu_parse_scans.argtypes = [vp, sz, C.c_uint32, C.c_uint32, C.POINTER(ImageDesc), sz, C.POINTER(sz)]
         L.jpgpu_geometry.argtypes = [C.POINTER(ImageDesc), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                      C.POINTER(C.c_uint32)]
         L.jpgpu_plan_info.argtypes = [C.POINTER(ImageDesc), sz, C.POINTER(C.c_uint64)]
@@ -158,7 +162,7 @@ def check(status, what=""):
 
 
 EXPORTED_SYMBOLS = [
-    "jpgpu_parse", "jpgpu_geometry", "jpgpu_status_string", "jpgpu_panic_message", "jpgpu_abi_version",
+    "jpgpu_parse", "jpgpu_parse_scans", "jpgpu_geometry", "jpgpu_status_string", "jpgpu_panic_message", "jpgpu_abi_version",
     "jpgpu_plan_info",
     "jpgpu_create", "jpgpu_destroy", "jpgpu_last_error", "jpgpu_set_stream", "jpgpu_sync",
     "jpgpu_decode", "jpgpu_decode_file",

@@ -276,7 +276,11 @@ size_t jpgenc_max_size(int width, int height) {
 //   (zigzag order, absolute DC) in decode order; coef_cap in int16 units.
 // Returns the number of bytes written, or 0 if out_cap / coef_cap is too small.
 // flags: 1 = image-specific Huffman tables (T.81 K.2; may contain 1-bit codes, which the reference cannot decode),
-//        2 = 16-bit quantisation tables (Pq = 1) with unclamped libjpeg scaling.
+//        2 = 16-bit quantisation tables (Pq = 1) with unclamped libjpeg scaling,
+//        4 = NON-INTERLEAVED: one scan per component (T.81 A.2.2: blocks in raster order over the component's own
+//            ceil(Xc/8) x ceil(Yc/8) grid, no MCU padding), Annex-K tables (flag 1 is ignored), restart intervals count
+//            blocks.  The reference returns after the first scan (mod.rs:416-417); coef_dump then holds every component
+//            in that raster order.
 size_t jpgenc_encode_ex(const uint8_t* rgb, int width, int height, int gray, int hy, int vy, int quality,
                         int restart_interval, int flags, uint8_t* out, size_t out_cap, int16_t* coef_dump,
                         size_t coef_cap, size_t* nblocks /*[3]*/) {
@@ -322,7 +326,8 @@ size_t jpgenc_encode_ex(const uint8_t* rgb, int width, int height, int gray, int
             }
     }
 
-    const bool optimise = (flags & 1) != 0, dqt16 = (flags & 2) != 0;
+    const bool planar_scans = (flags & 4) != 0 && !gray;
+    const bool optimise = (flags & 1) != 0 && !planar_scans, dqt16 = (flags & 2) != 0;
     uint16_t qt[2][64];
     scaled_qtable(kQLum, quality, qt[0], dqt16);
     scaled_qtable(kQChr, quality, qt[1], dqt16);
@@ -426,6 +431,59 @@ size_t jpgenc_encode_ex(const uint8_t* rgb, int width, int height, int gray, int
     }
     if (restart_interval > 0)
         put_marker_seg(o, 0xdd, {(uint8_t)(restart_interval >> 8), (uint8_t)restart_interval});
+    if (planar_scans) {
+        // one scan per component, blocks in raster order over the component's own block grid
+        size_t dump_at = 0;
+        for (int c = 0; c < ncomp; c++) {
+            const int wc = (width * H[c] + hy - 1) / hy, hc = (height * V[c] + vy - 1) / vy;
+            const int nbx = (wc + 7) / 8, nby = (hc + 7) / 8;
+            if (nblocks) nblocks[c] = (size_t)nbx * nby;
+            if (coef_dump && coef_cap < dump_at + (size_t)nbx * nby * 64) return 0;
+            put_marker_seg(o, 0xda, {1, (uint8_t)(c + 1), (uint8_t)(c == 0 ? 0x00 : 0x11), 0, 63, 0});
+            BitWriter bw(o);
+            const EncTable& dct = enc[c == 0 ? 0 : 2];
+            const EncTable& act = enc[c == 0 ? 1 : 3];
+            int first = 0;
+            for (int k = 0; k < c; k++) first += H[k] * V[k];
+            int pred = 0, rst_count = 0, in_interval = 0;
+            for (int by = 0; by < nby; by++)
+                for (int bx = 0; bx < nbx; bx++) {
+                    if (restart_interval > 0 && in_interval == restart_interval) {
+                        bw.flush_ones();
+                        o.push_back(0xff);
+                        o.push_back((uint8_t)(0xd0 + (rst_count & 7)));
+                        rst_count++;
+                        in_interval = 0;
+                        pred = 0;
+                    }
+                    const size_t mcu = (size_t)(by / V[c]) * mcux + bx / H[c];
+                    const int16_t* zz = blocks.data() + (mcu * bpm + first + (by % V[c]) * H[c] + bx % H[c]) * 64;
+                    if (coef_dump) { std::memcpy(coef_dump + dump_at, zz, 64 * sizeof(int16_t)); dump_at += 64; }
+                    int diff = zz[0] - pred;
+                    pred = zz[0];
+                    int sz0 = bit_size(diff);
+                    bw.put(dct.code[sz0], dct.size[sz0]);
+                    if (sz0) bw.put((uint32_t)(diff < 0 ? diff - 1 : diff), sz0);
+                    int run = 0;
+                    for (int k = 1; k < 64; k++) {
+                        if (zz[k] == 0) { run++; continue; }
+                        while (run > 15) { bw.put(act.code[0xf0], act.size[0xf0]); run -= 16; }
+                        int sz = bit_size(zz[k]);
+                        int sym = (run << 4) | sz;
+                        bw.put(act.code[sym], act.size[sym]);
+                        bw.put((uint32_t)(zz[k] < 0 ? zz[k] - 1 : zz[k]), sz);
+                        run = 0;
+                    }
+                    if (run > 0) bw.put(act.code[0x00], act.size[0x00]);
+                    in_interval++;
+                }
+            bw.flush_ones();
+        }
+        o.push_back(0xff); o.push_back(0xd9);  // EOI
+        if (o.size() > out_cap) return 0;
+        std::memcpy(out, o.data(), o.size());
+        return o.size();
+    }
     {  // SOS
         std::vector<uint8_t> p = {(uint8_t)ncomp};
         for (int c = 0; c < ncomp; c++) {

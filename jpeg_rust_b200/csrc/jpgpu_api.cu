@@ -550,9 +550,9 @@ extern "C" int jpgpu_batch_download(jpgpu_batch* b, uint8_t* const* outs) try {
     for (size_t i = 0; i < b->n; i++) {
         if (b->plan.status[i] != JPGPU_OK || !outs[i]) continue;
         const ImgDev& im = b->plan.imgs[i];
-        const size_t sb = sample_bytes(b);
-        CK(cudaMemcpyAsync(outs[i], b->dev.rgb + im.rgb_off * sb, (size_t)im.width * im.height * 3 * sb, cudaMemcpyDeviceToHost,
-                           ctx->stream));
+        const size_t sb = sample_bytes(b), nbytes = (size_t)b->plan.out_w[i] * b->plan.out_h[i] * 3 * sb;
+        if (!nbytes) continue;   // a further scan of a frame: the pixels belong to the frame's first scan
+        CK(cudaMemcpyAsync(outs[i], b->dev.rgb + im.rgb_off * sb, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
@@ -586,7 +586,7 @@ extern "C" int jpgpu_batch_set_normalisation(jpgpu_batch* b, const float scale[3
 extern "C" void* jpgpu_batch_device_rgb(jpgpu_batch* b, size_t i, size_t* nbytes) {
     if (!b || i >= b->n || b->plan.status[i] != JPGPU_OK) return nullptr;
     const ImgDev& im = b->plan.imgs[i];
-    if (nbytes) *nbytes = (size_t)im.width * im.height * 3 * sample_bytes(b);
+    if (nbytes) *nbytes = (size_t)b->plan.out_w[i] * b->plan.out_h[i] * 3 * sample_bytes(b);
     return b->dev.rgb + im.rgb_off * sample_bytes(b);
 }
 
@@ -596,7 +596,7 @@ extern "C" int jpgpu_batch_rgb_offset(const jpgpu_batch* b, size_t i, size_t* of
     if (!b || i >= b->n) return JPGPU_ERR_INVALID_ARG;
     const ImgDev& im = b->plan.imgs[i];
     if (offset) *offset = (size_t)im.rgb_off * sample_bytes(b);
-    if (nbytes) *nbytes = b->plan.status[i] == JPGPU_OK ? (size_t)im.width * im.height * 3 * sample_bytes(b) : 0;
+    if (nbytes) *nbytes = b->plan.status[i] == JPGPU_OK ? (size_t)b->plan.out_w[i] * b->plan.out_h[i] * 3 * sample_bytes(b) : 0;
     return JPGPU_OK;
 }
 
@@ -621,6 +621,13 @@ extern "C" int jpgpu_batch_results(jpgpu_batch* b, int32_t* statuses, uint64_t* 
         if (statuses) statuses[i] = st;
         if (bytes_read) bytes_read[i] = br;
     }
+    // a frame of several scans is as good as its worst scan: the first scan (which owns the pixels) reports it
+    if (statuses)
+        for (size_t i = 0; i < b->n; i++) {
+            if (b->plan.frame_part[i] != 1) continue;
+            for (size_t k = i + 1; k < b->n && b->plan.frame_part[k] == 2; k++)
+                if (statuses[i] == JPGPU_OK && statuses[k] != JPGPU_OK) statuses[i] = statuses[k];
+        }
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
 
@@ -704,6 +711,32 @@ extern "C" int jpgpu_decode(jpgpu_ctx* ctx, const jpgpu_image_desc* desc, uint8_
 extern "C" int jpgpu_decode_file(jpgpu_ctx* ctx, const uint8_t* file, size_t len, uint32_t ext_flags, uint32_t layout,
                                  uint8_t* rgb_out, size_t rgb_cap, uint32_t* width, uint32_t* height, size_t* bytes_read) try {
     if (!ctx || !file || !rgb_out) return JPGPU_ERR_INVALID_ARG;
+    if (ext_flags & JPGPU_EXT_MULTISCAN) {
+        // a file that may hold one non-interleaved scan per component: every scan is a descriptor, the frame's pixels
+        // are the output of the first
+        jpgpu_image_desc ds[4];
+        size_t n = 0;
+        int st = jpgpu_parse_scans(file, len, ext_flags, layout, ds, 4, &n);
+        if (st != JPGPU_OK) return st;
+        const uint32_t w = ds[0].frame_part ? ds[0].frame_width : ds[0].width, h = ds[0].frame_part ? ds[0].frame_height : ds[0].height;
+        if (width) *width = w;
+        if (height) *height = h;
+        if ((size_t)w * h * 3 > rgb_cap) return JPGPU_ERR_INVALID_ARG;
+        if (!ctx->single) st = jpgpu_batch_create(ctx, ds, n, &ctx->single);
+        else st = jpgpu_batch_replan(ctx->single, ds, n);
+        if (st != JPGPU_OK) return st;
+        jpgpu_batch* b = ctx->single;
+        int32_t ist[4] = {0, 0, 0, 0};
+        uint64_t br[4] = {0, 0, 0, 0};
+        uint8_t* outs[4] = {rgb_out, nullptr, nullptr, nullptr};
+        st = jpgpu_batch_upload(b);
+        if (st == JPGPU_OK) st = jpgpu_batch_decode(b);
+        if (st == JPGPU_OK) st = jpgpu_batch_download(b, outs);
+        if (st == JPGPU_OK) st = jpgpu_batch_results(b, ist, br);
+        if (st != JPGPU_OK) return st;
+        if (bytes_read) { *bytes_read = 0; for (size_t k = 0; k < n; k++) *bytes_read += (size_t)br[k]; }
+        return ist[0];
+    }
     jpgpu_image_desc d;
     int st = jpgpu_parse(file, len, ext_flags, layout, &d);
     if (st != JPGPU_OK) return st;

@@ -315,10 +315,15 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
     const uint64_t group_words = (uint64_t)32 << lw;  // one warp's 32 subsequences, lane-interleaved
     plan.imgs.resize(n);
     plan.status.assign(n, JPGPU_OK);
+    plan.out_w.assign(n, 0);
+    plan.out_h.assign(n, 0);
+    plan.frame_part.assign(n, 0);
+    for (size_t i = 0; i < n; i++) plan.frame_part[i] = (uint8_t)std::min<uint32_t>(descs[i].frame_part, 3u);
     std::map<std::string, uint32_t> lut_ids;
     std::map<std::string, uint32_t> qt_ids;
     std::map<std::string, uint64_t> map_ids;
     std::string cur_lutset;
+    long cur_frame = -1;   // the frame whose scans are being planned (index into plan.frames), -1: none
     // groups: contiguous image ranges of about equal scan bytes
     uint64_t tot_bytes = 0;
     for (size_t i = 0; i < n; i++) tot_bytes += descs[i].scan_len;
@@ -355,13 +360,25 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         const jpgpu_image_desc& d = descs[i];
         ImgDev& im = plan.imgs[i];
         memset(&im, 0, sizeof im);
-        if (i > 0 && acc_bytes >= (uint64_t)plan.groups.size() * group_bytes && plan.groups.size() < want_groups) {
+        if (i > 0 && acc_bytes >= (uint64_t)plan.groups.size() * group_bytes && plan.groups.size() < want_groups &&
+            d.frame_part != 2) {   // the scans of one frame stay in one group: its pixels are put together there
             close_group(i);
             open_group(i);
         }
         acc_bytes += d.scan_len;
         Geometry g;
         int st = compute_geometry(d, g);
+        if (st == JPGPU_OK && d.frame_part) {
+            // one non-interleaved scan of a frame (jpgpu_parse_scans): entropy-decoded as the one-component image it
+            // is, its pixels come from the compose path once all scans of the frame are there
+            if (d.frame_part > 2 || d.ncomp != 1 || d.layout == JPGPU_LAYOUT_REF || d.frame_ncomp != 3 || d.frame_comp > 2 ||
+                (d.frame_part == 2 && (i == 0 || cur_frame < 0 || plan.status[i - 1] != JPGPU_OK)))
+                st = JPGPU_ERR_INVALID_ARG;
+            g.fused_ok = false;
+            g.compose = true;
+        }
+        if (st == JPGPU_OK && d.frame_part && (uint64_t)d.frame_width * d.frame_height * 3 > 0xffffffffull) st = JPGPU_ERR_UNSUPPORTED;
+        if (st != JPGPU_OK || d.frame_part != 2) cur_frame = -1;
         if (st == JPGPU_OK && (d.scan == nullptr || d.scan_len < 4)) st = JPGPU_PANIC_INDEX_OOB;  // huffman.rs:127-128
         if (st == JPGPU_OK && d.scan_len > 0x1ff00000ull) st = JPGPU_ERR_UNSUPPORTED;             // bit positions are 32-bit
         if (st == JPGPU_OK && (uint64_t)g.units * g.blocks_per_mcu * 64 >= (uint64_t)kPosSat) st = JPGPU_ERR_UNSUPPORTED;   // positions saturate there (fold_advance)
@@ -528,15 +545,42 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         for (uint32_t q = 0; q < im.nseq; q++) plan.seqs.push_back(SeqDesc{(uint32_t)i, q * 32u});
         im.coef_off = plan.coef_elems;
         plan.coef_elems += im.total_coefs;
-        im.rgb_off = plan.rgb_bytes;
-        plan.rgb_bytes += align_up((uint64_t)im.width * im.height * 3, 256);
+        // output: an image's own size; for the scans of a frame the first one owns the frame's pixels, the others nothing
+        uint32_t ow = im.width, oh = im.height;
+        if (d.frame_part == 1) { ow = d.frame_width; oh = d.frame_height; }
+        if (d.frame_part == 2) { ow = oh = 0; }
+        plan.out_w[i] = ow; plan.out_h[i] = oh;
+        im.rgb_off = d.frame_part == 2 ? plan.frames[(size_t)cur_frame].rgb_off : plan.rgb_bytes;
+        plan.rgb_bytes += align_up((uint64_t)ow * oh * 3, 256);
         const uint32_t mcus_per_tile = 128u / (8u * g.hmax);
         im.tiles_x = (g.mcux + mcus_per_tile - 1) / mcus_per_tile;
         im.tiles_y = g.mcuy;
         plan.kind_imgs[im.kind].push_back((uint32_t)i);
         plan.kind_max_tiles[im.kind] = std::max(plan.kind_max_tiles[im.kind], im.tiles_x * im.tiles_y);
         plan.groups.back().kind_max_tiles[im.kind] = std::max(plan.groups.back().kind_max_tiles[im.kind], im.tiles_x * im.tiles_y);
-        if (g.compose) {
+        if (g.compose && d.frame_part) {
+            // compose path, frame of non-interleaved scans: this scan is one plane of it
+            if (d.frame_part == 1) {
+                FrameDev f;
+                memset(&f, 0, sizeof f);
+                f.width = d.frame_width; f.height = d.frame_height; f.ncomp = d.frame_ncomp;
+                f.fancy = d.layout == JPGPU_LAYOUT_SPEC_FANCY ? 1u : 0u;
+                f.rgb_off = im.rgb_off;
+                plan.frames.push_back(f);
+                cur_frame = (long)plan.frames.size() - 1;
+                const uint32_t quads = (uint32_t)(((uint64_t)f.width * f.height + 3) / 4);
+                plan.frame_max_quads = std::max(plan.frame_max_quads, quads);
+                plan.groups.back().frame_max_quads = std::max(plan.groups.back().frame_max_quads, quads);
+            }
+            PlaneRef& r = plan.frames[(size_t)cur_frame].pl[d.frame_comp];
+            r.smp_off = plan.sample_floats;
+            r.mcux = g.mcux; r.bpm = 1; r.first = 0; r.h = r.v = 1;
+            r.wc = d.width; r.hc = d.height;
+            r.fx = std::max<uint32_t>(1u, d.frame_hmax / std::max<uint32_t>(1u, d.frame_h));
+            r.fy = std::max<uint32_t>(1u, d.frame_vmax / std::max<uint32_t>(1u, d.frame_v));
+            r.bias = d.frame_comp == 0 ? 0.0f : -128.0f;   // block_idct_kernel level-shifts every one-component image
+            im.frame = (uint32_t)cur_frame + 1u;
+        } else if (g.compose) {
             // compose path: one frame of this image's own three components, chroma interpolated (jpgpu_core.h)
             FrameDev f;
             memset(&f, 0, sizeof f);
@@ -574,8 +618,8 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
 
         plan.tot_scan_bytes += im.raw_len;
         plan.tot_blocks += (uint64_t)g.units * g.blocks_per_mcu;
-        plan.tot_pixels += (uint64_t)im.width * im.height;
-        plan.tot_rgb_bytes += (uint64_t)im.width * im.height * 3;
+        plan.tot_pixels += (uint64_t)ow * oh;
+        plan.tot_rgb_bytes += (uint64_t)ow * oh * 3;
     }
     close_group(n);
     plan.lookback_bits = choose_lookback_bits(tot_bytes, sub_bits, max_bpm);
@@ -736,8 +780,11 @@ extern "C" const char* jpgpu_panic_message(int s) {
 }
 
 // JPEGImage::parse, mod.rs:202-414 — marker walk up to (not including) decode().
-extern "C" int jpgpu_parse(const uint8_t* file, size_t len, uint32_t ext, uint32_t layout, jpgpu_image_desc* out) {
-    if (!file || !out) return JPGPU_ERR_INVALID_ARG;
+// `scans` == nullptr: the reference's walk, which ends at the first SOS with the rest of the file as scan data.
+// Otherwise (jpgpu_parse_scans): every SOS appends a descriptor whose scan data ends at the next marker, and the walk
+// goes on; `out` is the running state (tables, frame) the descriptors are cut from.
+static int parse_walk(const uint8_t* file, size_t len, uint32_t ext, uint32_t layout, jpgpu_image_desc* out,
+                      std::vector<jpgpu_image_desc>* scans) {
     memset(out, 0, sizeof *out);
     out->layout = layout;
     const Cursor f{file, len};
@@ -846,7 +893,7 @@ extern "C" int jpgpu_parse(const uint8_t* file, size_t len, uint32_t ext, uint32
                     }
                     (void)f.at(i + 1); (void)f.at(i + 2); (void)f.at(i + 3);
                     i += 4;
-                    if (i < len && file[len - 1] == 0xff)
+                    if (!scans && i < len && file[len - 1] == 0xff)
                         return JPGPU_PANIC_INDEX_OOB;                        // mod.rs:378: vec[i + 1] past the end
                     if (!have_frame) return JPGPU_PANIC_NO_FRAME_HEADER;     // mod.rs:388
                     // builder semantics of decoder.rs:83-152: first matching id wins, scan order kept
@@ -863,7 +910,45 @@ extern "C" int jpgpu_parse(const uint8_t* file, size_t len, uint32_t ext, uint32
                     }
                     out->scan = i <= len ? file + i : file + len;
                     out->scan_len = i <= len ? len - i : 0;
-                    return JPGPU_OK;                                         // mod.rs:415: decode() happens on the GPU
+                    if (!scans) return JPGPU_OK;                             // mod.rs:415: decode() happens on the GPU
+                    {
+                        // multi-scan walk: this scan's entropy-coded data ends at the next marker that is neither a
+                        // stuffed FF00, a restart marker nor a fill byte
+                        size_t end = std::min(i, len);
+                        while (end < len) {
+                            if (file[end] == 0xff && end + 1 < len && file[end + 1] != 0x00 && file[end + 1] != 0xff &&
+                                !(file[end + 1] >= 0xd0 && file[end + 1] <= 0xd7)) break;
+                            end++;
+                        }
+                        jpgpu_image_desc d = *out;
+                        d.scan_len = end - std::min(i, len);
+                        if (scan.size() == frame.size()) {
+                            d.frame_part = 0;                                // every component interleaved: an image of its own
+                        } else if (scan.size() == 1) {
+                            // one component, non-interleaved (T.81 A.2.2): a one-component image of the component's own size
+                            int k = -1, hmax = 1, vmax = 1;
+                            for (size_t c = 0; c < frame.size(); c++) {
+                                if (frame[c].id == scan[0].id) k = (int)c;
+                                hmax = std::max<int>(hmax, frame[c].h);
+                                vmax = std::max<int>(vmax, frame[c].v);
+                            }
+                            if (k < 0 || frame.size() != 3) return JPGPU_ERR_UNSUPPORTED;
+                            d.frame_part = 2;
+                            d.frame_width = out->width; d.frame_height = out->height;
+                            d.frame_ncomp = (uint8_t)frame.size(); d.frame_comp = (uint8_t)k;
+                            d.frame_h = frame[(size_t)k].h; d.frame_v = frame[(size_t)k].v;
+                            d.frame_hmax = (uint8_t)hmax; d.frame_vmax = (uint8_t)vmax;
+                            d.width = (out->width * d.frame_h + hmax - 1) / hmax;
+                            d.height = (out->height * d.frame_v + vmax - 1) / vmax;
+                            d.comp[0].h = d.comp[0].v = 1;
+                            if (d.layout == JPGPU_LAYOUT_REF) d.layout = JPGPU_LAYOUT_SPEC;   // the reference never gets here
+                        } else {
+                            return JPGPU_ERR_UNSUPPORTED;                    // partly interleaved scans
+                        }
+                        scans->push_back(d);
+                        i = end;
+                        continue;
+                    }
                 }
                 case 0xdd:                                                   // DRI, mod.rs:424-428
                     if (!(ext & JPGPU_EXT_DRI)) return JPGPU_PANIC_DRI;
@@ -888,6 +973,45 @@ extern "C" int jpgpu_parse(const uint8_t* file, size_t len, uint32_t ext, uint32
         return JPGPU_ERR_INVALID_ARG;
     }
     return JPGPU_NO_SCAN;                                                    // mod.rs:464
+}
+
+extern "C" int jpgpu_parse(const uint8_t* file, size_t len, uint32_t ext, uint32_t layout, jpgpu_image_desc* out) {
+    if (!file || !out) return JPGPU_ERR_INVALID_ARG;
+    return parse_walk(file, len, ext & ~(uint32_t)JPGPU_EXT_MULTISCAN, layout, out, nullptr);
+}
+
+extern "C" int jpgpu_parse_scans(const uint8_t* file, size_t len, uint32_t ext, uint32_t layout, jpgpu_image_desc* out,
+                                 size_t max_out, size_t* n) try {
+    if (n) *n = 0;
+    if (!file || !out || !n || !max_out || !(ext & JPGPU_EXT_MULTISCAN)) return JPGPU_ERR_INVALID_ARG;
+    std::vector<jpgpu_image_desc> scans;
+    jpgpu_image_desc state;
+    const int st = parse_walk(file, len, ext, layout, &state, &scans);
+    if (st != JPGPU_NO_SCAN) return st;                  // the multi-scan walk only ends by running out of markers
+    if (scans.empty()) return JPGPU_NO_SCAN;
+    if (scans.size() == 1 && scans[0].frame_part == 0) {
+        // the ordinary file: as jpgpu_parse, except that the scan data ends at EOI instead of the end of the file
+        out[0] = scans[0];
+        *n = 1;
+        return JPGPU_OK;
+    }
+    // a frame of non-interleaved scans: every component exactly once, nothing else in the file
+    const size_t nc = scans[0].frame_ncomp;
+    if (scans.size() != nc || nc > max_out) return scans.size() > max_out ? JPGPU_ERR_INVALID_ARG : JPGPU_ERR_UNSUPPORTED;
+    uint32_t seen = 0;
+    for (size_t k = 0; k < nc; k++) {
+        if (scans[k].frame_part != 2 || scans[k].frame_ncomp != nc) return JPGPU_ERR_UNSUPPORTED;
+        seen |= 1u << scans[k].frame_comp;
+    }
+    if (seen != (1u << nc) - 1u) return JPGPU_ERR_UNSUPPORTED;
+    scans[0].frame_part = 1;
+    for (size_t k = 0; k < nc; k++) out[k] = scans[k];
+    *n = nc;
+    return JPGPU_OK;
+} catch (const std::bad_alloc&) {
+    return JPGPU_ERR_OOM;
+} catch (...) {
+    return JPGPU_ERR_INVALID_ARG;
 }
 
 extern "C" int jpgpu_geometry(const jpgpu_image_desc* desc, uint32_t* mcus, uint32_t* blocks_per_mcu, uint32_t nblocks[4]) {

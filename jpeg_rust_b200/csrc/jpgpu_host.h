@@ -58,6 +58,8 @@ struct HostPlan {
     uint32_t nsync = 0;          // images that need the synchronisation pass
     std::vector<ImgDev> imgs;
     std::vector<int32_t> status;  // per image: JPGPU_OK or why it is skipped
+    std::vector<uint32_t> out_w, out_h;   // per image: size of the output it owns (a frame's first scan: the frame; further scans: 0 x 0)
+    std::vector<uint8_t> frame_part;      // per image: jpgpu_image_desc::frame_part
     std::vector<SeqDesc> seqs;
     std::vector<HuffLut> luts;
     std::vector<uint32_t> mluts;      // multi-symbol tables of the synchronisation pass, one per entry of `luts`

@@ -1826,6 +1826,8 @@ __device__ __forceinline__ float frame_sample(const float* __restrict__ smp, con
 }
 __global__ void __launch_bounds__(kGatherThreads) compose_colour_kernel(BatchDev b, uint32_t frame0) {
     const FrameDev& f = b.frames[frame0 + blockIdx.y];
+    for (uint32_t c = 0; c < f.ncomp && c < 3u; c++)
+        if (f.pl[c].h == 0u || f.pl[c].wc == 0u) return;   // a scan of the frame failed to plan: no pixels (its status says why)
     const uint32_t W = f.width, npix = W * f.height;
     const uint32_t q = blockIdx.x * kGatherThreads + threadIdx.x;
     if (q * 4u >= npix) return;

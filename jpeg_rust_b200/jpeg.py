@@ -24,7 +24,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import _ffi
-from ._ffi import EXT_DRI, EXT_NONE, EXT_SKIP_APPN, LAYOUT_REF, LAYOUT_SPEC, LAYOUT_SPEC_FANCY  # noqa: F401
+from ._ffi import EXT_DRI, EXT_MULTISCAN, EXT_NONE, EXT_SKIP_APPN, LAYOUT_REF, LAYOUT_SPEC, LAYOUT_SPEC_FANCY  # noqa: F401
 
 
 class JPEGPanic(_ffi.JpgpuError):
@@ -235,6 +235,22 @@ def parse_descriptor(data, ext=EXT_NONE, layout=LAYOUT_REF):
     return st, d, buf
 
 
+def parse_scans(data, ext=EXT_NONE, layout=LAYOUT_SPEC):
+    """jpgpu_parse_scans: one descriptor per scan of the file (ext gets EXT_MULTISCAN).  A file of non-interleaved scans
+    gives the consecutive part descriptors of one frame; the ordinary file gives one descriptor.
+    Returns (status, list of ImageDesc, buffer that owns the bytes)."""
+    buf = data if isinstance(data, np.ndarray) else np.frombuffer(bytes(data), np.uint8).copy()
+    out = (_ffi.ImageDesc * 4)()
+    n = C.c_size_t(0)
+    st = _ffi.lib().jpgpu_parse_scans(buf.ctypes.data, buf.size, ext | _ffi.EXT_MULTISCAN, layout, out, 4, C.byref(n))
+    descs = []
+    for k in range(n.value):
+        d = _ffi.ImageDesc()
+        C.memmove(C.byref(d), C.byref(out[k]), C.sizeof(_ffi.ImageDesc))
+        descs.append(d)
+    return st, descs, buf
+
+
 def plan_info(files=None, descs=None, ext=EXT_NONE, layout=LAYOUT_SPEC, copies=1):
     """What the planner decides for a batch (jpgpu_plan_info; host only, needs no GPU): dict with sub_bits,
     lookback_bits, seg_bits, write_parts, groups, interval_images, warp_jobs, device_bytes.  `copies` repeats the
@@ -268,7 +284,26 @@ class JPEGImage:
     @staticmethod
     def parse(vec, ext=EXT_NONE, layout=LAYOUT_REF, device=0):
         """mod.rs:202-465. Raises JPEGPanic where the reference panics; like the reference it
-        decodes the first scan and returns."""
+        decodes the first scan and returns - unless ext holds EXT_MULTISCAN (a file of non-interleaved scans is then
+        decoded whole, jpgpu_decode_file)."""
+        if ext & EXT_MULTISCAN:
+            buf = vec if isinstance(vec, np.ndarray) else np.frombuffer(bytes(vec), np.uint8).copy()
+            _st, ds, _ = parse_scans(buf, ext, layout)
+            _check(_st, "parse")
+            d0 = ds[0]
+            w, h = (d0.frame_width, d0.frame_height) if d0.frame_part else (d0.width, d0.height)
+            img = JPEGImage()
+            img._dimensions = (w, h)
+            img.descriptor = d0
+            img._buf = buf
+            ctx = context(device)
+            out = np.empty((h * w, 3), np.uint8)
+            br, ww, hh = C.c_size_t(0), C.c_uint32(0), C.c_uint32(0)
+            ctx._ck(_ffi.lib().jpgpu_decode_file(ctx.handle, buf.ctypes.data, buf.size, ext, layout, out.ctypes.data, out.size,
+                                                 C.byref(ww), C.byref(hh), C.byref(br)), "jpgpu_decode_file")
+            img._image_data = out
+            img.bytes_read = br.value
+            return img
         st, d, buf = parse_descriptor(vec, ext, layout)
         _check(st, "parse")
         img = JPEGImage()
@@ -715,6 +750,48 @@ class MultiDevice:
             self.close()
         except Exception:
             pass
+
+
+def decode_scans(files, ext=EXT_NONE, layout=LAYOUT_SPEC, device=0, want_coefs=False):
+    """Decode files that may hold one non-interleaved scan per component (jpgpu_parse_scans: a feature the reference
+    lacks - it returns after the first scan, mod.rs:416-417).  Every scan becomes a descriptor of the one batch; a
+    frame's pixels are the output of its first scan.  Returns (list of HxWx3 arrays or None, statuses, and - with
+    want_coefs - per file the list of per-component (nblocks, 64) coefficient arrays in each scan's own block order)."""
+    descs, owners, first, count, pstat = [], [], [], [], []
+    for f in files:
+        st, ds, buf = parse_scans(f, ext, layout)
+        first.append(len(descs)); count.append(len(ds)); pstat.append(st)
+        descs += ds; owners.append(buf)
+    arr = (_ffi.ImageDesc * max(len(descs), 1))(*descs)
+    b = Batch(descs=arr if descs else (_ffi.ImageDesc * 0)(), device=device, keepalive=owners)
+    try:
+        b.upload().decode()
+        outs, ptrs = [], []
+        for i, f in enumerate(files):
+            d = descs[first[i]] if count[i] else None
+            if d is None:
+                outs.append(None)
+                continue
+            w, h = (d.frame_width, d.frame_height) if d.frame_part else (d.width, d.height)
+            outs.append(np.zeros((h, w, 3), np.uint8))
+        for k in range(len(descs)):
+            owner = [i for i in range(len(files)) if first[i] == k and count[i]]
+            ptrs.append(outs[owner[0]].ctypes.data if owner else 0)
+        if descs:
+            b.download_ptrs(ptrs)
+        st, _ = b.results() if descs else ([], [])
+        statuses = [pstat[i] if pstat[i] else st[first[i]] for i in range(len(files))]
+        if not want_coefs:
+            return outs, statuses
+        coefs = []
+        for i in range(len(files)):
+            per = []
+            for k in range(first[i], first[i] + count[i]):
+                per += b.coefficients(k) if st[k] == 0 else [None]
+            coefs.append(per)
+        return outs, statuses, coefs
+    finally:
+        b.close()
 
 
 def decode_batch(files, ext=EXT_NONE, layout=LAYOUT_SPEC, device=0):

@@ -52,11 +52,12 @@ def _coef_capacity(width, height):
     return ((width + 15) // 16) * ((height + 15) // 16) * 12 * 64
 
 
-def _flags(optimize, dqt16):
-    return (1 if optimize else 0) | (2 if dqt16 else 0)
+def _flags(optimize, dqt16, planar_scans=False):
+    return (1 if optimize else 0) | (2 if dqt16 else 0) | (4 if planar_scans else 0)
 
 
-def encode(rgb, subsampling="420", quality=85, restart_interval=0, want_coefs=False, optimize=False, dqt16=False):
+def encode(rgb, subsampling="420", quality=85, restart_interval=0, want_coefs=False, optimize=False, dqt16=False,
+           planar_scans=False):
     """Encode an HxWx3 uint8 array. Returns bytes, or (bytes, [per-component (nblocks,64) int16]) with want_coefs.
     optimize: image-specific Huffman tables (T.81 K.2; may hold 1-bit codes the reference cannot decode);
     dqt16: 16-bit quantisation tables with unclamped scaling."""
@@ -67,7 +68,7 @@ def encode(rgb, subsampling="420", quality=85, restart_interval=0, want_coefs=Fa
     out = np.empty(cap, np.uint8)
     nb = (C.c_size_t * 3)()
     coef = np.zeros(_coef_capacity(w, h), np.int16) if want_coefs else None
-    n = lib().jpgenc_encode_ex(rgb.ctypes.data, w, h, gray, hy, vy, quality, restart_interval, _flags(optimize, dqt16),
+    n = lib().jpgenc_encode_ex(rgb.ctypes.data, w, h, gray, hy, vy, quality, restart_interval, _flags(optimize, dqt16, planar_scans),
                                out.ctypes.data, cap, coef.ctypes.data if want_coefs else None,
                                coef.size if want_coefs else 0, nb)
     if n == 0:
@@ -83,15 +84,16 @@ def encode(rgb, subsampling="420", quality=85, restart_interval=0, want_coefs=Fa
 
 
 def synth_jpeg(index, width, height, subsampling="420", quality=85, restart_interval=0, noise_sigma=6.0,
-               want_coefs=False, optimize=False, dqt16=False):
-    """Synthetic image `index` (seed 0x5EED0000 + index) as a baseline JPEG."""
+               want_coefs=False, optimize=False, dqt16=False, planar_scans=False):
+    """Synthetic image `index` (seed 0x5EED0000 + index) as a baseline JPEG.  planar_scans: one non-interleaved scan per
+    component (a file the reference stops reading after its first scan); the coefficients then come in raster order."""
     gray, hy, vy = SUBSAMPLING[subsampling]
     cap = lib().jpgenc_max_size(width, height)
     out = np.empty(cap, np.uint8)
     nb = (C.c_size_t * 3)()
     coef = np.zeros(_coef_capacity(width, height), np.int16) if want_coefs else None
     n = lib().jpgenc_synth_encode_ex(SEED_BASE + index, width, height, noise_sigma, gray, hy, vy, quality,
-                                     restart_interval, _flags(optimize, dqt16), out.ctypes.data, cap,
+                                     restart_interval, _flags(optimize, dqt16, planar_scans), out.ctypes.data, cap,
                                      coef.ctypes.data if want_coefs else None, coef.size if want_coefs else 0, nb)
     if n == 0:
         raise RuntimeError("jpgenc_synth_encode failed")

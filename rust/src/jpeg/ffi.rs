@@ -1,4 +1,4 @@
-//! Binding of libjpgpu.so (include/jpgpu.h, ABI version 2).  Field order and types mirror the header;
+//! Binding of libjpgpu.so (include/jpgpu.h, ABI version 3).  Field order and types mirror the header;
 //! every function names the reference interface it replaces.
 #![allow(dead_code)]
 use std::ffi::CStr;
@@ -39,6 +39,17 @@ pub struct JpgpuImageDesc {
     /// file: the range mod.rs:371-385 walks; the GPU removes the stuffing.
     pub scan: *const u8,
     pub scan_len: usize,
+    /// Multi-scan files (jpgpu_parse_scans); all zero for the single scan the reference reads.
+    pub frame_part: u32,
+    pub frame_width: u32,
+    pub frame_height: u32,
+    pub frame_ncomp: u8,
+    pub frame_comp: u8,
+    pub frame_h: u8,
+    pub frame_v: u8,
+    pub frame_hmax: u8,
+    pub frame_vmax: u8,
+    pub frame_pad: [u8; 2],
 }
 
 pub const JPGPU_OK: c_int = 0;

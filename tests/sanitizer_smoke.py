@@ -64,6 +64,11 @@ def main():
         ref = O.decode(files[i], layout=O.LAYOUT_SPEC, ext=EXT_DRI).rgb
         assert np.abs(p.image(i).astype(int) - ref.astype(int)).max() <= 1
     p.close()
+    # the compose path: a file of non-interleaved scans, chroma interpolated (block IDCT + compose_colour_kernel)
+    from jpeg_rust_b200 import LAYOUT_SPEC_FANCY, decode_scans
+    planar = [synth.synth_jpeg(70, 250, 131, "420", restart_interval=3, planar_scans=True), synth.synth_jpeg(71, 64, 40, "422", planar_scans=True)]
+    outs, st = decode_scans(planar + [files[0]], ext=EXT_DRI, layout=LAYOUT_SPEC_FANCY)
+    assert st == [0, 0, 0] and outs[0].shape == (131, 250, 3)
     print("sanitizer smoke ok")
 
 

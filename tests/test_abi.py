@@ -30,22 +30,23 @@ def test_every_declared_symbol_is_exported():
 
 def test_abi_version_and_status_strings():
     L = _ffi.lib()
-    assert L.jpgpu_abi_version() == 2
+    assert L.jpgpu_abi_version() == 3
     assert "restart interval" in _ffi.status_string(_ffi.PANIC_DRI)
     assert "no CPU fallback" in _ffi.status_string(_ffi.ERR_NO_DEVICE)
 
 
 def test_struct_layout_matches_the_header(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "jpgpu.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "jpgpu.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(jpgpu_image_desc), offsetof(jpgpu_image_desc, qt), offsetof(jpgpu_image_desc, dc_bits),"
                    "offsetof(jpgpu_image_desc, ac_vals), offsetof(jpgpu_image_desc, restart_interval),"
-                   "offsetof(jpgpu_image_desc, scan));return 0;}\n")
+                   "offsetof(jpgpu_image_desc, scan), offsetof(jpgpu_image_desc, frame_part), offsetof(jpgpu_image_desc, frame_hmax));return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     D = _ffi.ImageDesc
-    assert got == [C.sizeof(D), D.qt.offset, D.dc_bits.offset, D.ac_vals.offset, D.restart_interval.offset, D.scan.offset]
+    assert got == [C.sizeof(D), D.qt.offset, D.dc_bits.offset, D.ac_vals.offset, D.restart_interval.offset, D.scan.offset,
+                   D.frame_part.offset, D.frame_hmax.offset]
 
 
 def test_product_sources_never_reach_the_oracle_or_the_simulation():

@@ -934,3 +934,46 @@ def test_fancy_upsampling_layout():
         assert np.array_equal(planar[i], fancy[i].transpose(2, 0, 1))
         assert np.allclose(f32[i], fancy[i].transpose(2, 0, 1).astype(np.float32) / 255.0, atol=1e-6)
     b.close()
+
+
+@pytest.mark.parametrize("layout_name", ["SPEC", "SPEC_FANCY"])
+def test_non_interleaved_scans(layout_name):
+    """SURVEY 8(f) row 4 (a feature the reference lacks: it returns after the first scan, mod.rs:416-417): files with one
+    non-interleaved scan per component (jpgpu_parse_scans).  Every scan is entropy-decoded as the one-component image it
+    is; the compose path puts the frame together.  The same coefficients coded as one interleaved scan must give the same
+    pixels (+-1: another IDCT instantiation), the coefficients of every scan equal the encoder's, and libjpeg agrees."""
+    import io
+    from PIL import Image
+    from jpeg_rust_b200 import EXT_MULTISCAN, LAYOUT_SPEC_FANCY, decode_scans
+    layout = LAYOUT_SPEC if layout_name == "SPEC" else LAYOUT_SPEC_FANCY
+    cases = [("420", 640, 480, 0), ("422", 333, 217, 0), ("444", 200, 100, 0), ("420", 131, 77, 5), ("440", 96, 160, 0),
+             ("420", 1920, 1080, 0), ("420", 64, 64, 1)]
+    planar, gts, inter = [], [], []
+    for i, (s, w, h, ri) in enumerate(cases):
+        f, g = synth.synth_jpeg(7900 + i, w, h, s, restart_interval=ri, planar_scans=True, want_coefs=True)
+        planar.append(f); gts.append(g)
+        inter.append(synth.synth_jpeg(7900 + i, w, h, s, restart_interval=ri))
+    inter.append(synth.synth_jpeg(7950, 320, 240, "420"))          # an ordinary file in the same call
+    outs, st, coefs = decode_scans(planar + [inter[-1]], ext=EXT_DRI, layout=layout, want_coefs=True)
+    assert st == [0] * (len(cases) + 1)
+    ref = run_batch(inter, layout, EXT_DRI)[0]
+    for i in range(len(cases)):
+        for a, w in zip(coefs[i], gts[i]):
+            assert np.array_equal(a, w), f"case {i}: coefficients of a scan differ from the encoder's"
+        d = np.abs(outs[i].astype(np.int16) - ref[i].astype(np.int16))
+        assert d.max() <= 1 and d.mean() < 0.01, (i, d.max(), d.mean())
+        pil = np.asarray(Image.open(io.BytesIO(planar[i])).convert("RGB")).astype(np.int16)
+        # libjpeg itself (integer IDCT and colour conversion, interpolated chroma): comparable where the up-sampling is the same
+        if layout_name == "SPEC_FANCY" or cases[i][0] == "444":
+            assert np.abs(outs[i].astype(np.int16) - pil).mean() < 1.0, (i, np.abs(outs[i].astype(np.int16) - pil).mean())
+    assert np.array_equal(outs[-1], ref[-1])
+    # the single-file entry point
+    img = JPEGImage.parse(planar[0], ext=EXT_DRI | EXT_MULTISCAN, layout=layout)
+    assert (img.width(), img.height()) == (640, 480) and np.array_equal(img.rgb(), outs[0])
+    # a damaged chroma scan fails the frame, not its neighbours
+    bad = bytearray(planar[1])
+    last_sos = bytes(bad).rindex(b"\xff\xda")
+    del bad[last_sos + 40:]
+    outs2, st2 = decode_scans([planar[0], bytes(bad), planar[2]], ext=EXT_DRI, layout=layout)
+    assert st2[0] == 0 and st2[2] == 0 and st2[1] != 0
+    assert np.array_equal(outs2[0], outs[0]) and np.array_equal(outs2[2], outs[2])

@@ -112,3 +112,28 @@ def test_builder_produces_the_same_descriptor_as_the_parser():
         assert getattr(d, f) == getattr(d2, f)
     assert bytes(d.qt) == bytes(d2.qt) and bytes(d.ac_vals) == bytes(d2.ac_vals) and bytes(d.dc_bits) == bytes(d2.dc_bits)
     assert bytes(d.comp) == bytes(d2.comp)
+
+
+def test_parse_scans_of_non_interleaved_files():
+    """jpgpu_parse_scans (host only): one descriptor per scan; a frame of non-interleaved scans comes as consecutive
+    one-component descriptors of the component's own size, the ordinary file as the one descriptor jpgpu_parse gives."""
+    from jpeg_rust_b200 import EXT_DRI, parse_scans, plan_info
+    f = synth.synth_jpeg(5, 131, 77, "420", restart_interval=5, planar_scans=True)
+    st, ds, _buf = parse_scans(f, EXT_DRI)
+    assert st == 0 and [d.frame_part for d in ds] == [1, 2, 2]
+    assert [(d.width, d.height) for d in ds] == [(131, 77), (66, 39), (66, 39)]
+    assert all((d.frame_width, d.frame_height, d.frame_ncomp, d.ncomp, d.restart_interval) == (131, 77, 3, 1, 5) for d in ds)
+    assert [(d.frame_comp, d.frame_h, d.frame_v, d.frame_hmax, d.frame_vmax) for d in ds] == [(0, 2, 2, 2, 2), (1, 1, 1, 2, 2), (2, 1, 1, 2, 2)]
+    assert [d.comp[0].tq for d in ds] == [0, 1, 1] and [d.comp[0].td for d in ds] == [0, 1, 1]
+    # the scans tile the file: each ends where the next SOS segment (or EOI) begins
+    ends = [d.scan + d.scan_len for d in ds]
+    assert ends[0] < ds[1].scan and ends[1] < ds[2].scan and ends[2] == _buf.ctypes.data + len(f) - 2
+    plain = synth.synth_jpeg(5, 64, 64, "420")
+    st, ds, _ = parse_scans(plain)
+    assert st == 0 and len(ds) == 1 and ds[0].frame_part == 0 and ds[0].ncomp == 3 and ds[0].scan_len == len(plain) - 2 - (ds[0].scan - _.ctypes.data)
+    # without DRI in the extension flags the restart-interval file is the reference's panic
+    assert parse_scans(f)[0] == 2
+    # the planner takes a frame's scans as images of one batch
+    st, ds, _buf = parse_scans(f, EXT_DRI)
+    info = plan_info(descs=ds)
+    assert info["groups"] == 1 and info["warp_jobs"] >= 3
