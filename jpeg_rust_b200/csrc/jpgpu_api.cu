@@ -782,8 +782,9 @@ extern "C" int jpgpu_pipeline_create(int device, const jpgpu_image_desc* descs, 
     int st = JPGPU_OK;
     for (int k = 0; k < 2 && st == JPGPU_OK; k++) st = jpgpu_create(device, &p->ctx[k]);
     size_t off = 0;
-    for (size_t i0 = 0; i0 < n && st == JPGPU_OK; i0 += chunk_images) {
-        const size_t m = std::min(chunk_images, n - i0);
+    for (size_t i0 = 0, m = 0; i0 < n && st == JPGPU_OK; i0 += m) {
+        m = std::min(chunk_images, n - i0);
+        while (i0 + m < n && descs[i0 + m].frame_part == 2) m++;   // the scans of one frame stay in one chunk
         jpgpu_batch* b = nullptr;
         st = jpgpu_batch_create(p->ctx[p->chunks.size() & 1], descs + i0, m, &b);
         if (st != JPGPU_OK) break;

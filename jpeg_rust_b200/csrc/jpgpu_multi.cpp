@@ -140,8 +140,8 @@ extern "C" int jpgpu_partition(const jpgpu_image_desc* descs, size_t n, size_t p
     for (size_t k = 0; k < parts; k++) {
         first[k] = i;
         const uint64_t goal = total / parts * (k + 1) + total % parts * (k + 1) / parts;
-        // an image goes to the range in which its middle byte falls
-        while (i < n && (k + 1 == parts || acc + descs[i].scan_len / 2 < goal)) acc += descs[i++].scan_len;
+        // an image goes to the range in which its middle byte falls; the scans of one frame (jpgpu_parse_scans) stay together
+        while (i < n && (k + 1 == parts || acc + descs[i].scan_len / 2 < goal || descs[i].frame_part == 2)) acc += descs[i++].scan_len;
     }
     first[parts] = n;
     return JPGPU_OK;

@@ -96,3 +96,19 @@ def test_multi_create_without_a_device_fails_cleanly():
     h = C.c_void_p()
     devs = (C.c_int * 2)(0, 1)
     assert _ffi.lib().jpgpu_multi_create(devs, 2, C.byref(h)) == _ffi.ERR_NO_DEVICE and not h
+
+
+def test_partition_keeps_the_scans_of_a_frame_together():
+    """A frame of non-interleaved scans is three consecutive descriptors (frame_part 1, 2, 2): no range may start inside it."""
+    import ctypes as C
+    from jpeg_rust_b200 import _ffi
+    n = 30
+    descs = (_ffi.ImageDesc * n)()
+    for i in range(n):
+        descs[i].scan_len = 1000 + 37 * i
+        descs[i].frame_part = (1, 2, 2)[i % 3]
+    for parts in (2, 3, 4, 7):
+        first = (C.c_size_t * (parts + 1))()
+        assert _ffi.lib().jpgpu_partition(descs, n, parts, first) == 0
+        assert first[0] == 0 and first[parts] == n
+        assert all(f == n or descs[f].frame_part != 2 for f in first)
