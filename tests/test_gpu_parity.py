@@ -705,6 +705,8 @@ def test_multi_device_handle_matches_one_device():
                 assert np.array_equal(a[:len(w)], w[:len(a)])
         ms = m.time_decode(2)
         assert len(ms) == len(devices) and all(x > 0 for x in ms)
+        o1, s1, b1 = m.decode_batch(files[:1])                # fewer images than devices: the other ranges are empty
+        assert s1 == ref_st[:1] and b1 == ref_br[:1] and np.array_equal(o1[0], ref[0])
         outs2, st2, br2 = m.decode_batch(files[:11])          # the one-call form, replanning the same handle
         assert st2 == ref_st[:11] and br2 == ref_br[:11]
         for i in range(11):

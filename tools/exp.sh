@@ -17,6 +17,7 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e, open("/tmp/b.err").read()[-300:])
 PY
 }
+shopt -s nullglob
 for so in build/variants/*.so; do
   cp $so jpeg_rust_b200/lib/libjpgpu.so
   run $(basename $so .so) X=1
