@@ -96,14 +96,37 @@ def recorded_traffic(key):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    Through NVML in-process (pynvml: two light queries every 10 ms from a thread) where that is available; the
+    `nvidia-smi -lms` loop it replaces is kept as the fallback.  Eight ranks each running their own nvidia-smi poller
+    cost the slowest rank 3 % at N = 8 (6.94 against 6.72 ms per step with the pollers running; the same GPUs driven
+    from one process after the pollers had stopped: 6.71-6.72 ms each, profiles/r02t)."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []          # nvidia-smi fallback: raw lines; NVML: (sm_mhz, reasons bitmask) tuples
+        self.nvml = None
+        self.stop_flag = False
 
     def start(self):
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            p = torch.cuda.get_device_properties(self.index)
+            bus = f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+            self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -115,11 +138,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.lines.append((mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            n = self.nvml
+            bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+            sm = sorted(x[0] for x in self.lines)
+            reasons = sorted(k for k, b in bits.items() if any(x[1] & b for x in self.lines))
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "NVML, 10 ms period, in-process"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -128,7 +175,6 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
@@ -138,12 +184,12 @@ class ClockSampler:
                 mx = float(f[1])
             except ValueError:
                 continue
-            for n, v in zip(names, f[2:6]):
+            for n, v in zip(self.NAMES, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def cpu_reference_throughput(files, width, height, nthreads, sample):
@@ -227,6 +273,7 @@ def time_decode(batch, stream, steps, barrier, max_over_ranks):
         batch.decode()            # the call a user makes: image groups pipelined over auxiliary streams inside the library
     e1.record(stream)
     barrier()
+    time_decode.last_local_ms = e0.elapsed_time(e1) / steps
     return max_over_ranks(e0.elapsed_time(e1)) / steps
 
 
@@ -386,12 +433,19 @@ def main():
         return float(t.item())
 
     ctx = context(local_rank)
-    stream = torch.cuda.current_stream()
+    # an ordinary (non-default) stream: the library replays repeated decodes as a CUDA graph, and the legacy default
+    # stream cannot be captured (on it every decode is enqueued kernel by kernel, which at N = 8 - eight processes
+    # launching 25 kernels per step over four streams on 32 vCPUs - cost the slowest rank 2-3 %, profiles/r02t, r02u)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
-    # ---- inputs: `distinct` synthetic images (different per rank), cycled to `images`, each copy with its own
-    # host region and its own device buffers
-    first = rank * args.distinct
+    # ---- inputs: `distinct` synthetic images, cycled to `images`, each copy with its own host region and its own device
+    # buffers.  Every rank decodes the SAME corpus: weak scaling means the same work per GPU, and the job's time is the
+    # slowest rank's - with a corpus of its own per rank (rounds 1 and early 2) the "scaling loss" at N = 8 was the rank
+    # whose images happened to code into the most bits (6.88 against 6.72 ms, while one process driving the same eight
+    # GPUs over identical images measured 6.71-6.72 ms on every one of them: profiles/r02v).
+    first = 0
 
     def gen(i, want_coefs=False):
         return synth.synth_jpeg(first + i, args.width, args.height, args.subsampling, args.quality, args.restart_interval,
@@ -417,9 +471,21 @@ def main():
     sampler.start()
     time.sleep(0.3)          # let nvidia-smi start sampling before the timed region
     ms_per_step = time_decode(batch, stream, args.steps, barrier, max_over_ranks)
+    per_rank_ms = None
+    if world > 1:   # bookkeeping: every rank's own time, so that the line shows how far the slowest is from the rest
+        mine = torch.tensor([time_decode.last_local_ms], dtype=torch.float64, device="cuda")
+        allms = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allms, mine)
+        per_rank_ms = [float(t.item()) for t in allms]
     launches = batch.launch_count() - launches0
     value = world * pixels / (ms_per_step * 1e-3) / 1e6
     ent_ms, idct_ms, prof = stage_times(batch, stream, args.steps)
+    if not sampler.lines:   # very short runs: keep the GPU busy with the same work until the sampler has reported
+        t_end = time.perf_counter() + 1.0
+        while not sampler.lines and time.perf_counter() < t_end:
+            batch.decode()
+            torch.cuda.synchronize()
+    clocks = sampler.stop()   # sampled over the timed region and the per-stage loops: the GPU was under load throughout
     tkey = f"{args.width}x{args.height}_{args.subsampling}"
     roofline = roofline_of(stats, ent_ms, idct_ms, prof, args.subsampling, n, tkey)
 
@@ -482,13 +548,6 @@ def main():
                        "once.  copy_ceiling = plain cudaMemcpyAsync of the same bytes both ways at once, all ranks together, same run",
                "numa": "single-node VM: sysfs reports numa_node -1 for the GPUs, one NUMA node, no binding attempted"}
         pipe.close()
-
-    if not sampler.lines:   # very short runs: keep the GPU busy with the same work until nvidia-smi has reported
-        t_end = time.perf_counter() + 1.0
-        while not sampler.lines and time.perf_counter() < t_end:
-            batch.decode()
-            torch.cuda.synchronize()
-    clocks = sampler.stop()
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -638,13 +697,13 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (IDCT/colour), i16/u8 (entropy)", "data": "synthetic",
             "config": {"workload": f"{n} synthetic {args.width}x{args.height} {args.subsampling} q{args.quality} baseline "
-                                   f"JPEGs per GPU ({args.distinct} distinct, own buffers per copy), SPEC layout"
+                                   f"JPEGs per GPU ({args.distinct} distinct, own buffers per copy; the same images on every GPU), SPEC layout"
                                    + (f", restart interval {args.restart_interval} MCUs" if args.restart_interval else ""),
                        "images_per_gpu": n, "bits_per_pixel": 8.0 * sum(wl.sizes) / pixels,
                        "l2": "inputs larger than L2 (no flush needed): "
                        f"{stats['scan_bytes'] / 1e6:.0f} MB bitstream, {stats['coef_bytes'] / 1e9:.2f} GB coefficients",
                        "parallelism": f"images sharded over {world} GPU(s), no collective"},
-            "parity": parity, "determinism": determinism,
+            "parity": parity, "determinism": determinism, "per_rank_ms_per_step": per_rank_ms,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "config0_single_image": config0, "extra": extra,
             "stage_ms": {"entropy": ent_ms, "idct_colour": idct_ms, "note": "stages run one after the other on one stream; "
