@@ -284,6 +284,9 @@ extern "C" int jpgpu_batch_replan(jpgpu_batch* b, const jpgpu_image_desc* descs,
     // (the coefficient arena is not cleared: the write pass stores every block of a complete scan, and the blocks a
     // damaged scan never reaches are zero-filled from ImgDyn::coef_end on by zero_tail_kernel)
     CK(cudaMemsetAsync(d.segtab, 0, (p.seg_entries + 8) * 4, ctx->stream));
+    // (a caller-owned arena kept across the replan still holds the previous wave's pixels at the previous plan's offsets:
+    // its gaps are cleared when jpgpu_batch_set_device_output() points the new plan at its slice)
+    if (d.rgb == b->own_rgb) { launch_zero_output_pads(d, ctx->stream); b->launches += 1; }
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
 
@@ -389,12 +392,18 @@ extern "C" int jpgpu_batch_set_device_output(jpgpu_batch* b, void* dev_base, siz
         b->dev.rgb = b->own_rgb;
         b->ext_rgb_cap = 0;
         b->dev_gen++;
+        launch_zero_output_pads(b->dev, ctx->stream);
         return JPGPU_OK;
     }
     if (capacity < b->plan.rgb_bytes * sample_bytes(b) || (reinterpret_cast<uintptr_t>(dev_base) & 255u)) return JPGPU_ERR_INVALID_ARG;
     b->dev.rgb = static_cast<uint8_t*>(dev_base);
     b->ext_rgb_cap = capacity;
     b->dev_gen++;
+    {
+        jpgpu_ctx* ctx = b->ctx;
+        CK(cudaSetDevice(ctx->device));
+        launch_zero_output_pads(b->dev, ctx->stream);
+    }
     return JPGPU_OK;
 } JPGPU_CATCH_ALL
 
@@ -572,6 +581,7 @@ extern "C" int jpgpu_batch_set_output_format(jpgpu_batch* b, uint32_t format) tr
         if (st != JPGPU_OK) return st;
         b->dev.rgb = b->own_rgb;
         b->ext_rgb_cap = 0;
+        launch_zero_output_pads(b->dev, ctx->stream);
     }
     return JPGPU_OK;
 } JPGPU_CATCH_ALL

@@ -144,6 +144,8 @@ struct ImgDev {
     uint64_t smp_off;                     // float offset of this image's per-block IDCT samples
     uint32_t map_plane;                   // entries per component plane (W*H rounded up to 4)
     uint32_t frame;                       // compose path: index + 1 of the FrameDev this image's samples feed (0: none)
+    uint32_t out_pixels;                  // pixels of the output this image owns in the RGB arena (a frame's first scan: the frame's; further scans: 0)
+    uint32_t pad2;
 };
 
 // ---- compose path: per-block IDCT samples (block_idct_kernel) -> pixels, plane by plane.  Serves what the fused

@@ -550,6 +550,7 @@ int build_plan(const jpgpu_image_desc* descs, size_t n, HostPlan& plan, uint32_t
         if (d.frame_part == 1) { ow = d.frame_width; oh = d.frame_height; }
         if (d.frame_part == 2) { ow = oh = 0; }
         plan.out_w[i] = ow; plan.out_h[i] = oh;
+        im.out_pixels = ow * oh;
         im.rgb_off = d.frame_part == 2 ? plan.frames[(size_t)cur_frame].rgb_off : plan.rgb_bytes;
         plan.rgb_bytes += align_up((uint64_t)ow * oh * 3, 256);
         const uint32_t mcus_per_tile = 128u / (8u * g.hmax);

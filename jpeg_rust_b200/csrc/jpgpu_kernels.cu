@@ -1201,6 +1201,19 @@ __global__ void __launch_bounds__(256) zero_tail_kernel(BatchDev b) {
     for (size_t i = threadIdx.x; i < nvec; i += 256) dst[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// Every image's output lies at a 256-byte aligned offset of the RGB arena; the up to 255 bytes (1020 with float output)
+// between the end of one and the start of the next are never written by a decode.  jpgpu_batch_download_contiguous and the
+// pipeline copy the arena as a whole, so those gaps are given defined contents once per plan / output arena / format.
+__global__ void __launch_bounds__(256) zero_output_pads_kernel(BatchDev b) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= b.n_images) return;
+    const ImgDev& im = b.imgs[b.img0 + i];
+    const size_t sb = b.out_planar == 2u ? 4u : 1u;
+    const size_t n = (size_t)im.out_pixels * 3u, end = (n + 255u) & ~(size_t)255u;
+    uint8_t* base = b.rgb + im.rgb_off * sb;
+    for (size_t k = n * sb; k < end * sb; k++) base[k] = 0u;
+}
+
 // ============================================ stage 2+3: dequant + IDCT + upsample + colour
 constexpr int kIdctThreads = 128;
 #ifndef JPGPU_IDCT_TMA
@@ -1881,6 +1894,9 @@ void launch_prepass_step(const BatchDev& b, cudaStream_t s, int step) {
         if (step == 0) prepass_count_kernel<<<grid, kPreThreads, 0, s>>>(d);
         else prepass_write_kernel<<<grid, kPreThreads, 0, s>>>(d);
     });
+}
+void launch_zero_output_pads(const BatchDev& b, cudaStream_t s) {
+    if (b.n_images && b.rgb) zero_output_pads_kernel<<<(b.n_images + 255u) / 256u, 256, 0, s>>>(b);
 }
 void launch_gather_scans(const BatchDev& b, const void* base, const uint64_t* dev_offs, cudaStream_t s) {
     if (!b.n_images || !b.max_chunks) return;

@@ -65,6 +65,8 @@ cudaError_t init_constants();
 
 // Scan bytes that already lie in device memory (image i at base + dev_offs[i], indexed like BatchDev::imgs) -> raw arena.
 void launch_gather_scans(const BatchDev& b, const void* base, const uint64_t* dev_offs, cudaStream_t s);
+// The alignment gaps between the images' outputs in the RGB arena get defined contents (once per plan / arena / format).
+void launch_zero_output_pads(const BatchDev& b, cudaStream_t s);
 // Stage 1a: byte-unstuffing + RSTn detection: count per 4 KiB chunk, scan per image, compact per chunk.
 void launch_prepass(const BatchDev& b, cudaStream_t s);
 void launch_prepass_step(const BatchDev& b, cudaStream_t s, int step);  // 0 count, 1 scan, 2 write (profiling)
