@@ -28,6 +28,7 @@ struct SimBatch {
     std::vector<ImgDyn> dyn;
     std::vector<int16_t> coefs;
     std::vector<uint8_t> rgb;
+    std::vector<float> samples;    // per-block IDCT samples of the compose-path images
     uint8_t store_pos[64];
     // diagnostics
     uint32_t repair_iters = 0;     // most repair iterations any image needed
@@ -379,6 +380,55 @@ void sim_idct_colour(SimBatch& sb, size_t img) {
         }
 }
 
+// mirrors block_idct_kernel for an image of the compose path: per-block samples into the shared sample arena
+void sim_block_idct_all(SimBatch& sb, size_t img) {
+    const ImgDev& im = sb.plan.imgs[img];
+    const uint32_t nblk = im.units * im.blocks_per_mcu;
+    const int16_t* coefs = sb.coefs.data() + im.coef_off;
+    const float* qt = sb.plan.qt.data();
+    for (uint32_t blk = 0; blk < nblk; blk++) {
+        const int comp = im.blk_comp[blk % im.blocks_per_mcu];
+        sim_block_idct(coefs + (size_t)blk * 64, blk < coef_block_limit(sb.dyn[img]), qt + im.qt_off[comp], comp == 0 ? 128.0f : 0.0f,
+                       sb.samples.data() + im.smp_off + (size_t)blk * 64);
+    }
+}
+
+// mirror compose_colour_kernel (plane_sample / frame_sample: same clamping, same weights, same operation order)
+float sim_plane_sample(const SimBatch& sb, const PlaneRef& p, int xs, int ys) {
+    xs = std::min(std::max(xs, 0), (int)p.wc - 1);
+    ys = std::min(std::max(ys, 0), (int)p.hc - 1);
+    const uint32_t bx = (uint32_t)xs >> 3, by = (uint32_t)ys >> 3;
+    const uint32_t blk = ((by / p.v) * p.mcux + bx / p.h) * p.bpm + p.first + (by % p.v) * p.h + bx % p.h;
+    return sb.samples[p.smp_off + (size_t)blk * 64 + ((uint32_t)ys & 7u) * 8u + ((uint32_t)xs & 7u)] + p.bias;
+}
+float sim_frame_sample(const SimBatch& sb, const PlaneRef& p, bool fancy, int x, int y) {
+    if (p.fx == 1u && p.fy == 1u) return sim_plane_sample(sb, p, x, y);
+    const int xs = p.fx == 2u ? x >> 1 : x, ys = p.fy == 2u ? y >> 1 : y;
+    if (!fancy) return sim_plane_sample(sb, p, xs, ys);
+    const int xn = p.fx == 2u ? xs + ((x & 1) ? 1 : -1) : xs, yn = p.fy == 2u ? ys + ((y & 1) ? 1 : -1) : ys;
+    float a = sim_plane_sample(sb, p, xs, ys), c = sim_plane_sample(sb, p, xn, ys);
+    if (p.fy == 2u) {
+        a = 0.75f * a + 0.25f * sim_plane_sample(sb, p, xs, yn);
+        c = 0.75f * c + 0.25f * sim_plane_sample(sb, p, xn, yn);
+    }
+    return p.fx == 2u ? 0.75f * a + 0.25f * c : a;
+}
+void sim_compose(SimBatch& sb, const FrameDev& f) {
+    for (uint32_t c = 0; c < f.ncomp && c < 3u; c++)
+        if (f.pl[c].h == 0u || f.pl[c].wc == 0u) return;   // a scan of the frame failed to plan
+    uint8_t* rgb = sb.rgb.data() + f.rgb_off;
+    for (uint32_t y = 0; y < f.height; y++)
+        for (uint32_t x = 0; x < f.width; x++) {
+            uint8_t* o = rgb + ((size_t)y * f.width + x) * 3;
+            const float yy = sim_frame_sample(sb, f.pl[0], f.fancy != 0u, (int)x, (int)y);
+            if (f.ncomp == 1u) { o[0] = o[1] = o[2] = sat_u8_trunc(yy); continue; }
+            const float cb = sim_frame_sample(sb, f.pl[1], f.fancy != 0u, (int)x, (int)y), cr = sim_frame_sample(sb, f.pl[2], f.fancy != 0u, (int)x, (int)y);
+            o[0] = sat_u8_trunc(fmaf(cr, 1.402f, yy));
+            o[1] = sat_u8_trunc(fmaf(cb, -0.34413629f, fmaf(cr, -0.71413629f, yy)));
+            o[2] = sat_u8_trunc(fmaf(cb, 1.772f, yy));
+        }
+}
+
 // mirrors block_idct_kernel + gather_colour_kernel (REF placement / generic sampling)
 void sim_gather(SimBatch& sb, size_t img) {
     const ImgDev& im = sb.plan.imgs[img];
@@ -445,6 +495,7 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
     sb.dyn.assign(n + 1, ImgDyn());
     sb.coefs.assign(p.coef_elems + 64, 0x5555);  // the write pass must produce every coefficient itself
     sb.rgb.assign(p.rgb_bytes + 256, 0);
+    sb.samples.assign(p.sample_floats + 64, 0.0f);
     for (int k = 0; k < 64; k++) sb.store_pos[k] = (uint8_t)zigzag_to_colmajor(k, kZigzagNaturalHost);
     for (size_t i = 0; i < n; i++)
         if (p.status[i] == JPGPU_OK) memcpy(sb.raw.data() + p.imgs[i].raw_off, descs[i].scan, p.imgs[i].raw_len);
@@ -467,10 +518,11 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
         for (uint32_t group = 0; group < (1u << p.wp_shift); group++) sim_decode_write(sb, sd, group);
     for (size_t i = 0; i < n; i++)
         if (p.status[i] == JPGPU_OK) {
-            if (p.imgs[i].frame) p.status[i] = JPGPU_ERR_UNSUPPORTED;   // the compose path (fancy up-sampling) is not mirrored here
+            if (p.imgs[i].frame) sim_block_idct_all(sb, i);   // compose path: samples now, pixels once all planes of the frame are there
             else if (p.imgs[i].kind == kKindGeneric) sim_gather(sb, i);
             else sim_idct_colour(sb, i);
         }
+    for (const FrameDev& f : p.frames) sim_compose(sb, f);
     for (size_t i = 0; i < n; i++) {
         int32_t s = p.status[i];
         uint64_t br = 0;
@@ -482,13 +534,19 @@ int jpsim_decode_batch(const jpgpu_image_desc* descs, size_t n, uint8_t* const* 
             else if (!(f & kStDone)) s = JPGPU_ERR_TRUNCATED;
             br = ((uint64_t)sb.dyn[i].bits_consumed + 7) / 8;
             const ImgDev& im = p.imgs[i];
-            if (rgb_out && rgb_out[i]) memcpy(rgb_out[i], sb.rgb.data() + im.rgb_off, (size_t)im.width * im.height * 3);
+            if (rgb_out && rgb_out[i]) memcpy(rgb_out[i], sb.rgb.data() + im.rgb_off, (size_t)p.out_w[i] * p.out_h[i] * 3);
             if (coef_out && coef_out[i] && coef_cap[i] >= im.total_coefs)
                 export_reference_order(im, sb.coefs.data() + im.coef_off, coef_out[i], nblocks + 4 * i);
         }
         if (statuses) statuses[i] = s;
         if (bytes_read) bytes_read[i] = br;
     }
+    if (statuses)   // a frame of several scans is as good as its worst scan (jpgpu_batch_results)
+        for (size_t i = 0; i < n; i++) {
+            if (p.frame_part[i] != 1) continue;
+            for (size_t k = i + 1; k < n && p.frame_part[k] == 2; k++)
+                if (statuses[i] == JPGPU_OK && statuses[k] != JPGPU_OK) statuses[i] = statuses[k];
+        }
     if (diag) { diag[0] = sb.repair_iters; diag[1] = sb.repairs; diag[2] = sb.sync_decodes; diag[3] = sb.flush_phases; diag[4] = sb.sync_digest; }
     return JPGPU_OK;
 }

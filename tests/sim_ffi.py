@@ -36,16 +36,44 @@ class SimResult:
     pass
 
 
-def decode_batch(files, layout=_ffi.LAYOUT_SPEC, ext=_ffi.EXT_NONE, sub_bits=0):
-    """files: list of bytes. Returns (list of SimResult, diag)."""
+def decode_scans(files, layout=_ffi.LAYOUT_SPEC, ext=_ffi.EXT_NONE, sub_bits=0):
+    """Files that may hold one non-interleaved scan per component (jpgpu_parse_scans): every scan a descriptor of the
+    one simulated batch.  Returns (list of HxWx3 arrays, statuses, per file the list of per-scan SimResult)."""
+    from jpeg_rust_b200.jpeg import parse_scans
+    descs, owners, first, count = [], [], [], []
+    for f in files:
+        st, ds, buf = parse_scans(f, ext, layout)
+        assert st == 0, st
+        first.append(len(descs)); count.append(len(ds))
+        descs += ds; owners.append(buf)
+    rs, _ = decode_batch(None, layout=layout, ext=ext, sub_bits=sub_bits, descs=descs)
+    outs = [rs[first[i]].rgb for i in range(len(files))]
+    return outs, [rs[first[i]].status for i in range(len(files))], [rs[first[i]:first[i] + count[i]] for i in range(len(files))]
+
+
+def decode_batch(files, layout=_ffi.LAYOUT_SPEC, ext=_ffi.EXT_NONE, sub_bits=0, descs=None):
+    """files: list of bytes (or descs: a list of ready descriptors). Returns (list of SimResult, diag)."""
     L = lib()
-    n = len(files)
-    descs = (_ffi.ImageDesc * n)()
-    bufs = [np.frombuffer(f, np.uint8).copy() for f in files]
-    parse_status = []
-    for i, b in enumerate(bufs):
-        parse_status.append(L.jpgpu_parse(b.ctypes.data, len(b), ext, layout, C.byref(descs[i])))
-    rgb = [np.zeros((max(1, descs[i].height), max(1, descs[i].width), 3), np.uint8) for i in range(n)]
+    if descs is not None:
+        n = len(descs)
+        arr = (_ffi.ImageDesc * n)(*descs)
+        descs = arr
+        parse_status = [0] * n
+    else:
+        n = len(files)
+        descs = (_ffi.ImageDesc * n)()
+        bufs = [np.frombuffer(f, np.uint8).copy() for f in files]
+        parse_status = []
+        for i, b in enumerate(bufs):
+            parse_status.append(L.jpgpu_parse(b.ctypes.data, len(b), ext, layout, C.byref(descs[i])))
+
+    def out_shape(d):   # a frame's first scan owns the frame's pixels, further scans none
+        if d.frame_part == 1:
+            return (d.frame_height, d.frame_width, 3)
+        if d.frame_part == 2:
+            return (1, 1, 3)
+        return (max(1, d.height), max(1, d.width), 3)
+    rgb = [np.zeros(out_shape(descs[i]), np.uint8) for i in range(n)]
     cap = [(((descs[i].width + 15) // 16 + 1) * ((descs[i].height + 15) // 16 + 1) * 12 * 64) for i in range(n)]
     coefs = [np.zeros(cap[i], np.int16) for i in range(n)]
     rgb_p = (C.c_void_p * n)(*[a.ctypes.data for a in rgb])
