@@ -669,25 +669,31 @@ def main():
             barrier()
             dist.barrier(group=host_group)
             if rank == 0:
-                md = MultiDevice(list(range(world)))
-                allf = [files[i % args.distinct] for i in range(n * world)]
-                from jpeg_rust_b200 import pack_files, parse_packed
-                mbuf, moffs, mown = pack_files(allf, pinned=False)
-                mdescs, pst = parse_packed(mbuf, moffs, [len(f) for f in allf], ext)
-                assert not any(pst)
-                md.plan(descs=mdescs, keepalive=(mbuf, mown)).upload().decode().sync()
-                st, _ = md.results()
-                assert all(s == 0 for s in st)
-                md.time_decode(2)
-                per_dev = md.time_decode(esteps)
-                mms = max(per_dev) / esteps
-                extra["multi_device_single_process"] = {
-                    "devices": world, "images": n * world, "value": n * world * args.width * args.height / (mms * 1e-3) / 1e6,
-                    "unit": UNIT, "ms_per_step": mms, "per_device_ms_per_step": [x / esteps for x in per_dev],
-                    "ranges": md.ranges(), "scaling": "weak",
-                    "note": "jpgpu_multi_*: one process, one context + stream set + worker thread per device, contiguous image "
-                            "ranges balanced by scan bytes, CUDA events per device, job time = slowest device"}
-                md.close()
+                # (whatever happens in here, rank 0 reaches the barrier below: the other ranks are waiting at it)
+                try:
+                    if torch.cuda.device_count() < world:
+                        raise RuntimeError(f"rank 0 sees {torch.cuda.device_count()} of {world} devices")
+                    md = MultiDevice(list(range(world)))
+                    allf = [files[i % args.distinct] for i in range(n * world)]
+                    from jpeg_rust_b200 import pack_files, parse_packed
+                    mbuf, moffs, mown = pack_files(allf, pinned=False)
+                    mdescs, pst = parse_packed(mbuf, moffs, [len(f) for f in allf], ext)
+                    assert not any(pst)
+                    md.plan(descs=mdescs, keepalive=(mbuf, mown)).upload().decode().sync()
+                    st, _ = md.results()
+                    assert all(s == 0 for s in st)
+                    md.time_decode(2)
+                    per_dev = md.time_decode(esteps)
+                    mms = max(per_dev) / esteps
+                    extra["multi_device_single_process"] = {
+                        "devices": world, "images": n * world, "value": n * world * args.width * args.height / (mms * 1e-3) / 1e6,
+                        "unit": UNIT, "ms_per_step": mms, "per_device_ms_per_step": [x / esteps for x in per_dev],
+                        "ranges": md.ranges(), "scaling": "weak",
+                        "note": "jpgpu_multi_*: one process, one context + stream set + worker thread per device, contiguous image "
+                                "ranges balanced by scan bytes, CUDA events per device, job time = slowest device"}
+                    md.close()
+                except Exception as e:   # the headline line must not be lost to an extra
+                    extra["multi_device_single_process"] = {"error": f"{type(e).__name__}: {e}"}
             dist.barrier(group=host_group)   # the other ranks wait on the host: their GPUs are rank 0's for this arm
             barrier()
 
