@@ -323,7 +323,7 @@ struct FastCtx {
 
 struct FastState {
     uint32_t w0, w1, w2;     // stream words p>>5, +1, +2: the next 32 bits are funnelshift_l(w1, w0, p & 31)
-    uint32_t off;            // physical word offset of w2 in the lane-interleaved stream
+    const uint32_t* kp;      // stream + the group and lane bits of w2's physical word offset (fast_kbase)
     uint32_t p;
     int32_t g;
     uint32_t info_ptr;       // shared address of the FastTables::info entry of the current block-in-MCU
@@ -340,7 +340,7 @@ struct FastTablesT {
     static constexpr int kThreads = THREADS;
     uint4 info[THREADS / 32][kMaxBlocksPerMcu];  // per job and block of an MCU: {dc lut addr | ac lut addr << 16, DC slot offset, address of the next entry, c}
     uint32_t dc[3 * THREADS];
-    uint8_t sp[64];
+    uint8_t sp[128];   // byte offset of zigzag position k in a block buffer; k >= 64 (a block's last symbol may step past 63) as 63
 };
 using FastTables = FastTablesT<kSeqThreads>;
 
@@ -357,8 +357,8 @@ __device__ __forceinline__ void fast_tables_init(FT& ft, const SM& sm, bool vali
             ft.info[slot][i] = make_uint4(a_dc | (a_ac << 16), (info >> 16) * 4u * FT::kThreads, info0 + (i + 1 < nblk ? i + 1 : 0) * 16u, (uint32_t)i);
         }
     }
-    for (int i = threadIdx.x; i < 64; i += nthreads) {
-        const uint32_t pos = sm.store_pos[i];
+    for (int i = threadIdx.x; i < 128; i += nthreads) {
+        const uint32_t pos = sm.store_pos[i < 64 ? i : 63];
         ft.sp[i] = (uint8_t)(((pos >> 3) << 4) | ((pos & 7u) << 1));
     }
 }
@@ -367,33 +367,34 @@ __device__ __forceinline__ const uint32_t* fast_word_ptr(const FastCtx& cx, uint
     const uint32_t phys = (i & cx.gmask_inv) | ((i << 5) & cx.wmask5) | (((i >> cx.lw) & 31u) << kPieceShift) | (i & (kPieceWords - 1u));
     return cx.words + phys;
 }
+// The part of a physical word offset that stays the same while the window moves inside one subsequence's words.
+__device__ __forceinline__ const uint32_t* fast_kbase(const FastCtx& cx, uint32_t i) { return cx.words + ((i & cx.gmask_inv) | (((i >> cx.lw) & 31u) << kPieceShift)); }
 __device__ __forceinline__ uint32_t fast_peek(const FastState& st) { return __funnelshift_l(st.w1, st.w0, st.p); }
 __device__ __forceinline__ void fast_set_lim(FastState& st) { st.lim = min(st.seg_lim, st.wrap_lim); }
 __device__ __forceinline__ void fast_seek(const FastCtx& cx, FastState& st, uint32_t p) {
     st.p = p;
     const uint32_t i = p >> 5;
-    const uint32_t* p2 = fast_word_ptr(cx, i + 2);
     st.w0 = __ldg(fast_word_ptr(cx, i));
     st.w1 = __ldg(fast_word_ptr(cx, i + 1));
-    st.w2 = __ldg(p2);
-    st.off = (uint32_t)(p2 - cx.words);
+    st.w2 = __ldg(fast_word_ptr(cx, i + 2));
+    st.kp = fast_kbase(cx, i + 2);
     st.wrap_lim = ((((i + 2u) >> cx.lw) + 1u) << (cx.lw + 5u)) - 64u;
     fast_set_lim(st);
 }
 // The bit position moved from st.p to pn (at most 32 bits on): when that crosses a word boundary the window
-// slides by one word.  The next word to fetch is the next one of this lane's 32-byte piece or, after its
-// last, the first of the lane's piece in the next row block (stream_phys) — except once per sub_bits, when the
-// window's last word enters the next subsequence.  That slide (the one that takes the position to wrap_lim or
-// past it) fetches from the row block below the group instead (allocated, see the stream arena) and is put right
-// by fast_fix_wrap(), which the caller runs when it sees st.p >= st.wrap_lim — before the word can reach the
-// decoder, two slides later.
+// slides by one word.  The word to fetch, (pn >> 5) + 2, is the next one of this lane's 32-byte piece or, after its
+// last, the first of the lane's piece in the next row block: its physical offset (stream_phys) is st.kp plus row
+// and in-piece bits that come straight from pn — except once per sub_bits, when the window's last word enters the
+// next subsequence and st.kp no longer holds.  That slide (the one that takes the position to wrap_lim or past it)
+// fetches the lane's own first word instead and is put right by fast_fix_wrap(), which the caller runs when it sees
+// st.p >= st.wrap_lim — before the word can reach the decoder, two slides later.
 __device__ __forceinline__ void fast_advance(const FastCtx& cx, FastState& st, uint32_t pn) {
     const bool cross = ((st.p ^ pn) & ~31u) != 0u;
     st.p = pn;
     st.w0 = cross ? st.w1 : st.w0;
     st.w1 = cross ? st.w2 : st.w1;
-    const uint32_t step = (~st.off & (kPieceWords - 1u)) != 0u ? 1u : 32u * kPieceWords - (kPieceWords - 1u);
-    st.off += cross ? step : 0u;
+    const uint32_t t = pn + 64u;   // t >> 5 = index of the window's last word; wmask5 has no bit below 5
+    const uint32_t rel = (t & cx.wmask5) | ((t >> 5) & (kPieceWords - 1u));
 #ifndef JPGPU_PF_BYTES
 #define JPGPU_PF_BYTES (128 << JPGPU_PIECE_SHIFT)   // the lane's piece in the next row block
 #endif
@@ -401,12 +402,11 @@ __device__ __forceinline__ void fast_advance(const FastCtx& cx, FastState& st, u
 #if JPGPU_PF_BYTES > 0
         " @q prefetch.global.L1 [a + %4];\n"
 #endif
-        "}" : "+r"(st.w2) : "l"(cx.words), "r"(st.off), "r"((uint32_t)cross), "n"(JPGPU_PF_BYTES));
+        "}" : "+r"(st.w2) : "l"(st.kp), "r"(rel), "r"((uint32_t)cross), "n"(JPGPU_PF_BYTES));
 }
 __device__ __forceinline__ void fast_fix_wrap(const FastCtx& cx, FastState& st) {   // st.p >= st.wrap_lim
-    const uint32_t* p2 = fast_word_ptr(cx, (st.p >> 5) + 2u);
-    st.w2 = __ldg(p2);
-    st.off = (uint32_t)(p2 - cx.words);
+    st.w2 = __ldg(fast_word_ptr(cx, (st.p >> 5) + 2u));
+    st.kp = fast_kbase(cx, (st.p >> 5) + 2u);
     st.wrap_lim += 32u << cx.lw;
     fast_set_lim(st);
 }
@@ -458,7 +458,7 @@ __device__ __forceinline__ void fast_init(const FastCtx& cx, FastState& st, uint
         st.seg_end = cx.stream_bits;
         st.seg_lim = st.seg_end >= 7u ? st.seg_end - 7u : 0u;
         st.p = p; st.w0 = st.w1 = st.w2 = 0u;
-        st.off = (uint32_t)(fast_word_ptr(cx, (cx.stream_bits >> 5) + 2) - cx.words);   // inside the zero padding
+        st.kp = fast_kbase(cx, (cx.stream_bits >> 5) + 2);   // whatever a step fetches from here on lies inside the image's stream
         st.lim = st.seg_lim;
         st.g = g;
     } else {
@@ -523,7 +523,7 @@ template <int NBUF>
 struct WriteLane {
     static_assert(NBUF >= 1 && NBUF <= 2, "two completion slots");
     enum : uint32_t { kRun = 0, kBlocked = 1, kFinished = 2, kBlockEnd = 3 };
-    uint32_t row_addr, swz16;  // shared address / piece swizzle of the buffer being filled
+    uint32_t row_swz;          // shared address of the buffer being filled | its piece swizzle (bits 4-6): a coefficient at byte offset `off` goes to row_swz ^ off
     uint32_t rows_addr, row0;  // address of this lane's first row, its row number
     uint32_t cur, ndone;       // ring position, completed (unflushed) buffers
     uint32_t dest0, dest1;     // arena block index of each completed buffer, oldest first (0xffffffff = discard)
@@ -535,8 +535,8 @@ struct WriteLane {
     int16_t* coefs;            // coefficient arena of the image
     __device__ __forceinline__ void select(uint32_t c) {
         cur = c;
-        row_addr = rows_addr + c * 128u;
-        swz16 = ((row0 + c) & 7u) << 4;
+        row_swz = (rows_addr + c * 128u) | (((row0 + c) & 7u) << 4);
+        JPGPU_PIN32(row_swz);   // one register, not recomputed from threadIdx in every step
     }
     // the buffer being filled is complete (block index d) or to be discarded; z == 0 now
     __device__ __forceinline__ void close_block(uint32_t d, uint32_t p, int32_t g) {
@@ -573,6 +573,13 @@ struct WriteLane {
 };
 struct NoLane { enum : uint32_t { kBlockEnd = 3 }; uint32_t state; };
 
+// EXTEND (huffman.rs:256-268) of the `size` (0..16) bits at the top of `top`: first bit 1 -> the bits v as they are,
+// 0 -> v - (2^size - 1).  With neg = all ones in the second case, (neg << size | v) is v - 2^size; size 0 gives 0.
+__device__ __forceinline__ int32_t fast_extend(uint32_t top, uint32_t size) {
+    const uint32_t neg = (uint32_t)((int32_t)~top >> 31);
+    return (int32_t)(__funnelshift_l(top, neg, size) - neg);
+}
+
 // CHECK = false: the caller guarantees st.p < st.lim (no look at the interval end, no window wrap pending).
 template <bool WRITE, bool CHECK, typename LANE>
 __device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, LANE& wl) {
@@ -595,17 +602,15 @@ __device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, 
     const uint32_t tb = e & 255u, len = __byte_perm(e, 0u, 0x4441), adv = __byte_perm(e, 0u, 0x4442);
     const uint32_t size = tb - len;
     const uint32_t top = hi << len;               // len <= 16
-    // EXTEND (huffman.rs:256-268): first value bit 1 -> the bits as they are, 0 -> minus their complement
-    const uint32_t sgn = (uint32_t)((int32_t)top >> 31);
-    const uint32_t mag = __funnelshift_l(top ^ ~sgn, 0u, size);
-    const int32_t val = (int32_t)((mag ^ ~sgn) - ~sgn);
+    const int32_t val = fast_extend(top, size);
     const bool is_dc = z == 0u;
-    st.dcur += is_dc ? val : 0;                   // decoder.rs:208-210
+    // decoder.rs:208-210: st.dcur += is_dc ? val : 0, as one predicated add
+    asm("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q add.s32 %0, %0, %1;\n}" : "+r"(st.dcur) : "r"(val), "r"((uint32_t)is_dc));
     const uint32_t nz = z + adv;
     if constexpr (WRITE) {
         // huffman.rs:183-189.  Symbols without a value (EOB, ZRL) store a zero at a position the block has not reached.
-        const uint32_t off = lds8(cx.sp_addr + min(nz - 1u, 63u));
-        sts16_if(wl.row_addr | (off ^ wl.swz16), (uint32_t)(is_dc ? st.dcur : val), wl.store_on != 0u);
+        const uint32_t off = lds8(cx.sp_addr + nz - 1u);   // nz - 1 <= 126: FastTablesT::sp
+        sts16_if(wl.row_swz ^ off, (uint32_t)(is_dc ? st.dcur : val), wl.store_on != 0u);
     }
     fast_advance(cx, st, st.p + tb);
     if constexpr (WRITE) {
@@ -655,9 +660,7 @@ __device__ __forceinline__ void fast_mstep(const FastCtx& cx, FastState& st) {
     // DC difference (decoder.rs:208-210): EXTEND of the tb - len bits after the code, as in fast_step
     const uint32_t len = is_dc ? pre : 0u;
     const uint32_t top = hi << len;
-    const uint32_t sgn = (uint32_t)((int32_t)top >> 31);
-    const uint32_t mag = __funnelshift_l(top ^ ~sgn, 0u, tb - len);
-    const int32_t val = (int32_t)((mag ^ ~sgn) - ~sgn);
+    const int32_t val = fast_extend(top, tb - len);
     st.dcur += is_dc ? val : 0;
     fast_advance(cx, st, st.p + tb);
     if (z + adv >= 64u) {  // block complete
@@ -1107,7 +1110,7 @@ __global__ void __launch_bounds__(kWriteThreads) decode_write_kernel(BatchDev b)
         store_on = (st.g & 63) == 0;
         if ((uint32_t)st.g >= (uint32_t)total || (st.p >= end_bit && store_on)) active = false;   // past the scan (or a saturated position)
     } else {
-        st.p = 0; st.g = 0; st.flags = 0; st.info_ptr = cx.info_addr; st.w0 = st.w1 = st.w2 = 0; st.off = 0;
+        st.p = 0; st.g = 0; st.flags = 0; st.info_ptr = cx.info_addr; st.w0 = st.w1 = st.w2 = 0; st.kp = cx.words;
         st.seg = 0; st.seg_end = st.seg_lim = st.lim = 0; st.wrap_lim = 0xffffffffu; st.dcur = 0; st.dc_off = 0; st.lut_dc = st.lut_ac = cx.lut0_addr;
     }
     const int32_t g_start = st.g;
