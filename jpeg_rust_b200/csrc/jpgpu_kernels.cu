@@ -54,14 +54,19 @@ __device__ __forceinline__ PreBytes pre_classify(const uint8_t* __restrict__ in,
     PreBytes r;
     r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0u;
     r.keep = r.rstm = r.next = 0u;
-    if (o >= n) return r;
-    uint32_t prev = 0;
-    {
+    // All 32 lanes of a warp come here together (consecutive 16-byte vectors): the byte before / after a lane's vector
+    // is the neighbouring lane's last / first byte; only the warp's first and last lane read theirs from memory.
+    const uint32_t lane = threadIdx.x & 31u;
+    if (o < n) {
         const uint4 v = *reinterpret_cast<const uint4*>(in + o);  // raw arena is 16-byte padded
         r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
-        if (o > 0) prev = in[o - 1];
-        if (o + 16 < n) r.next = in[o + 16];
     }
+    uint32_t prev = __shfl_up_sync(0xffffffffu, r.w[3], 1) >> 24;
+    r.next = __shfl_down_sync(0xffffffffu, r.w[0], 1) & 0xffu;
+    if (o >= n) return r;
+    if (lane == 0u) prev = o > 0 ? in[o - 1] : 0u;
+    if (o + 16 >= n) r.next = 0u;
+    else if (lane == 31u) r.next = in[o + 16];
     const uint32_t valid = n - o >= 16u ? 0xffffu : (1u << (n - o)) - 1u;
     // byte k is 0xff / 0x00 (bit k), four bytes per word at a time
     const uint32_t ff = marks16(bytes_eq(r.w[0], 0xffffffffu), bytes_eq(r.w[1], 0xffffffffu), bytes_eq(r.w[2], 0xffffffffu),
@@ -110,16 +115,47 @@ __device__ __forceinline__ void pre_scan(uint32_t cnt, uint32_t nr, uint32_t (*s
     exr = wr + ir - nr;
 }
 
+// The same for one chunk, whose counters fit 16 bits each (<= 4096 kept bytes, <= 2048 markers): one packed scan.
+__device__ __forceinline__ void pre_scan_chunk(uint32_t cnt, uint32_t nr, uint32_t* s_wsum, uint32_t& exc, uint32_t& exr,
+                                               uint32_t& totc, uint32_t& totr) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, v = cnt | (nr << 16);
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += t;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < kPreThreads / 32; i++) {
+        const uint32_t a = s_wsum[i];
+        if ((uint32_t)i < warp) before += a;
+        tot += a;
+    }
+    const uint32_t ex = before + inc - v;
+    exc = ex & 0xffffu; exr = ex >> 16;
+    totc = tot & 0xffffu; totr = tot >> 16;
+}
+
 // (1) grid (max chunks of any image, images): counts per chunk.
 __global__ void __launch_bounds__(kPreThreads) prepass_count_kernel(BatchDev b) {
-    __shared__ uint32_t s_wsum[2][kPreThreads / 32];
+    __shared__ uint32_t s_wsum[kPreThreads / 32];
     const ImgDev& im = b.imgs[b.img0 + blockIdx.y];
     const uint32_t n = im.raw_len, base = blockIdx.x * kPreChunk;
     if (base >= n) return;
     const PreBytes pb = pre_classify(b.raw + im.raw_off, n, base + threadIdx.x * 16, im.restart_interval != 0);
-    uint32_t exc, exr, totc, totr;
-    pre_scan(__popc(pb.keep), __popc(pb.rstm), s_wsum, exc, exr, totc, totr);
-    if (threadIdx.x == 0) b.chunk_counts[im.chunk_off + blockIdx.x] = make_uint2(totc, totr);
+    // only the chunk's totals are wanted here: kept bytes (<= 4096) and markers (<= 2048) as one packed sum
+    const uint32_t wsum = __reduce_add_sync(0xffffffffu, __popc(pb.keep) | (__popc(pb.rstm) << 16));
+    if ((threadIdx.x & 31u) == 0u) s_wsum[threadIdx.x >> 5] = wsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < kPreThreads / 32; i++) t += s_wsum[i];
+        b.chunk_counts[im.chunk_off + blockIdx.x] = make_uint2(t & 0xffffu, t >> 16);
+    }
 }
 
 // (2) one CTA per image: exclusive scan of its chunk counts; stream length, interval count, padding.
@@ -165,7 +201,7 @@ __global__ void __launch_bounds__(kPreThreads) prepass_scan_kernel(BatchDev b) {
 // chunk only partly covers byte by byte.
 __global__ void __launch_bounds__(kPreThreads) prepass_write_kernel(BatchDev b) {
     __shared__ __align__(16) uint32_t s_stage[kPreChunk / 4 + 2 * kPieceWords];
-    __shared__ uint32_t s_wsum[2][kPreThreads / 32];
+    __shared__ uint32_t s_wsum[kPreThreads / 32];
     const uint32_t img = b.img0 + blockIdx.y;
     const ImgDev& im = b.imgs[img];
     const uint32_t n = im.raw_len, base = blockIdx.x * kPreChunk;
@@ -174,7 +210,7 @@ __global__ void __launch_bounds__(kPreThreads) prepass_write_kernel(BatchDev b) 
     const PreBytes pb = pre_classify(b.raw + im.raw_off, n, base + tid * 16, im.restart_interval != 0);
     const uint2 start = b.chunk_counts[im.chunk_off + blockIdx.x];   // bytes / markers before this chunk
     uint32_t exc, exr, totc, totr;
-    pre_scan(__popc(pb.keep), __popc(pb.rstm), s_wsum, exc, exr, totc, totr);
+    pre_scan_chunk(__popc(pb.keep), __popc(pb.rstm), s_wsum, exc, exr, totc, totr);
     uint8_t* stage_bytes = reinterpret_cast<uint8_t*>(s_stage);
     const uint32_t carry = start.x & (4u * kPieceWords - 1u);       // the chunk's first byte inside its first piece
     uint32_t pos = carry + exc;
@@ -573,6 +609,12 @@ struct WriteLane {
 };
 struct NoLane { enum : uint32_t { kBlockEnd = 3 }; uint32_t state; };
 
+// base + 4 * i as one multiply-add (the compiler's own shift, mask and add are three instructions on the busier pipe)
+__device__ __forceinline__ uint32_t fast_index4(uint32_t base, uint32_t i) {
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(i), "r"(base));
+    return a;
+}
 // EXTEND (huffman.rs:256-268) of the `size` (0..16) bits at the top of `top`: first bit 1 -> the bits v as they are,
 // 0 -> v - (2^size - 1).  With neg = all ones in the second case, (neg << size | v) is v - 2^size; size 0 gives 0.
 __device__ __forceinline__ int32_t fast_extend(uint32_t top, uint32_t size) {
@@ -597,7 +639,7 @@ __device__ __forceinline__ uint32_t fast_step(const FastCtx& cx, FastState& st, 
     const uint32_t hi = fast_peek(st);            // the next 32 bits
     const uint32_t z = (uint32_t)st.g & 63u;
     const uint32_t lut = z ? st.lut_ac : st.lut_dc;
-    uint32_t e = lds32(lut + ((hi >> (32 - kLutBits)) << 2));
+    uint32_t e = lds32(fast_index4(lut, hi >> (32 - kLutBits)));
     if ((int32_t)e <= 0) e = fast_long_code(cx, st, lut, e, hi);
     const uint32_t tb = e & 255u, len = __byte_perm(e, 0u, 0x4441), adv = __byte_perm(e, 0u, 0x4442);
     const uint32_t size = tb - len;
@@ -647,7 +689,7 @@ __device__ __forceinline__ void fast_mstep(const FastCtx& cx, FastState& st) {
     const uint32_t hi = fast_peek(st);
     const uint32_t z = (uint32_t)st.g & 63u;
     const bool is_dc = z == 0u;
-    const uint32_t e = lds32((is_dc ? st.m_dc : st.m_ac) + ((hi >> (is_dc ? 32 - kMultiBitsDc : 32 - kMultiBitsAc)) << 2));
+    const uint32_t e = lds32(fast_index4(is_dc ? st.m_dc : st.m_ac, hi >> (is_dc ? 32 - kMultiBitsDc : 32 - kMultiBitsAc)));
     if (e == 0u) {   // code longer than the window, no such code, oversized DC symbol: the single-symbol step knows
         NoLane nl;
         fast_step<false, false>(cx, st, nl);
