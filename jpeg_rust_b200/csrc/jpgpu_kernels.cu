@@ -50,23 +50,33 @@ __device__ __forceinline__ uint32_t marks16(uint32_t m0, uint32_t m1, uint32_t m
     auto pack = [](uint32_t m) { return ((m >> 7) * 0x00204081u >> 21) & 0xfu; };  // bits 7,15,23,31 -> 0..3
     return pack(m0) | (pack(m1) << 4) | (pack(m2) << 8) | (pack(m3) << 12);
 }
-__device__ __forceinline__ PreBytes pre_classify(const uint8_t* __restrict__ in, uint32_t n, uint32_t o, bool dri) {
-    PreBytes r;
-    r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0u;
-    r.keep = r.rstm = r.next = 0u;
-    // All 32 lanes of a warp come here together (consecutive 16-byte vectors): the byte before / after a lane's vector
-    // is the neighbouring lane's last / first byte; only the warp's first and last lane read theirs from memory.
-    const uint32_t lane = threadIdx.x & 31u;
+// What a thread reads from memory for its 16-byte vector at offset o: the vector (zeros past the end) and, for the
+// first / last lane of a warp, the byte before / after the warp's 512 bytes (the other lanes get theirs by shuffle).
+struct PreRaw { uint4 v; uint32_t edge; };
+__device__ __forceinline__ PreRaw pre_load(const uint8_t* __restrict__ in, uint32_t n, uint32_t o) {
+    PreRaw r;
+    r.v = make_uint4(0u, 0u, 0u, 0u);
+    r.edge = 0u;
     if (o < n) {
-        const uint4 v = *reinterpret_cast<const uint4*>(in + o);  // raw arena is 16-byte padded
-        r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+        const uint32_t lane = threadIdx.x & 31u;
+        r.v = *reinterpret_cast<const uint4*>(in + o);  // raw arena is 16-byte padded
+        if (lane == 0u && o > 0) r.edge = in[o - 1];
+        if (lane == 31u && o + 16 < n) r.edge = in[o + 16];
     }
+    return r;
+}
+// All 32 lanes of a warp come here together, with consecutive vectors.
+__device__ __forceinline__ PreBytes pre_classify(const PreRaw& raw, uint32_t n, uint32_t o, bool dri) {
+    PreBytes r;
+    r.w[0] = raw.v.x; r.w[1] = raw.v.y; r.w[2] = raw.v.z; r.w[3] = raw.v.w;
+    r.keep = r.rstm = 0u;
+    const uint32_t lane = threadIdx.x & 31u;
     uint32_t prev = __shfl_up_sync(0xffffffffu, r.w[3], 1) >> 24;
     r.next = __shfl_down_sync(0xffffffffu, r.w[0], 1) & 0xffu;
-    if (o >= n) return r;
-    if (lane == 0u) prev = o > 0 ? in[o - 1] : 0u;
+    if (lane == 0u) prev = raw.edge;
+    if (lane == 31u) r.next = raw.edge;
     if (o + 16 >= n) r.next = 0u;
-    else if (lane == 31u) r.next = in[o + 16];
+    if (o >= n) { r.next = 0u; return r; }
     const uint32_t valid = n - o >= 16u ? 0xffffu : (1u << (n - o)) - 1u;
     // byte k is 0xff / 0x00 (bit k), four bytes per word at a time
     const uint32_t ff = marks16(bytes_eq(r.w[0], 0xffffffffu), bytes_eq(r.w[1], 0xffffffffu), bytes_eq(r.w[2], 0xffffffffu),
@@ -140,21 +150,32 @@ __device__ __forceinline__ void pre_scan_chunk(uint32_t cnt, uint32_t nr, uint32
 }
 
 // (1) grid (max chunks of any image, images): counts per chunk.
+// A CTA takes kCountChunks consecutive chunks and reads them all before it looks at any (the kernel is a stream of
+// short-lived threads: what bounds it is the number of loads in flight).
+constexpr int kCountChunks = 4;
 __global__ void __launch_bounds__(kPreThreads) prepass_count_kernel(BatchDev b) {
-    __shared__ uint32_t s_wsum[kPreThreads / 32];
+    __shared__ uint32_t s_wsum[kCountChunks][kPreThreads / 32];
     const ImgDev& im = b.imgs[b.img0 + blockIdx.y];
-    const uint32_t n = im.raw_len, base = blockIdx.x * kPreChunk;
+    const uint32_t n = im.raw_len, base = blockIdx.x * (kCountChunks * kPreChunk);
     if (base >= n) return;
-    const PreBytes pb = pre_classify(b.raw + im.raw_off, n, base + threadIdx.x * 16, im.restart_interval != 0);
-    // only the chunk's totals are wanted here: kept bytes (<= 4096) and markers (<= 2048) as one packed sum
-    const uint32_t wsum = __reduce_add_sync(0xffffffffu, __popc(pb.keep) | (__popc(pb.rstm) << 16));
-    if ((threadIdx.x & 31u) == 0u) s_wsum[threadIdx.x >> 5] = wsum;
+    const uint8_t* in = b.raw + im.raw_off;
+    const bool dri = im.restart_interval != 0;
+    PreRaw raw[kCountChunks];
+#pragma unroll
+    for (int c = 0; c < kCountChunks; c++) raw[c] = pre_load(in, n, base + c * kPreChunk + threadIdx.x * 16);
+#pragma unroll
+    for (int c = 0; c < kCountChunks; c++) {
+        const PreBytes pb = pre_classify(raw[c], n, base + c * kPreChunk + threadIdx.x * 16, dri);
+        // only the chunk's totals are wanted here: kept bytes (<= 4096) and markers (<= 2048) as one packed sum
+        const uint32_t wsum = __reduce_add_sync(0xffffffffu, __popc(pb.keep) | (__popc(pb.rstm) << 16));
+        if ((threadIdx.x & 31u) == 0u) s_wsum[c][threadIdx.x >> 5] = wsum;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < kCountChunks && base + threadIdx.x * kPreChunk < n) {
         uint32_t t = 0;
 #pragma unroll
-        for (int i = 0; i < kPreThreads / 32; i++) t += s_wsum[i];
-        b.chunk_counts[im.chunk_off + blockIdx.x] = make_uint2(t & 0xffffu, t >> 16);
+        for (int i = 0; i < kPreThreads / 32; i++) t += s_wsum[threadIdx.x][i];
+        b.chunk_counts[im.chunk_off + blockIdx.x * kCountChunks + threadIdx.x] = make_uint2(t & 0xffffu, t >> 16);
     }
 }
 
@@ -207,7 +228,7 @@ __global__ void __launch_bounds__(kPreThreads) prepass_write_kernel(BatchDev b) 
     const uint32_t n = im.raw_len, base = blockIdx.x * kPreChunk;
     if (base >= n) return;
     const uint32_t lw = b.lw, tid = threadIdx.x;
-    const PreBytes pb = pre_classify(b.raw + im.raw_off, n, base + tid * 16, im.restart_interval != 0);
+    const PreBytes pb = pre_classify(pre_load(b.raw + im.raw_off, n, base + tid * 16), n, base + tid * 16, im.restart_interval != 0);
     const uint2 start = b.chunk_counts[im.chunk_off + blockIdx.x];   // bytes / markers before this chunk
     uint32_t exc, exr, totc, totr;
     pre_scan_chunk(__popc(pb.keep), __popc(pb.rstm), s_wsum, exc, exr, totc, totr);
@@ -1935,9 +1956,8 @@ void launch_prepass_step(const BatchDev& b, cudaStream_t s, int step) {
     if (!b.n_images || !b.max_chunks) return;
     if (step == 1) { prepass_scan_kernel<<<b.n_images, kPreThreads, 0, s>>>(b); return; }
     for_image_slices(b, [&](const BatchDev& d) {
-        const dim3 grid(d.max_chunks, d.n_images);
-        if (step == 0) prepass_count_kernel<<<grid, kPreThreads, 0, s>>>(d);
-        else prepass_write_kernel<<<grid, kPreThreads, 0, s>>>(d);
+        if (step == 0) prepass_count_kernel<<<dim3((d.max_chunks + kCountChunks - 1) / kCountChunks, d.n_images), kPreThreads, 0, s>>>(d);
+        else prepass_write_kernel<<<dim3(d.max_chunks, d.n_images), kPreThreads, 0, s>>>(d);
     });
 }
 void launch_zero_output_pads(const BatchDev& b, cudaStream_t s) {
