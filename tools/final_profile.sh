@@ -11,4 +11,7 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/$
 JPGPU_GRAPH=0 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${T}_launches_1024img.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-extra --no-parity > gpurun_out/${T}_ncu_bench.log 2>&1
 JPGPU_GRAPH=0 timeout 500 ncu --set full --clock-control none --import-source on -s 26 -c 8 -o gpurun_out/${T}_full python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extra --no-parity > gpurun_out/${T}_ncu_full.log 2>&1; tail -3 gpurun_out/${T}_ncu_full.log | cut -c1-200
 timeout 200 compute-sanitizer --tool memcheck python tests/sanitizer_smoke.py 2>&1 | tail -3 > gpurun_out/${T}_sanitizer_memcheck.log; cat gpurun_out/${T}_sanitizer_memcheck.log
+for tool in initcheck racecheck; do
+  timeout 300 compute-sanitizer --tool $tool python tests/sanitizer_smoke.py 2>&1 | tail -3 > gpurun_out/${T}_sanitizer_$tool.log; cat gpurun_out/${T}_sanitizer_$tool.log
+done
 bash tools/idct_variants.sh $T
