@@ -46,10 +46,22 @@ int compute_geometry(const jpgpu_image_desc& d, Geometry& g) {
     for (uint32_t c = 0; c < d.ncomp; c++) {
         const jpgpu_component& k = d.comp[c];
         if (k.h < 1 || k.h > 2 || k.v < 1 || k.v > 2) return JPGPU_ERR_UNSUPPORTED;  // mod.rs:275-277
-        if (k.tq >= 4 || k.td >= 4 || k.ta >= 4) return JPGPU_PANIC_INDEX_OOB;      // decoder.rs:155,159,222
-        if (!d.qt_present[k.tq] || !d.dc_present[k.td] || !d.ac_present[k.ta]) return JPGPU_PANIC_MISSING_TABLE;
         g.h[c] = k.h;
         g.v[c] = k.v;
+    }
+    // In the order the reference meets them: the first MCU looks up every component's AC, then DC table
+    // (decoder.rs:197-198 -> 154-160); the quantization tables come after the entropy decode (decoder.rs:222-224).
+    for (uint32_t c = 0; c < d.ncomp; c++) {
+        const jpgpu_component& k = d.comp[c];
+        if (k.ta >= 4) return JPGPU_PANIC_INDEX_OOB;
+        if (!d.ac_present[k.ta]) return JPGPU_PANIC_MISSING_TABLE;
+        if (k.td >= 4) return JPGPU_PANIC_INDEX_OOB;
+        if (!d.dc_present[k.td]) return JPGPU_PANIC_MISSING_TABLE;
+    }
+    for (uint32_t c = 0; c < d.ncomp; c++) {
+        const jpgpu_component& k = d.comp[c];
+        if (k.tq >= 4) return JPGPU_PANIC_INDEX_OOB;
+        if (!d.qt_present[k.tq]) return JPGPU_PANIC_MISSING_TABLE;
     }
     if (d.layout != JPGPU_LAYOUT_REF && d.ncomp == 1) { g.h[0] = 1; g.v[0] = 1; }  // T.81 A.2.2
     g.hmax = g.vmax = 1;
@@ -903,10 +915,27 @@ static int parse_walk(const uint8_t* file, size_t len, uint32_t ext, uint32_t la
                     for (size_t c = 0; c < scan.size(); c++) {
                         const FrameComp* fc = nullptr;  // decoder.rs:86-95: a later frame entry with the same id overwrites
                         for (const FrameComp& k : frame) if (k.id == scan[c].id) fc = &k;
-                        if (!fc) return JPGPU_PANIC_ARITH;  // decoder.rs:130-134: 0xff*0xff sampling product overflows
                         // decoder.rs:116-123 updates the selectors in scan order: the last entry with this id wins
                         uint8_t td = scan[c].td, ta = scan[c].ta;
-                        for (size_t k = 0; k < scan.size(); k++) if (scan[k].id == scan[c].id) { td = scan[k].td; ta = scan[k].ta; }
+                        bool first = true;
+                        for (size_t k = 0; k < scan.size(); k++) {
+                            if (scan[k].id != scan[c].id) continue;
+                            // decoder.rs:126-136: a component the frame does not know enters with its selectors swapped
+                            if (!fc && first) { td = scan[k].ta; ta = scan[k].td; } else { td = scan[k].td; ta = scan[k].ta; }
+                            first = false;
+                        }
+                        if (!fc) {
+                            // Its sampling factors are 0xff: the product overflows in the first MCU (decoder.rs:200-201, debug
+                            // build) - unless a table lookup of this or an earlier scan component panics before that.
+                            for (size_t e = 0; e <= c; e++) {
+                                const uint8_t e_td = e < c ? out->comp[e].td : td, e_ta = e < c ? out->comp[e].ta : ta;
+                                if (e_ta >= 4) return JPGPU_PANIC_INDEX_OOB;
+                                if (!out->ac_present[e_ta]) return JPGPU_PANIC_MISSING_TABLE;
+                                if (e_td >= 4) return JPGPU_PANIC_INDEX_OOB;
+                                if (!out->dc_present[e_td]) return JPGPU_PANIC_MISSING_TABLE;
+                            }
+                            return JPGPU_PANIC_ARITH;
+                        }
                         out->comp[c] = jpgpu_component{fc->id, fc->h, fc->v, fc->tq, td, ta};
                     }
                     out->scan = i <= len ? file + i : file + len;

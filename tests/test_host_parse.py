@@ -137,3 +137,52 @@ def test_parse_scans_of_non_interleaved_files():
     st, ds, _buf = parse_scans(f, EXT_DRI)
     info = plan_info(descs=ds)
     assert info["groups"] == 1 and info["warp_jobs"] >= 3
+
+
+def test_seeded_header_mutations_keep_the_references_verdict():
+    """800 seeded mutations of a small file's header region (byte changes, deletions, insertions, truncation): the host
+    side must give the reference's verdict - at parse time the parser's panic (mod.rs), for what the reference only
+    meets inside decode() the descriptor check every decode starts with (jpgpu_geometry: table selectors and missing
+    tables in the order decoder.rs:197-198 / 222-224 meets them, component count).  Entropy-stage panics (9, 10, 12,
+    reads past the data) belong to the GPU tests.  35 / 36 are the library's own refusals (sampling factors outside the
+    decodable subset, BITS/HUFFVAL that are no prefix code), 16 is the oracle's (more than four scan components).
+    One ordering the host cannot know: a component whose entropy data fails in the first MCU panics in the reference
+    before a later component's selector / table / sampling panic; the mutations here leave the entropy data intact."""
+    import random
+    good = synth.synth_jpeg(2, 48, 32, "420")
+    hdr_end = good.index(b"\xff\xda") + 14
+    rng = random.Random(1)
+    seen = set()
+    for it in range(800):
+        b = bytearray(good)
+        for _ in range(rng.choice([1, 1, 2, 3])):
+            op = rng.random()
+            pos = rng.randrange(2, max(3, min(hdr_end, len(b))))
+            if pos >= len(b):
+                continue
+            if op < 0.6:
+                b[pos] = rng.choice([0, 1, 0xff, rng.randrange(256), b[pos] ^ (1 << rng.randrange(8))])
+            elif op < 0.75:
+                del b[pos:pos + rng.randrange(1, 8)]
+            elif op < 0.9:
+                b[pos:pos] = bytes(rng.randrange(256) for _ in range(rng.randrange(1, 6)))
+            else:
+                b = b[:rng.randrange(2, len(b))]
+        data = bytes(b)
+        st, d, _ = parse_descriptor(data, EXT_NONE, LAYOUT_REF)
+        o = O.decode(data)
+        gs = _ffi.lib().jpgpu_geometry(C.byref(d), None, None, None) if st == 0 else -1
+        seen.add((st, gs, o.status))
+        if st in (35, 36) or gs == 35 or o.status == 16:
+            continue
+        if st != 0:
+            assert st == o.status, (it, st, o.status, o.msg)
+        elif o.status in (0, 9, 10, 12):
+            assert gs == 0, (it, gs, o.status, o.msg)
+        elif o.status in (8, 11):
+            assert gs == o.status, (it, gs, o.status, o.msg)
+        elif o.status == 6:    # "the len is 4": a table selector >= 4 (host); any other length: a read past the scan data (GPU)
+            assert gs == (6 if "the len is 4" in o.msg else 0), (it, gs, o.msg)
+        else:
+            raise AssertionError((it, st, gs, o.status, o.msg))
+    assert {s for s, _, _ in seen} >= {0, 1, 4, 5, 6, 15}, seen   # the campaign reaches the panics it is about
