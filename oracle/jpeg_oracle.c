@@ -596,7 +596,16 @@ static void decode_spec(ctx *c, const imgstate *im, const compfields *cf_in, int
         }
         size_t todo = ri ? (nmcu - mcu_done < ri ? nmcu - mcu_done : ri) : nmcu;
         hdecoder hd;
-        hd_new(c, &hd, un, n);
+        if (ri && n < 4 && raw_len >= 4) {
+            /* restart-interval extension (not in the reference): an interval may hold fewer than the four bytes
+             * HuffmanDecoder::new reads (huffman.rs:127-128) - a few flat MCUs at low quality.  The window is
+             * filled the way the refill fills it past the end of the data (huffman.rs:246: 0xaa). */
+            hd.data = un; hd.len = n; hd.current = 0;
+            for (size_t k = 0; k < 4; k++) hd.current = (hd.current << 8) | (k < n ? un[k] : 0xaau);
+            hd.next_index = 4; hd.bits_read = 0;
+        } else {
+            hd_new(c, &hd, un, n);
+        }
         float previous_dc[4] = {0, 0, 0, 0};
         for (size_t m = 0; m < todo; m++) {
             for (int ci = 0; ci < ncomp; ci++) {
