@@ -19,7 +19,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        path = os.path.join(_HERE, "sim", "libjpsim.so")
+        path = os.environ.get("JPSIM_LIB") or os.path.join(_HERE, "sim", "libjpsim.so")   # JPSIM_LIB: e.g. an ASAN build
         if not os.path.exists(path):
             subprocess.check_call(["make", "-s", "-C", ROOT, "tests/sim/libjpsim.so"])
         L = C.CDLL(path)
